@@ -1,0 +1,1170 @@
+// lmcma_capi.cu — the C ABI declared in include/lmcma_b200.h: handles, HBM layout, kernel launches,
+// the per-generation CUDA graph.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/lmcma_b200.h"
+#include "lmcma_host.hpp"
+#include "lmcma_kernels.cuh"
+
+using namespace lmcma;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(LMCMA_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define ARG(cond, msg)                                                   \
+    do {                                                                 \
+        if (!(cond)) return fail(LMCMA_B200_ERR_ARG, "%s (%s)", msg, #cond); \
+    } while (0)
+
+template <class T>
+int dmalloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
+    return 0;
+}
+#define DM(ptr, count)                              \
+    do {                                            \
+        int rc__ = dmalloc(&(ptr), (count));        \
+        if (rc__) return rc__;                      \
+    } while (0)
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+struct DeviceProps {
+    int sm_count = 0;
+    size_t l2 = 0, smem_optin = 0, persist_max = 0;
+    int cc = 0;
+    bool ok = false;
+};
+DeviceProps g_props[64];
+int query_props(int device, DeviceProps** out) {
+    ARG(device >= 0 && device < 64, "device ordinal out of range");
+    DeviceProps& p = g_props[device];
+    if (!p.ok) {
+        cudaDeviceProp dp;
+        CU(cudaGetDeviceProperties(&dp, device));
+        p.sm_count = dp.multiProcessorCount;
+        p.l2 = dp.l2CacheSize;
+        p.smem_optin = dp.sharedMemPerBlockOptin;
+        p.persist_max = dp.persistingL2CacheMaxSize;
+        p.cc = dp.major * 10 + dp.minor;
+        if (dp.major < 10) return fail(LMCMA_B200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, dp.major, dp.minor);
+        p.ok = true;
+    }
+    *out = &p;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// handles
+// =================================================================================================
+struct lmcma_b200_map {
+    int device = 0;
+    MapDev dev{};
+    int storage = 0;
+    float c_min = 0.5f, scale = 1.f;
+    size_t cells = 0;
+    float* d_g32 = nullptr;
+    unsigned char* d_q8 = nullptr;
+    float* d_lut = nullptr;
+    bool persist = false;
+    cudaStream_t stream = nullptr;   // private stream for the stand-alone evaluate calls
+    // staging for the host-buffer evaluate path
+    float* d_X = nullptr; size_t d_X_cap = 0;
+    float* d_f = nullptr; int* d_nc = nullptr; int* d_ns = nullptr; size_t d_out_cap = 0;
+    float* d_ends = nullptr;
+};
+
+struct lmcma_b200_opt {
+    lmcma_b200_config cfg{};
+    OptDev d{};
+    DeviceProps* props = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // host mirrors
+    std::vector<double> weights;       // mu
+    std::vector<float> lo_f, hi_f;
+    float* d_lo = nullptr; float* d_hi = nullptr; float* d_w = nullptr;
+    // rng
+    HansenStream hansen{1};
+    std::vector<float> z_host;         // staging for HANSEN
+    bool needs_sample = false, pending_z = false;
+    // reference one-at-a-time protocol
+    int sample_idx = 0;
+    std::vector<float> x_cache; bool x_cache_valid = false;
+    std::vector<float> f_host;
+    // attached cost
+    lmcma_b200_map* map = nullptr;
+    lmcma_b200_objective obj{};
+    float* d_ends = nullptr;
+    // graph
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t graph_built_for = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_run_timing = false;
+    // sample launch config
+    int smp_threads = 128, smp_kc = 1, smp_nv = 1, smp_rb = 1;
+    size_t smp_smem = 0;
+    int cost_tpt = 128;
+    size_t cost_smem = 0;
+};
+
+// =================================================================================================
+// launch helpers
+// =================================================================================================
+namespace {
+
+template <int DIMS, int STORAGE, bool TRACE>
+int launch_cost_t(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, cudaStream_t st) {
+    const size_t smem = sizeof(float) * DIMS * (a.W + 2) + sizeof(int) * (a.W + 2) + (STORAGE == 1 ? 1024 : 0);
+    auto kern = k_cost<DIMS, STORAGE, TRACE>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(rows, B), tpt, smem, st>>>(mp, a);
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, bool trace, cudaStream_t st) {
+    if (rows <= 0 || B <= 0) return 0;
+    if (trace) {
+        if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, tpt, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, tpt, st);
+        return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, tpt, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, tpt, st);
+    }
+    if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false>(mp, a, rows, B, tpt, st) : launch_cost_t<2, 1, false>(mp, a, rows, B, tpt, st);
+    return mp.storage == 0 ? launch_cost_t<3, 0, false>(mp, a, rows, B, tpt, st) : launch_cost_t<3, 1, false>(mp, a, rows, B, tpt, st);
+}
+
+int pick_cost_tpt(int W, const float* start, const float* goal, int dims) {
+    const int forced = env_int("LMCMA_B200_COST_TPT", 0);
+    if (forced >= 32 && forced <= 256 && (forced & (forced - 1)) == 0) return forced;
+    float linf = 0.f;
+    if (start && goal)
+        for (int c = 0; c < dims; ++c) linf = std::max(linf, std::fabs(goal[c] - start[c]));
+    const double est = 2.0 * (W + 1) + linf;     // expected samples per trajectory
+    int tpt = 32;
+    while (tpt < 256 && est / tpt > 24.0) tpt <<= 1;
+    return tpt;
+}
+
+template <int NV, int RB, int MAXT>
+int launch_sample_t(lmcma_b200_opt* o, cudaStream_t st) {
+    auto kern = k_sample<NV, RB, MAXT>;
+    if (o->smp_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_smem));
+    const int rows_per_cta = (o->smp_threads / 32) * RB;
+    const int ctas = (o->d.pop_count + rows_per_cta - 1) / rows_per_cta;
+    kern<<<dim3(ctas, o->d.B), o->smp_threads, o->smp_smem, st>>>(o->d, o->smp_kc);
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_sample(lmcma_b200_opt* o, cudaStream_t st) {
+    switch (o->smp_nv) {
+        case 1: return launch_sample_t<1, 4, 512>(o, st);
+        case 2: return launch_sample_t<2, 4, 512>(o, st);
+        case 4: return launch_sample_t<4, 2, 512>(o, st);
+        case 8: return launch_sample_t<8, 1, 512>(o, st);
+        case 12: return launch_sample_t<12, 1, 256>(o, st);
+        case 16: return launch_sample_t<16, 1, 256>(o, st);
+    }
+    return fail(LMCMA_B200_ERR_ARG, "unsupported n for k_sample (nv=%d)", o->smp_nv);
+}
+
+int configure_sample(lmcma_b200_opt* o) {
+    const int nq = o->d.ns / 4;
+    const int need = (nq + 31) / 32;
+    static const int nvs[] = {1, 2, 4, 8, 12, 16};
+    o->smp_nv = 0;
+    for (int v : nvs)
+        if (v >= need) { o->smp_nv = v; break; }
+    if (!o->smp_nv) return fail(LMCMA_B200_ERR_ARG, "n = %d too large (max 2048)", o->d.n);
+    o->smp_rb = o->smp_nv <= 2 ? 4 : (o->smp_nv <= 4 ? 2 : 1);
+    const int maxt = o->smp_nv >= 12 ? 256 : 512;
+    // as many warps per CTA as keeps >= ~1 CTA per SM
+    int threads = maxt;
+    const int forced = env_int("LMCMA_B200_SAMPLE_THREADS", 0);
+    if (forced >= 32 && forced <= maxt && forced % 32 == 0) threads = forced;
+    else
+        while (threads > 64) {
+            const int rows_per_cta = (threads / 32) * o->smp_rb;
+            const long long ctas = (long long)((o->d.pop_count + rows_per_cta - 1) / rows_per_cta) * o->d.B;
+            if (ctas >= o->props->sm_count) break;
+            threads >>= 1;
+        }
+    o->smp_threads = threads;
+    const size_t pair_bytes = (size_t)2 * o->d.ns * sizeof(float);
+    int kc = (int)std::max<size_t>(1, (size_t)env_int("LMCMA_B200_SAMPLE_STAGE_KB", 32) * 1024 / pair_bytes);
+    kc = std::min(kc, o->d.m);
+    o->smp_kc = kc;
+    o->smp_smem = 2 * kc * pair_bytes + 64;
+    if (o->smp_smem > o->props->smem_optin) return fail(LMCMA_B200_ERR_ARG, "k_sample needs %zu B shared memory", o->smp_smem);
+    return 0;
+}
+
+int launch_rank(lmcma_b200_opt* o, const float* f_all, cudaStream_t st) {
+    k_rank<<<dim3((o->d.pop_count + 255) / 256, o->d.B), 256, 0, st>>>(o->d, f_all);
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int launch_recombine(lmcma_b200_opt* o, cudaStream_t st) {
+    const int nq = o->d.ns / 4;
+    k_recombine<<<dim3((nq + 127) / 128, o->d.RS, o->d.B), 128, 0, st>>>(o->d);
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int launch_update(lmcma_b200_opt* o, const float* slices, int n_slices, long long slice_stride, long long inst_stride,
+                  const float* f_all, int payload_mode, cudaStream_t st) {
+    const int threads = std::min(512, std::max(64, 32 * std::min(16, o->d.m)));
+    k_update<<<o->d.B, threads, sizeof(int) * o->d.m, st>>>(o->d, slices, n_slices, slice_stride, inst_stride, f_all, payload_mode);
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int cost_args_for(lmcma_b200_opt* o, CostArgs* a) {
+    if (!o->map) return fail(LMCMA_B200_ERR_STATE, "no cost attached (call lmcma_b200_attach_cost)");
+    memset(a, 0, sizeof(*a));
+    a->W = o->obj.waypoints; a->w_len = o->obj.w_len; a->w_clr = o->obj.w_clr; a->w_col = o->obj.w_col;
+    a->X = o->d.X; a->ld = o->d.ns; a->inst_rows = o->d.pop_count;
+    a->ends = o->d_ends; a->ends_per_instance = 1;
+    a->f = o->d.fit; a->f_stride = o->d.lambda; a->f_offset = o->d.pop_offset;
+    a->ncoll = o->d.ncoll; a->nsamp = o->d.nsamp;
+    return 0;
+}
+
+// generate / stage deviates on the host for HANSEN mode, then sample
+int host_rng_and_sample(lmcma_b200_opt* o, cudaStream_t st) {
+    if (o->cfg.rng == LMCMA_B200_RNG_HANSEN) {
+        const size_t rows = (size_t)o->d.pop_count;
+        o->z_host.assign(rows * o->d.ns, 0.f);
+        // the reference draws row by row, N deviates per offspring (lmcma.cpp:303-305, 212-215)
+        for (size_t r = 0; r < rows; ++r)
+            for (int k = 0; k < o->d.n; ++k) o->z_host[r * o->d.ns + k] = (float)o->hansen.gauss();
+        CU(cudaMemcpyAsync(o->d.Z, o->z_host.data(), o->z_host.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // z_host is pageable and reused
+    }
+    return launch_sample(o, st);
+}
+
+// update() + sample() after the fitness of a generation is in d.fit
+int generation_tail(lmcma_b200_opt* o, cudaStream_t st) {
+    int rc;
+    if ((rc = launch_rank(o, o->d.fit, st))) return rc;
+    if ((rc = launch_recombine(o, st))) return rc;
+    if ((rc = launch_update(o, o->d.partial, o->d.RS, o->d.ns, (long long)o->d.RS * o->d.ns, o->d.fit, 0, st))) return rc;
+    o->x_cache_valid = false;
+    o->sample_idx = 0;
+    if (o->cfg.rng == LMCMA_B200_RNG_INJECT && !o->pending_z) { o->needs_sample = true; return 0; }
+    o->pending_z = false;
+    return host_rng_and_sample(o, st);
+}
+
+int ensure_graph(lmcma_b200_opt* o) {
+    if (o->graph_exec && o->graph_built_for == o->stream) return 0;
+    if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
+    CostArgs ca;
+    int rc = cost_args_for(o, &ca);
+    if (rc) return rc;
+    cudaStream_t st = o->stream;
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches.load();
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+    if (!rc) rc = launch_rank(o, o->d.fit, st);
+    if (!rc) rc = launch_recombine(o, st);
+    if (!rc) rc = launch_update(o, o->d.partial, o->d.RS, o->d.ns, (long long)o->d.RS * o->d.ns, o->d.fit, 0, st);
+    if (!rc) rc = launch_sample(o, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    g_launches.store(before);   // capture enqueues nothing
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&o->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    o->graph_built_for = st;
+    return 0;
+}
+
+// dense <-> pitched copies
+int d2h_rows(void* dst, const void* src, size_t rows, size_t width_bytes, size_t src_pitch_bytes, cudaStream_t st) {
+    CU(cudaMemcpy2DAsync(dst, width_bytes, src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+int h2d_rows(void* dst, const void* src, size_t rows, size_t width_bytes, size_t dst_pitch_bytes, cudaStream_t st) {
+    CU(cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, width_bytes, width_bytes, rows, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// library / device
+// =================================================================================================
+extern "C" {
+
+int lmcma_b200_abi_version(void) { return LMCMA_B200_ABI_VERSION; }
+const char* lmcma_b200_last_error(void) { return g_err.c_str(); }
+int64_t lmcma_b200_launch_count(void) { return g_launches.load(); }
+
+int lmcma_b200_device_count(int* count_out) {
+    ARG(count_out, "null output");
+    CU(cudaGetDeviceCount(count_out));
+    return 0;
+}
+int lmcma_b200_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t* hbm_bytes, int* cc) {
+    cudaDeviceProp dp;
+    CU(cudaGetDeviceProperties(&dp, device));
+    if (sm_count) *sm_count = dp.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = dp.l2CacheSize;
+    if (hbm_bytes) *hbm_bytes = (int64_t)dp.totalGlobalMem;
+    if (cc) *cc = dp.major * 10 + dp.minor;
+    return 0;
+}
+
+// =================================================================================================
+// cost map
+// =================================================================================================
+int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const float* dist, int storage, float u8_scale,
+                          float c_min, lmcma_b200_map** out) {
+    ARG(out && shape && dist, "null pointer");
+    ARG(dims == 2 || dims == 3, "dims must be 2 or 3");
+    ARG(storage == LMCMA_B200_MAP_F32 || storage == LMCMA_B200_MAP_U8, "unknown storage");
+    ARG(c_min > 0.f, "c_min must be > 0");
+    ARG(storage == LMCMA_B200_MAP_F32 || u8_scale > 0.f, "u8_scale must be > 0");
+    for (int c = 0; c < dims; ++c) ARG(shape[c] >= 1, "bad shape");
+    DeviceProps* props;
+    int rc = query_props(device, &props);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    lmcma_b200_map* m = new lmcma_b200_map();
+    m->device = device; m->storage = storage; m->c_min = c_min; m->scale = u8_scale;
+    m->dev.dims = dims; m->dev.nx = shape[0]; m->dev.ny = shape[1]; m->dev.nz = dims == 3 ? shape[2] : 1;
+    m->dev.storage = storage; m->dev.g_coll = 1.0f / c_min;
+    m->cells = (size_t)m->dev.nx * m->dev.ny * m->dev.nz;
+    CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    // the transform E -> stored representation is a one-off, element-wise host pass (upload path, not hot)
+    if (storage == LMCMA_B200_MAP_F32) {
+        std::vector<float> g(m->cells);
+        for (size_t i = 0; i < m->cells; ++i) {
+            const float e = dist[i];
+            g[i] = (e > 0.f) ? 1.0f / std::max(e, c_min) : -m->dev.g_coll;
+        }
+        DM(m->d_g32, m->cells);
+        CU(cudaMemcpy(m->d_g32, g.data(), m->cells * sizeof(float), cudaMemcpyHostToDevice));
+        m->dev.g32 = m->d_g32;
+    } else {
+        std::vector<unsigned char> q(m->cells);
+        for (size_t i = 0; i < m->cells; ++i) {
+            const float e = dist[i];
+            int v = 0;
+            if (e > 0.f) { v = (int)std::floor(e / u8_scale); v = std::min(255, std::max(1, v)); }
+            q[i] = (unsigned char)v;
+        }
+        float lut[256];
+        lut[0] = -m->dev.g_coll;
+        for (int v = 1; v < 256; ++v) lut[v] = 1.0f / std::max((float)v * u8_scale, c_min);
+        DM(m->d_q8, m->cells);
+        DM(m->d_lut, 256);
+        CU(cudaMemcpy(m->d_q8, q.data(), m->cells, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(m->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        m->dev.q8 = m->d_q8; m->dev.lut = m->d_lut;
+    }
+    DM(m->d_ends, 6);
+    *out = m;
+    return 0;
+}
+
+int lmcma_b200_map_destroy(lmcma_b200_map* m) {
+    if (!m) return 0;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_g32); cudaFree(m->d_q8); cudaFree(m->d_lut); cudaFree(m->d_X); cudaFree(m->d_f);
+    cudaFree(m->d_nc); cudaFree(m->d_ns); cudaFree(m->d_ends);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return 0;
+}
+
+int lmcma_b200_map_dequantized(const lmcma_b200_map* m, float* out) {
+    ARG(m && out, "null pointer");
+    CU(cudaSetDevice(m->device));
+    if (m->storage == LMCMA_B200_MAP_F32) {
+        // stored g = 1/max(E, c_min) is not invertible below c_min; report the effective clearance
+        std::vector<float> g(m->cells);
+        CU(cudaMemcpy(g.data(), m->d_g32, m->cells * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m->cells; ++i) out[i] = g[i] < 0.f ? 0.f : 1.0f / g[i];
+    } else {
+        std::vector<unsigned char> q(m->cells);
+        CU(cudaMemcpy(q.data(), m->d_q8, m->cells, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m->cells; ++i) out[i] = (float)q[i] * m->scale;
+    }
+    return 0;
+}
+
+int lmcma_b200_map_set_l2_persist(lmcma_b200_map* m, int enable) {
+    ARG(m, "null map");
+    CU(cudaSetDevice(m->device));
+    DeviceProps* props;
+    int rc = query_props(m->device, &props);
+    if (rc) return rc;
+    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->cells * 4 : m->cells;
+    if (enable) CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, props->persist_max)));
+    m->persist = enable != 0;
+    return 0;
+}
+
+static int apply_l2_window(lmcma_b200_map* m, cudaStream_t st) {
+    if (!m->persist) return 0;
+    DeviceProps* props;
+    int rc = query_props(m->device, &props);
+    if (rc) return rc;
+    int max_win = 0;
+    CU(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, m->device));
+    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->cells * 4 : m->cells;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = m->storage == LMCMA_B200_MAP_F32 ? (void*)m->d_g32 : (void*)m->d_q8;
+    v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_win);
+    v.accessPolicyWindow.hitRatio = std::min(1.0f, (float)props->persist_max / (float)std::max<size_t>(bytes, 1));
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
+    return 0;
+}
+
+static int check_obj(const lmcma_b200_map* m, const lmcma_b200_objective* obj) {
+    ARG(m && obj, "null pointer");
+    ARG(obj->waypoints >= 1 && obj->waypoints <= 8190, "waypoints out of range");
+    return 0;
+}
+
+int lmcma_b200_cost_evaluate_dev(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
+                                 const float* X_dev, int64_t ld, int32_t count, float* f_dev, int32_t* ncoll_dev,
+                                 int32_t* nsamp_dev, void* stream) {
+    int rc = check_obj(m, obj);
+    if (rc) return rc;
+    ARG(ends && X_dev && f_dev, "null pointer");
+    ARG(count >= 0 && ld >= (int64_t)m->dev.dims * obj->waypoints, "bad count / ld");
+    if (count == 0) return 0;
+    CU(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float e6[6] = {ends->start[0], ends->start[1], ends->start[2], ends->goal[0], ends->goal[1], ends->goal[2]};
+    CU(cudaMemcpyAsync(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice, st));
+    CostArgs a;
+    memset(&a, 0, sizeof(a));
+    a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
+    a.X = X_dev; a.ld = ld; a.inst_rows = count; a.ends = m->d_ends; a.ends_per_instance = 0;
+    a.f = f_dev; a.f_stride = count; a.f_offset = 0; a.ncoll = ncoll_dev; a.nsamp = nsamp_dev;
+    if ((rc = apply_l2_window(m, st))) return rc;
+    return launch_cost(m->dev, a, count, 1, pick_cost_tpt(a.W, ends->start, ends->goal, m->dev.dims), false, st);
+}
+
+int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
+                             const float* X_host, int32_t count, float* f_host, int32_t* ncoll_host, int32_t* nsamp_host) {
+    int rc = check_obj(m, obj);
+    if (rc) return rc;
+    ARG(ends && X_host && f_host && count >= 0, "null pointer / negative count");
+    if (count == 0) return 0;
+    CU(cudaSetDevice(m->device));
+    const size_t n = (size_t)m->dev.dims * obj->waypoints;
+    if (m->d_X_cap < (size_t)count * n) {
+        cudaFree(m->d_X); m->d_X = nullptr; m->d_X_cap = 0;
+        DM(m->d_X, (size_t)count * n);
+        m->d_X_cap = (size_t)count * n;
+    }
+    if (m->d_out_cap < (size_t)count) {
+        cudaFree(m->d_f); cudaFree(m->d_nc); cudaFree(m->d_ns);
+        m->d_f = nullptr; m->d_nc = nullptr; m->d_ns = nullptr; m->d_out_cap = 0;
+        DM(m->d_f, count); DM(m->d_nc, count); DM(m->d_ns, count);
+        m->d_out_cap = count;
+    }
+    CU(cudaMemcpyAsync(m->d_X, X_host, (size_t)count * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    rc = lmcma_b200_cost_evaluate_dev(m, obj, ends, m->d_X, (int64_t)n, count, m->d_f, m->d_nc, m->d_ns, m->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(f_host, m->d_f, count * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    if (ncoll_host) CU(cudaMemcpyAsync(ncoll_host, m->d_nc, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (nsamp_host) CU(cudaMemcpyAsync(nsamp_host, m->d_ns, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int lmcma_b200_cost_trace(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
+                          const float* x_host, int64_t* cells_host, int64_t max_cells, int64_t* n_cells_out) {
+    int rc = check_obj(m, obj);
+    if (rc) return rc;
+    ARG(ends && x_host && cells_host && n_cells_out && max_cells > 0, "null pointer");
+    CU(cudaSetDevice(m->device));
+    const size_t n = (size_t)m->dev.dims * obj->waypoints;
+    float* dX = nullptr; float* df = nullptr; int* dns = nullptr; long long* dcells = nullptr;
+    DM(dX, n); DM(df, 1); DM(dns, 1); DM(dcells, (size_t)max_cells);
+    CU(cudaMemset(dcells, 0xff, (size_t)max_cells * sizeof(long long)));
+    CU(cudaMemcpy(dX, x_host, n * sizeof(float), cudaMemcpyHostToDevice));
+    float e6[6] = {ends->start[0], ends->start[1], ends->start[2], ends->goal[0], ends->goal[1], ends->goal[2]};
+    CU(cudaMemcpy(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice));
+    CostArgs a;
+    memset(&a, 0, sizeof(a));
+    a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
+    a.X = dX; a.ld = (long long)n; a.inst_rows = 1; a.ends = m->d_ends; a.ends_per_instance = 0;
+    a.f = df; a.f_stride = 1; a.nsamp = dns; a.cells = dcells; a.max_cells = max_cells;
+    rc = launch_cost(m->dev, a, 1, 1, pick_cost_tpt(a.W, ends->start, ends->goal, m->dev.dims), true, m->stream);
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "trace kernel: %s", cudaGetErrorString(e));
+    }
+    int ns = 0;
+    if (!rc) {
+        cudaMemcpy(&ns, dns, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(cells_host, dcells, (size_t)std::min<int64_t>(ns, max_cells) * sizeof(long long), cudaMemcpyDeviceToHost);
+        *n_cells_out = ns;
+    }
+    cudaFree(dX); cudaFree(df); cudaFree(dns); cudaFree(dcells);
+    return rc;
+}
+
+// =================================================================================================
+// optimiser
+// =================================================================================================
+int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const double* lo, const double* hi,
+                      lmcma_b200_opt** out) {
+    ARG(cfg && out, "null pointer");
+    ARG(cfg->n >= 1, "n must be >= 1");
+    ARG(cfg->batch >= 1, "batch must be >= 1");
+    ARG(cfg->rng >= 0 && cfg->rng <= 2, "unknown rng mode");
+    ARG(cfg->sigma0 > 0.0, "sigma0 must be > 0");
+    ARG(x0 || cfg->rng == LMCMA_B200_RNG_HANSEN, "x0 == NULL needs the HANSEN rng (uniform start, lmcma.cpp:161-163)");
+    ARG(cfg->rng != LMCMA_B200_RNG_HANSEN || cfg->batch == 1, "HANSEN rng is a single serial stream: batch must be 1");
+    DeviceProps* props;
+    int rc = query_props(cfg->device, &props);
+    if (rc) return rc;
+    CU(cudaSetDevice(cfg->device));
+
+    lmcma_b200_opt* o = new lmcma_b200_opt();
+    o->cfg = *cfg;
+    o->props = props;
+    OptDev& d = o->d;
+    d.n = cfg->n;
+    d.ns = (cfg->n + 3) & ~3;
+    d.lambda = cfg->lambda < 1 ? 4 + int(3 * std::log((double)cfg->n)) : cfg->lambda;   // lmcma.cpp:134-135
+    d.mu = d.lambda / 2;                                                                  // lmcma.cpp:136
+    d.m = cfg->m < 1 ? d.lambda : cfg->m;                                                 // lmcma.cpp:266
+    d.B = cfg->batch;
+    if (d.lambda < 2 || d.mu < 1 || d.m < 2) { delete o; return fail(LMCMA_B200_ERR_ARG, "need lambda >= 2 and m >= 2"); }
+    d.pop_offset = cfg->pop_count < 1 ? 0 : cfg->pop_offset;
+    d.pop_count = cfg->pop_count < 1 ? d.lambda : cfg->pop_count;
+    if (d.pop_offset < 0 || d.pop_offset + d.pop_count > d.lambda) { delete o; return fail(LMCMA_B200_ERR_ARG, "population slice out of range"); }
+    if (cfg->rng == LMCMA_B200_RNG_HANSEN && d.pop_count != d.lambda) { delete o; return fail(LMCMA_B200_ERR_ARG, "HANSEN rng cannot be split"); }
+    d.rng_mode = cfg->rng;
+    d.record_z = cfg->record_z;
+    d.seed = (unsigned long long)cfg->seed;
+    o->hansen.reseed(cfg->seed);
+
+    // constants (lmcma.cpp:144-156, 238, 268-272)
+    o->weights.resize(d.mu);
+    double sw = 0;
+    for (int i = 0; i < d.mu; ++i) { o->weights[i] = std::log(double(d.mu) + 0.5) - std::log(double(1 + i)); sw += o->weights[i]; }
+    double mueff = 0;
+    for (int i = 0; i < d.mu; ++i) { o->weights[i] /= sw; mueff += o->weights[i] * o->weights[i]; }
+    d.mueff = 1.0 / mueff;
+    d.c1 = 1.0 / (10 * std::log((double)(d.n + 1)));
+    d.cc = 1.0 / d.m;
+    d.cs = 0.3; d.target = 0.25;
+    d.K = 1 / std::sqrt(1 - d.c1);
+    d.M = std::sqrt(1 - d.c1);
+
+    CU(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
+    o->stream = o->own_stream;
+    CU(cudaEventCreate(&o->ev0));
+    CU(cudaEventCreate(&o->ev1));
+
+    const size_t B = d.B, ns = d.ns, lam = d.lambda, pc = d.pop_count, m = d.m;
+    DM(d.X, B * pc * ns);
+    if (cfg->rng != LMCMA_B200_RNG_PHILOX || cfg->record_z) DM(d.Z, B * pc * ns);
+    DM(d.fit, B * lam); DM(d.fit_sorted, B * lam); DM(d.prev_fit, B * lam);
+    DM(d.rank, B * lam); DM(d.arindex, B * lam);
+    DM(d.ncoll, B * pc); DM(d.nsamp, B * pc);
+    DM(d.xmean, B * ns); DM(d.pc, B * ns);
+    DM(d.V, B * m * ns); DM(d.P, B * m * ns);
+    DM(d.Nj, B * m); DM(d.Lj, B * m); DM(d.Njf, B * m);
+    DM(d.t, B * m); DM(d.vec, B * m);
+    DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B);
+    d.RS = std::max(1, std::min(256, (d.pop_count + 15) / 16));
+    DM(d.partial, B * d.RS * ns);
+
+    std::vector<float> wf(o->weights.begin(), o->weights.end());
+    DM(o->d_w, d.mu);
+    CU(cudaMemcpy(o->d_w, wf.data(), d.mu * sizeof(float), cudaMemcpyHostToDevice));
+    d.w = o->d_w;
+    if (lo) {
+        o->lo_f.assign(lo, lo + d.n);
+        DM(o->d_lo, d.n);
+        CU(cudaMemcpy(o->d_lo, o->lo_f.data(), d.n * sizeof(float), cudaMemcpyHostToDevice));
+        d.lo = o->d_lo;
+    }
+    if (hi) {
+        o->hi_f.assign(hi, hi + d.n);
+        DM(o->d_hi, d.n);
+        CU(cudaMemcpy(o->d_hi, o->hi_f.data(), d.n * sizeof(float), cudaMemcpyHostToDevice));
+        d.hi = o->d_hi;
+    }
+    // initial mean (lmcma.cpp:158-163)
+    std::vector<double> xm(B * ns, 0.0);
+    for (size_t b = 0; b < B; ++b)
+        for (int k = 0; k < d.n; ++k) xm[b * ns + k] = x0 ? x0[b * d.n + k] : o->hansen.uniform();
+    CU(cudaMemcpy(d.xmean, xm.data(), xm.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<Scalars> sc(B);
+    for (auto& s : sc) {
+        memset(&s, 0, sizeof(s));
+        s.sigma = cfg->sigma0; s.s = 0.0; s.best_f = std::numeric_limits<double>::max();
+    }
+    CU(cudaMemcpy(d.sc, sc.data(), B * sizeof(Scalars), cudaMemcpyHostToDevice));
+
+    rc = configure_sample(o);
+    if (rc) { lmcma_b200_destroy(o); return rc; }
+    o->f_host.assign(B * lam, 0.f);
+    // first population (LMCMA::init -> sample(), lmcma.cpp:298)
+    if (cfg->rng == LMCMA_B200_RNG_INJECT) o->needs_sample = true;
+    else {
+        rc = host_rng_and_sample(o, o->stream);
+        if (!rc) { cudaError_t e = cudaStreamSynchronize(o->stream); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "first sample: %s", cudaGetErrorString(e)); }
+        if (rc) { lmcma_b200_destroy(o); return rc; }
+    }
+    *out = o;
+    return 0;
+}
+
+int lmcma_b200_destroy(lmcma_b200_opt* o) {
+    if (!o) return 0;
+    cudaSetDevice(o->cfg.device);
+    if (o->stream) cudaStreamSynchronize(o->stream);
+    OptDev& d = o->d;
+    void* ptrs[] = {d.X, d.Z, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
+                    d.Nj, d.Lj, d.Njf, d.t, d.vec, d.sc, d.best_x, d.S_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
+    for (void* p : ptrs) cudaFree(p);
+    if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
+    if (o->ev0) cudaEventDestroy(o->ev0);
+    if (o->ev1) cudaEventDestroy(o->ev1);
+    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    delete o;
+    return 0;
+}
+
+int lmcma_b200_set_stream(lmcma_b200_opt* o, void* cuda_stream) {
+    ARG(o, "null handle");
+    CU(cudaStreamSynchronize(o->stream));
+    o->stream = cuda_stream ? (cudaStream_t)cuda_stream : o->own_stream;
+    return 0;
+}
+
+int lmcma_b200_shape(const lmcma_b200_opt* o, int32_t* out8) {
+    ARG(o && out8, "null pointer");
+    const OptDev& d = o->d;
+    out8[0] = d.n; out8[1] = d.lambda; out8[2] = d.mu; out8[3] = d.m; out8[4] = d.B;
+    out8[5] = d.pop_offset; out8[6] = d.pop_count; out8[7] = d.ns;
+    return 0;
+}
+
+int lmcma_b200_inject_z(lmcma_b200_opt* o, const float* Z) {
+    ARG(o && Z, "null pointer");
+    if (o->cfg.rng != LMCMA_B200_RNG_INJECT) return fail(LMCMA_B200_ERR_STATE, "inject_z needs rng == INJECT");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    int rc = h2d_rows(d.Z, Z, (size_t)d.B * d.pop_count, d.n * sizeof(float), d.ns * sizeof(float), o->stream);
+    if (rc) return rc;
+    if (o->needs_sample) {
+        o->needs_sample = false;
+        rc = launch_sample(o, o->stream);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(o->stream));
+    } else {
+        o->pending_z = true;
+    }
+    return 0;
+}
+
+int lmcma_b200_resample(lmcma_b200_opt* o) {
+    ARG(o, "null handle");
+    if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no deviates yet: inject_z first");
+    if (o->cfg.rng == LMCMA_B200_RNG_HANSEN) return fail(LMCMA_B200_ERR_STATE, "resample would advance the serial HANSEN stream");
+    CU(cudaSetDevice(o->cfg.device));
+    int rc = launch_sample(o, o->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(o->stream));
+    o->x_cache_valid = false;
+    return 0;
+}
+
+int lmcma_b200_ask_all(lmcma_b200_opt* o, float* X) {
+    ARG(o && X, "null pointer");
+    if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no population yet: inject_z first");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    return d2h_rows(X, d.X, (size_t)d.B * d.pop_count, d.n * sizeof(float), d.ns * sizeof(float), o->stream);
+}
+
+int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
+    ARG(o && f, "null pointer");
+    if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no population yet: inject_z first");
+    if (o->d.pop_count != o->d.lambda) return fail(LMCMA_B200_ERR_STATE, "split-population handles use the mg_* entry points");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    CU(cudaMemcpyAsync(d.fit, f, (size_t)d.B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, o->stream));
+    int rc = generation_tail(o, o->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(o->stream));
+    return 0;
+}
+
+int lmcma_b200_ask_one(lmcma_b200_opt* o, double* params, int32_t n) {
+    ARG(o && params, "null pointer");
+    ARG(n == o->d.n, "N mismatch");
+    if (o->d.B != 1 || o->d.pop_count != o->d.lambda) return fail(LMCMA_B200_ERR_STATE, "ask_one needs batch == 1 and an unsplit population");
+    if (!o->x_cache_valid) {
+        o->x_cache.resize((size_t)o->d.lambda * o->d.n);
+        int rc = lmcma_b200_ask_all(o, o->x_cache.data());
+        if (rc) return rc;
+        o->x_cache_valid = true;
+    }
+    for (int k = 0; k < n; ++k) params[k] = (double)o->x_cache[(size_t)o->sample_idx * n + k];
+    return 0;
+}
+
+int lmcma_b200_tell_one(lmcma_b200_opt* o, const double* feedbacks, int32_t num) {
+    ARG(o && (feedbacks || num == 0) && num >= 0, "null pointer");
+    if (o->d.B != 1 || o->d.pop_count != o->d.lambda) return fail(LMCMA_B200_ERR_STATE, "tell_one needs batch == 1 and an unsplit population");
+    double f = 0.0;                                    // lmcma.cpp:186-188
+    for (int i = 0; i < num; ++i) f += feedbacks[i];
+    o->f_host[o->sample_idx] = (float)f;
+    if (++o->sample_idx % o->d.lambda == 0) {          // lmcma.cpp:199-204
+        o->sample_idx = 0;
+        return lmcma_b200_tell_all(o, o->f_host.data());
+    }
+    return 0;
+}
+
+int lmcma_b200_is_done(lmcma_b200_opt* o, int32_t* done) {
+    ARG(o && done, "null pointer");
+    CU(cudaSetDevice(o->cfg.device));
+    std::vector<Scalars> sc(o->d.B);
+    CU(cudaMemcpyAsync(sc.data(), o->d.sc, sc.size() * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
+    CU(cudaStreamSynchronize(o->stream));
+    for (int b = 0; b < o->d.B; ++b) done[b] = sc[b].sigma < 1e-20 ? 1 : 0;   // lmcma.cpp:426-429
+    return 0;
+}
+
+int lmcma_b200_attach_cost(lmcma_b200_opt* o, lmcma_b200_map* map, const lmcma_b200_objective* obj,
+                           const lmcma_b200_endpoints* ends) {
+    ARG(o && ends, "null pointer");
+    int rc = check_obj(map, obj);
+    if (rc) return rc;
+    ARG(map->device == o->cfg.device, "map and optimiser live on different devices");
+    ARG(map->dev.dims * obj->waypoints == o->d.n, "n != dims * waypoints");
+    CU(cudaSetDevice(o->cfg.device));
+    o->map = map; o->obj = *obj;
+    std::vector<float> e6((size_t)o->d.B * 6);
+    for (int b = 0; b < o->d.B; ++b)
+        for (int c = 0; c < 3; ++c) { e6[b * 6 + c] = ends[b].start[c]; e6[b * 6 + 3 + c] = ends[b].goal[c]; }
+    if (!o->d_ends) DM(o->d_ends, (size_t)o->d.B * 6);
+    CU(cudaMemcpy(o->d_ends, e6.data(), e6.size() * sizeof(float), cudaMemcpyHostToDevice));
+    o->cost_tpt = pick_cost_tpt(obj->waypoints, ends[0].start, ends[0].goal, map->dev.dims);
+    if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
+    return 0;
+}
+
+int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
+    ARG(o && generations >= 0, "bad argument");
+    if (!o->map) return fail(LMCMA_B200_ERR_STATE, "no cost attached");
+    if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no population yet: inject_z first");
+    if (o->d.pop_count != o->d.lambda) return fail(LMCMA_B200_ERR_STATE, "split-population handles use the mg_* entry points");
+    CU(cudaSetDevice(o->cfg.device));
+    int rc = apply_l2_window(o->map, o->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(o->ev0, o->stream));
+    if (o->cfg.rng == LMCMA_B200_RNG_PHILOX) {
+        if ((rc = ensure_graph(o))) return rc;
+        for (int g = 0; g < generations; ++g) {
+            CU(cudaGraphLaunch(o->graph_exec, o->stream));
+            g_launches += 5;
+        }
+    } else {
+        if (o->cfg.rng == LMCMA_B200_RNG_INJECT && generations > 1)
+            return fail(LMCMA_B200_ERR_STATE, "INJECT rng: run one generation per injected Z");
+        CostArgs ca;
+        if ((rc = cost_args_for(o, &ca))) return rc;
+        for (int g = 0; g < generations; ++g) {
+            if ((rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, o->stream))) return rc;
+            if ((rc = generation_tail(o, o->stream))) return rc;
+        }
+    }
+    CU(cudaEventRecord(o->ev1, o->stream));
+    o->have_run_timing = true;
+    o->x_cache_valid = false;
+    return 0;
+}
+
+int lmcma_b200_sync(lmcma_b200_opt* o) {
+    ARG(o, "null handle");
+    CU(cudaSetDevice(o->cfg.device));
+    CU(cudaStreamSynchronize(o->stream));
+    return 0;
+}
+
+int lmcma_b200_last_run_ms(lmcma_b200_opt* o, float* ms) {
+    ARG(o && ms, "null pointer");
+    if (!o->have_run_timing) return fail(LMCMA_B200_ERR_STATE, "no run yet");
+    CU(cudaEventSynchronize(o->ev1));
+    CU(cudaEventElapsedTime(ms, o->ev0, o->ev1));
+    return 0;
+}
+
+int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms5) {
+    ARG(o && ms5 && generations >= 1, "bad argument");
+    if (!o->map) return fail(LMCMA_B200_ERR_STATE, "no cost attached");
+    if (o->cfg.rng != LMCMA_B200_RNG_PHILOX) return fail(LMCMA_B200_ERR_STATE, "profile_kernels needs the PHILOX rng");
+    CU(cudaSetDevice(o->cfg.device));
+    CostArgs ca;
+    int rc = cost_args_for(o, &ca);
+    if (rc) return rc;
+    cudaStream_t st = o->stream;
+    std::vector<cudaEvent_t> ev((size_t)generations * 6);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    for (int g = 0; g < generations && !rc; ++g) {
+        cudaEvent_t* e = &ev[(size_t)g * 6];
+        cudaEventRecord(e[0], st);
+        rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+        cudaEventRecord(e[1], st);
+        if (!rc) rc = launch_rank(o, o->d.fit, st);
+        cudaEventRecord(e[2], st);
+        if (!rc) rc = launch_recombine(o, st);
+        cudaEventRecord(e[3], st);
+        if (!rc) rc = launch_update(o, o->d.partial, o->d.RS, o->d.ns, (long long)o->d.RS * o->d.ns, o->d.fit, 0, st);
+        cudaEventRecord(e[4], st);
+        if (!rc) rc = launch_sample(o, st);
+        cudaEventRecord(e[5], st);
+    }
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (!rc && se != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "profile run: %s", cudaGetErrorString(se));
+    for (int k = 0; k < 5; ++k) ms5[k] = 0.f;
+    if (!rc)
+        for (int g = 0; g < generations; ++g)
+            for (int k = 0; k < 5; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[(size_t)g * 6 + k], ev[(size_t)g * 6 + k + 1]);
+                ms5[k] += ms / generations;
+            }
+    for (auto& e : ev) cudaEventDestroy(e);
+    o->x_cache_valid = false;
+    return rc;
+}
+
+int lmcma_b200_best(lmcma_b200_opt* o, float* x_best, float* f_best) {
+    ARG(o, "null handle");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    if (x_best) {
+        int rc = d2h_rows(x_best, d.best_x, d.B, d.n * sizeof(float), d.ns * sizeof(float), o->stream);
+        if (rc) return rc;
+    }
+    if (f_best) {
+        std::vector<Scalars> sc(d.B);
+        CU(cudaMemcpyAsync(sc.data(), d.sc, sc.size() * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
+        CU(cudaStreamSynchronize(o->stream));
+        for (int b = 0; b < d.B; ++b) f_best[b] = (float)sc[b].best_f;
+    }
+    return 0;
+}
+
+// ---- state access ------------------------------------------------------------------------------
+int lmcma_b200_get_f64(lmcma_b200_opt* o, int32_t which, double* out, int64_t cap) {
+    ARG(o && out, "null pointer");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    const size_t B = d.B;
+    switch (which) {
+        case LMCMA_B200_F64_XMEAN:
+            ARG(cap >= (int64_t)(B * d.n), "capacity");
+            return d2h_rows(out, d.xmean, B, d.n * sizeof(double), d.ns * sizeof(double), o->stream);
+        case LMCMA_B200_F64_SIGMA: case LMCMA_B200_F64_S: case LMCMA_B200_F64_BESTF: {
+            ARG(cap >= (int64_t)B, "capacity");
+            std::vector<Scalars> sc(B);
+            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            for (size_t b = 0; b < B; ++b)
+                out[b] = which == LMCMA_B200_F64_SIGMA ? sc[b].sigma : (which == LMCMA_B200_F64_S ? sc[b].s : sc[b].best_f);
+            return 0;
+        }
+        case LMCMA_B200_F64_CONSTS:
+            ARG(cap >= 7, "capacity");
+            out[0] = d.c1; out[1] = d.cc; out[2] = d.cs; out[3] = d.target; out[4] = d.K; out[5] = d.M; out[6] = d.mueff;
+            return 0;
+        case LMCMA_B200_F64_WEIGHTS:
+            ARG(cap >= d.mu, "capacity");
+            std::copy(o->weights.begin(), o->weights.end(), out);
+            return 0;
+        case LMCMA_B200_F64_NJ: case LMCMA_B200_F64_LJ:
+            ARG(cap >= (int64_t)(B * d.m), "capacity");
+            CU(cudaMemcpyAsync(out, which == LMCMA_B200_F64_NJ ? d.Nj : d.Lj, B * d.m * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            return 0;
+    }
+    return fail(LMCMA_B200_ERR_ARG, "unknown f64 field %d", which);
+}
+
+int lmcma_b200_get_f32(lmcma_b200_opt* o, int32_t which, float* out, int64_t cap) {
+    ARG(o && out, "null pointer");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    const size_t B = d.B, w = d.n * sizeof(float), p = d.ns * sizeof(float);
+    switch (which) {
+        case LMCMA_B200_F32_X:
+            ARG(cap >= (int64_t)(B * d.pop_count * d.n), "capacity");
+            return d2h_rows(out, d.X, B * d.pop_count, w, p, o->stream);
+        case LMCMA_B200_F32_Z:
+            if (!d.Z) return fail(LMCMA_B200_ERR_STATE, "deviates are not recorded (record_z = 0)");
+            ARG(cap >= (int64_t)(B * d.pop_count * d.n), "capacity");
+            return d2h_rows(out, d.Z, B * d.pop_count, w, p, o->stream);
+        case LMCMA_B200_F32_PC:
+            ARG(cap >= (int64_t)(B * d.n), "capacity");
+            return d2h_rows(out, d.pc, B, w, p, o->stream);
+        case LMCMA_B200_F32_V: case LMCMA_B200_F32_P:
+            ARG(cap >= (int64_t)(B * d.m * d.n), "capacity");
+            return d2h_rows(out, which == LMCMA_B200_F32_V ? d.V : d.P, B * d.m, w, p, o->stream);
+        case LMCMA_B200_F32_FIT: case LMCMA_B200_F32_FIT_SORTED: case LMCMA_B200_F32_PREV_FIT: {
+            ARG(cap >= (int64_t)(B * d.lambda), "capacity");
+            const float* src = which == LMCMA_B200_F32_FIT ? d.fit : (which == LMCMA_B200_F32_FIT_SORTED ? d.fit_sorted : d.prev_fit);
+            CU(cudaMemcpyAsync(out, src, B * d.lambda * sizeof(float), cudaMemcpyDeviceToHost, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            if (which == LMCMA_B200_F32_PREV_FIT)   // the device keeps it in evaluation order; the reference keeps it sorted
+                for (size_t b = 0; b < B; ++b) std::sort(out + b * d.lambda, out + (b + 1) * d.lambda);
+            return 0;
+        }
+    }
+    return fail(LMCMA_B200_ERR_ARG, "unknown f32 field %d", which);
+}
+
+int lmcma_b200_get_i32(lmcma_b200_opt* o, int32_t which, int32_t* out, int64_t cap) {
+    ARG(o && out, "null pointer");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    const size_t B = d.B;
+    const int* src = nullptr; size_t cnt = 0;
+    switch (which) {
+        case LMCMA_B200_I32_T: src = d.t; cnt = B * d.m; break;
+        case LMCMA_B200_I32_VEC: src = d.vec; cnt = B * d.m; break;
+        case LMCMA_B200_I32_ARINDEX: src = d.arindex; cnt = B * d.lambda; break;
+        case LMCMA_B200_I32_RANK: src = d.rank; cnt = B * d.lambda; break;
+        case LMCMA_B200_I32_NCOLL: src = d.ncoll; cnt = B * d.pop_count; break;
+        case LMCMA_B200_I32_NSAMP: src = d.nsamp; cnt = B * d.pop_count; break;
+        case LMCMA_B200_I32_ITR: case LMCMA_B200_I32_LIVE: case LMCMA_B200_I32_COUNTEVAL: {
+            ARG(cap >= (int64_t)B, "capacity");
+            std::vector<Scalars> sc(B);
+            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            for (size_t b = 0; b < B; ++b)
+                out[b] = which == LMCMA_B200_I32_ITR ? sc[b].itr : (which == LMCMA_B200_I32_LIVE ? sc[b].live : (int)sc[b].counteval);
+            return 0;
+        }
+        default: return fail(LMCMA_B200_ERR_ARG, "unknown i32 field %d", which);
+    }
+    ARG(cap >= (int64_t)cnt, "capacity");
+    CU(cudaMemcpyAsync(out, src, cnt * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    CU(cudaStreamSynchronize(o->stream));
+    return 0;
+}
+
+int lmcma_b200_set_f64(lmcma_b200_opt* o, int32_t which, const double* in, int64_t count) {
+    ARG(o && in, "null pointer");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    const size_t B = d.B;
+    switch (which) {
+        case LMCMA_B200_F64_XMEAN:
+            ARG(count == (int64_t)(B * d.n), "count");
+            return h2d_rows(d.xmean, in, B, d.n * sizeof(double), d.ns * sizeof(double), o->stream);
+        case LMCMA_B200_F64_SIGMA: case LMCMA_B200_F64_S: {
+            ARG(count == (int64_t)B, "count");
+            std::vector<Scalars> sc(B);
+            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            for (size_t b = 0; b < B; ++b) (which == LMCMA_B200_F64_SIGMA ? sc[b].sigma : sc[b].s) = in[b];
+            CU(cudaMemcpyAsync(d.sc, sc.data(), B * sizeof(Scalars), cudaMemcpyHostToDevice, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            return 0;
+        }
+        case LMCMA_B200_F64_NJ: case LMCMA_B200_F64_LJ: {
+            ARG(count == (int64_t)(B * d.m), "count");
+            CU(cudaMemcpyAsync(which == LMCMA_B200_F64_NJ ? d.Nj : d.Lj, in, B * d.m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+            if (which == LMCMA_B200_F64_NJ) {
+                std::vector<float> f(in, in + B * d.m);
+                CU(cudaMemcpyAsync(d.Njf, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, o->stream));
+                CU(cudaStreamSynchronize(o->stream));
+            }
+            CU(cudaStreamSynchronize(o->stream));
+            return 0;
+        }
+    }
+    return fail(LMCMA_B200_ERR_ARG, "f64 field %d is not settable", which);
+}
+
+int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_t count) {
+    ARG(o && in, "null pointer");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    const size_t B = d.B, w = d.n * sizeof(float), p = d.ns * sizeof(float);
+    switch (which) {
+        case LMCMA_B200_F32_PC:
+            ARG(count == (int64_t)(B * d.n), "count");
+            return h2d_rows(d.pc, in, B, w, p, o->stream);
+        case LMCMA_B200_F32_V: case LMCMA_B200_F32_P:
+            ARG(count == (int64_t)(B * d.m * d.n), "count");
+            return h2d_rows(which == LMCMA_B200_F32_V ? d.V : d.P, in, B * d.m, w, p, o->stream);
+        case LMCMA_B200_F32_X:
+            ARG(count == (int64_t)(B * d.pop_count * d.n), "count");
+            o->x_cache_valid = false;
+            return h2d_rows(d.X, in, B * d.pop_count, w, p, o->stream);
+        case LMCMA_B200_F32_PREV_FIT:
+            ARG(count == (int64_t)(B * d.lambda), "count");
+            CU(cudaMemcpyAsync(d.prev_fit, in, B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            return 0;
+    }
+    return fail(LMCMA_B200_ERR_ARG, "f32 field %d is not settable", which);
+}
+
+int lmcma_b200_set_i32(lmcma_b200_opt* o, int32_t which, const int32_t* in, int64_t count) {
+    ARG(o && in, "null pointer");
+    CU(cudaSetDevice(o->cfg.device));
+    const OptDev& d = o->d;
+    const size_t B = d.B;
+    switch (which) {
+        case LMCMA_B200_I32_T: case LMCMA_B200_I32_VEC:
+            ARG(count == (int64_t)(B * d.m), "count");
+            CU(cudaMemcpyAsync(which == LMCMA_B200_I32_T ? d.t : d.vec, in, B * d.m * sizeof(int), cudaMemcpyHostToDevice, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            return 0;
+        case LMCMA_B200_I32_ITR: case LMCMA_B200_I32_LIVE: case LMCMA_B200_I32_COUNTEVAL: {
+            ARG(count == (int64_t)B, "count");
+            std::vector<Scalars> sc(B);
+            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            for (size_t b = 0; b < B; ++b) {
+                if (which == LMCMA_B200_I32_ITR) sc[b].itr = in[b];
+                else if (which == LMCMA_B200_I32_LIVE) sc[b].live = in[b];
+                else sc[b].counteval = in[b];
+            }
+            CU(cudaMemcpyAsync(d.sc, sc.data(), B * sizeof(Scalars), cudaMemcpyHostToDevice, o->stream));
+            CU(cudaStreamSynchronize(o->stream));
+            return 0;
+        }
+    }
+    return fail(LMCMA_B200_ERR_ARG, "i32 field %d is not settable", which);
+}
+
+// ---- split-population mode ---------------------------------------------------------------------
+int lmcma_b200_mg_payload_floats(lmcma_b200_opt* o, int32_t* floats_out) {
+    ARG(o && floats_out, "null pointer");
+    *floats_out = o->d.ns + 4;
+    return 0;
+}
+
+int lmcma_b200_mg_evaluate(lmcma_b200_opt* o, float* f_local_dev, void* stream) {
+    ARG(o && f_local_dev, "null pointer");
+    if (o->d.B != 1) return fail(LMCMA_B200_ERR_STATE, "split-population mode needs batch == 1");
+    if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no population yet");
+    CU(cudaSetDevice(o->cfg.device));
+    CostArgs ca;
+    int rc = cost_args_for(o, &ca);
+    if (rc) return rc;
+    ca.f = f_local_dev; ca.f_stride = o->d.pop_count; ca.f_offset = 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : o->stream;
+    if ((rc = apply_l2_window(o->map, st))) return rc;
+    return launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+}
+
+int lmcma_b200_mg_rank(lmcma_b200_opt* o, const float* f_all_dev, float* payload_dev, void* stream) {
+    ARG(o && f_all_dev && payload_dev, "null pointer");
+    if (o->d.B != 1) return fail(LMCMA_B200_ERR_STATE, "split-population mode needs batch == 1");
+    CU(cudaSetDevice(o->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : o->stream;
+    // keep the gathered fitness: k_update needs it for prev_fit / best tracking
+    CU(cudaMemcpyAsync(o->d.fit, f_all_dev, (size_t)o->d.lambda * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    int rc;
+    if ((rc = launch_rank(o, o->d.fit, st))) return rc;
+    if ((rc = launch_recombine(o, st))) return rc;
+    k_pack_payload<<<dim3((o->d.ns + 127) / 128, o->d.B), 128, 0, st>>>(o->d, payload_dev);
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lmcma_b200_mg_update(lmcma_b200_opt* o, const float* payload_all_dev, int32_t world, void* stream) {
+    ARG(o && payload_all_dev && world >= 1, "bad argument");
+    CU(cudaSetDevice(o->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : o->stream;
+    const long long pf = o->d.ns + 4;
+    int rc = launch_update(o, payload_all_dev, world, (long long)o->d.B * pf, pf, o->d.fit, 1, st);
+    if (rc) return rc;
+    o->x_cache_valid = false;
+    if (o->cfg.rng != LMCMA_B200_RNG_PHILOX) return fail(LMCMA_B200_ERR_STATE, "split-population mode needs the PHILOX rng");
+    return launch_sample(o, st);
+}
+
+// ---- host-side reference pieces ------------------------------------------------------------------
+int lmcma_b200_hansen_gauss(int64_t seed, int64_t skip, int64_t count, double* out) {
+    ARG(out && count >= 0 && skip >= 0, "bad argument");
+    HansenStream r(seed);
+    for (int64_t i = 0; i < skip; ++i) (void)r.gauss();
+    for (int64_t i = 0; i < count; ++i) out[i] = r.gauss();
+    return 0;
+}
+int lmcma_b200_hansen_uniform(int64_t seed, int64_t count, double* out) {
+    ARG(out && count >= 0, "bad argument");
+    HansenStream r(seed);
+    for (int64_t i = 0; i < count; ++i) out[i] = r.uniform();
+    return 0;
+}
+int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out) {
+    ARG(out && dims >= 1 && waypoints >= 1, "bad argument");
+    if (!smoothness_covariance(dims, waypoints, out)) return fail(LMCMA_B200_ERR_ARG, "singular finite-difference block");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// lmcma_host.cpp — see lmcma_host.hpp
+#include "lmcma_host.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace lmcma {
+
+bool smoothness_covariance(int dims, int waypoints, double* out) {
+    const int W = waypoints, n = dims * waypoints;
+    // centred 7-tap acceleration rule of the reference (DIFF_RULES[2], lmcma.cpp:763), dt = 1
+    static const double taps[7] = {0.0, -1.0 / 12.0, 16.0 / 12.0, -30.0 / 12.0, 16.0 / 12.0, -1.0 / 12.0, 0.0};
+    std::vector<double> A(static_cast<size_t>(W) * W, 0.0), AA(static_cast<size_t>(W) * W, 0.0);
+    for (int i = 0; i < W; ++i)
+        for (int j = -3; j <= 3; ++j) {
+            const int c = i + j;
+            if (c < 0 || c >= W) continue;          // truncated at the trajectory ends (lmcma.cpp:826-829)
+            A[static_cast<size_t>(i) * W + c] += taps[j + 3];
+        }
+    for (int i = 0; i < W; ++i)                      // A*A (lmcma.cpp:793-798), banded so skip zeros
+        for (int k = std::max(0, i - 3); k <= std::min(W - 1, i + 3); ++k) {
+            const double a = A[static_cast<size_t>(i) * W + k];
+            if (a == 0.0) continue;
+            for (int j = std::max(0, k - 3); j <= std::min(W - 1, k + 3); ++j)
+                AA[static_cast<size_t>(i) * W + j] += a * A[static_cast<size_t>(k) * W + j];
+        }
+    // inverse of one block by Gauss-Jordan with partial pivoting
+    std::vector<double> inv(static_cast<size_t>(W) * W, 0.0);
+    for (int i = 0; i < W; ++i) inv[static_cast<size_t>(i) * W + i] = 1.0;
+    for (int col = 0; col < W; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < W; ++r)
+            if (std::fabs(AA[static_cast<size_t>(r) * W + col]) > std::fabs(AA[static_cast<size_t>(piv) * W + col])) piv = r;
+        if (AA[static_cast<size_t>(piv) * W + col] == 0.0) return false;
+        if (piv != col)
+            for (int j = 0; j < W; ++j) {
+                std::swap(AA[static_cast<size_t>(col) * W + j], AA[static_cast<size_t>(piv) * W + j]);
+                std::swap(inv[static_cast<size_t>(col) * W + j], inv[static_cast<size_t>(piv) * W + j]);
+            }
+        const double p = AA[static_cast<size_t>(col) * W + col];
+        for (int j = 0; j < W; ++j) { AA[static_cast<size_t>(col) * W + j] /= p; inv[static_cast<size_t>(col) * W + j] /= p; }
+        for (int r = 0; r < W; ++r) {
+            if (r == col) continue;
+            const double f = AA[static_cast<size_t>(r) * W + col];
+            if (f == 0.0) continue;
+            for (int j = 0; j < W; ++j) {
+                AA[static_cast<size_t>(r) * W + j] -= f * AA[static_cast<size_t>(col) * W + j];
+                inv[static_cast<size_t>(r) * W + j] -= f * inv[static_cast<size_t>(col) * W + j];
+            }
+        }
+    }
+    double vmax = 0.0;                                // lmcma.cpp:802-806
+    for (int i = 0; i < W; ++i) vmax = std::max(vmax, inv[static_cast<size_t>(i) * W + i]);
+    const double scaling = vmax * W;
+    std::memset(out, 0, sizeof(double) * static_cast<size_t>(n) * n);
+    for (int d = 0; d < dims; ++d)                    // dimension-major blocks (lmcma.cpp:786-791)
+        for (int i = 0; i < W; ++i)
+            for (int j = 0; j < W; ++j)
+                out[static_cast<size_t>(d * W + i) * n + (d * W + j)] = inv[static_cast<size_t>(i) * W + j] / scaling;
+    return true;
+}
+
+}  // namespace lmcma

@@ -1,0 +1,392 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bars: integer / index work bit-exact; costs 1e-5 relative; optimiser state after a
+teacher-forced generation 1e-5 relative (FP32 device vs FP64 oracle); sigma 1e-12."""
+import numpy as np
+import pytest
+
+import lmcma_path_planner_b200 as L
+from lmcma_path_planner_b200 import maps
+from conftest import weighted_sphere
+
+pytestmark = pytest.mark.gpu
+
+COST_RTOL = 1e-5
+
+
+def rel_err(a, b, floor=1e-30):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# cost kernel
+# ------------------------------------------------------------------------------------------------
+def _candidates(rng, x0, count, sigma, lo, hi):
+    X = x0[None, :] + sigma * rng.standard_normal((count, len(x0)))
+    return np.clip(X, lo, hi).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["problem1", "problem2", "two_bars"])
+@pytest.mark.parametrize("weights", [L.LONGSAFE, L.SHORTRISKY])
+def test_cost_2d_bundled_maps(po, golden_maps, name, weights):
+    """C1 shape: the reference's 100x100 maps, query (99,0)->(0,99) (planner.cpp:701-706), 20 waypoints."""
+    dist = po.edt_exact(golden_maps[name])
+    W, start, goal = 20, (99.0, 0.0), (0.0, 99.0)
+    rng = np.random.default_rng(3)
+    lo, hi = maps.box_bounds((100, 100), W)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 257, 6.0, lo, hi)
+    ref = po.CostProblem(dist, start, goal, W, *weights, w_col=1e4).evaluate(X)
+    cm = L.CostMap(dist, "f32")
+    got = cm.evaluate(X, start, goal, W, weights, 1e4)
+    assert np.array_equal(got["ncoll"], ref["ncoll"])          # collision flags: bit-exact
+    assert np.array_equal(got["nsamp"], ref["nsamp"])
+    assert rel_err(got["f"], ref["f"]) < COST_RTOL
+    assert ref["ncoll"].max() > 0 and ref["ncoll"].min() == 0 or name == "two_bars"
+
+
+def test_cost_cell_indices_bit_exact(po, golden_maps):
+    dist = po.edt_exact(golden_maps["problem1"])
+    W, start, goal = 20, (99.0, 0.0), (0.0, 99.0)
+    rng = np.random.default_rng(11)
+    lo, hi = maps.box_bounds((100, 100), W)
+    cm = L.CostMap(dist, "f32")
+    prob = po.CostProblem(dist, start, goal, W)
+    x0 = maps.straight_line(start, goal, W)
+    for i in range(8):
+        x = _candidates(rng, x0, 1, 8.0, lo - 3, hi + 3)[0]   # some samples leave the map
+        if i == 0:
+            x = (np.round(x * 2) / 2).astype(np.float32)      # half-integer coordinates: rint ties
+        assert np.array_equal(cm.trace(x, start, goal, W), prob.trace(x))
+
+
+def test_cost_edge_cases(po, golden_maps):
+    dist = po.edt_exact(golden_maps["two_bars"])
+    W, start, goal = 5, (99.0, 0.0), (0.0, 99.0)
+    x0 = maps.straight_line(start, goal, W).astype(np.float32)
+    X = np.stack([x0, x0, x0, x0, x0])
+    X[1, 2] = np.nan                     # NaN waypoint
+    X[2, :] = 50.0                       # degenerate: all waypoints coincide (zero-length segments)
+    X[3, 0] = -40.0; X[3, 7] = 400.0     # far outside the map
+    X[4, :] = 0.25                       # sub-cell segments
+    ref = po.CostProblem(dist, start, goal, W).evaluate(X)
+    got = L.CostMap(dist, "f32").evaluate(X, start, goal, W)
+    assert np.array_equal(got["ncoll"], ref["ncoll"])
+    assert np.array_equal(got["nsamp"], ref["nsamp"])
+    assert np.isnan(got["f"][1]) and np.isnan(ref["f"][1])
+    ok = [0, 2, 3, 4]
+    assert rel_err(got["f"][ok], ref["f"][ok]) < COST_RTOL
+    # empty batch
+    e = L.CostMap(dist, "f32").evaluate(np.zeros((0, 2 * W), np.float32), start, goal, W)
+    assert e["f"].shape == (0,)
+
+
+def test_cost_u8_storage_matches_oracle_on_dequantized_map(po):
+    dist, start, goal = maps.config2_map(size=512, n_rects=64, seed=5, clamp=60.0)
+    W = 60
+    cm = L.CostMap(dist, "u8", u8_scale=0.25)
+    dq = cm.dequantized()
+    assert np.array_equal(dq == 0, dist == 0)            # obstacles preserved exactly
+    assert np.all(dq <= dist + 1e-6) and np.all((dist - dq)[dist < 63] < 0.25 + 1e-6)
+    rng = np.random.default_rng(2)
+    lo, hi = maps.box_bounds((512, 512), W)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 300, 12.0, lo, hi)
+    ref = po.CostProblem(dq, start, goal, W).evaluate(X)
+    got = cm.evaluate(X, start, goal, W)
+    assert np.array_equal(got["ncoll"], ref["ncoll"])
+    assert rel_err(got["f"], ref["f"]) < COST_RTOL
+
+
+def test_cost_3d(po):
+    dist, start, goal = maps.config4_map(size=64, n_boxes=4096, seed=9, clamp=16.0)
+    W = 40
+    rng = np.random.default_rng(4)
+    lo, hi = maps.box_bounds((64, 64, 64), W)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 200, 3.0, lo, hi)
+    for storage, d in (("f32", dist), ("u8", None)):
+        cm = L.CostMap(dist, storage, u8_scale=0.125)
+        dd = dist if d is not None else cm.dequantized()
+        prob = po.CostProblem(dd, start, goal, W)
+        ref = prob.evaluate(X)
+        got = cm.evaluate(X, start, goal, W)
+        assert np.array_equal(got["ncoll"], ref["ncoll"])
+        assert np.array_equal(got["nsamp"], ref["nsamp"])
+        assert rel_err(got["f"], ref["f"]) < COST_RTOL
+        assert np.array_equal(cm.trace(X[0], start, goal, W), prob.trace(X[0]))
+
+
+def test_cost_full_size_properties(po):
+    """C2 size (4096^2, n = 400, lambda = 1024): a seeded sample is checked against the oracle, the whole
+    population through size-independent properties (reversal symmetry, sample count, monotone penalty)."""
+    dist, start, goal = maps.config2_map()
+    W = 200
+    rng = np.random.default_rng(42)
+    lo, hi = maps.box_bounds((4096, 4096), W)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 1024, 32.0, lo, hi)
+    cm = L.CostMap(dist, "f32")
+    got = cm.evaluate(X, start, goal, W)
+    idx = rng.choice(1024, 48, replace=False)
+    ref = po.CostProblem(dist, start, goal, W, threads=8).evaluate(X[idx])
+    assert np.array_equal(got["ncoll"][idx], ref["ncoll"])
+    assert np.array_equal(got["nsamp"][idx], ref["nsamp"])
+    assert rel_err(got["f"][idx], ref["f"]) < COST_RTOL
+    # the same poly-line walked goal->start has the same length / sample count (cells may differ by rounding)
+    Xr = X.reshape(1024, 2, W)[:, :, ::-1].reshape(1024, -1).copy()
+    rev = cm.evaluate(Xr, goal, start, W)
+    assert np.array_equal(rev["nsamp"], got["nsamp"])
+    # raising the collision weight can only raise the cost, and by exactly w_col * ncoll
+    hi_pen = cm.evaluate(X, start, goal, W, L.LONGSAFE, 2e4)
+    assert np.all(hi_pen["f"] >= got["f"] - 1e-3)
+    assert rel_err(hi_pen["f"] - got["f"], 1e4 * got["ncoll"], floor=1.0) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser: teacher-forced generations against the FP64 oracle
+# ------------------------------------------------------------------------------------------------
+def _teacher_forced(po, n, lam, m, gens, seed, lo=None, hi=None, sigma=1.0, fobj=weighted_sphere, x0=None,
+                    tol=2e-5):
+    rng = np.random.default_rng(seed)
+    x0 = np.full(n, 0.5) if x0 is None else x0
+    dev = L.Optimizer(n, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=sigma, rng="inject")
+    lam = dev.lam
+    zs = rng.standard_normal((gens + 1, lam, n)).astype(np.float32)
+    ora = po.OracleLMCMA(n, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma=sigma, seed=1, Z0=zs[0].astype(np.float64))
+    dev.inject_z(zs[0])
+    worst = {}
+    for g in range(gens):
+        Xo = ora.array("X")
+        Xd = dev.ask_all()[0]
+        worst["X"] = max(worst.get("X", 0), rel_err(Xd, Xo, floor=1e-3))
+        f = fobj(Xo).astype(np.float32)            # both sides are told the same FP32 fitness
+        ora.tell_all(f.astype(np.float64), zs[g + 1].astype(np.float64))
+        dev.inject_z(zs[g + 1])
+        dev.tell_all(f)
+        so = ora.state()
+        # integer state: bit-exact
+        assert np.array_equal(dev.get("t")[0][:so["live"]], so["t"][:so["live"]]), g
+        live_slots = so["t"][:so["live"]]
+        assert np.array_equal(dev.get("vec")[0][live_slots], so["vec"][live_slots]), g
+        assert int(dev.get("itr")[0]) == so["itr"] and int(dev.get("live")[0]) == so["live"]
+        assert np.array_equal(dev.get("arindex")[0], ora.int_array("arindex")), g
+        assert int(dev.get("counteval")[0]) == so["counteval"]
+        # floating state
+        scale = max(1e-3, float(np.abs(so["xmean"]).max()))
+        worst["xmean"] = max(worst.get("xmean", 0), float(np.abs(dev.get("xmean")[0] - so["xmean"]).max()) / scale)
+        worst["sigma"] = max(worst.get("sigma", 0), abs(dev.get("sigma")[0] - so["sigma"]) / so["sigma"])
+        pcs = max(1e-6, float(np.abs(so["pc"]).max()))
+        worst["pc"] = max(worst.get("pc", 0), float(np.abs(dev.get("pc")[0] - so["pc"]).max()) / pcs)
+        Vd, Pd = dev.get("V")[0], dev.get("P")[0]
+        for slot in live_slots:
+            vs = max(1e-6, float(np.abs(so["V"][slot]).max()))
+            worst["V"] = max(worst.get("V", 0), float(np.abs(Vd[slot] - so["V"][slot]).max()) / vs)
+            worst["P"] = max(worst.get("P", 0), float(np.abs(Pd[slot] - so["P"][slot]).max()) / vs)
+        worst["Nj"] = max(worst.get("Nj", 0), rel_err(dev.get("Nj")[0][live_slots], so["Nj"][live_slots]))
+        worst["Lj"] = max(worst.get("Lj", 0), rel_err(dev.get("Lj")[0][live_slots], so["Lj"][live_slots]))
+        assert abs(dev.get("best_f")[0] - so["best_f"]) <= 1e-6 * max(1.0, abs(so["best_f"]))
+        # teacher forcing: the device continues from the oracle's exact state
+        dev.load_state(so)
+        dev.resample()            # X of the next generation comes from the oracle's exact state + the same z
+    assert worst["sigma"] < 1e-12, worst
+    for k in ("X", "xmean", "pc", "V", "P"):
+        assert worst[k] < tol, (k, worst)
+    assert worst["Nj"] < 1e-4 and worst["Lj"] < 1e-4, worst
+    return worst
+
+
+def test_lmcma_teacher_forced_small(po):
+    """n = 10, lambda = m = 6 (the golden trace's shape): covers the slot-recycling logic (itr >= m)."""
+    _teacher_forced(po, 10, 6, 0, 30, seed=1)
+
+
+def test_lmcma_teacher_forced_default_lambda(po):
+    """C1 shape: n = 40, default lambda = 15, m = lambda."""
+    _teacher_forced(po, 40, 0, 0, 40, seed=2)
+
+
+def test_lmcma_teacher_forced_bounds(po):
+    _teacher_forced(po, 10, 8, 0, 20, seed=5, lo=np.full(10, 0.2), hi=np.full(10, 1.0))
+
+
+def test_lmcma_teacher_forced_m_not_lambda(po):
+    """C2-like shape scaled down: n = 400, lambda = 128, m = 2*sqrt(n) = 40."""
+    _teacher_forced(po, 400, 128, 40, 50, seed=3, sigma=0.5)
+
+
+def test_lmcma_teacher_forced_large_n(po):
+    """C4-like row length: n = 1500, m = 77 (multi-chunk bulk-copy pipeline, NV = 12)."""
+    _teacher_forced(po, 1500, 32, 77, 6, seed=4, sigma=0.3)
+
+
+def test_rank_ties_and_nan(po, golden):
+    """Ties keep the lower id (stable), -0 == +0 (golden vector from the reference's myqsort); NaN ranks last."""
+    ties = np.array(golden["qsort_ties"]["in"], np.float32)
+    lam = len(ties)
+    dev = L.Optimizer(4, x0=np.zeros(4), lam=lam, rng="inject")
+    dev.inject_z(np.zeros((lam, 4), np.float32))
+    dev.inject_z(np.zeros((lam, 4), np.float32))
+    dev.tell_all(ties)
+    assert dev.get("arindex")[0].tolist() == golden["qsort_ties"]["ids"]
+    assert np.array_equal(dev.get("fit_sorted")[0], np.array(golden["qsort_ties"]["sorted"], np.float32))
+    f = ties.copy(); f[3] = np.nan
+    dev.inject_z(np.zeros((lam, 4), np.float32))
+    dev.tell_all(f)
+    assert dev.get("arindex")[0][-1] == 3
+
+
+def test_free_running_matches_oracle_short_window(po):
+    """Free-running (no teacher forcing) for a few generations on a well-conditioned problem: the FP32
+    device trajectory stays within 1e-4 of the FP64 oracle fed the device's own recorded deviates."""
+    n, lam = 40, 16
+    dev = L.Optimizer(n, x0=np.full(n, 0.5), lam=lam, sigma0=0.3, seed=7, rng="philox", record_z=True)
+    z0 = dev.get("Z")[0].astype(np.float64)
+    ora = po.OracleLMCMA(n, x0=np.full(n, 0.5), lam=lam, sigma=0.3, seed=1, Z0=z0)
+    for g in range(6):
+        Xd = dev.ask_all()[0]
+        assert rel_err(Xd, ora.array("X"), floor=1e-2) < 1e-4, g
+        f = weighted_sphere(Xd).astype(np.float32)
+        dev.tell_all(f)
+        ora.tell_all(f.astype(np.float64), dev.get("Z")[0].astype(np.float64))
+    assert abs(dev.get("sigma")[0] - ora.doubles()["sigma"]) / ora.doubles()["sigma"] < 1e-9
+
+
+def test_reference_class_protocol_hansen_stream(po, golden):
+    """The reference-shaped class with inseed = 1 draws the reference's own deviates: the first candidate
+    is x0 + sigma * z with the golden normals (lmcma.cpp:296, 435) and a short run tracks the golden sigmas."""
+    g = golden["run_n10"]
+    opt = L.LMCMA(np.array(g["x0"]), lambda_=g["lambda"], sigma=g["sigma0"], inseed=1)
+    opt.init(10)
+    x = opt.getNextParameterVector()
+    want = np.array(g["x0"]) + g["sigma0"] * np.array(golden["rng"]["1"]["gauss"][:10])
+    assert np.allclose(x, want, rtol=1e-6, atol=1e-6)
+    x2 = opt.getNextParameterVector()          # does not advance (lmcma.cpp:172-182)
+    assert np.array_equal(x, x2)
+    sig = [g["sigma0"]]
+    for gen in range(6):
+        for i in range(g["lambda"]):
+            xi = opt.getNextParameterVector()
+            assert np.allclose(xi, np.array(g["gens"][gen]["X"][i]), rtol=2e-4, atol=2e-4), (gen, i)
+            opt.setEvaluationFeedback([float(weighted_sphere(xi)[0])], 1)
+        sig.append(float(opt._opt.get("sigma")[0]))
+    assert opt.counteval == 6 * g["lambda"]
+    assert not opt.isBehaviorLearningDone()
+    assert np.allclose(sig, g["sigma"][:7], rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused on-device planning
+# ------------------------------------------------------------------------------------------------
+def test_fused_generation_equals_ask_evaluate_tell(po, golden_maps):
+    """One graph-replayed generation == ask_all -> cost_evaluate -> tell_all through host buffers."""
+    dist = po.edt_exact(golden_maps["problem1"])
+    W, start, goal = 20, (99.0, 0.0), (0.0, 99.0)
+    lo, hi = maps.box_bounds((100, 100), W)
+    x0 = maps.straight_line(start, goal, W)
+    cm = L.CostMap(dist, "f32")
+    a = L.Optimizer(2 * W, x0=x0, lo=lo, hi=hi, sigma0=5.0, seed=3, rng="philox")
+    b = L.Optimizer(2 * W, x0=x0, lo=lo, hi=hi, sigma0=5.0, seed=3, rng="philox")
+    a.attach_cost(cm, [start], [goal], W)
+    for g in range(25):
+        a.run(1)
+        X = b.ask_all()[0]
+        r = cm.evaluate(X, start, goal, W)
+        b.tell_all(r["f"])
+        assert np.array_equal(a.get("fit")[0], r["f"])
+        assert np.array_equal(a.get("ncoll")[0], r["ncoll"])
+    assert np.array_equal(a.get("xmean"), b.get("xmean"))
+    assert np.array_equal(a.get("sigma"), b.get("sigma"))
+    assert np.array_equal(a.ask_all(), b.ask_all())
+    xa, fa = a.best(); xb, fb = b.best()
+    assert np.array_equal(xa, xb) and fa == fb
+
+
+def test_planning_c1_finds_collision_free_path(po, golden_maps):
+    """C1: 100x100 bundled map, 20 waypoints, default lambda; the optimiser must reach a collision-free path
+    whose oracle cost equals the device's best cost."""
+    W, start, goal = 20, (99.0, 0.0), (0.0, 99.0)
+    lo, hi = maps.box_bounds((100, 100), W)
+    for name in ("problem1", "two_bars"):
+        dist = po.edt_exact(golden_maps[name])
+        cm = L.CostMap(dist, "f32")
+        opt = L.Optimizer(2 * W, x0=maps.straight_line(start, goal, W), lam=64, lo=lo, hi=hi, sigma0=8.0, seed=5)
+        opt.attach_cost(cm, [start], [goal], W, L.LONGSAFE, 1e4)
+        f0 = cm.evaluate(maps.straight_line(start, goal, W).astype(np.float32), start, goal, W)
+        opt.run(400)
+        xb, fb = opt.best()
+        ref = po.CostProblem(dist, start, goal, W).evaluate(xb[0])
+        assert ref["ncoll"][0] == 0, name
+        assert f0["ncoll"][0] > 0
+        assert rel_err(fb[0], ref["f"][0]) < COST_RTOL
+        assert fb[0] < f0["f"][0]
+
+
+def test_batched_instances_are_independent(po, golden_maps, monkeypatch):
+    """C3 mechanics: B instances in one launch == the same instances run one at a time."""
+    monkeypatch.setenv("LMCMA_B200_COST_TPT", "64")   # same reduction tree whatever the query length
+    dist = po.edt_exact(golden_maps["problem2"])
+    W = 12
+    lo, hi = maps.box_bounds((100, 100), W)
+    cm = L.CostMap(dist, "f32")
+    starts, goals = maps.random_queries(dist, 5, seed=7, min_sep=40)
+    x0 = np.stack([maps.straight_line(s, g, W) for s, g in zip(starts, goals)])
+    batched = L.Optimizer(2 * W, x0=x0, lam=16, m=8, batch=5, lo=lo, hi=hi, sigma0=4.0, seed=11, record_z=True)
+    batched.attach_cost(cm, starts, goals, W)
+    z0 = batched.get("Z")
+    batched.run(12)
+    for b in (0, 3, 4):
+        one = L.Optimizer(2 * W, x0=x0[b], lam=16, m=8, lo=lo, hi=hi, sigma0=4.0, rng="inject")
+        one.attach_cost(cm, [starts[b]], [goals[b]], W)
+        # replay instance b's deviates: regenerate them with a batch whose instance index matches
+        ref = L.Optimizer(2 * W, x0=x0, lam=16, m=8, batch=5, lo=lo, hi=hi, sigma0=4.0, seed=11, record_z=True)
+        ref.attach_cost(cm, starts, goals, W)
+        one.inject_z(ref.get("Z")[b])
+        for g in range(12):
+            ref.run(1)
+            one.inject_z(ref.get("Z")[b])
+            one.run(1)
+        assert np.array_equal(one.get("xmean")[0], batched.get("xmean")[b])
+        assert one.get("sigma")[0] == batched.get("sigma")[b]
+
+
+def test_split_population_single_process(po, golden_maps):
+    """C4 mechanics on one GPU: two handles owning lambda/2 rows each, 'all-gather' done by hand, must
+    reproduce the unsplit optimiser bit for bit (same Philox rows, same deterministic reductions)."""
+    import torch
+    dist = po.edt_exact(golden_maps["problem1"])
+    W, start, goal = 20, (99.0, 0.0), (0.0, 99.0)
+    lo, hi = maps.box_bounds((100, 100), W)
+    x0 = maps.straight_line(start, goal, W)
+    cm = L.CostMap(dist, "f32")
+    lam, G = 64, 2
+    whole = L.Optimizer(2 * W, x0=x0, lam=lam, m=12, lo=lo, hi=hi, sigma0=5.0, seed=9)
+    whole.attach_cost(cm, [start], [goal], W)
+    parts = []
+    for r in range(G):
+        p = L.Optimizer(2 * W, x0=x0, lam=lam, m=12, lo=lo, hi=hi, sigma0=5.0, seed=9, pop_offset=r * lam // G,
+                        pop_count=lam // G)
+        p.attach_cost(cm, [start], [goal], W)
+        parts.append(p)
+    pf = parts[0].mg_payload_floats()
+    f_all = torch.zeros(lam, dtype=torch.float32, device="cuda")
+    pay_all = torch.zeros(G * pf, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for g in range(8):
+        whole.run(1)
+        for r, p in enumerate(parts):
+            p.mg_evaluate(f_all.data_ptr() + 4 * r * (lam // G))
+            p.sync()
+        for r, p in enumerate(parts):
+            p.mg_rank(f_all.data_ptr(), pay_all.data_ptr() + 4 * r * pf)
+            p.sync()
+        for p in parts:
+            p.mg_update(pay_all.data_ptr(), G)
+            p.sync()
+        if g == 0:   # identical Philox rows -> identical first population and fitness
+            assert np.array_equal(f_all.cpu().numpy(), whole.get("fit")[0])
+        # the split sums its partials in a different (fixed) association, so FP32 rounding differs slightly
+        assert np.allclose(f_all.cpu().numpy(), whole.get("fit")[0], rtol=1e-3)
+        for p in parts:
+            assert np.allclose(p.get("xmean"), whole.get("xmean"), rtol=1e-5, atol=1e-2)
+            assert abs(p.get("sigma")[0] - whole.get("sigma")[0]) <= 1e-9 * whole.get("sigma")[0]
+        assert np.array_equal(parts[0].get("xmean"), parts[1].get("xmean"))   # replicas stay bit-identical
+        assert parts[0].get("sigma")[0] == parts[1].get("sigma")[0]
+    X = np.concatenate([p.ask_all()[0] for p in parts])
+    assert np.allclose(X, whole.ask_all()[0], rtol=1e-4, atol=1e-2)
