@@ -110,7 +110,9 @@ def run_b200(args):
     cmap = L.CostMap(dist, "f32", device=local)
     opt = L.Optimizer(2 * W, x0=x0, lam=LAM, m=M, lo=lo, hi=hi, sigma0=SIGMA0, seed=1000 + rank, rng="philox", device=local)
     opt.attach_cost(cmap, [start], [goal], W, L.LONGSAFE, 1e4)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                     # a real (non-null) stream: the library enqueues on it
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     opt.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -297,7 +299,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

@@ -1,0 +1,117 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/lmcma_b200.h declares, its
+host-side pieces match the golden vectors, and every compute entry point FAILS LOUDLY without a device
+(no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lmcma_path_planner_b200 as L
+from lmcma_path_planner_b200 import _capi as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cuda_present():
+    c = C.c_int(0)
+    return K.lib().lmcma_b200_device_count(C.byref(c)) == 0 and c.value > 0
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "lmcma_b200.h")).read()
+    declared = set(re.findall(r"\b(lmcma_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    lib = K.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(K.SIGNATURES), declared ^ set(K.SIGNATURES)
+    assert lib.lmcma_b200_abi_version() == 1
+
+
+def test_header_cites_the_reference_for_every_entry_point_group():
+    hdr = open(os.path.join(ROOT, "include", "lmcma_b200.h")).read()
+    for cite in ("lmcma.hpp:131", "lmcma.cpp:172-182", "lmcma.cpp:184-205", "lmcma.cpp:313-424", "lmcma.cpp:301-311",
+                 "planner.cpp:591", "planner.cpp:677-690", "lmcma.cpp:426-429", "lmcma.cpp:14-82", "lmcma.cpp:769-810"):
+        assert cite in hdr, cite
+
+
+def test_hansen_stream_matches_reference_golden(golden):
+    for seed, vec in golden["rng"].items():
+        out = np.zeros(16)
+        assert K.lib().lmcma_b200_hansen_gauss(int(seed), 0, 16, K.dptr(out)) == 0
+        assert out.tolist() == vec["gauss"]
+        u = np.zeros(8)
+        assert K.lib().lmcma_b200_hansen_uniform(int(seed), 8, K.dptr(u)) == 0
+        assert u.tolist() == vec["uniform"]
+    a, b = np.zeros(5), np.zeros(8)
+    K.lib().lmcma_b200_hansen_gauss(1, 3, 5, K.dptr(a))
+    K.lib().lmcma_b200_hansen_gauss(1, 0, 8, K.dptr(b))
+    assert np.array_equal(a, b[3:])
+
+
+def test_covariance_known_answers(golden):
+    """covariance(2,1) is the 2x2 identity; covariance(2,4) matches the reference compiled
+    against the Eigen stand-in (shim-pinned); the heap-based builder works where the reference's stack arrays
+    overflow (n = 1500)."""
+    c = np.zeros(4)
+    assert K.lib().lmcma_b200_covariance(2, 1, K.dptr(c)) == 0
+    assert np.allclose(c, golden["covariance_2_1"]) and np.allclose(c.reshape(2, 2), np.eye(2))
+    c = np.zeros(64)
+    assert K.lib().lmcma_b200_covariance(2, 4, K.dptr(c)) == 0
+    assert np.allclose(c, golden["covariance_2_4_shim_pinned"], rtol=1e-9, atol=1e-12)
+    n = 3 * 500
+    big = np.zeros(n * n)
+    assert K.lib().lmcma_b200_covariance(3, 500, K.dptr(big)) == 0
+    big = big.reshape(n, n)
+    assert np.allclose(big, big.T, atol=1e-9)
+    assert np.all(big[:500, 500:] == 0)                       # block diagonal, dimension-major
+    assert abs(big.diagonal().max() - 1.0 / 500) < 1e-12      # scaled by max variance * waypoints
+    assert np.all(np.linalg.eigvalsh(big[:500, :500]) > 0)
+
+
+def test_argument_errors_are_reported():
+    h = C.c_void_p()
+    cfg = K.Config()
+    cfg.n, cfg.batch, cfg.sigma0 = 0, 1, 1.0
+    assert K.lib().lmcma_b200_create(C.byref(cfg), None, None, None, C.byref(h)) == K.ERR_ARG
+    assert b"n must be" in K.lib().lmcma_b200_last_error()
+    assert K.lib().lmcma_b200_covariance(0, 3, None) == K.ERR_ARG
+    assert K.lib().lmcma_b200_sync(None) == K.ERR_ARG
+
+
+@pytest.mark.skipif(_cuda_present(), reason="this check is about machines WITHOUT a GPU")
+def test_no_cpu_fallback_without_a_gpu():
+    with pytest.raises(K.LmcmaError) as e:
+        L.Optimizer(8, x0=np.zeros(8))
+    assert e.value.code == K.ERR_CUDA
+    with pytest.raises(K.LmcmaError):
+        L.CostMap(np.ones((8, 8), np.float32))
+    opt = L.LMCMA(np.zeros(4))
+    with pytest.raises(K.LmcmaError):
+        opt.init(4)
+
+
+def test_library_is_in_tree_and_missing_library_is_fatal(tmp_path, monkeypatch):
+    assert os.path.dirname(K.LIB_PATH) == os.path.join(ROOT, "lmcma_path_planner_b200")
+    monkeypatch.setattr(K, "_lib", None)
+    monkeypatch.setattr(K, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        K.lib()
+
+
+def test_workload_generators():
+    from lmcma_path_planner_b200 import maps
+    x0 = maps.straight_line((0, 0), (10, 20), 4)
+    assert np.allclose(x0, [2, 4, 6, 8, 4, 8, 12, 16])         # dimension-major
+    lo, hi = maps.box_bounds((100, 50), 3)
+    assert lo.tolist() == [0] * 6 and hi.tolist() == [99] * 3 + [49] * 3
+    d, s, g = maps.config2_map(size=256, n_rects=8, seed=3, clamp=20.0)
+    assert d.shape == (256, 256) and d.max() <= 20.0 and d[int(s[1]), int(s[0])] > 0 and d[int(g[1]), int(g[0])] > 0
+    assert np.all(d[:2] == 0) and np.all(d[:, -2:] == 0)       # solid border
+    d2, _, _ = maps.config2_map(size=256, n_rects=8, seed=3, clamp=20.0)
+    assert np.array_equal(d, d2)                               # seeded
+    st, gl = maps.random_queries(d, 9, seed=1, min_sep=60)
+    assert st.shape == (9, 2) and np.all(np.linalg.norm(st - gl, axis=1) >= 60)
+    assert all(d[int(p[1]), int(p[0])] > 0 for p in st)
