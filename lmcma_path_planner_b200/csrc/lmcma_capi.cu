@@ -99,7 +99,7 @@ struct lmcma_b200_map {
     MapDev dev{};
     int storage = 0;
     float c_min = 0.5f, scale = 1.f;
-    size_t cells = 0;
+    size_t cells = 0, stored = 0;   // logical cells / stored elements (bricked, padded)
     float* d_g32 = nullptr;
     unsigned char* d_q8 = nullptr;
     float* d_lut = nullptr;
@@ -141,6 +141,8 @@ struct lmcma_b200_opt {
     int smp_threads = 128, smp_kc = 1, smp_nv = 1, smp_rb = 1;
     size_t smp_smem = 0;
     int cost_tpt = 128;
+    int upd_threads = 512, upd_cap_rows = 0;
+    size_t upd_smem = 0;
     size_t cost_smem = 0;
 };
 
@@ -151,7 +153,7 @@ namespace {
 
 template <int DIMS, int STORAGE, bool TRACE>
 int launch_cost_t(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, cudaStream_t st) {
-    const size_t smem = sizeof(float) * DIMS * (a.W + 2) + sizeof(int) * (a.W + 2) + (STORAGE == 1 ? 1024 : 0);
+    const size_t smem = (size_t)32 * (a.W + 1) + sizeof(int) * (a.W + 2) + (STORAGE == 1 ? 1024 : 0);
     auto kern = k_cost<DIMS, STORAGE, TRACE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(rows, B), tpt, smem, st>>>(mp, a);
@@ -232,30 +234,43 @@ int configure_sample(lmcma_b200_opt* o) {
     int kc = (int)std::max<size_t>(1, (size_t)env_int("LMCMA_B200_SAMPLE_STAGE_KB", 32) * 1024 / pair_bytes);
     kc = std::min(kc, o->d.m);
     o->smp_kc = kc;
-    o->smp_smem = 2 * kc * pair_bytes + 64;
+    o->smp_smem = 2 * kc * pair_bytes + 64 + (size_t)o->d.m * sizeof(float);
     if (o->smp_smem > o->props->smem_optin) return fail(LMCMA_B200_ERR_ARG, "k_sample needs %zu B shared memory", o->smp_smem);
     return 0;
 }
 
 int launch_rank(lmcma_b200_opt* o, const float* f_all, cudaStream_t st) {
-    k_rank<<<dim3((o->d.pop_count + 255) / 256, o->d.B), 256, 0, st>>>(o->d, f_all);
+    k_rank<<<dim3((o->d.pop_count + 31) / 32, o->d.B), 256, 0, st>>>(o->d, f_all);
     g_launches++;
     CU(cudaGetLastError());
     return 0;
 }
 int launch_recombine(lmcma_b200_opt* o, cudaStream_t st) {
     const int nq = o->d.ns / 4;
-    k_recombine<<<dim3((nq + 127) / 128, o->d.RS, o->d.B), 128, 0, st>>>(o->d);
+    k_recombine<<<dim3((nq + 127) / 128, o->d.RS, o->d.B), 512, 0, st>>>(o->d);
     g_launches++;
     CU(cudaGetLastError());
     return 0;
 }
 int launch_update(lmcma_b200_opt* o, const float* slices, int n_slices, long long slice_stride, long long inst_stride,
                   const float* f_all, int payload_mode, cudaStream_t st) {
-    const int threads = std::min(512, std::max(64, 32 * std::min(16, o->d.m)));
-    k_update<<<o->d.B, threads, sizeof(int) * o->d.m, st>>>(o->d, slices, n_slices, slice_stride, inst_stride, f_all, payload_mode);
+    k_update<<<o->d.B, o->upd_threads, o->upd_smem, st>>>(o->d, slices, n_slices, slice_stride, inst_stride, f_all,
+                                                          payload_mode, o->upd_cap_rows);
     g_launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int configure_update(lmcma_b200_opt* o) {
+    // one warp per pending row where possible; pending rows live in shared memory while they fit
+    o->upd_threads = std::min(1024, std::max(64, 32 * o->d.m));
+    const size_t row_bytes = (size_t)o->d.ns * sizeof(float);
+    const size_t fixed = (size_t)o->d.m * 8 + 256;
+    const size_t budget = std::min<size_t>(o->props->smem_optin, 200 * 1024);
+    o->upd_cap_rows = (int)std::min<size_t>(o->d.m, budget > fixed ? (budget - fixed) / row_bytes : 0);
+    o->upd_smem = (size_t)o->upd_cap_rows * row_bytes + fixed;
+    if (o->upd_smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->upd_smem));
     return 0;
 }
 
@@ -382,30 +397,45 @@ int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const floa
     m->dev.storage = storage; m->dev.g_coll = 1.0f / c_min;
     m->cells = (size_t)m->dev.nx * m->dev.ny * m->dev.nz;
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    // the transform E -> stored representation is a one-off, element-wise host pass (upload path, not hot)
+    // the transform E -> stored representation (values + bricked layout, lmcma_layout.hpp) is a one-off
+    // host pass on the upload path, not the hot path
+    const BrickShape bs = dims == 2 ? (storage == 0 ? brick_shape<2, 0>() : brick_shape<2, 1>())
+                                    : (storage == 0 ? brick_shape<3, 0>() : brick_shape<3, 1>());
+    const unsigned nbx = (m->dev.nx + bs.bx - 1) / bs.bx, nby = (m->dev.ny + bs.by - 1) / bs.by,
+                   nbz = (m->dev.nz + bs.bz - 1) / bs.bz;
+    m->dev.nbx = nbx; m->dev.nby = nby;
+    m->stored = (size_t)nbx * nby * nbz * bs.bx * bs.by * bs.bz;
+    auto offset_of = [&](unsigned x, unsigned y, unsigned z) -> size_t {
+        if (dims == 2) return storage == 0 ? brick_offset<2, 0>(x, y, z, nbx, nby) : brick_offset<2, 1>(x, y, z, nbx, nby);
+        return storage == 0 ? brick_offset<3, 0>(x, y, z, nbx, nby) : brick_offset<3, 1>(x, y, z, nbx, nby);
+    };
     if (storage == LMCMA_B200_MAP_F32) {
-        std::vector<float> g(m->cells);
-        for (size_t i = 0; i < m->cells; ++i) {
-            const float e = dist[i];
-            g[i] = (e > 0.f) ? 1.0f / std::max(e, c_min) : -m->dev.g_coll;
-        }
-        DM(m->d_g32, m->cells);
-        CU(cudaMemcpy(m->d_g32, g.data(), m->cells * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<float> g(m->stored, -m->dev.g_coll);          // padding cells are never addressed
+        for (int z = 0; z < m->dev.nz; ++z)
+            for (int y = 0; y < m->dev.ny; ++y)
+                for (int x = 0; x < m->dev.nx; ++x) {
+                    const float e = dist[((size_t)z * m->dev.ny + y) * m->dev.nx + x];
+                    g[offset_of(x, y, z)] = (e > 0.f) ? 1.0f / std::max(e, c_min) : -m->dev.g_coll;
+                }
+        DM(m->d_g32, m->stored);
+        CU(cudaMemcpy(m->d_g32, g.data(), m->stored * sizeof(float), cudaMemcpyHostToDevice));
         m->dev.g32 = m->d_g32;
     } else {
-        std::vector<unsigned char> q(m->cells);
-        for (size_t i = 0; i < m->cells; ++i) {
-            const float e = dist[i];
-            int v = 0;
-            if (e > 0.f) { v = (int)std::floor(e / u8_scale); v = std::min(255, std::max(1, v)); }
-            q[i] = (unsigned char)v;
-        }
+        std::vector<unsigned char> q(m->stored, 0);
+        for (int z = 0; z < m->dev.nz; ++z)
+            for (int y = 0; y < m->dev.ny; ++y)
+                for (int x = 0; x < m->dev.nx; ++x) {
+                    const float e = dist[((size_t)z * m->dev.ny + y) * m->dev.nx + x];
+                    int v = 0;
+                    if (e > 0.f) { v = (int)std::floor(e / u8_scale); v = std::min(255, std::max(1, v)); }
+                    q[offset_of(x, y, z)] = (unsigned char)v;
+                }
         float lut[256];
         lut[0] = -m->dev.g_coll;
         for (int v = 1; v < 256; ++v) lut[v] = 1.0f / std::max((float)v * u8_scale, c_min);
-        DM(m->d_q8, m->cells);
+        DM(m->d_q8, m->stored);
         DM(m->d_lut, 256);
-        CU(cudaMemcpy(m->d_q8, q.data(), m->cells, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(m->d_q8, q.data(), m->stored, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(m->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
         m->dev.q8 = m->d_q8; m->dev.lut = m->d_lut;
     }
@@ -427,16 +457,28 @@ int lmcma_b200_map_destroy(lmcma_b200_map* m) {
 int lmcma_b200_map_dequantized(const lmcma_b200_map* m, float* out) {
     ARG(m && out, "null pointer");
     CU(cudaSetDevice(m->device));
-    if (m->storage == LMCMA_B200_MAP_F32) {
-        // stored g = 1/max(E, c_min) is not invertible below c_min; report the effective clearance
-        std::vector<float> g(m->cells);
-        CU(cudaMemcpy(g.data(), m->d_g32, m->cells * sizeof(float), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < m->cells; ++i) out[i] = g[i] < 0.f ? 0.f : 1.0f / g[i];
+    const int dims = m->dev.dims, storage = m->storage;
+    const unsigned nbx = m->dev.nbx, nby = m->dev.nby;
+    auto offset_of = [&](unsigned x, unsigned y, unsigned z) -> size_t {
+        if (dims == 2) return storage == 0 ? brick_offset<2, 0>(x, y, z, nbx, nby) : brick_offset<2, 1>(x, y, z, nbx, nby);
+        return storage == 0 ? brick_offset<3, 0>(x, y, z, nbx, nby) : brick_offset<3, 1>(x, y, z, nbx, nby);
+    };
+    std::vector<float> g; std::vector<unsigned char> q;
+    if (storage == LMCMA_B200_MAP_F32) {
+        g.resize(m->stored);
+        CU(cudaMemcpy(g.data(), m->d_g32, m->stored * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
-        std::vector<unsigned char> q(m->cells);
-        CU(cudaMemcpy(q.data(), m->d_q8, m->cells, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < m->cells; ++i) out[i] = (float)q[i] * m->scale;
+        q.resize(m->stored);
+        CU(cudaMemcpy(q.data(), m->d_q8, m->stored, cudaMemcpyDeviceToHost));
     }
+    for (int z = 0; z < m->dev.nz; ++z)
+        for (int y = 0; y < m->dev.ny; ++y)
+            for (int x = 0; x < m->dev.nx; ++x) {
+                const size_t o = offset_of(x, y, z), i = ((size_t)z * m->dev.ny + y) * m->dev.nx + x;
+                // F32 stores 1/max(E, c_min): not invertible below c_min, so report the effective clearance
+                if (storage == LMCMA_B200_MAP_F32) out[i] = g[o] < 0.f ? 0.f : 1.0f / g[o];
+                else out[i] = (float)q[o] * m->scale;
+            }
     return 0;
 }
 
@@ -446,7 +488,7 @@ int lmcma_b200_map_set_l2_persist(lmcma_b200_map* m, int enable) {
     DeviceProps* props;
     int rc = query_props(m->device, &props);
     if (rc) return rc;
-    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->cells * 4 : m->cells;
+    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->stored * 4 : m->stored;
     if (enable) CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, props->persist_max)));
     m->persist = enable != 0;
     return 0;
@@ -459,7 +501,7 @@ static int apply_l2_window(lmcma_b200_map* m, cudaStream_t st) {
     if (rc) return rc;
     int max_win = 0;
     CU(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, m->device));
-    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->cells * 4 : m->cells;
+    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->stored * 4 : m->stored;
     cudaStreamAttrValue v;
     memset(&v, 0, sizeof(v));
     v.accessPolicyWindow.base_ptr = m->storage == LMCMA_B200_MAP_F32 ? (void*)m->d_g32 : (void*)m->d_q8;
@@ -626,7 +668,7 @@ int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const doub
     DM(d.Nj, B * m); DM(d.Lj, B * m); DM(d.Njf, B * m);
     DM(d.t, B * m); DM(d.vec, B * m);
     DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B);
-    d.RS = std::max(1, std::min(256, (d.pop_count + 15) / 16));
+    d.RS = std::max(1, std::min(256, (d.pop_count + 31) / 32));
     DM(d.partial, B * d.RS * ns);
 
     std::vector<float> wf(o->weights.begin(), o->weights.end());
@@ -658,6 +700,7 @@ int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const doub
     CU(cudaMemcpy(d.sc, sc.data(), B * sizeof(Scalars), cudaMemcpyHostToDevice));
 
     rc = configure_sample(o);
+    if (!rc) rc = configure_update(o);
     if (rc) { lmcma_b200_destroy(o); return rc; }
     o->f_host.assign(B * lam, 0.f);
     // first population (LMCMA::init -> sample(), lmcma.cpp:298)

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "lmcma_layout.hpp"
+
 namespace lmcma {
 
 constexpr int KMAX_SUBSTEPS = 65536;   // cap on sub-steps per segment (cost model)
@@ -65,6 +67,7 @@ struct OptDev {
 
 struct MapDev {
     int dims, nx, ny, nz;
+    unsigned nbx, nby;         // bricks per row / per column (lmcma_layout.hpp)
     int storage;               // 0 = F32 sign-tagged reciprocal clearance, 1 = U8 quantised distance
     const float* g32;
     const unsigned char* q8;
@@ -178,6 +181,7 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
     float* stage_base = reinterpret_cast<float*>(smem_raw);
     const size_t stage_floats = (size_t)kc * 2 * ns;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_base + 2 * stage_floats);
+    float* nj_s = reinterpret_cast<float*>(bars + 2);             // Nj of the live pairs, in sequence order
     const int nchunks = (live + kc - 1) / kc;
 
     if (threadIdx.x == 0) {
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
         mbar_init(&bars[1], 1);
         fence_barrier_init();
     }
+    for (int k = threadIdx.x; k < live; k += blockDim.x) nj_s[k] = o.Njf[(size_t)b * o.m + order[k]];
     __syncthreads();
     auto issue = [&](int chunk) {   // thread 0 only
         const int st = chunk & 1;
@@ -231,48 +236,64 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
         }
     }
 
-    // ---- stream the pairs ----
+    // ---- stream the pairs, four at a time: their dots are mutually independent (all against the original z),
+    //      so the 4*RB warp reductions overlap; only the M*Az + d*pc_j recurrence is ordered ----
     const float Mf = (float)o.M;
-    const float* njf = o.Njf + (size_t)b * o.m;
     for (int c = 0; c < nchunks; ++c) {
         const int st = c & 1;
         mbar_wait(&bars[st], (unsigned)((c >> 1) & 1));
         const float* sb = stage_base + st * stage_floats;
         const int k0 = c * kc, cnt = min(kc, live - k0);
-        for (int k = 0; k < cnt; ++k) {
-            const float4* v4 = reinterpret_cast<const float4*>(sb + (size_t)(2 * k) * ns);
-            const float4* p4 = reinterpret_cast<const float4*>(sb + (size_t)(2 * k + 1) * ns);
-            float d[RB];
+        for (int k = 0; k < cnt; k += 4) {
+            const int gcnt = min(4, cnt - k);
+            float d[4][RB];
 #pragma unroll
-            for (int r = 0; r < RB; ++r) d[r] = 0.f;
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int r = 0; r < RB; ++r) d[g][r] = 0.f;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int q = lane + 32 * i;
                 if (q < nq) {
-                    const float4 v = v4[q];
 #pragma unroll
-                    for (int r = 0; r < RB; ++r) {
-                        d[r] = fmaf(v.x, z[r][i].x, d[r]);
-                        d[r] = fmaf(v.y, z[r][i].y, d[r]);
-                        d[r] = fmaf(v.z, z[r][i].z, d[r]);
-                        d[r] = fmaf(v.w, z[r][i].w, d[r]);
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < gcnt) {
+                            const float4 v = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g)) * ns)[q];
+#pragma unroll
+                            for (int r = 0; r < RB; ++r)
+                                d[g][r] += fmaf(v.x, z[r][i].x, v.y * z[r][i].y) + fmaf(v.z, z[r][i].z, v.w * z[r][i].w);
+                        }
                     }
                 }
             }
-            const float nj = njf[order[k0 + k]];
 #pragma unroll
-            for (int r = 0; r < RB; ++r) d[r] = nj * warp_sum(d[r]);
+            for (int ofs = 16; ofs > 0; ofs >>= 1)
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) d[g][r] += __shfl_xor_sync(0xffffffffu, d[g][r], ofs);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float nj = (g < gcnt) ? nj_s[k0 + k + g] : 0.f;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) d[g][r] *= nj;
+            }
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int q = lane + 32 * i;
                 if (q < nq) {
-                    const float4 p = p4[q];
 #pragma unroll
-                    for (int r = 0; r < RB; ++r) {
-                        az[r][i].x = fmaf(Mf, az[r][i].x, d[r] * p.x);
-                        az[r][i].y = fmaf(Mf, az[r][i].y, d[r] * p.y);
-                        az[r][i].z = fmaf(Mf, az[r][i].z, d[r] * p.z);
-                        az[r][i].w = fmaf(Mf, az[r][i].w, d[r] * p.w);
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < gcnt) {
+                            const float4 p = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g) + 1) * ns)[q];
+#pragma unroll
+                            for (int r = 0; r < RB; ++r) {
+                                az[r][i].x = fmaf(Mf, az[r][i].x, d[g][r] * p.x);
+                                az[r][i].y = fmaf(Mf, az[r][i].y, d[g][r] * p.y);
+                                az[r][i].z = fmaf(Mf, az[r][i].z, d[g][r] * p.z);
+                                az[r][i].w = fmaf(Mf, az[r][i].w, d[g][r] * p.w);
+                            }
+                        }
                     }
                 }
             }
@@ -323,10 +344,12 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
 // ------------------------------------------------------------------------------------------------
 // k_cost — batched trajectory cost (DESIGN.md "cost model"; the reference's per-state pieces are
 // ValidityChecker::isValid/clearance planner.cpp:591-631, ClearanceObjective::stateCost :655-669,
-// weights :677-690).  One CTA per trajectory.  Phase 1: waypoints -> shared memory, per-segment
-// sub-step counts + block scan.  Phase 2: the flattened sample sequence is cut into blockDim equal
-// contiguous ranges; every thread walks its range along the poly-line (consecutive samples are <= 1
-// cell apart, so its loads stay in the same / neighbouring sectors).  Phase 3: block reduction.
+// weights :677-690).  One CTA per trajectory.  Phase 1: per-segment records {A, B-A, 1/K, len/K} and
+// sub-step counts into shared memory + block scan.  Phase 2: the flattened sample sequence is cut into
+// 32-sample blocks, a contiguous run of blocks per warp, consecutive samples on consecutive lanes: they
+// are <= 1 cell apart, and the map is stored in 128-byte bricks (lmcma_layout.hpp), so one warp load
+// touches a handful of lines instead of 32 (the L1 wavefront rate, not DRAM, bounds a row-major
+// gather).  Phase 3: block reduction.
 // The index path (t = k * (1/K); q = A + t*d; rint; bounds test) uses explicitly rounded FP32
 // mul/add so that no FMA contraction can change a cell index relative to the CPU oracle.
 // ------------------------------------------------------------------------------------------------
@@ -338,110 +361,103 @@ __device__ __forceinline__ int substeps_of(float linf) {
 template <int DIMS, int STORAGE, bool TRACE>
 __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int W = a.W, NP = W + 2, NSEG = W + 1;
-    float* pts = reinterpret_cast<float*>(smem_raw);            // DIMS x NP
-    int* off = reinterpret_cast<int*>(pts + DIMS * NP);         // NSEG + 1 exclusive offsets
-    float* lut = reinterpret_cast<float*>(off + NSEG + 1);      // 256 (U8 only)
+    const int W = a.W, NSEG = W + 1;
+    float4* segA = reinterpret_cast<float4*>(smem_raw);          // 2-D {Ax, Ay, dx, dy}   3-D {Ax, Ay, Az, dx}
+    float4* segB = segA + NSEG;                                  // 2-D {invK, scale, -, -} 3-D {dy, dz, invK, scale}
+    int* off = reinterpret_cast<int*>(segB + NSEG);              // NSEG + 1 exclusive sample offsets
+    float* lut = reinterpret_cast<float*>(off + NSEG + 1);       // 256 (U8 only)
     __shared__ float red_f[2][8];
     __shared__ int red_i[8];
-    __shared__ int carry_s;
+    __shared__ int warp_tot[8];
 
     const int row = blockIdx.x, b = blockIdx.y;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const float* x = a.X + ((size_t)b * a.inst_rows + row) * a.ld;
     const float* en = a.ends + (a.ends_per_instance ? (size_t)b * 6 : 0);
-
-    for (int i = tid; i < DIMS * W; i += nthr) {
-        const int d = i / W, w = i - d * W;
-        pts[d * NP + 1 + w] = x[i];
-    }
-    if (tid < DIMS) { pts[tid * NP] = en[tid]; pts[tid * NP + NP - 1] = en[3 + tid]; }
     if (STORAGE == 1) for (int i = tid; i < 256; i += nthr) lut[i] = mp.lut[i];
-    __syncthreads();
 
-    // ---- phase 1: sub-step counts, lengths ----
-    float len_acc = 0.f;
-    for (int s = tid; s < NSEG; s += nthr) {
-        float linf = 0.f, l2 = 0.f; bool bad = false;
+    // ---- phase 1: per-segment records, sub-step counts, lengths; block scan of the sample counts ----
+    const int spt = (NSEG + nthr - 1) / nthr;                    // consecutive segments per thread
+    const int s_begin = min(NSEG, tid * spt), s_end = min(NSEG, s_begin + spt);
+    float len_acc = 0.f; int my_cnt = 0;
+    for (int s = s_begin; s < s_end; ++s) {
+        float A[3], D[3]; float linf = 0.f, l2 = 0.f; bool bad = false;
 #pragma unroll
         for (int c = 0; c < DIMS; ++c) {
-            const float d = __fsub_rn(pts[c * NP + s + 1], pts[c * NP + s]);
-            const float ad = fabsf(d);
+            A[c] = (s == 0) ? en[c] : x[c * W + s - 1];
+            const float Bc = (s == W) ? en[3 + c] : x[c * W + s];
+            D[c] = __fsub_rn(Bc, A[c]);
+            const float ad = fabsf(D[c]);
             bad |= (ad != ad);
             if (ad > linf) linf = ad;
-            l2 = fmaf(d, d, l2);
+            l2 = fmaf(D[c], D[c], l2);
         }
         if (bad) linf = __int_as_float(0x7fc00000);
-        off[s + 1] = substeps_of(linf) + 1;     // samples of this segment
-        len_acc += sqrtf(l2);
+        const int K = substeps_of(linf);
+        const float invK = __frcp_rn((float)K);                  // == 1.0f / (float)K, IEEE round-to-nearest
+        const float len = sqrtf(l2);
+        len_acc += len;
+        if (DIMS == 2) { segA[s] = make_float4(A[0], A[1], D[0], D[1]); segB[s] = make_float4(invK, len * invK, 0.f, 0.f); }
+        else { segA[s] = make_float4(A[0], A[1], A[2], D[0]); segB[s] = make_float4(D[1], D[2], invK, len * invK); }
+        off[s + 1] = K + 1;                                      // samples of this segment (rewritten below)
+        my_cnt += K + 1;
     }
-    if (tid == 0) { off[0] = 0; carry_s = 0; }
-    __syncthreads();
-    if (warp == 0) {                              // inclusive scan of off[1..NSEG] by one warp
-        int carry = 0;
-        for (int base = 1; base <= NSEG; base += 32) {
-            const int i = base + lane;
-            int v = (i <= NSEG) ? off[i] : 0;
+    int incl = my_cnt;                                           // block-wide exclusive scan of my_cnt
 #pragma unroll
-            for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                const int nb = __shfl_up_sync(0xffffffffu, v, o2);
-                if (lane >= o2) v += nb;
-            }
-            if (i <= NSEG) off[i] = v + carry;
-            carry += __shfl_sync(0xffffffffu, v, 31);
-        }
-        if (lane == 0) carry_s = carry;
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += nb;
     }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    const int T = carry_s;
+    int base = incl - my_cnt, T = 0;
+    for (int w2 = 0; w2 < nwarps; ++w2) { const int v = warp_tot[w2]; if (w2 < warp) base += v; T += v; }
+    if (tid == 0) off[0] = 0;
+    for (int s = s_begin; s < s_end; ++s) { base += off[s + 1]; off[s + 1] = base; }
+    __syncthreads();
 
-    // ---- phase 2: walk my contiguous sample range ----
-    const int t0 = (int)(((long long)tid * T) / nthr), t1 = (int)(((long long)(tid + 1) * T) / nthr);
+    // ---- phase 2: consecutive samples on consecutive lanes (<= 1 cell apart -> few lines per warp load) ----
+    const int nblk = (T + 31) >> 5;
+    const int blk0 = (int)(((long long)warp * nblk) / nwarps), blk1 = (int)(((long long)(warp + 1) * nblk) / nwarps);
     float clr_acc = 0.f; int coll = 0;
-    if (t0 < t1) {
-        int lo = 0, hi = NSEG - 1;               // last s with off[s] <= t0
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= t0) lo = mid; else hi = mid - 1; }
-        int s = lo, k = t0 - off[s], t = t0;
+    if (blk0 < blk1) {
+        int lo = 0, hi = NSEG - 1;                               // warp-uniform: last s with off[s] <= first sample
+        const int tfirst = blk0 << 5;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= tfirst) lo = mid; else hi = mid - 1; }
+        int s_warp = lo;
         const float nxm1 = (float)(mp.nx - 1), nym1 = (float)(mp.ny - 1), nzm1 = (float)(mp.nz - 1);
-        while (t < t1) {
-            const int K = off[s + 1] - off[s] - 1;
-            float A[DIMS], D[DIMS]; float l2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < DIMS; ++c) {
-                A[c] = pts[c * NP + s];
-                D[c] = __fsub_rn(pts[c * NP + s + 1], A[c]);
-                l2 = fmaf(D[c], D[c], l2);
+        for (int blk = blk0; blk < blk1; ++blk) {
+            const int t = (blk << 5) + lane;
+            const bool valid = t < T;
+            const int tt = valid ? t : T - 1;
+            int s = s_warp;
+            while (tt >= off[s + 1]) ++s;
+            s_warp = __shfl_sync(0xffffffffu, s, 31);
+            const int o0 = off[s], K = off[s + 1] - o0 - 1, k = tt - o0;
+            const float4 ra = segA[s], rb = segB[s];
+            const float invK = DIMS == 2 ? rb.x : rb.z, scale = DIMS == 2 ? rb.y : rb.w;
+            const float tk = __fmul_rn((float)k, invK);
+            const float rx = rintf(__fadd_rn(ra.x, __fmul_rn(tk, DIMS == 2 ? ra.z : ra.w)));
+            const float ry = rintf(__fadd_rn(ra.y, __fmul_rn(tk, DIMS == 2 ? ra.w : rb.x)));
+            bool inb = (rx >= 0.f) && (rx <= nxm1) && (ry >= 0.f) && (ry <= nym1);
+            float rz = 0.f;
+            if (DIMS == 3) {
+                rz = rintf(__fadd_rn(ra.z, __fmul_rn(tk, rb.y)));
+                inb = inb && (rz >= 0.f) && (rz <= nzm1);
             }
-            const float invK = __frcp_rn((float)K);
-            const float scale = sqrtf(l2) * invK;
-            const int kend = min(K, k + (t1 - t) - 1);
-            const bool last_seg = (s == NSEG - 1);
-            float seg_acc = 0.f;
-#pragma unroll 4
-            for (int kk = k; kk <= kend; ++kk) {
-                const float tk = __fmul_rn((float)kk, invK);
-                const float rx = rintf(__fadd_rn(A[0], __fmul_rn(tk, D[0])));
-                const float ry = rintf(__fadd_rn(A[1], __fmul_rn(tk, D[1])));
-                bool inb = (rx >= 0.f) && (rx <= nxm1) && (ry >= 0.f) && (ry <= nym1);
-                long long idx = (long long)(int)ry * mp.nx + (int)rx;
-                if (DIMS == 3) {
-                    const float rz = rintf(__fadd_rn(A[DIMS - 1], __fmul_rn(tk, D[DIMS - 1])));
-                    inb = inb && (rz >= 0.f) && (rz <= nzm1);
-                    idx += (long long)(int)rz * mp.nx * mp.ny;
-                }
-                float g = -mp.g_coll;
-                if (inb) {
-                    if (STORAGE == 0) g = __ldg(mp.g32 + idx);
-                    else g = lut[__ldg(mp.q8 + idx)];
-                }
-                const float wgt = (kk == 0 || kk == K) ? 0.5f : 1.0f;
-                seg_acc = fmaf(fabsf(g), wgt, seg_acc);
-                coll += (g < 0.f) && (kk < K || last_seg);
-                if (TRACE) { const long long tt = t + (kk - k); if (tt < a.max_cells) a.cells[tt] = inb ? idx : -1; }
+            float g = -mp.g_coll;
+            if (inb) {
+                const size_t adr = brick_offset<DIMS, STORAGE>((unsigned)(int)rx, (unsigned)(int)ry, (unsigned)(int)rz, mp.nbx, mp.nby);
+                if (STORAGE == 0) g = __ldg(mp.g32 + adr);
+                else g = lut[__ldg(mp.q8 + adr)];
             }
-            clr_acc = fmaf(seg_acc, scale, clr_acc);
-            t += kend - k + 1;
-            k = 0; ++s;
+            if (valid) {
+                const float wgt = (k == 0 || k == K) ? 0.5f : 1.0f;
+                clr_acc = fmaf(fabsf(g) * wgt, scale, clr_acc);
+                coll += (g < 0.f) && (k < K || s == NSEG - 1);
+                if (TRACE && t < a.max_cells)
+                    a.cells[t] = inb ? ((long long)(int)rz * mp.ny + (int)ry) * mp.nx + (int)rx : -1;
+            }
         }
     }
 
@@ -453,7 +469,7 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
     __syncthreads();
     if (tid == 0) {
         float L = 0.f, C = 0.f; int NC = 0;
-        for (int w2 = 0; w2 < (nthr + 31) / 32; ++w2) { L += red_f[0][w2]; C += red_f[1][w2]; NC += red_i[w2]; }
+        for (int w2 = 0; w2 < nwarps; ++w2) { L += red_f[0][w2]; C += red_f[1][w2]; NC += red_i[w2]; }
         const float f = fmaf(a.w_col, (float)NC, fmaf(a.w_clr, C, a.w_len * L));
         a.f[(size_t)b * a.f_stride + a.f_offset + row] = f;
         if (a.ncoll) a.ncoll[(size_t)b * a.inst_rows + row] = NC;
@@ -466,56 +482,62 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
 // rule (lmcma.cpp:393-411) as rank-by-counting: rank_i = #{j: f_j < f_i or (f_j == f_i and j < i)}
 // reproduces the stable ascending order (ties keep the lower id, -0 == +0); the merged ranking only
 // enters through S = #{(i,j): prev_j < cur_i} (see k_update).  NaN fitness ranks as +inf (the
-// reference's comparator is undefined for NaN).  grid = (ceil(pop_count/256), B).
+// reference's comparator is undefined for NaN).  grid = (ceil(pop_count/32), B): one candidate per lane,
+// the 8 warps of a CTA split the comparison range.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rank(OptDev o, const float* __restrict__ f_all) {
-    __shared__ float cur_s[1024];
-    __shared__ float prev_s[1024];
-    __shared__ unsigned long long red[8];
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const int il = blockIdx.x * 256 + tid;                 // local row
+    __shared__ int part_c[8][32];
+    __shared__ unsigned long long part_p[8][32];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int il = blockIdx.x * 32 + lane;                 // local row: one candidate per lane
     const int i = o.pop_offset + il;                       // global candidate id
     const bool valid = il < o.pop_count;
     const float* cur = f_all + (size_t)b * o.lambda;
     const float* prev = o.prev_fit + (size_t)b * o.lambda;
     const float ki = valid ? canon_fitness(cur[i]) : 0.f;
+    // the 8 warps split the j range; every lane of a warp reads the same f_j (broadcast loads)
+    const int j0 = (int)(((long long)warp * o.lambda) / 8), j1 = (int)(((long long)(warp + 1) * o.lambda) / 8);
     int c_lt = 0; unsigned long long p_lt = 0;
-    for (int base = 0; base < o.lambda; base += 1024) {
-        const int cnt = min(1024, o.lambda - base);
-        __syncthreads();
-        for (int j = tid; j < cnt; j += 256) { cur_s[j] = canon_fitness(cur[base + j]); prev_s[j] = prev[base + j]; }
-        __syncthreads();
-        if (valid) {
-            int pl = 0;
-#pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const float kj = cur_s[j];
-                c_lt += (kj < ki) || (kj == ki && (base + j) < i);
-                pl += prev_s[j] < ki;
-            }
-            p_lt += pl;
-        }
-    }
-    if (valid) {
-        o.rank[(size_t)b * o.lambda + i] = c_lt;
-        o.arindex[(size_t)b * o.lambda + c_lt] = i;
-        o.fit_sorted[(size_t)b * o.lambda + c_lt] = ki;
-    }
-    // block-reduce p_lt -> one integer atomic per CTA (order-independent, deterministic)
-    unsigned lo32 = (unsigned)p_lt, hi32 = (unsigned)(p_lt >> 32);
-    // p_lt <= lambda <= 2^31 per thread: reduce as 64-bit via two shuffles
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {
+        float kj[4], pj[4];
 #pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1) {
-        const unsigned l2 = __shfl_xor_sync(0xffffffffu, lo32, ofs), h2 = __shfl_xor_sync(0xffffffffu, hi32, ofs);
-        unsigned long long a = ((unsigned long long)hi32 << 32) | lo32, c = ((unsigned long long)h2 << 32) | l2;
-        a += c; lo32 = (unsigned)a; hi32 = (unsigned)(a >> 32);
+        for (int u = 0; u < 4; ++u) { kj[u] = canon_fitness(cur[j + u]); pj[u] = prev[j + u]; }
+        int pl = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            c_lt += (kj[u] < ki) || (kj[u] == ki && (j + u) < i);
+            pl += pj[u] < ki;
+        }
+        p_lt += pl;
     }
-    if ((tid & 31) == 0) red[tid >> 5] = ((unsigned long long)hi32 << 32) | lo32;
+    for (; j < j1; ++j) {
+        const float kj = canon_fitness(cur[j]);
+        c_lt += (kj < ki) || (kj == ki && j < i);
+        p_lt += prev[j] < ki;
+    }
+    part_c[warp][lane] = c_lt;
+    part_p[warp][lane] = p_lt;
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long tot = 0;
-        for (int w2 = 0; w2 < 8; ++w2) tot += red[w2];
-        atomicAdd(o.S_count + b, tot);
+    if (warp == 0) {
+        int c = 0; unsigned long long p = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) { c += part_c[w2][lane]; p += part_p[w2][lane]; }
+        if (!valid) p = 0;
+        if (valid) {
+            o.rank[(size_t)b * o.lambda + i] = c;
+            o.arindex[(size_t)b * o.lambda + c] = i;
+            o.fit_sorted[(size_t)b * o.lambda + c] = ki;
+        }
+        // warp-reduce p (<= 32 * lambda) -> one integer atomic per CTA (order-independent, deterministic)
+        unsigned lo32 = (unsigned)p, hi32 = (unsigned)(p >> 32);
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            const unsigned l2 = __shfl_xor_sync(0xffffffffu, lo32, ofs), h2 = __shfl_xor_sync(0xffffffffu, hi32, ofs);
+            const unsigned long long a = (((unsigned long long)hi32 << 32) | lo32) + (((unsigned long long)h2 << 32) | l2);
+            lo32 = (unsigned)a; hi32 = (unsigned)(a >> 32);
+        }
+        if (lane == 0) atomicAdd(o.S_count + b, ((unsigned long long)hi32 << 32) | lo32);
     }
 }
 
@@ -523,30 +545,46 @@ __global__ void __launch_bounds__(256) k_rank(OptDev o, const float* __restrict_
 // k_recombine — the weighted recombination of LMCMA::update (lmcma.cpp:316-326) as partial sums of
 // w_{rank(i)} * (x_i - xmean) over the rows this handle owns (candidate order, fixed split -> run-to-run
 // deterministic).  Summing differences keeps the FP32 sum accurate relative to the mean SHIFT, which
-// is what the evolution path needs (lmcma.cpp:327-329).  grid = (ceil(nq/128), RS, B), block 128.
+// is what the evolution path needs (lmcma.cpp:327-329).  grid = (ceil(nq/128), RS, B), block 512 =
+// 128 float4 columns x 4 row groups, 4 independent row loads in flight per thread.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_recombine(OptDev o) {
+__global__ void __launch_bounds__(512) k_recombine(OptDev o) {
+    __shared__ float4 red[3][128];
     const int b = blockIdx.z, rs = blockIdx.y;
-    const int q = blockIdx.x * 128 + threadIdx.x, nq = o.ns >> 2;
-    if (q >= nq) return;
+    const int tq = threadIdx.x & 127, grp = threadIdx.x >> 7;     // 128 float4 columns x 4 row groups
+    const int q = blockIdx.x * 128 + tq, nq = o.ns >> 2;
     const int rows_per = (o.pop_count + o.RS - 1) / o.RS;
     const int r0 = rs * rows_per, r1 = min(o.pop_count, r0 + rows_per);
-    const double* xm = o.xmean + (size_t)b * o.ns + 4 * q;
-    const float4 m4 = make_float4((float)xm[0], (float)xm[1], (float)xm[2], (float)xm[3]);
     const int* rk = o.rank + (size_t)b * o.lambda + o.pop_offset;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = r0; r < r1; ++r) {
-        const int rnk = rk[r];
-        if (rnk < o.mu) {
-            const float w = o.w[rnk];
-            const float4 x = reinterpret_cast<const float4*>(o.X + ((size_t)b * o.pop_count + r) * o.ns)[q];
-            acc.x = fmaf(w, x.x - m4.x, acc.x);
-            acc.y = fmaf(w, x.y - m4.y, acc.y);
-            acc.z = fmaf(w, x.z - m4.z, acc.z);
-            acc.w = fmaf(w, x.w - m4.w, acc.w);
+    if (q < nq) {
+        const double* xm = o.xmean + (size_t)b * o.ns + 4 * q;
+        const float4 m4 = make_float4((float)xm[0], (float)xm[1], (float)xm[2], (float)xm[3]);
+        for (int rbase = r0 + grp; rbase < r1; rbase += 16) {     // 4 rows in flight per thread
+            float w[4]; float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rbase + 4 * u;
+                const int rnk = (r < r1) ? rk[r] : o.mu;
+                w[u] = (rnk < o.mu) ? o.w[rnk] : 0.f;
+                x[u] = (rnk < o.mu) ? reinterpret_cast<const float4*>(o.X + ((size_t)b * o.pop_count + r) * o.ns)[q] : m4;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc.x = fmaf(w[u], x[u].x - m4.x, acc.x);
+                acc.y = fmaf(w[u], x[u].y - m4.y, acc.y);
+                acc.z = fmaf(w[u], x[u].z - m4.z, acc.z);
+                acc.w = fmaf(w[u], x[u].w - m4.w, acc.w);
+            }
         }
     }
-    reinterpret_cast<float4*>(o.partial + ((size_t)b * o.RS + rs) * o.ns)[q] = acc;
+    if (grp > 0) red[grp - 1][tq] = acc;
+    __syncthreads();
+    if (grp == 0 && q < nq) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) { const float4 t = red[g][tq]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+        reinterpret_cast<float4*>(o.partial + ((size_t)b * o.RS + rs) * o.ns)[q] = acc;
+    }
 }
 
 // split mode: fold the RS local partials and the local S count into the all-gather payload
@@ -576,16 +614,18 @@ __global__ void __launch_bounds__(128) k_pack_payload(OptDev o, float* __restric
 // slices: n_slices partial-sum slices per instance; slice k of instance b starts at
 //         slices + k * slice_stride + b * inst_stride.  S: see s_src.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_update(OptDev o, const float* __restrict__ slices, int n_slices,
-                                                long long slice_stride, long long inst_stride,
-                                                const float* __restrict__ f_all, int payload_mode) {
+__global__ void __launch_bounds__(1024) k_update(OptDev o, const float* __restrict__ slices, int n_slices,
+                                                 long long slice_stride, long long inst_stride,
+                                                 const float* __restrict__ f_all, int payload_mode, int cap_rows) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    int* order = reinterpret_cast<int*>(smem_raw);               // m
+    const int m = o.m, ns = o.ns;
+    float* rows_s = reinterpret_cast<float*>(smem_raw);           // cap_rows x ns: the pending rows live here
+    float* lj_s = rows_s + (size_t)cap_rows * ns;                 // m: Lj in sequence order
+    int* order = reinterpret_cast<int*>(lj_s + m);                // m: slot order
     __shared__ int sh_first_stale, sh_live, sh_slot_new;
     __shared__ double sh_sigma_old;
     const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    const int m = o.m, ns = o.ns;
     Scalars* scp = o.sc + b;
     int* tg = o.t + (size_t)b * m;
     int* vg = o.vec + (size_t)b * m;
@@ -617,9 +657,16 @@ __global__ void __launch_bounds__(512) k_update(OptDev o, const float* __restric
         sh_sigma_old = scp->sigma;
     }
     __syncthreads();
-    for (int i = tid; i < m; i += nthr) order[i] = tg[i];
     const int first_stale = sh_first_stale, live = sh_live, slot_new = sh_slot_new;
     const double sigma_old = sh_sigma_old;
+    double* Njd = o.Nj + (size_t)b * m;
+    double* Ljd = o.Lj + (size_t)b * m;
+    float* Njf = o.Njf + (size_t)b * m;
+    for (int i = tid; i < m; i += nthr) {
+        const int slot = tg[i];
+        order[i] = slot;
+        lj_s[i] = (i < live) ? (float)Ljd[slot] : 0.f;            // rows >= first_stale are rewritten below
+    }
 
     // ---- mean, evolution path, new pc_j (lmcma.cpp:316-329, 365-366) ----
     {
@@ -628,8 +675,17 @@ __global__ void __launch_bounds__(512) k_update(OptDev o, const float* __restric
         float* pc = o.pc + (size_t)b * ns;
         float* pnew = o.P + ((size_t)b * m + slot_new) * ns;
         for (int e = tid; e < ns; e += nthr) {
+            const float* sp = slices + (size_t)b * inst_stride + e;
             float d = 0.f;
-            for (int k = 0; k < n_slices; ++k) d += slices[(size_t)k * slice_stride + (size_t)b * inst_stride + e];
+            int k = 0;
+            for (; k + 8 <= n_slices; k += 8) {                   // 8 independent loads in flight
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = sp[(size_t)(k + u) * slice_stride];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d += v[u];
+            }
+            for (; k < n_slices; ++k) d += sp[(size_t)k * slice_stride];
             const double xold_f = (double)(float)xm[e];          // the partials are relative to float(xmean)
             const double shift = (xold_f - xm[e]) + (double)d;    // new mean - old mean
             xm[e] = xm[e] + shift;
@@ -643,42 +699,45 @@ __global__ void __launch_bounds__(512) k_update(OptDev o, const float* __restric
     // ---- recompute v from the first stale position (lmcma.cpp:373-390) ----
     float* Vb = o.V + (size_t)b * m * ns;
     const float* Pb = o.P + (size_t)b * m * ns;
-    double* Njd = o.Nj + (size_t)b * m;
-    double* Ljd = o.Lj + (size_t)b * m;
-    float* Njf = o.Njf + (size_t)b * m;
     const float Kf = (float)o.K;
     const int nq = ns >> 2;
+    // row i of the sequence: pending rows (i >= first_stale) sit in shared memory while they fit, the
+    // untouched older rows (and any overflow) are addressed in place in HBM/L2
+    auto row_ptr = [&](int i) -> float* {
+        const int p = i - first_stale;
+        return (p >= 0 && p < cap_rows) ? rows_s + (size_t)p * ns : Vb + (size_t)order[i] * ns;
+    };
     for (int i = first_stale + warp; i < live; i += nwarps) {      // pending rows start as pc_j
         const float4* src = reinterpret_cast<const float4*>(Pb + (size_t)order[i] * ns);
-        float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
+        float4* dst = reinterpret_cast<float4*>(row_ptr(i));
         for (int q = lane; q < nq; q += 32) dst[q] = src[q];
     }
-    auto finalize = [&](int slot) {    // warp-collective: |v|^2 and the two closed forms, in FP64
-        const float4* v = reinterpret_cast<const float4*>(Vb + (size_t)slot * ns);
+    auto finalize = [&](int i) {       // warp-collective: |v|^2 and the two closed forms, in FP64
+        const float4* v = reinterpret_cast<const float4*>(row_ptr(i));
         float nvf = 0.f;
-        for (int q = lane; q < nq; q += 32) { const float4 x = v[q]; nvf = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, nvf)))); }
+        for (int q = lane; q < nq; q += 32) { const float4 x = v[q]; nvf += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w); }
         nvf = warp_sum(nvf);
         if (lane == 0) {
+            const int slot = order[i];
             const double nv = (double)nvf, c1 = o.c1;
             const double nj = (sqrt(1.0 - c1) / nv) * (sqrt(1.0 + (c1 / (1.0 - c1)) * nv) - 1.0);
             const double lj = (1.0 / (sqrt(1.0 - c1) * nv)) * (1.0 - (1.0 / sqrt(1.0 + (c1 / (1.0 - c1)) * nv)));
-            Njd[slot] = nj; Ljd[slot] = lj; Njf[slot] = (float)nj;
+            Njd[slot] = nj; Ljd[slot] = lj; Njf[slot] = (float)nj; lj_s[i] = (float)lj;
         }
     };
     __syncthreads();
-    if (first_stale == 0 && warp == 0 && live > 0) finalize(order[0]);   // row 0 has no factors
+    if (first_stale == 0 && warp == 0 && live > 0) finalize(0);   // row 0 has no factors
     for (int j = 0; j + 1 < live; ++j) {
         __syncthreads();                                           // row j (and its Lj) is final
-        const int slot_j = order[j];
-        const float4* vj = reinterpret_cast<const float4*>(Vb + (size_t)slot_j * ns);
-        const float lj = (float)Ljd[slot_j];
+        const float4* vj = reinterpret_cast<const float4*>(row_ptr(j));
+        const float lj = lj_s[j];
         const int i_begin = max(j + 1, first_stale);
         for (int i = i_begin + warp; i < live; i += nwarps) {
-            float4* vi = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
+            float4* vi = reinterpret_cast<float4*>(row_ptr(i));
             float d = 0.f;
             for (int q = lane; q < nq; q += 32) {
                 const float4 a4 = vj[q], c4 = vi[q];
-                d = fmaf(a4.x, c4.x, fmaf(a4.y, c4.y, fmaf(a4.z, c4.z, fmaf(a4.w, c4.w, d))));
+                d += fmaf(a4.x, c4.x, a4.y * c4.y) + fmaf(a4.z, c4.z, a4.w * c4.w);
             }
             d = lj * warp_sum(d);
             for (int q = lane; q < nq; q += 32) {
@@ -689,10 +748,15 @@ __global__ void __launch_bounds__(512) k_update(OptDev o, const float* __restric
                 c4.w = fmaf(Kf, c4.w, -d * a4.w);
                 vi[q] = c4;
             }
-            if (i == j + 1) { __syncwarp(); finalize(order[i]); }
+            if (i == j + 1) { __syncwarp(); finalize(i); }
         }
     }
     __syncthreads();
+    for (int i = first_stale + warp; i < live && i - first_stale < cap_rows; i += nwarps) {   // write back
+        const float4* src = reinterpret_cast<const float4*>(rows_s + (size_t)(i - first_stale) * ns);
+        float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
+        for (int q = lane; q < nq; q += 32) dst[q] = src[q];
+    }
 
     // ---- population-success step size (lmcma.cpp:393-419), bookkeeping (lmcma.cpp:420-423, 192-194) ----
     if (tid == 0) {
@@ -727,7 +791,7 @@ __global__ void __launch_bounds__(512) k_update(OptDev o, const float* __restric
         const float* fa = f_all + (size_t)b * o.lambda;
         __shared__ int sh_best_row; __shared__ int sh_take;
         // the rank-0 candidate: first occurrence of the minimum in evaluation order (block arg-min)
-        __shared__ float am_v[16]; __shared__ int am_i[16];
+        __shared__ float am_v[32]; __shared__ int am_i[32];
         float bf = __int_as_float(0x7f800000); int bi = 0x7fffffff;
         for (int j = tid; j < o.lambda; j += nthr) { const float v = canon_fitness(fa[j]); if (v < bf || (v == bf && j < bi)) { bf = v; bi = j; } }
 #pragma unroll
