@@ -265,7 +265,7 @@ int configure_update(lmcma_b200_opt* o) {
     // one warp per pending row where possible; pending rows live in shared memory while they fit
     o->upd_threads = std::min(1024, std::max(64, 32 * o->d.m));
     const size_t row_bytes = (size_t)o->d.ns * sizeof(float);
-    const size_t fixed = (size_t)o->d.m * 8 + 256;
+    const size_t fixed = (size_t)o->d.m * 16 + 256;
     const size_t budget = std::min<size_t>(o->props->smem_optin, 200 * 1024);
     o->upd_cap_rows = (int)std::min<size_t>(o->d.m, budget > fixed ? (budget - fixed) / row_bytes : 0);
     o->upd_smem = (size_t)o->upd_cap_rows * row_bytes + fixed;
@@ -405,6 +405,7 @@ int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const floa
                    nbz = (m->dev.nz + bs.bz - 1) / bs.bz;
     m->dev.nbx = nbx; m->dev.nby = nby;
     m->stored = (size_t)nbx * nby * nbz * bs.bx * bs.by * bs.bz;
+    if (m->stored >= ((size_t)1 << 32)) { delete m; return fail(LMCMA_B200_ERR_ARG, "map too large: %zu stored cells (limit 2^32)", m->stored); }
     auto offset_of = [&](unsigned x, unsigned y, unsigned z) -> size_t {
         if (dims == 2) return storage == 0 ? brick_offset<2, 0>(x, y, z, nbx, nby) : brick_offset<2, 1>(x, y, z, nbx, nby);
         return storage == 0 ? brick_offset<3, 0>(x, y, z, nbx, nby) : brick_offset<3, 1>(x, y, z, nbx, nby);
@@ -651,6 +652,7 @@ int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const doub
     d.cs = 0.3; d.target = 0.25;
     d.K = 1 / std::sqrt(1 - d.c1);
     d.M = std::sqrt(1 - d.c1);
+    d.pc_coef = std::sqrt(d.cc * (2 - d.cc) * d.mueff);
 
     CU(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
     o->stream = o->own_stream;

@@ -63,6 +63,7 @@ struct OptDev {
     int RS;
     unsigned long long* S_count;   // B : #{(i,j): prev_j < cur_i}
     double c1, cc, cs, target, K, M, mueff;
+    double pc_coef;    // sqrt(cc (2 - cc) mueff), lmcma.cpp:328
 };
 
 struct MapDev {
@@ -397,6 +398,16 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
         const float invK = __frcp_rn((float)K);                  // == 1.0f / (float)K, IEEE round-to-nearest
         const float len = sqrtf(l2);
         len_acc += len;
+        // A segment with a non-finite end point has no sample inside the map (NaN / inf coordinates fail the
+        // oracle's bounds test for every k): encode that as a finite far-away anchor so that the sample loop
+        // can use integer conversion + unsigned bounds tests (NaN would convert to 0).
+        bool finite = true;
+#pragma unroll
+        for (int c = 0; c < DIMS; ++c) finite = finite && (fabsf(A[c]) < 3.0e38f) && (fabsf(D[c]) < 3.0e38f);
+        if (!finite) {
+#pragma unroll
+            for (int c = 0; c < DIMS; ++c) { A[c] = -1.0e9f; D[c] = 0.f; }
+        }
         if (DIMS == 2) { segA[s] = make_float4(A[0], A[1], D[0], D[1]); segB[s] = make_float4(invK, len * invK, 0.f, 0.f); }
         else { segA[s] = make_float4(A[0], A[1], A[2], D[0]); segB[s] = make_float4(D[1], D[2], invK, len * invK); }
         off[s + 1] = K + 1;                                      // samples of this segment (rewritten below)
@@ -425,38 +436,40 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
         const int tfirst = blk0 << 5;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= tfirst) lo = mid; else hi = mid - 1; }
         int s_warp = lo;
-        const float nxm1 = (float)(mp.nx - 1), nym1 = (float)(mp.ny - 1), nzm1 = (float)(mp.nz - 1);
+        const unsigned nxm1 = (unsigned)(mp.nx - 1), nym1 = (unsigned)(mp.ny - 1), nzm1 = (unsigned)(mp.nz - 1);
+        const int last = NSEG - 1;
         for (int blk = blk0; blk < blk1; ++blk) {
             const int t = (blk << 5) + lane;
             const bool valid = t < T;
             const int tt = valid ? t : T - 1;
             int s = s_warp;
-            while (tt >= off[s + 1]) ++s;
+            int cur = off[s], nxt = off[s + 1];                  // warp-uniform (broadcast) loads
+            while (tt >= nxt) { ++s; cur = nxt; nxt = off[s + 1]; }
             s_warp = __shfl_sync(0xffffffffu, s, 31);
-            const int o0 = off[s], K = off[s + 1] - o0 - 1, k = tt - o0;
-            const float4 ra = segA[s], rb = segB[s];
-            const float invK = DIMS == 2 ? rb.x : rb.z, scale = DIMS == 2 ? rb.y : rb.w;
+            const int K = nxt - cur - 1, k = tt - cur;
+            const float4 ra = segA[s];
+            float invK, scale, dx, dy, dz = 0.f, az = 0.f;
+            if (DIMS == 2) { const float2 rb = *reinterpret_cast<const float2*>(&segB[s]); invK = rb.x; scale = rb.y; dx = ra.z; dy = ra.w; }
+            else { const float4 rb = segB[s]; dx = ra.w; dy = rb.x; dz = rb.y; invK = rb.z; scale = rb.w; az = ra.z; }
             const float tk = __fmul_rn((float)k, invK);
-            const float rx = rintf(__fadd_rn(ra.x, __fmul_rn(tk, DIMS == 2 ? ra.z : ra.w)));
-            const float ry = rintf(__fadd_rn(ra.y, __fmul_rn(tk, DIMS == 2 ? ra.w : rb.x)));
-            bool inb = (rx >= 0.f) && (rx <= nxm1) && (ry >= 0.f) && (ry <= nym1);
-            float rz = 0.f;
+            // round-half-even conversion == (int)rintf(q); saturates for huge |q| (-> fails the unsigned test)
+            const int ix = __float2int_rn(__fadd_rn(ra.x, __fmul_rn(tk, dx)));
+            const int iy = __float2int_rn(__fadd_rn(ra.y, __fmul_rn(tk, dy)));
+            bool inb = ((unsigned)ix <= nxm1) && ((unsigned)iy <= nym1);
+            int iz = 0;
             if (DIMS == 3) {
-                rz = rintf(__fadd_rn(ra.z, __fmul_rn(tk, rb.y)));
-                inb = inb && (rz >= 0.f) && (rz <= nzm1);
+                iz = __float2int_rn(__fadd_rn(az, __fmul_rn(tk, dz)));
+                inb = inb && ((unsigned)iz <= nzm1);
             }
-            float g = -mp.g_coll;
-            if (inb) {
-                const size_t adr = brick_offset<DIMS, STORAGE>((unsigned)(int)rx, (unsigned)(int)ry, (unsigned)(int)rz, mp.nbx, mp.nby);
-                if (STORAGE == 0) g = __ldg(mp.g32 + adr);
-                else g = lut[__ldg(mp.q8 + adr)];
-            }
-            if (valid) {
-                const float wgt = (k == 0 || k == K) ? 0.5f : 1.0f;
-                clr_acc = fmaf(fabsf(g) * wgt, scale, clr_acc);
-                coll += (g < 0.f) && (k < K || s == NSEG - 1);
-                if (TRACE && t < a.max_cells)
-                    a.cells[t] = inb ? ((long long)(int)rz * mp.ny + (int)ry) * mp.nx + (int)rx : -1;
+            const unsigned adr = inb ? brick_offset<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, mp.nbx, mp.nby) : 0u;
+            float g = (STORAGE == 0) ? __ldg(mp.g32 + adr) : lut[__ldg(mp.q8 + adr)];   // branch-free: cell 0 when outside
+            g = inb ? g : -mp.g_coll;
+            float wgt = (k == 0 || k == K) ? 0.5f : 1.0f;
+            wgt = valid ? wgt : 0.f;
+            clr_acc = fmaf(fabsf(g) * wgt, scale, clr_acc);
+            coll += (valid && g < 0.f && (k < K || s == last)) ? 1 : 0;
+            if (TRACE) {
+                if (valid && t < a.max_cells) a.cells[t] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
             }
         }
     }
@@ -621,7 +634,9 @@ __global__ void __launch_bounds__(1024) k_update(OptDev o, const float* __restri
     const int m = o.m, ns = o.ns;
     float* rows_s = reinterpret_cast<float*>(smem_raw);           // cap_rows x ns: the pending rows live here
     float* lj_s = rows_s + (size_t)cap_rows * ns;                 // m: Lj in sequence order
-    int* order = reinterpret_cast<int*>(lj_s + m);                // m: slot order
+    float* nv_s = lj_s + m;                                       // m: |v|^2 of the recomputed rows
+    int* order = reinterpret_cast<int*>(nv_s + m);                // m: slot order
+    int* stamp = order + m;                                       // m: generation stamp per SLOT
     __shared__ int sh_first_stale, sh_live, sh_slot_new;
     __shared__ double sh_sigma_old;
     const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
@@ -630,28 +645,31 @@ __global__ void __launch_bounds__(1024) k_update(OptDev o, const float* __restri
     int* tg = o.t + (size_t)b * m;
     int* vg = o.vec + (size_t)b * m;
 
-    // ---- slot bookkeeping (lmcma.cpp:331-364), data-independent integer logic, one thread ----
+    // ---- slot bookkeeping (lmcma.cpp:331-364): data-independent integer logic.  t[] / vec[] are staged in
+    //      shared memory with one coalesced load so the serial part never waits on HBM ----
+    for (int i = tid; i < m; i += nthr) { order[i] = tg[i]; stamp[i] = vg[i]; }
+    __syncthreads();
     if (tid == 0) {
         const int itr = scp->itr;
         int first_stale = 1;
         if (itr < m) {
-            tg[itr] = itr;
+            order[itr] = itr;
         } else {
-            int gap_min = vg[tg[1]] - vg[tg[0]];
+            int gap_min = stamp[order[1]] - stamp[order[0]];
             for (int j = 1; j < m - 1; ++j) {
-                const int gap = vg[tg[j + 1]] - vg[tg[j]];
+                const int gap = stamp[order[j + 1]] - stamp[order[j]];
                 if (gap < gap_min) { gap_min = gap; first_stale = j + 1; }
             }
             if (gap_min >= m /* maxsteps = nvectors, lmcma.cpp:267 */) first_stale = 0;
             if (first_stale != m - 1) {
-                const int recycled = tg[first_stale];
-                for (int j = first_stale; j < m - 1; ++j) tg[j] = tg[j + 1];
-                tg[m - 1] = recycled;
+                const int recycled = order[first_stale];
+                for (int j = first_stale; j < m - 1; ++j) order[j] = order[j + 1];
+                order[m - 1] = recycled;
             }
         }
         const int live = min(itr + 1, m);
-        const int slot_new = tg[live - 1];
-        vg[slot_new] = itr;
+        const int slot_new = order[live - 1];
+        stamp[slot_new] = itr;
         if (first_stale == 1) first_stale = 0;                   // lmcma.cpp:373-374
         sh_first_stale = first_stale; sh_live = live; sh_slot_new = slot_new;
         sh_sigma_old = scp->sigma;
@@ -663,14 +681,14 @@ __global__ void __launch_bounds__(1024) k_update(OptDev o, const float* __restri
     double* Ljd = o.Lj + (size_t)b * m;
     float* Njf = o.Njf + (size_t)b * m;
     for (int i = tid; i < m; i += nthr) {
-        const int slot = tg[i];
-        order[i] = slot;
+        const int slot = order[i];
+        tg[i] = slot; vg[i] = stamp[i];
         lj_s[i] = (i < live) ? (float)Ljd[slot] : 0.f;            // rows >= first_stale are rewritten below
     }
 
     // ---- mean, evolution path, new pc_j (lmcma.cpp:316-329, 365-366) ----
     {
-        const double coef = sqrt(o.cc * (2.0 - o.cc) * o.mueff) / sigma_old;
+        const double coef = o.pc_coef / sigma_old;               // sqrt(cc (2 - cc) mueff) / sigma
         double* xm = o.xmean + (size_t)b * ns;
         float* pc = o.pc + (size_t)b * ns;
         float* pnew = o.P + ((size_t)b * m + slot_new) * ns;
@@ -712,17 +730,21 @@ __global__ void __launch_bounds__(1024) k_update(OptDev o, const float* __restri
         float4* dst = reinterpret_cast<float4*>(row_ptr(i));
         for (int q = lane; q < nq; q += 32) dst[q] = src[q];
     }
-    auto finalize = [&](int i) {       // warp-collective: |v|^2 and the two closed forms, in FP64
+    // Closed forms of lmcma.cpp:386-389 with t = sqrt(1 + c1/(1-c1) |v|^2), rewritten without cancellation:
+    //   Nj = (sqrt(1-c1)/|v|^2)(t - 1)            = sqrt(1-c1) * r / (t + 1)
+    //   Lj = (1/(sqrt(1-c1)|v|^2))(1 - 1/t)       = r / (sqrt(1-c1) * t * (t + 1)),   r = c1/(1-c1)
+    // (identical in exact arithmetic; finite where the reference divides 0/0 for a zero vector).  The FP32
+    // value of Lj feeds the next factor step; the FP64 state is filled in after the loop, off the critical path.
+    const float r_f = (float)(o.c1 / (1.0 - o.c1)), a_f = (float)o.M;
+    auto finalize = [&](int i) {       // warp-collective: |v|^2 and Lj of sequence row i
         const float4* v = reinterpret_cast<const float4*>(row_ptr(i));
         float nvf = 0.f;
         for (int q = lane; q < nq; q += 32) { const float4 x = v[q]; nvf += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w); }
         nvf = warp_sum(nvf);
         if (lane == 0) {
-            const int slot = order[i];
-            const double nv = (double)nvf, c1 = o.c1;
-            const double nj = (sqrt(1.0 - c1) / nv) * (sqrt(1.0 + (c1 / (1.0 - c1)) * nv) - 1.0);
-            const double lj = (1.0 / (sqrt(1.0 - c1) * nv)) * (1.0 - (1.0 / sqrt(1.0 + (c1 / (1.0 - c1)) * nv)));
-            Njd[slot] = nj; Ljd[slot] = lj; Njf[slot] = (float)nj; lj_s[i] = (float)lj;
+            const float t = sqrtf(fmaf(r_f, nvf, 1.0f));
+            nv_s[i] = nvf;
+            lj_s[i] = r_f / (a_f * t * (t + 1.0f));
         }
     };
     __syncthreads();
@@ -752,6 +774,13 @@ __global__ void __launch_bounds__(1024) k_update(OptDev o, const float* __restri
         }
     }
     __syncthreads();
+    for (int i = first_stale + tid; i < live; i += nthr) {        // FP64 scalar state of the recomputed rows
+        const int slot = order[i];
+        const double nv = (double)nv_s[i], r = o.c1 / (1.0 - o.c1), a = o.M;
+        const double t = sqrt(1.0 + r * nv);
+        const double nj = a * r / (t + 1.0), lj = r / (a * t * (t + 1.0));
+        Njd[slot] = nj; Ljd[slot] = lj; Njf[slot] = (float)nj;
+    }
     for (int i = first_stale + warp; i < live && i - first_stale < cap_rows; i += nwarps) {   // write back
         const float4* src = reinterpret_cast<const float4*>(rows_s + (size_t)(i - first_stale) * ns);
         float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);

@@ -1,10 +1,10 @@
-// lmcma_layout.hpp — HBM layout of the cost map.  The map is stored in 128-byte bricks (one L1/L2 line)
-// whose 32-byte sectors are themselves small boxes, so that the ~1-cell-apart samples of a rasterised
-// segment — which the cost kernel assigns to consecutive lanes — fall into few lines and few sectors
-// whatever the direction of travel (a row-major map costs one line per sample on a diagonal).
+// lmcma_layout.hpp — HBM layout of the cost map.  The map is stored in 128-byte bricks (one L1/L2 line),
+// so that the ~1-cell-apart samples of a rasterised segment — which the cost kernel assigns to
+// consecutive lanes — fall into few lines whatever the direction of travel (a row-major map costs one
+// line per sample on a diagonal, and the L1 wavefront rate then bounds the gather).
 //
-//   2-D f32: brick  8 x 4      cells, sector 4 x 2        2-D u8: brick 16 x 8     cells, sector 8 x 4
-//   3-D f32: brick  4 x 4 x 2  cells, sector 2 x 2 x 2    3-D u8: brick  8 x 4 x 4 cells, sector 4 x 4 x 2
+//   2-D f32: brick  8 x 4      cells        2-D u8: brick 16 x 8     cells
+//   3-D f32: brick  4 x 4 x 2  cells        3-D u8: brick  8 x 4 x 4 cells
 //
 // The logical (row-major) cell index ((z*ny + y)*nx + x) stays the API-visible index (lmcma_b200_cost_trace).
 #pragma once
@@ -27,29 +27,17 @@ LMCMA_HD BrickShape brick_shape() {
     return STORAGE == 0 ? BrickShape{4, 4, 2} : BrickShape{8, 4, 4};
 }
 
-// element offset of cell (ix, iy, iz) in the bricked array; nbx / nby = bricks per row / per column
+// element offset of cell (ix, iy, iz) in the bricked array; nbx / nby = bricks per row / per column.
+// Cells are row-major inside a brick (a handful of shifts and masks on the hot path); 32-bit offsets:
+// a map holds fewer than 2^32 stored elements (checked at upload).
 template <int DIMS, int STORAGE>
-LMCMA_HD size_t brick_offset(unsigned ix, unsigned iy, unsigned iz, unsigned nbx, unsigned nby) {
+LMCMA_HD unsigned brick_offset(unsigned ix, unsigned iy, unsigned iz, unsigned nbx, unsigned nby) {
     if (DIMS == 2) {
-        if (STORAGE == 0) {
-            const size_t brick = (size_t)(iy >> 2) * nbx + (ix >> 3);
-            const unsigned o = (ix & 3u) | ((iy & 1u) << 2) | (((ix >> 2) & 1u) << 3) | (((iy >> 1) & 1u) << 4);
-            return brick * 32 + o;
-        } else {
-            const size_t brick = (size_t)(iy >> 3) * nbx + (ix >> 4);
-            const unsigned o = (ix & 7u) | ((iy & 3u) << 3) | (((ix >> 3) & 1u) << 5) | (((iy >> 2) & 1u) << 6);
-            return brick * 128 + o;
-        }
+        if (STORAGE == 0) return (((iy >> 2) * nbx + (ix >> 3)) << 5) | ((iy & 3u) << 3) | (ix & 7u);
+        return (((iy >> 3) * nbx + (ix >> 4)) << 7) | ((iy & 7u) << 4) | (ix & 15u);
     } else {
-        if (STORAGE == 0) {
-            const size_t brick = ((size_t)(iz >> 1) * nby + (iy >> 2)) * nbx + (ix >> 2);
-            const unsigned o = (ix & 1u) | ((iy & 1u) << 1) | ((iz & 1u) << 2) | (((ix >> 1) & 1u) << 3) | (((iy >> 1) & 1u) << 4);
-            return brick * 32 + o;
-        } else {
-            const size_t brick = ((size_t)(iz >> 2) * nby + (iy >> 2)) * nbx + (ix >> 3);
-            const unsigned o = (ix & 3u) | ((iy & 3u) << 2) | ((iz & 1u) << 4) | (((ix >> 2) & 1u) << 5) | (((iz >> 1) & 1u) << 6);
-            return brick * 128 + o;
-        }
+        if (STORAGE == 0) return ((((iz >> 1) * nby + (iy >> 2)) * nbx + (ix >> 2)) << 5) | ((iz & 1u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
+        return ((((iz >> 2) * nby + (iy >> 2)) * nbx + (ix >> 3)) << 7) | ((iz & 3u) << 5) | ((iy & 3u) << 3) | (ix & 7u);
     }
 }
 
