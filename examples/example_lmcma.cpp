@@ -1,0 +1,102 @@
+// example_lmcma.cpp — the reference's demo programs (lmcma_path_planner/src/example_lmcma.cpp:28-76 and
+// sample_based_optimisation_based_path_planner.cpp:694-775) written against the B200 façade.
+//
+//   example_lmcma demo  [seed]                    two-Gaussian test function, reference ask/tell protocol,
+//                                                 writes path_to_min.csv like the reference demo
+//   example_lmcma plan  [out.txt] [generations]   one 2-D query (99,0)->(0,99) on the reference's hard-coded
+//                                                 two-bar 100x100 map, fused on-device planner; the path is
+//                                                 written one state per line (OMPL printAsMatrix convention)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <vector>
+
+#include "lmcma_b200.hpp"
+
+namespace {
+
+// f(x,y) = -(4 exp(-((x-4)^2+(y-4)^2)) + 2 exp(-((x-2)^2+(y-2)^2))): global basin (4,4), local basin (2,2)
+double two_gaussians(double x, double y) {
+    const double a = (x - 4) * (x - 4) + (y - 4) * (y - 4), b = (x - 2) * (x - 2) + (y - 2) * (y - 2);
+    return -(4.0 * std::exp(-a) + 2.0 * std::exp(-b));
+}
+
+int demo(int seed) {
+    const int N = 2;
+    double lo[N] = {-2, -2}, hi[N] = {15, 15}, x[N] = {0, 0};
+    lmcma_b200::LMCMA opt(x, -1, lo, hi, 1.0, 0, seed);
+    opt.init(N);
+    std::ofstream csv("path_to_min.csv");
+    csv << "x,y,z,\n";
+    double f = 0;
+    for (int i = 0; i < 1000; ++i) {
+        opt.getNextParameterVector(x, N);
+        f = two_gaussians(x[0], x[1]);
+        opt.setEvaluationFeedback(&f, 1);
+        csv << x[0] << " , " << x[1] << " , " << f << "\n";
+    }
+    std::printf("the optimum point is: %.6f,%.6f f=%.6f BestF=%.6f counteval=%d done=%d\n", x[0], x[1], f, opt.BestF,
+                opt.counteval, (int)opt.isBehaviorLearningDone());
+    return 0;
+}
+
+// exact Euclidean distance to the nearest obstacle cell, brute force (100x100 only)
+std::vector<float> distance_map(const std::vector<unsigned char>& occ, int nx, int ny) {
+    std::vector<int> ox, oy;
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x)
+            if (occ[y * nx + x]) { ox.push_back(x); oy.push_back(y); }
+    std::vector<float> d(occ.size(), 1e9f);
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) {
+            long best = 1L << 40;
+            for (size_t k = 0; k < ox.size(); ++k) {
+                const long dx = x - ox[k], dy = y - oy[k], q = dx * dx + dy * dy;
+                if (q < best) best = q;
+            }
+            d[y * nx + x] = ox.empty() ? 1e9f : (float)std::sqrt((double)best);
+        }
+    return d;
+}
+
+int plan(const char* out_path, int generations) {
+    const int nx = 100, ny = 100;
+    std::vector<unsigned char> occ(nx * ny, 0);      // the two bars of planner.cpp:269-297
+    for (int y = 65; y < 75; ++y) for (int x = 0; x < 60; ++x) occ[y * nx + x] = 1;
+    for (int y = 35; y < 45; ++y) for (int x = 40; x < 99; ++x) occ[y * nx + x] = 1;
+    const std::vector<float> dist = distance_map(occ, nx, ny);
+    const int32_t shape[3] = {nx, ny, 1};
+    lmcma_b200::CostMap map(2, shape, dist.data());
+    const float start[2] = {99.f, 0.f}, goal[2] = {0.f, 99.f};   // planner.cpp:701-706
+    lmcma_b200::PlanOptions po;
+    po.waypoints = 20; po.lambda = 64; po.generations = generations; po.sigma0 = 8.0; po.seed = 1;
+    std::vector<float> path;
+    const float best = lmcma_b200::plan(map, shape, start, goal, po, &path);
+    // re-evaluate the returned path through the host-buffer cost entry point
+    float f = 0.f; int32_t ncoll = -1, nsamp = 0;
+    map.evaluate(path.data(), 1, po.waypoints, start, goal, po.weights, po.w_col, &f, &ncoll, &nsamp);
+    std::FILE* fh = std::fopen(out_path, "w");
+    if (!fh) return 2;
+    std::fprintf(fh, "%g %g\n", start[0], start[1]);
+    for (int w = 0; w < po.waypoints; ++w) std::fprintf(fh, "%g %g\n", path[w], path[po.waypoints + w]);
+    std::fprintf(fh, "%g %g\n", goal[0], goal[1]);
+    std::fclose(fh);
+    std::printf("best cost %.4f re-evaluated %.4f collisions %d samples %d launches %lld\n", best, f, ncoll, nsamp,
+                (long long)lmcma_b200_launch_count());
+    return (ncoll == 0 && std::fabs(best - f) <= 1e-5f * std::fabs(f)) ? 0 : 1;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        if (argc >= 2 && !std::strcmp(argv[1], "plan"))
+            return plan(argc >= 3 ? argv[2] : "path.txt", argc >= 4 ? std::atoi(argv[3]) : 300);
+        return demo(argc >= 3 ? std::atoi(argv[2]) : 1);
+    } catch (const lmcma_b200::Error& e) {
+        std::fprintf(stderr, "%s (code %d)\n", e.what(), e.code);
+        return 3;
+    }
+}

@@ -115,3 +115,25 @@ def test_workload_generators():
     st, gl = maps.random_queries(d, 9, seed=1, min_sep=60)
     assert st.shape == (9, 2) and np.all(np.linalg.norm(st - gl, axis=1) >= 60)
     assert all(d[int(p[1]), int(p[0])] > 0 for p in st)
+
+
+EXAMPLE = os.path.join(ROOT, "examples", "example_lmcma")
+
+
+def test_cpp_facade_compiles_against_the_c_abi():
+    """The C++ host side (include/lmcma_b200.hpp + examples/example_lmcma.cpp) is built by csrc/Makefile with
+    plain g++ -std=c++11: the facade keeps the reference's constructor and method signatures."""
+    assert os.path.exists(EXAMPLE), "run __graft_entry__.build()"
+    hpp = open(os.path.join(ROOT, "include", "lmcma_b200.hpp")).read()
+    for sig in ("LMCMA(double* initialParams, int lambda = 0, double* loBounds = 0, double* hiBounds = 0, double sigma = 1.0,",
+                "void init(int N)", "void getNextParameterVector(double* params, int N)",
+                "void setEvaluationFeedback(double* feedbacks, int numFeedbacks)", "bool isBehaviorLearningDone()",
+                "int counteval;", "double BestF;"):
+        assert sig in hpp, sig
+
+
+@pytest.mark.skipif(_cuda_present(), reason="this check is about machines WITHOUT a GPU")
+def test_cpp_example_fails_loudly_without_a_gpu(tmp_path):
+    import subprocess
+    r = subprocess.run([EXAMPLE, "demo"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3 and "lmcma_b200" in r.stderr

@@ -393,3 +393,35 @@ def test_split_population_single_process(po, golden_maps):
         assert parts[0].get("sigma")[0] == parts[1].get("sigma")[0]
     X = np.concatenate([p.ask_all()[0] for p in parts])
     assert np.allclose(X, whole.ask_all()[0], rtol=1e-4, atol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------
+# the C++ host side (the reference's language): facade header + demo / planner driver
+# ------------------------------------------------------------------------------------------------
+def _example(args, cwd):
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "example_lmcma")
+    return subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=300)
+
+
+def test_cpp_facade_demo_converges_like_the_reference(tmp_path):
+    """example_lmcma.cpp:28-76 against lmcma_b200::LMCMA: 1000 evaluations of the two-Gaussian function with
+    bounds [-2,15]^2 from (0,0); the reference converges to (3.99966, 3.99966), f = -4.00067."""
+    r = _example(["demo", "1"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    tail = r.stdout.strip().split("is:")[1].split()
+    x, y = (float(v) for v in tail[0].split(","))
+    best = float(tail[2].split("=")[1])
+    assert abs(x - 3.99966) < 2e-2 and abs(y - 3.99966) < 2e-2
+    assert abs(best + 4.00067) < 1e-3
+    assert "counteval=1000" in r.stdout
+    rows = open(tmp_path / "path_to_min.csv").read().strip().splitlines()
+    assert rows[0] == "x,y,z," and len(rows) == 1001
+
+
+def test_cpp_planner_driver_writes_a_collision_free_path(tmp_path):
+    r = _example(["plan", "path.txt", "300"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    pts = np.loadtxt(tmp_path / "path.txt")
+    assert pts.shape == (22, 2) and tuple(pts[0]) == (99.0, 0.0) and tuple(pts[-1]) == (0.0, 99.0)
