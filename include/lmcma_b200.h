@@ -159,7 +159,7 @@ int lmcma_b200_is_done(lmcma_b200_opt* opt, int32_t* done_host);
 /* ends: batch end-point pairs (one query per instance).  The map must live on the same device. */
 int lmcma_b200_attach_cost(lmcma_b200_opt* opt, lmcma_b200_map* map, const lmcma_b200_objective* obj,
                            const lmcma_b200_endpoints* ends);
-/* `generations` x [cost -> rank -> recombine -> update -> sample] replayed from a CUDA graph with no
+/* `generations` x [cost -> rank -> update -> sample] replayed from a CUDA graph with no
  * host round trip (the loop of example_lmcma.cpp:49-55 with the cost on the device). Asynchronous. */
 int lmcma_b200_run(lmcma_b200_opt* opt, int32_t generations);
 int lmcma_b200_sync(lmcma_b200_opt* opt);
@@ -168,8 +168,8 @@ int64_t lmcma_b200_launch_count(void);
 /* CUDA-event timing of everything enqueued by the last lmcma_b200_run on this handle (ms) */
 int lmcma_b200_last_run_ms(lmcma_b200_opt* opt, float* ms_out);
 /* per-kernel CUDA-event timing: runs `generations` un-graphed generations with an event pair around
- * each of the 5 kernels; ms_out5 = mean ms per launch of {cost, rank, recombine, update, sample} */
-int lmcma_b200_profile_kernels(lmcma_b200_opt* opt, int32_t generations, float* ms_out5);
+ * each of the 4 kernels; ms_out4 = mean ms per launch of {cost, rank (+ recombination partial sums), update, sample} */
+int lmcma_b200_profile_kernels(lmcma_b200_opt* opt, int32_t generations, float* ms_out4);
 
 /* best evaluated candidate so far per instance (the reference keeps only BestF, lmcma.cpp:192-194) */
 int lmcma_b200_best(lmcma_b200_opt* opt, float* x_best_host /* batch x n */, float* f_best_host /* batch */);

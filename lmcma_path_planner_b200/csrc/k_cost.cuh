@@ -1,0 +1,155 @@
+// k_cost.cuh — batched trajectory cost kernel.
+#pragma once
+#include "lmcma_common.cuh"
+
+namespace lmcma {
+
+// ------------------------------------------------------------------------------------------------
+// k_cost — batched trajectory cost (DESIGN.md "cost model"; the reference's per-state pieces are
+// ValidityChecker::isValid/clearance planner.cpp:591-631, ClearanceObjective::stateCost :655-669,
+// weights :677-690).  One CTA per trajectory.  Phase 1: per-segment records {A, B-A, 1/K, len/K} and
+// sub-step counts into shared memory + block scan.  Phase 2: the flattened sample sequence is cut into
+// 32-sample blocks, a contiguous run of blocks per warp, consecutive samples on consecutive lanes: they
+// are <= 1 cell apart, and the map is stored in 128-byte bricks (lmcma_layout.hpp), so one warp load
+// touches a handful of lines instead of 32 (the L1 wavefront rate, not DRAM, bounds a row-major
+// gather).  Phase 3: block reduction.
+// The index path (t = k * (1/K); q = A + t*d; rint; bounds test) uses explicitly rounded FP32
+// mul/add so that no FMA contraction can change a cell index relative to the CPU oracle.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int substeps_of(float linf) {
+    if (linf >= 1.0f) return linf <= (float)KMAX_SUBSTEPS ? (int)ceilf(linf) : KMAX_SUBSTEPS;
+    return 1;   // also NaN
+}
+
+template <int DIMS, int STORAGE, bool TRACE>
+__global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = a.W, NSEG = W + 1;
+    float4* segA = reinterpret_cast<float4*>(smem_raw);          // 2-D {Ax, Ay, dx, dy}   3-D {Ax, Ay, Az, dx}
+    float4* segB = segA + NSEG;                                  // 2-D {invK, scale, -, -} 3-D {dy, dz, invK, scale}
+    int* off = reinterpret_cast<int*>(segB + NSEG);              // NSEG + 1 exclusive sample offsets
+    float* lut = reinterpret_cast<float*>(off + NSEG + 1);       // 256 (U8 only)
+    __shared__ float red_f[2][8];
+    __shared__ int red_i[8];
+    __shared__ int warp_tot[8];
+
+    const int row = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const float* x = a.X + ((size_t)b * a.inst_rows + row) * a.ld;
+    const float* en = a.ends + (a.ends_per_instance ? (size_t)b * 6 : 0);
+    if (STORAGE == 1) for (int i = tid; i < 256; i += nthr) lut[i] = mp.lut[i];
+
+    // ---- phase 1: per-segment records, sub-step counts, lengths; block scan of the sample counts ----
+    const int spt = (NSEG + nthr - 1) / nthr;                    // consecutive segments per thread
+    const int s_begin = min(NSEG, tid * spt), s_end = min(NSEG, s_begin + spt);
+    float len_acc = 0.f; int my_cnt = 0;
+    for (int s = s_begin; s < s_end; ++s) {
+        float A[3], D[3]; float linf = 0.f, l2 = 0.f; bool bad = false;
+#pragma unroll
+        for (int c = 0; c < DIMS; ++c) {
+            A[c] = (s == 0) ? en[c] : x[c * W + s - 1];
+            const float Bc = (s == W) ? en[3 + c] : x[c * W + s];
+            D[c] = __fsub_rn(Bc, A[c]);
+            const float ad = fabsf(D[c]);
+            bad |= (ad != ad);
+            if (ad > linf) linf = ad;
+            l2 = fmaf(D[c], D[c], l2);
+        }
+        if (bad) linf = __int_as_float(0x7fc00000);
+        const int K = substeps_of(linf);
+        const float invK = __frcp_rn((float)K);                  // == 1.0f / (float)K, IEEE round-to-nearest
+        const float len = sqrtf(l2);
+        len_acc += len;
+        // A segment with a non-finite end point has no sample inside the map (NaN / inf coordinates fail the
+        // oracle's bounds test for every k): encode that as a finite far-away anchor so that the sample loop
+        // can use integer conversion + unsigned bounds tests (NaN would convert to 0).
+        bool finite = true;
+#pragma unroll
+        for (int c = 0; c < DIMS; ++c) finite = finite && (fabsf(A[c]) < 3.0e38f) && (fabsf(D[c]) < 3.0e38f);
+        if (!finite) {
+#pragma unroll
+            for (int c = 0; c < DIMS; ++c) { A[c] = -1.0e9f; D[c] = 0.f; }
+        }
+        if (DIMS == 2) { segA[s] = make_float4(A[0], A[1], D[0], D[1]); segB[s] = make_float4(invK, len * invK, 0.f, 0.f); }
+        else { segA[s] = make_float4(A[0], A[1], A[2], D[0]); segB[s] = make_float4(D[1], D[2], invK, len * invK); }
+        off[s + 1] = K + 1;                                      // samples of this segment (rewritten below)
+        my_cnt += K + 1;
+    }
+    int incl = my_cnt;                                           // block-wide exclusive scan of my_cnt
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += nb;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int base = incl - my_cnt, T = 0;
+    for (int w2 = 0; w2 < nwarps; ++w2) { const int v = warp_tot[w2]; if (w2 < warp) base += v; T += v; }
+    if (tid == 0) off[0] = 0;
+    for (int s = s_begin; s < s_end; ++s) { base += off[s + 1]; off[s + 1] = base; }
+    __syncthreads();
+
+    // ---- phase 2: consecutive samples on consecutive lanes (<= 1 cell apart -> few lines per warp load) ----
+    const int nblk = (T + 31) >> 5;
+    const int blk0 = (int)(((long long)warp * nblk) / nwarps), blk1 = (int)(((long long)(warp + 1) * nblk) / nwarps);
+    float clr_acc = 0.f; int coll = 0;
+    if (blk0 < blk1) {
+        int lo = 0, hi = NSEG - 1;                               // warp-uniform: last s with off[s] <= first sample
+        const int tfirst = blk0 << 5;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= tfirst) lo = mid; else hi = mid - 1; }
+        int s_warp = lo;
+        const unsigned nxm1 = (unsigned)(mp.nx - 1), nym1 = (unsigned)(mp.ny - 1), nzm1 = (unsigned)(mp.nz - 1);
+        const int last = NSEG - 1;
+        for (int blk = blk0; blk < blk1; ++blk) {
+            const int t = (blk << 5) + lane;
+            const bool valid = t < T;
+            const int tt = valid ? t : T - 1;
+            int s = s_warp;
+            int cur = off[s], nxt = off[s + 1];                  // warp-uniform (broadcast) loads
+            while (tt >= nxt) { ++s; cur = nxt; nxt = off[s + 1]; }
+            s_warp = __shfl_sync(0xffffffffu, s, 31);
+            const int K = nxt - cur - 1, k = tt - cur;
+            const float4 ra = segA[s];
+            float invK, scale, dx, dy, dz = 0.f, az = 0.f;
+            if (DIMS == 2) { const float2 rb = *reinterpret_cast<const float2*>(&segB[s]); invK = rb.x; scale = rb.y; dx = ra.z; dy = ra.w; }
+            else { const float4 rb = segB[s]; dx = ra.w; dy = rb.x; dz = rb.y; invK = rb.z; scale = rb.w; az = ra.z; }
+            const float tk = __fmul_rn((float)k, invK);
+            // round-half-even conversion == (int)rintf(q); saturates for huge |q| (-> fails the unsigned test)
+            const int ix = __float2int_rn(__fadd_rn(ra.x, __fmul_rn(tk, dx)));
+            const int iy = __float2int_rn(__fadd_rn(ra.y, __fmul_rn(tk, dy)));
+            bool inb = ((unsigned)ix <= nxm1) && ((unsigned)iy <= nym1);
+            int iz = 0;
+            if (DIMS == 3) {
+                iz = __float2int_rn(__fadd_rn(az, __fmul_rn(tk, dz)));
+                inb = inb && ((unsigned)iz <= nzm1);
+            }
+            const unsigned adr = inb ? brick_offset<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, mp.nbx, mp.nby) : 0u;
+            float g = (STORAGE == 0) ? __ldg(mp.g32 + adr) : lut[__ldg(mp.q8 + adr)];   // branch-free: cell 0 when outside
+            g = inb ? g : -mp.g_coll;
+            float wgt = (k == 0 || k == K) ? 0.5f : 1.0f;
+            wgt = valid ? wgt : 0.f;
+            clr_acc = fmaf(fabsf(g) * wgt, scale, clr_acc);
+            coll += (valid && g < 0.f && (k < K || s == last)) ? 1 : 0;
+            if (TRACE) {
+                if (valid && t < a.max_cells) a.cells[t] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
+            }
+        }
+    }
+
+    // ---- phase 3: block reduction ----
+    len_acc = warp_sum(len_acc);
+    clr_acc = warp_sum(clr_acc);
+    coll = warp_sum_i(coll);
+    if (lane == 0) { red_f[0][warp] = len_acc; red_f[1][warp] = clr_acc; red_i[warp] = coll; }
+    __syncthreads();
+    if (tid == 0) {
+        float L = 0.f, C = 0.f; int NC = 0;
+        for (int w2 = 0; w2 < nwarps; ++w2) { L += red_f[0][w2]; C += red_f[1][w2]; NC += red_i[w2]; }
+        const float f = fmaf(a.w_col, (float)NC, fmaf(a.w_clr, C, a.w_len * L));
+        a.f[(size_t)b * a.f_stride + a.f_offset + row] = f;
+        if (a.ncoll) a.ncoll[(size_t)b * a.inst_rows + row] = NC;
+        if (a.nsamp) a.nsamp[(size_t)b * a.inst_rows + row] = T;
+    }
+}
+
+}  // namespace lmcma

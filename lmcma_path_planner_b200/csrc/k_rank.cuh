@@ -1,0 +1,210 @@
+// k_rank.cuh — ranking + recombination partial sums of LMCMA::update (lmcma.cpp:315-326, 393-411).
+//
+// grid = (RS, B): RS row slices per optimiser instance.  Every CTA computes the ranks of its slice's
+// candidates by counting (myqsort/compare, lmcma.cpp:84-104: stable ascending order, ties keep the lower id,
+// -0 == +0, NaN last) together with the pair count S of the merged 2*lambda ranking of the step-size rule,
+// and the slice's weighted partial sum of (x - xmean).  k_update (k_update.cuh) folds the partials.
+// Split-population mode (RANK_PACK): the last CTA of an instance to finish — fence + atomic ticket, no CTA
+// ever waits on another — folds the partials into the all-gather payload.
+#pragma once
+#include "lmcma_common.cuh"
+
+namespace lmcma {
+
+enum { RANK_PLAIN = 0, RANK_PACK = 1 };
+
+constexpr int TELL_FTILE = 4096;       // fitness values staged per shared-memory tile
+constexpr int TELL_MAX_ROWS = 256;     // rows per slice upper bound (rows_per = max(32, ceil(pop/256)))
+
+// ------------------------------------------------------------------------------------------------
+// ranks + partial sums of one slice
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __restrict__ f_all, int b, int rs,
+                                             unsigned char* smem_raw) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const int lambda = o.lambda;
+    const int rows_per = (o.pop_count + o.RS - 1) / o.RS;
+    const int r0 = rs * rows_per, r1 = min(o.pop_count, r0 + rows_per), nrows = max(0, r1 - r0);
+
+    float* cur_s = reinterpret_cast<float*>(smem_raw);               // TELL_FTILE
+    float* prev_s = cur_s + TELL_FTILE;                              // TELL_FTILE
+    int* rk_s = reinterpret_cast<int*>(prev_s + TELL_FTILE);         // TELL_MAX_ROWS ranks of the slice's rows
+    int* sel_row = rk_s + TELL_MAX_ROWS;                             // compacted selected rows (rank < mu)
+    float* sel_w = reinterpret_cast<float*>(sel_row + TELL_MAX_ROWS);
+    float4* red = reinterpret_cast<float4*>(sel_w + TELL_MAX_ROWS);  // 7 x 128 cross-group reduction
+    __shared__ int sh_nsel;
+    __shared__ unsigned long long sh_S;
+
+    const float* cur = f_all + (size_t)b * lambda;
+    const float* prev = o.prev_fit + (size_t)b * lambda;
+    if (tid == 0) sh_S = 0ull;
+    // requested now, used after the ranking: float(xmean) of this thread's columns (first column tile)
+    float4 m4_first = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((tid & 127) < (o.ns >> 2)) {
+        const double* xm = o.xmean + (size_t)b * o.ns + 4 * (tid & 127);
+        m4_first = make_float4((float)xm[0], (float)xm[1], (float)xm[2], (float)xm[3]);
+    }
+
+    // threads per row: a power of two <= 32 so that a row's partial counts fold with warp shuffles
+    int tpr = 32;
+    while (tpr > 1 && (nthr / tpr) < nrows) tpr >>= 1;
+    const int rows_par = nthr / tpr, sub = tid % tpr, grp = tid / tpr;
+
+    const int npass = (nrows + rows_par - 1) / rows_par;
+    // counts for (up to) npass rows per thread group are kept in registers across the fitness tiles when
+    // npass == 1 (the common shape); otherwise the tiles are re-staged per pass (lambda > 4096 only).
+    for (int pass = 0; pass < npass; ++pass) {
+        const int il = r0 + pass * rows_par + grp;                   // local row
+        const bool valid = (pass * rows_par + grp) < nrows;
+        const int i = o.pop_offset + il;                             // global candidate id
+        const float ki = valid ? canon_fitness(cur[i]) : 0.f;
+        int c_lt = 0; unsigned long long p_lt = 0;
+        for (int base = 0; base < lambda; base += TELL_FTILE) {
+            const int cnt = min(TELL_FTILE, lambda - base), cnt4 = (cnt + 3) & ~3;
+            __syncthreads();                                         // previous tile fully consumed
+            for (int j = tid; j < cnt4; j += nthr) {
+                const bool in = j < cnt;
+                cur_s[j] = in ? canon_fitness(cur[base + j]) : __int_as_float(0x7f800000);
+                prev_s[j] = in ? prev[base + j] : __int_as_float(0x7f800000);
+            }
+            __syncthreads();
+            if (valid) {
+                int pl = 0;
+                for (int j = sub * 4; j < cnt4; j += tpr * 4) {
+                    const float4 kj = *reinterpret_cast<const float4*>(cur_s + j);
+                    const float4 pj = *reinterpret_cast<const float4*>(prev_s + j);
+                    const int jg = base + j;
+                    // ties keep the lower id first: j < i counts on "<=", j >= i on "<" (j == i compares equal)
+                    if (jg + 3 < i) {
+                        c_lt += (kj.x <= ki) + (kj.y <= ki) + (kj.z <= ki) + (kj.w <= ki);
+                    } else if (jg >= i) {
+                        c_lt += (kj.x < ki) + (kj.y < ki) + (kj.z < ki) + (kj.w < ki);
+                    } else {
+                        c_lt += (kj.x < ki) || (kj.x == ki && jg < i);
+                        c_lt += (kj.y < ki) || (kj.y == ki && jg + 1 < i);
+                        c_lt += (kj.z < ki) || (kj.z == ki && jg + 2 < i);
+                        c_lt += (kj.w < ki) || (kj.w == ki && jg + 3 < i);
+                    }
+                    pl += (pj.x < ki) + (pj.y < ki) + (pj.z < ki) + (pj.w < ki);
+                }
+                p_lt += (unsigned long long)pl;
+            }
+        }
+        // fold over the tpr lanes of the row (groups are aligned inside a warp)
+        unsigned plo = (unsigned)p_lt, phi = (unsigned)(p_lt >> 32);
+        for (int ofs = tpr >> 1; ofs > 0; ofs >>= 1) {
+            c_lt += __shfl_xor_sync(0xffffffffu, c_lt, ofs);
+            const unsigned l2 = __shfl_xor_sync(0xffffffffu, plo, ofs), h2 = __shfl_xor_sync(0xffffffffu, phi, ofs);
+            const unsigned long long a = (((unsigned long long)phi << 32) | plo) + (((unsigned long long)h2 << 32) | l2);
+            plo = (unsigned)a; phi = (unsigned)(a >> 32);
+        }
+        if (valid && sub == 0) {
+            o.rank[(size_t)b * lambda + i] = c_lt;
+            o.arindex[(size_t)b * lambda + c_lt] = i;
+            o.fit_sorted[(size_t)b * lambda + c_lt] = ki;
+            rk_s[pass * rows_par + grp] = c_lt;
+            atomicAdd(&sh_S, ((unsigned long long)phi << 32) | plo);   // integer: order-independent
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && sh_S) atomicAdd(o.S_count + b, sh_S);
+
+    // ---- compact the selected rows (rank < mu) in row order: deterministic summation order ----
+    if (tid < 32) {
+        int nsel = 0;
+        for (int basei = 0; basei < nrows; basei += 32) {
+            const int r = basei + lane;
+            const int rk = (r < nrows) ? rk_s[r] : o.mu;
+            const bool s = rk < o.mu;
+            const unsigned bal = __ballot_sync(0xffffffffu, s);
+            if (s) {
+                const int pos = nsel + __popc(bal & ((1u << lane) - 1u));
+                sel_row[pos] = r0 + r;
+                sel_w[pos] = o.w[rk];
+            }
+            nsel += __popc(bal);
+        }
+        if (lane == 0) sh_nsel = nsel;
+    }
+    __syncthreads();
+    const int nsel = sh_nsel;
+
+    // ---- weighted partial sums of (x - xmean): 128 float4 columns x (nthr/128) row groups ----
+    const int nq = o.ns >> 2, ngrp = nthr >> 7, tq = tid & 127, g = tid >> 7;
+    float* part = o.partial + ((size_t)b * o.RS + rs) * o.ns;
+    for (int q0 = 0; q0 < nq; q0 += 128) {
+        const int q = q0 + tq;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < nq) {
+            float4 m4 = m4_first;
+            if (q0 > 0) {
+                const double* xm = o.xmean + (size_t)b * o.ns + 4 * q;
+                m4 = make_float4((float)xm[0], (float)xm[1], (float)xm[2], (float)xm[3]);
+            }
+            for (int k = g; k < nsel; k += 4 * ngrp) {               // up to 4 rows in flight per thread
+                float w[4]; float4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + u * ngrp;
+                    const bool on = kk < nsel;
+                    w[u] = on ? sel_w[kk] : 0.f;
+                    x[u] = on ? reinterpret_cast<const float4*>(o.X + ((size_t)b * o.pop_count + sel_row[kk]) * o.ns)[q] : m4;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc.x = fmaf(w[u], x[u].x - m4.x, acc.x);
+                    acc.y = fmaf(w[u], x[u].y - m4.y, acc.y);
+                    acc.z = fmaf(w[u], x[u].z - m4.z, acc.z);
+                    acc.w = fmaf(w[u], x[u].w - m4.w, acc.w);
+                }
+            }
+        }
+        if (g > 0) red[(g - 1) * 128 + tq] = acc;
+        __syncthreads();
+        if (g == 0 && q < nq) {
+            for (int gg = 0; gg + 1 < ngrp; ++gg) { const float4 t = red[gg * 128 + tq]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+            reinterpret_cast<float4*>(part)[q] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// A_PACK tail (split mode): fold the RS local partials and the local S count into the all-gather payload
+__device__ __forceinline__ void tell_pack_payload(const OptDev& o, float* __restrict__ payload, int b) {
+    float* pay = payload + (size_t)b * (o.ns + 4);
+    for (int e = threadIdx.x; e < o.ns; e += blockDim.x) {
+        float acc = 0.f;
+        for (int rs = 0; rs < o.RS; ++rs) acc += __ldcg(o.partial + ((size_t)b * o.RS + rs) * o.ns + e);
+        pay[e] = acc;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long S = atomicExch(o.S_count + b, 0ull);
+        pay[o.ns] = __uint_as_float((unsigned)S);
+        pay[o.ns + 1] = __uint_as_float((unsigned)(S >> 32));
+        pay[o.ns + 2] = 0.f; pay[o.ns + 3] = 0.f;
+    }
+}
+
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict__ f_all, int mode, float* __restrict__ payload) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int sh_last;
+    griddep_launch_dependents();          // k_update's prologue does not depend on this kernel (see k_update.cuh)
+    const int b = blockIdx.y;
+    tell_phase_a(o, f_all, b, blockIdx.x, smem_raw);
+    if (mode != RANK_PACK) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(o.done_count + b, 1u);
+        sh_last = (ticket == (unsigned)(gridDim.x - 1)) ? 1 : 0;
+        if (sh_last) o.done_count[b] = 0u;
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    tell_pack_payload(o, payload, b);
+}
+
+}  // namespace lmcma

@@ -1,0 +1,406 @@
+// k_sample.cuh — offspring sampling kernel.
+#pragma once
+#include "lmcma_common.cuh"
+
+namespace lmcma {
+
+constexpr int SAMPLE_G = 8;   // direction pairs per group: their dots are independent, reduced together
+
+// Sum v[g] over the 32 lanes for 8 values with 9 shuffles instead of 40: three exchange-and-halve stages
+// (each lane gives away the half of the values it will not own), then two butterfly stages.  On return
+// every lane holds the total of value p = lane >> 2 & 7, i.e. value g lives on lanes 4g .. 4g+3.
+__device__ __forceinline__ float reduce_scatter8(const float (&v)[SAMPLE_G], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float a[4], b[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float send = h16 ? v[k] : v[k + 4], keep = h16 ? v[k + 4] : v[k];
+        a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float send = h8 ? a[k] : a[k + 2], keep = h8 ? a[k + 2] : a[k];
+        b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = h4 ? b[0] : b[1], keep = h4 ? b[1] : b[0];
+    float c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sample — LMCMA::sample + computeAz + applyBoundaries (lmcma.cpp:301-311, 431-447, 220-230) for
+// all offspring at once.  One CTA per tile of (blockDim/32)*RB offspring rows of one instance; the
+// live (v_j, pc_j) pairs are streamed through shared memory in sequence order by 1-D bulk async
+// copies (double-buffered, mbarrier-tracked); each warp keeps RB rows of z and Az in registers,
+// lanes own float4 column slots (lane + 32*i).
+//
+// Pairs are processed in groups of 8.  All dots are against the ORIGINAL z (lmcma.cpp:441-443), so the
+// 8*RB dot products of a group are independent FMA chains and are summed over the lanes with one
+// reduce-scatter.  The ordered recurrence Az <- M*Az + d_j*pc_j (lmcma.cpp:444-445) is unrolled over a
+// group as  Az <- M^8 * (Az + sum_g (d_g * M^-(g+1)) * pc_g): the same value in exact arithmetic, one
+// FMA per element and pair instead of a multiply and an FMA.
+// ------------------------------------------------------------------------------------------------
+
+// x = xmean + sigma * Az in FP64, clamp lo then hi (lmcma.cpp:307-310, 222-229); lo / hi are padded to ns with
+// -FLT_MAX / +FLT_MAX, the padding lanes of X are forced to 0
+__device__ __forceinline__ float4 sample_finish(const OptDev& o, const double* __restrict__ xm, double sigma, float4 az, int q) {
+    const double2 m01 = reinterpret_cast<const double2*>(xm)[2 * q];
+    const double2 m23 = reinterpret_cast<const double2*>(xm)[2 * q + 1];
+    float4 lo4 = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f), hi4 = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f);
+    if (o.lo) lo4 = reinterpret_cast<const float4*>(o.lo)[q];
+    if (o.hi) hi4 = reinterpret_cast<const float4*>(o.hi)[q];
+    float4 x;
+    x.x = fminf(fmaxf((float)(m01.x + sigma * (double)az.x), lo4.x), hi4.x);
+    x.y = fminf(fmaxf((float)(m01.y + sigma * (double)az.y), lo4.y), hi4.y);
+    x.z = fminf(fmaxf((float)(m23.x + sigma * (double)az.z), lo4.z), hi4.z);
+    x.w = fminf(fmaxf((float)(m23.y + sigma * (double)az.w), lo4.w), hi4.w);
+    const int e = q * 4;
+    if (e + 1 >= o.n) x.y = 0.f;
+    if (e + 2 >= o.n) x.z = 0.f;
+    if (e + 3 >= o.n) x.w = 0.f;
+    return x;
+}
+
+constexpr int SAMPLE_MAX_STAGES = 8;
+
+template <int NV, int RB, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per stage, multiple of 8 */, int nstages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ns = o.ns, nq = ns >> 2;
+    float* stage_base = reinterpret_cast<float*>(smem_raw);
+    const size_t stage_floats = (size_t)kc * 2 * ns;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_base + (size_t)nstages * stage_floats);
+    float* nj_s = reinterpret_cast<float*>(bars + SAMPLE_MAX_STAGES);   // Nj of the live pairs, in sequence order (padded to 8)
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < nstages; ++s2) mbar_init(&bars[s2], 1);
+        fence_barrier_init();
+    }
+    // launched as a programmatic dependent of k_update: resident early, but every input is k_update's output
+    griddep_wait();
+    const Scalars sc = o.sc[b];
+    const int live = sc.live;
+    const int nchunks = (live + kc - 1) / kc;
+    // the (v_j, pc_j) pairs of a chunk are one contiguous block of the sequence-ordered mirror: ONE bulk async copy
+    const float* vps = o.VPs + (size_t)b * o.m * 2 * ns;
+    auto issue = [&](int chunk) {   // thread 0
+        const int st = chunk % nstages;
+        const int k0 = chunk * kc, cnt = min(kc, live - k0);
+        const unsigned bytes = (unsigned)(cnt * 2 * ns * sizeof(float));
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage_base + st * stage_floats, vps + (size_t)k0 * 2 * ns, bytes, &bars[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int c = 0; c < nchunks && c < nstages; ++c) issue(c);
+    const int live8 = (live + SAMPLE_G - 1) & ~(SAMPLE_G - 1);
+    for (int k = threadIdx.x; k < live8; k += blockDim.x) nj_s[k] = (k < live) ? o.Njs[(size_t)b * o.m + k] : 0.f;
+    // (nj_s is first read after the __syncthreads below)
+
+    // ---- load / generate z for this warp's RB rows ----
+    const int row0 = (blockIdx.x * nwarps + warp) * RB;       // local row index
+    float4 z[RB][NV], az[RB][NV];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        const bool rv = row < o.pop_count;
+        const size_t roff = ((size_t)b * o.pop_count + (rv ? row : 0)) * ns;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int q = lane + 32 * i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rv && q < nq) {
+                if (o.rng_mode == 0) {
+                    v = philox_normal4((unsigned)q, (unsigned)(o.pop_offset + row), (unsigned)sc.itr, (unsigned)b, o.seed);
+                    const int e = q * 4;
+                    if (e + 1 >= o.n) v.y = 0.f;
+                    if (e + 2 >= o.n) v.z = 0.f;
+                    if (e + 3 >= o.n) v.w = 0.f;
+                    if (o.Z) reinterpret_cast<float4*>(o.Z + roff)[q] = v;
+                } else {
+                    v = reinterpret_cast<const float4*>(o.Z + roff)[q];
+                }
+            }
+            z[r][i] = v;
+            az[r][i] = v;
+        }
+    }
+
+    // per-lane constants of the unrolled recurrence: this lane owns pair p = (lane >> 2) & 7 of every group
+    const float Mf = (float)o.M, Minv = 1.0f / Mf;
+    float M8 = 1.0f;                                           // M^8
+#pragma unroll
+    for (int c = 0; c < SAMPLE_G; ++c) M8 *= Mf;
+    const int p_lane = (lane >> 2) & 7;
+    float minv_lane = Minv;                                    // M^-(p+1)
+    for (int c = 0; c < p_lane; ++c) minv_lane *= Minv;
+
+    __syncthreads();                          // nj_s
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c % nstages;
+        mbar_wait(&bars[st], (unsigned)((c / nstages) & 1));
+        const float* sb = stage_base + st * stage_floats;
+        const int k0 = c * kc, cnt = min(kc, live - k0);
+        for (int k = 0; k < cnt; k += SAMPLE_G) {
+            const int gcnt = min(SAMPLE_G, cnt - k);           // pairs in this group (warp-uniform)
+            // ---- 8*RB dot products against the original z ----
+            float d[RB][SAMPLE_G];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int g = 0; g < SAMPLE_G; ++g) d[r][g] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int q = lane + 32 * i;
+                if (q < nq) {
+#pragma unroll
+                    for (int g = 0; g < SAMPLE_G; ++g) {
+                        if (g < gcnt) {
+                            const float4 v = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g)) * ns)[q];
+#pragma unroll
+                            for (int r = 0; r < RB; ++r) {
+                                d[r][g] = fmaf(v.x, z[r][i].x, d[r][g]);
+                                d[r][g] = fmaf(v.y, z[r][i].y, d[r][g]);
+                                d[r][g] = fmaf(v.z, z[r][i].z, d[r][g]);
+                                d[r][g] = fmaf(v.w, z[r][i].w, d[r][g]);
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- lane-sum, scale: c_g = Nj_g * (v_g . z) * M^-(g+1); broadcast to every lane ----
+            const float scale_lane = (p_lane < gcnt) ? nj_s[k0 + k + p_lane] * minv_lane : 0.f;
+            float w[RB][SAMPLE_G];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const float tot = reduce_scatter8(d[r], lane) * scale_lane;
+#pragma unroll
+                for (int g = 0; g < SAMPLE_G; ++g) w[r][g] = __shfl_sync(0xffffffffu, tot, 4 * g);
+            }
+            // ---- Az <- M^gcnt * (Az + sum_g c_g * pc_g) ----
+            float mg = M8;
+            if (gcnt < SAMPLE_G) { mg = 1.0f; for (int c2 = 0; c2 < gcnt; ++c2) mg *= Mf; }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int q = lane + 32 * i;
+                if (q < nq) {
+#pragma unroll
+                    for (int g = 0; g < SAMPLE_G; ++g) {
+                        if (g < gcnt) {
+                            const float4 p = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g) + 1) * ns)[q];
+#pragma unroll
+                            for (int r = 0; r < RB; ++r) {
+                                az[r][i].x = fmaf(w[r][g], p.x, az[r][i].x);
+                                az[r][i].y = fmaf(w[r][g], p.y, az[r][i].y);
+                                az[r][i].z = fmaf(w[r][g], p.z, az[r][i].z);
+                                az[r][i].w = fmaf(w[r][g], p.w, az[r][i].w);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) { az[r][i].x *= mg; az[r][i].y *= mg; az[r][i].z *= mg; az[r][i].w *= mg; }
+                }
+            }
+        }
+        if (c + nstages < nchunks) {
+            __syncthreads();                  // every warp is done with stage st
+            if (threadIdx.x == 0) issue(c + nstages);
+        }
+    }
+
+    // ---- x = xmean + sigma * Az, clamp lo then hi (lmcma.cpp:307-310, 222-229) ----
+    const double* xm = o.xmean + (size_t)b * ns;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        if (row >= o.pop_count) continue;
+        float* xrow = o.X + ((size_t)b * o.pop_count + row) * ns;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int q = lane + 32 * i;
+            if (q < nq) reinterpret_cast<float4*>(xrow)[q] = sample_finish(o, xm, sc.sigma, az[r][i], q);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sample_wide — the same computation for ONE large population (lambda in the hundreds and up), where a
+// warp per offspring row leaves the SMs almost empty (lambda / 2 warps over 592 warp schedulers) and every
+// dependent FMA / shared-memory load latency is exposed.  Here a row is split over CW warps (each lane owns one
+// float4 column), a warp carries RBW rows for its columns (each pair element read from shared memory serves RBW
+// rows: shared-memory bandwidth is the scarce resource), a CTA holds R row-groups x CW column-warps, and the
+// 8 partial dot products of a group are exchanged through shared memory with one named barrier per row-group
+// and group.  4x..16x more resident warps per SM than the warp-per-row kernel.
+// grid = (ceil(pop_count / (R * RBW)), B), block = 32 * R * CW.
+// ------------------------------------------------------------------------------------------------
+template <int RBW, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nstages, int R, int CW, int qpw /* float4 columns per warp */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+#define SMP_STAMP(k) do { if (o.dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) o.dbg[32 + k] = gtime(); } while (0)
+    SMP_STAMP(0);
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = warp / CW, cw = warp - rl * CW;              // row-group within the CTA, column-warp within the row
+    const int ns = o.ns, nq = ns >> 2;
+    float* stage_base = reinterpret_cast<float*>(smem_raw);
+    const size_t stage_floats = (size_t)kc * 2 * ns;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_base + (size_t)nstages * stage_floats);
+    float* nj_s = reinterpret_cast<float*>(bars + SAMPLE_MAX_STAGES);   // Nj * M^-(g+1) of the live pairs (padded to 8)
+    float* dpart = nj_s + o.m + SAMPLE_G;                               // (groups per round) x R x CW x RBW x 8 partial dot products
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < nstages; ++s2) mbar_init(&bars[s2], 1);
+        fence_barrier_init();
+    }
+    griddep_wait();                            // every input is k_update's output
+    SMP_STAMP(1);
+    const float* vps = o.VPs + (size_t)b * o.m * 2 * ns;
+    // one bulk async copy per chunk of consecutive pairs; sized by m, not by the live count, so that the first
+    // chunks are requested before the scalar state has even been read (rows beyond `live` are never used)
+    auto issue = [&](int chunk) {   // thread 0
+        const int st = chunk % nstages;
+        const int k0 = chunk * kc, cnt = min(kc, o.m - k0);
+        const unsigned bytes = (unsigned)(cnt * 2 * ns * sizeof(float));
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage_base + st * stage_floats, vps + (size_t)k0 * 2 * ns, bytes, &bars[st]);
+    };
+    const int max_chunks = (o.m + kc - 1) / kc;
+    if (threadIdx.x == 0)
+        for (int c = 0; c < max_chunks && c < nstages; ++c) issue(c);
+    const Scalars sc = o.sc[b];
+    const int live = sc.live;
+    const int nchunks = (live + kc - 1) / kc;
+    SMP_STAMP(2);
+    const float Mf = (float)o.M, Minv = 1.0f / Mf;
+    const int live8 = (live + SAMPLE_G - 1) & ~(SAMPLE_G - 1);
+    for (int k = threadIdx.x; k < live8; k += blockDim.x) {
+        float sc8 = Minv;                                       // M^-((k mod 8) + 1)
+        for (int c = 0; c < (k & 7); ++c) sc8 *= Minv;
+        nj_s[k] = (k < live) ? o.Njs[(size_t)b * o.m + k] * sc8 : 0.f;
+    }
+    float M8 = 1.0f;
+#pragma unroll
+    for (int c = 0; c < SAMPLE_G; ++c) M8 *= Mf;
+
+    // ---- z of this lane's float4 column, RBW rows ----
+    const int row0 = (blockIdx.x * R + rl) * RBW;
+    const int q = cw * qpw + lane;
+    const bool qon = lane < qpw && q < nq;
+    const int qs = qon ? q : 0;                                 // idle lanes read column 0 and contribute z = 0
+    float4 z[RBW], az[RBW];
+#pragma unroll
+    for (int r = 0; r < RBW; ++r) {
+        const int row = row0 + r;
+        const bool on = qon && row < o.pop_count;
+        const size_t roff = ((size_t)b * o.pop_count + (row < o.pop_count ? row : 0)) * ns;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+            if (o.rng_mode == 0) {
+                v = philox_normal4((unsigned)q, (unsigned)(o.pop_offset + row), (unsigned)sc.itr, (unsigned)b, o.seed);
+                const int e = q * 4;
+                if (e + 1 >= o.n) v.y = 0.f;
+                if (e + 2 >= o.n) v.z = 0.f;
+                if (e + 3 >= o.n) v.w = 0.f;
+                if (o.Z) reinterpret_cast<float4*>(o.Z + roff)[q] = v;
+            } else {
+                v = reinterpret_cast<const float4*>(o.Z + roff)[q];
+            }
+        }
+        z[r] = v; az[r] = v;
+    }
+    SMP_STAMP(3);
+    __syncthreads();                                            // nj_s
+    // The chunks are consumed in rounds of up to `nstages` resident chunks.  Within a round every dot product comes
+    // first (all against the ORIGINAL z: no ordering between pairs), the partial sums are exchanged ONCE, then the
+    // ordered recurrence runs over the round's pairs: one named barrier per round instead of one per group.
+    const int gpc = (kc + SAMPLE_G - 1) / SAMPLE_G;             // groups per chunk
+    for (int c0 = 0; c0 < nchunks; c0 += nstages) {
+        const int c1 = min(nchunks, c0 + nstages);
+        float* dp0 = dpart + (size_t)rl * CW * RBW * SAMPLE_G;
+        const size_t grp_stride = (size_t)R * CW * RBW * SAMPLE_G;
+        int grp = 0;
+        for (int c = c0; c < c1; ++c) {
+            const int st = c % nstages;
+            mbar_wait(&bars[st], (unsigned)((c / nstages) & 1));
+            if (c == 0) SMP_STAMP(4);
+            if (c < 8) SMP_STAMP(7 + c);
+            const float* sb = stage_base + st * stage_floats;
+            const int cnt = min(kc, live - c * kc);
+            for (int k = 0; k < cnt; k += SAMPLE_G, ++grp) {
+                const int gcnt = min(SAMPLE_G, cnt - k);       // pairs in this group (CTA-uniform)
+                float d[RBW][SAMPLE_G];
+#pragma unroll
+                for (int g = 0; g < SAMPLE_G; ++g) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g < gcnt) v = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g)) * ns)[qs];
+#pragma unroll
+                    for (int r = 0; r < RBW; ++r) d[r][g] = fmaf(v.x, z[r].x, fmaf(v.y, z[r].y, fmaf(v.z, z[r].z, v.w * z[r].w)));
+                }
+                float* dp = dp0 + grp * grp_stride;
+#pragma unroll
+                for (int r = 0; r < RBW; ++r) {
+                    const float part = reduce_scatter8(d[r], lane);   // pair (lane >> 2) & 7, summed over this warp's columns
+                    if ((lane & 3) == 0) dp[(cw * RBW + r) * SAMPLE_G + (lane >> 2)] = part;
+                }
+            }
+        }
+        SMP_STAMP(15);
+        if (CW > 1) named_bar_sync(1 + rl, CW * 32);            // the CW warps of this row-group (ids 1..15: R <= 15)
+        else __syncwarp();
+        SMP_STAMP(16);
+        grp = 0;
+        for (int c = c0; c < c1; ++c) {
+            const int st = c % nstages;
+            const float* sb = stage_base + st * stage_floats;
+            const int k0 = c * kc, cnt = min(kc, live - k0);
+            for (int k = 0; k < cnt; k += SAMPLE_G, ++grp) {
+                const int gcnt = min(SAMPLE_G, cnt - k);
+                const float* dp = dp0 + grp * grp_stride;
+                float tot = 0.f;                                // lane = r * 8 + g: c_g of row r
+                if (lane < RBW * SAMPLE_G) {
+                    const int r = lane >> 3, g = lane & 7;
+                    for (int w2 = 0; w2 < CW; ++w2) tot += dp[(w2 * RBW + r) * SAMPLE_G + g];
+                    tot *= nj_s[k0 + k + g];                    // c_g = Nj_g (v_g . z) M^-(g+1); 0 beyond gcnt
+                }
+                float4 acc[RBW];
+#pragma unroll
+                for (int r = 0; r < RBW; ++r) acc[r] = az[r];
+#pragma unroll
+                for (int g = 0; g < SAMPLE_G; ++g) {
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g < gcnt) p = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g) + 1) * ns)[qs];
+#pragma unroll
+                    for (int r = 0; r < RBW; ++r) {
+                        const float w = __shfl_sync(0xffffffffu, tot, r * SAMPLE_G + g);
+                        acc[r].x = fmaf(w, p.x, acc[r].x); acc[r].y = fmaf(w, p.y, acc[r].y);
+                        acc[r].z = fmaf(w, p.z, acc[r].z); acc[r].w = fmaf(w, p.w, acc[r].w);
+                    }
+                }
+                float mg = M8;
+                if (gcnt < SAMPLE_G) { mg = 1.0f; for (int c2 = 0; c2 < gcnt; ++c2) mg *= Mf; }
+#pragma unroll
+                for (int r = 0; r < RBW; ++r) az[r] = make_float4(acc[r].x * mg, acc[r].y * mg, acc[r].z * mg, acc[r].w * mg);
+            }
+        }
+        if (c1 < nchunks) {                                     // next round: every warp is done with all stages
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int c = c1; c < max_chunks && c < c1 + nstages; ++c) issue(c);
+        }
+    }
+    (void)gpc;
+    SMP_STAMP(5);
+#pragma unroll
+    for (int r = 0; r < RBW; ++r) {
+        const int row = row0 + r;
+        if (qon && row < o.pop_count) {
+            float* xrow = o.X + ((size_t)b * o.pop_count + row) * ns;
+            reinterpret_cast<float4*>(xrow)[q] = sample_finish(o, o.xmean + (size_t)b * ns, sc.sigma, az[r], q);
+        }
+    }
+    SMP_STAMP(6);
+#undef SMP_STAMP
+}
+
+}  // namespace lmcma

@@ -1,0 +1,526 @@
+// k_update.cuh — the serial part of LMCMA::update (lmcma.cpp:316-424): mean, evolution path, slot
+// bookkeeping, recomputation of the inverse-direction vectors (invAz, lmcma.cpp:449-463), population-success
+// step size, best-so-far.  One CTA of 8 warps per optimiser instance.
+//
+// A single query is latency-bound (one generation moves a few MB), so this kernel is organised around
+// its dependency chain:
+//  * it is launched with programmatic dependent launch: everything that does not need this generation's
+//    ranks — slot bookkeeping, the 1-D bulk async copies that bring the direction rows into shared memory,
+//    their norms, the best-so-far arg-min — runs while k_rank is still ranking; griddep_wait() sits in front
+//    of the first read of k_rank's partial sums;
+//  * the triangular recompute runs factor-major (step j applies factor j to every pending row i > j: same
+//    per-row operation order as the reference's row-major loops, lmcma.cpp:375-390).  All ~live^2/2 row-steps
+//    run on this one SM, where shared-memory bandwidth is the scarce resource, so the pending rows are held in
+//    REGISTERS by the warp that owns them and only finished rows pass through shared memory.
+#pragma once
+#include "lmcma_common.cuh"
+
+namespace lmcma {
+
+constexpr int UPD_WARPS = 16;
+constexpr int UPD_GROUPS = UPD_WARPS / 4;   // 128-thread groups of the mean phase
+constexpr int UPD_THREADS = 32 * UPD_WARPS;
+
+struct UpdateArgs {
+    const float* f_all;        // B x lambda fitness of this generation (global candidate order)
+    const float* slices;       // n_slices partial sums of w (x - xmean) per instance
+    int n_slices;
+    long long slice_stride, inst_stride;
+    int payload_mode;          // slices are all-gather payloads (S rides in the 2 floats after ns)
+    long long* dbg;            // optional: globaltimer stamps (LMCMA_B200_UPDATE_DBG)
+};
+
+#define UPD_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[k] = gtime(); } while (0)
+
+template <bool SMEM> __device__ __forceinline__ float4 ld_row4(const float4* p) { return SMEM ? *p : __ldcg(p); }
+
+// NVB  = float4 column slots per lane (ns <= 128 * NVB)
+// RMAX = pending rows a warp can hold in registers (m <= UPD_WARPS * RMAX); 0 = streaming sweep (rows stay in
+//        shared memory, or in HBM/L2 when SMEM is false: shapes whose rows fit neither registers nor smem)
+template <int NVB, int RMAX, bool SMEM>
+__global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs a) {
+    static_assert(RMAX == 0 || SMEM, "the register sweep publishes finished rows through shared memory");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int m = o.m, ns = o.ns, nq = ns >> 2;
+    float* lj_s = reinterpret_cast<float*>(smem_raw);             // m: Lj / K in sequence order
+    float* nv_s = lj_s + m;                                       // m: |v|^2 (final rows) / |y|^2 (pending rows)
+    int* order = reinterpret_cast<int*>(nv_s + m);                // m: slot order
+    int* stamp = order + m;                                       // m: generation stamp per SLOT
+    float* ljslot = reinterpret_cast<float*>(stamp + m);          // m: Lj by slot (prefetched)
+    unsigned long long* rowbar = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)m * 20 + 7) & ~(size_t)7));   // m mbarriers: row i is final
+    float4* red4 = reinterpret_cast<float4*>(smem_raw + (((size_t)m * 28 + 8 + 127) & ~(size_t)127));                      // 128 float4 scratch
+    float* rows_s = reinterpret_cast<float*>(red4 + 128 * (UPD_GROUPS - 1));                                                                  // m x ns (SMEM)
+    __shared__ unsigned long long sh_key;
+    __shared__ __align__(8) unsigned long long sh_bar;
+    __shared__ float am_v[UPD_WARPS];
+    __shared__ int am_i[UPD_WARPS];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, nthr = UPD_THREADS;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = UPD_WARPS;
+    Scalars* scp = o.sc + b;
+    int* tg = o.t + (size_t)b * m;
+    int* vg = o.vec + (size_t)b * m;
+    double* Njd = o.Nj + (size_t)b * m;
+    double* Ljd = o.Lj + (size_t)b * m;
+    float* Njf = o.Njf + (size_t)b * m;
+    float* Vb = o.V + (size_t)b * m * ns;
+    float* Pb = o.P + (size_t)b * m * ns;
+    float* VPb = o.VPs + (size_t)b * m * 2 * ns;                   // sequence-ordered mirror for k_sample
+    float* Njsb = o.Njs + (size_t)b * m;
+    const float* fa = a.f_all + (size_t)b * o.lambda;
+
+    griddep_launch_dependents();          // k_sample may be scheduled; it waits for this grid before reading anything
+    UPD_STAMP(0);
+    // =============================== prologue: independent of k_rank ===============================
+    const Scalars sc0 = *scp;
+    for (int i = tid; i < m; i += nthr) { order[i] = tg[i]; stamp[i] = vg[i]; ljslot[i] = (float)Ljd[i]; mbar_init(&rowbar[i], 1); }
+    if (tid == 0) { sh_key = ~0ull; if (SMEM) mbar_init(&sh_bar, 1); }
+    fence_barrier_init();
+    __syncthreads();
+
+    // ---- slot bookkeeping (lmcma.cpp:331-364): data-independent integer logic on shared-memory copies ----
+    const int itr = sc0.itr;
+    const double sigma_old = sc0.sigma;
+    int first_stale = 0;
+    if (itr < m) {
+        if (tid == 0) order[itr] = itr;
+    } else {
+        // first minimal gap between adjacent generation stamps: key = (gap, j) lexicographic minimum
+        if (warp == 0) {
+            unsigned long long key = ~0ull;
+            for (int j = lane; j < m - 1; j += 32) {
+                const unsigned gap = (unsigned)(stamp[order[j + 1]] - stamp[order[j]]);
+                const unsigned long long k2 = ((unsigned long long)gap << 32) | (unsigned)j;
+                key = k2 < key ? k2 : key;
+            }
+#pragma unroll
+            for (int ofs = 16; ofs > 0; ofs >>= 1) {
+                const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, ofs);
+                key = k2 < key ? k2 : key;
+            }
+            if (lane == 0) sh_key = key;
+        }
+        __syncthreads();
+        const unsigned long long key = sh_key;
+        first_stale = (int)(unsigned)key + 1;
+        if ((int)(key >> 32) >= m /* maxsteps = nvectors, lmcma.cpp:267 */) first_stale = 0;
+        if (first_stale != m - 1) {                                  // rotate the recycled slot to the end
+            const int recycled = order[first_stale];
+            int* tmp = reinterpret_cast<int*>(nv_s);                  // nv_s is not in use yet
+            for (int j = first_stale + tid; j < m - 1; j += nthr) tmp[j] = order[j + 1];
+            __syncthreads();
+            for (int j = first_stale + tid; j < m - 1; j += nthr) order[j] = tmp[j];
+            if (tid == 0) order[m - 1] = recycled;
+        }
+    }
+    __syncthreads();
+    const int live = min(itr + 1, m);
+    const int slot_new = order[live - 1];
+    if (first_stale == 1) first_stale = 0;                           // lmcma.cpp:373-374
+    UPD_STAMP(1);
+
+    // ---- direction rows -> shared memory by 1-D bulk async copies issued by the lanes of warp 0: final rows
+    //      (i < first_stale) come from V, pending rows start as their pc_j (lmcma.cpp:376-378); the newest
+    //      pending row is this generation's pc, formed below ----
+    if (SMEM && warp == 0) {
+        const unsigned row_bytes = (unsigned)(ns * sizeof(float));
+        if (lane == 0 && live > 1) mbar_expect_tx(&sh_bar, row_bytes * (unsigned)(live - 1));
+        __syncwarp();
+        for (int i = lane; i + 1 < live; i += 32) {
+            const float* src = (i < first_stale ? Vb : Pb) + (size_t)order[i] * ns;
+            bulk_g2s(rows_s + (size_t)i * ns, src, row_bytes, &sh_bar);
+        }
+    }
+    auto row_ptr = [&](int i) -> float* { return SMEM ? rows_s + (size_t)i * ns : Vb + (size_t)order[i] * ns; };
+    const float invK = (float)(1.0 / o.K);
+    for (int i = tid; i < m; i += nthr) {
+        const int slot = order[i];
+        tg[i] = slot;
+        vg[i] = (i == slot_new) ? itr : stamp[i];                   // stamp is per SLOT
+        lj_s[i] = (i < live) ? ljslot[slot] * invK : 0.f;           // rows >= first_stale are recomputed below
+    }
+
+    // ---- best-so-far: first occurrence of the minimum in evaluation order; strict improvement, or the very first
+    //      evaluation (lmcma.cpp:192-198).  The fitness is k_cost's output, complete before k_rank started ----
+    {
+        float bf = __int_as_float(0x7f800000); int bi = 0x7fffffff;
+        for (int j0 = 0; j0 < o.lambda; j0 += 4 * nthr) {            // 4 loads in flight per thread
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr + tid; v[u] = (j < o.lambda) ? canon_fitness(__ldcg(fa + j)) : __int_as_float(0x7f800000); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr + tid; if (j < o.lambda && (v[u] < bf || (v[u] == bf && j < bi))) { bf = v[u]; bi = j; } }
+        }
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, bf, ofs); const int i2 = __shfl_xor_sync(0xffffffffu, bi, ofs);
+            if (v2 < bf || (v2 == bf && i2 < bi)) { bf = v2; bi = i2; }
+        }
+        if (lane == 0) { am_v[warp] = bf; am_i[warp] = bi; }
+    }
+    if (!SMEM) {                                                     // rows stay in HBM/L2: pending rows start as pc_j
+        for (int i = first_stale + warp; i + 1 < live; i += nwarps) {
+            const float4* src = reinterpret_cast<const float4*>(Pb + (size_t)order[i] * ns);
+            float4* dst = reinterpret_cast<float4*>(row_ptr(i));
+            for (int q = lane; q < nq; q += 32) dst[q] = __ldcg(src + q);
+        }
+        __threadfence();
+    } else if (live > 1) {
+        mbar_wait(&sh_bar, 0);
+    }
+    __syncthreads();
+    {
+        float bf = am_v[0]; int bi = am_i[0];
+        for (int w2 = 1; w2 < nwarps; ++w2) if (am_v[w2] < bf || (am_v[w2] == bf && am_i[w2] < bi)) { bf = am_v[w2]; bi = am_i[w2]; }
+        if (bi == 0x7fffffff) bi = 0;
+        const bool take = ((double)bf < sc0.best_f) || (sc0.counteval == 0);
+        const bool local = bi >= o.pop_offset && bi < o.pop_offset + o.pop_count;
+        if (take && local && warp == nwarps - 1) {
+            const float4* src = reinterpret_cast<const float4*>(o.X + ((size_t)b * o.pop_count + (bi - o.pop_offset)) * ns);
+            float4* dst = reinterpret_cast<float4*>(o.best_x + (size_t)b * ns);
+            for (int q = lane; q < nq; q += 32) dst[q] = src[q];
+        }
+        if (take && tid == 0) { scp->best_f = (double)bf; scp->best_local = local ? 1 : 0; }
+    }
+    // |v_j|^2 of the final rows and |pc_i|^2 of the pending ones (all but the newest)
+    auto row_norm = [&](int i) {                                     // warp-collective
+        const float4* v = reinterpret_cast<const float4*>(row_ptr(i));
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int it = 0; it < NVB; ++it) {
+            const int q = lane + 32 * it;
+            if (q < nq) { const float4 x = ld_row4<SMEM>(v + q); s0 = fmaf(x.x, x.x, s0); s1 = fmaf(x.y, x.y, s1); s0 = fmaf(x.z, x.z, s0); s1 = fmaf(x.w, x.w, s1); }
+        }
+        const float tot = warp_sum(s0 + s1);
+        if (lane == 0) nv_s[i] = tot;
+    };
+    for (int i = warp; i + 1 < live; i += nwarps) row_norm(i);
+    UPD_STAMP(2);
+
+    // =============================== needs k_rank's partial sums ===============================
+    griddep_wait();
+    UPD_STAMP(3);
+    // prev_fit (lmcma.cpp:420-421): k_rank has finished reading the previous generation's values
+    for (int j = tid; j < o.lambda; j += nthr) o.prev_fit[(size_t)b * o.lambda + j] = canon_fitness(__ldcg(fa + j));
+
+    // ---- mean, evolution path, new pc_j (lmcma.cpp:316-329, 365-366): 128 float4 columns x 2 slice groups, up to
+    //      8 slice loads in flight per thread; fixed summation order -> deterministic ----
+    {
+        const double coef = o.pc_coef / sigma_old;                   // sqrt(cc (2 - cc) mueff) / sigma
+        double* xm = o.xmean + (size_t)b * ns;
+        float* pc = o.pc + (size_t)b * ns;
+        float* pnew = Pb + (size_t)slot_new * ns;
+        float* rnew = row_ptr(live - 1);
+        const int tq = tid & 127, g = tid >> 7;                      // UPD_GROUPS x 128 threads
+        for (int q0 = 0; q0 < nq; q0 += 128) {
+            const int q = q0 + tq;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            double2 xm01 = make_double2(0.0, 0.0), xm23 = xm01;
+            float4 pc4 = acc;
+            if (q < nq) {
+                if (g == 0) {
+                    xm01 = reinterpret_cast<const double2*>(xm)[2 * q]; xm23 = reinterpret_cast<const double2*>(xm)[2 * q + 1];
+                    pc4 = reinterpret_cast<const float4*>(pc)[q];
+                }
+                const float4* sp = reinterpret_cast<const float4*>(a.slices + (size_t)b * a.inst_stride) + q;
+                const size_t sstride4 = (size_t)a.slice_stride >> 2;
+                int k = g;
+                for (; k + 7 * UPD_GROUPS < a.n_slices; k += 8 * UPD_GROUPS) {   // 8 loads in flight
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = __ldcg(sp + (size_t)(k + UPD_GROUPS * u) * sstride4);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                }
+                for (; k < a.n_slices; k += UPD_GROUPS) { const float4 v = __ldcg(sp + (size_t)k * sstride4); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+            }
+            if (g > 0) red4[(g - 1) * 128 + tq] = acc;
+            __syncthreads();
+            if (g == 0 && q < nq) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int g2 = 0; g2 + 1 < UPD_GROUPS; ++g2) { const float4 u4 = red4[g2 * 128 + tq]; t.x += u4.x; t.y += u4.y; t.z += u4.z; t.w += u4.w; }
+                const float d[4] = {acc.x + t.x, acc.y + t.y, acc.z + t.z, acc.w + t.w};
+                const double xo[4] = {xm01.x, xm01.y, xm23.x, xm23.y};
+                const float po[4] = {pc4.x, pc4.y, pc4.z, pc4.w};
+                double xn[4]; float pn[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double xold_f = (double)(float)xo[c];      // the partials are relative to float(xmean)
+                    const double shift = (xold_f - xo[c]) + (double)d[c];   // new mean - old mean
+                    xn[c] = xo[c] + shift;
+                    pn[c] = (float)((1.0 - o.cc) * (double)po[c] + coef * shift);
+                }
+                reinterpret_cast<double2*>(xm)[2 * q] = make_double2(xn[0], xn[1]);
+                reinterpret_cast<double2*>(xm)[2 * q + 1] = make_double2(xn[2], xn[3]);
+                const float4 p4 = make_float4(pn[0], pn[1], pn[2], pn[3]);
+                reinterpret_cast<float4*>(pc)[q] = p4;
+                reinterpret_cast<float4*>(pnew)[q] = p4;
+                reinterpret_cast<float4*>(rnew)[q] = p4;
+            }
+            __syncthreads();
+        }
+    }
+    if (!SMEM) __threadfence();
+    if (warp == 0) row_norm(live - 1);
+    __syncthreads();
+    UPD_STAMP(4);
+
+    // ---- recompute v from the first stale position (lmcma.cpp:373-390) ----
+    // Closed forms of lmcma.cpp:386-389 with t = sqrt(1 + c1/(1-c1) |v|^2), rewritten without cancellation:
+    //   Nj = (sqrt(1-c1)/|v|^2)(t - 1)            = sqrt(1-c1) * r / (t + 1)
+    //   Lj = (1/(sqrt(1-c1)|v|^2))(1 - 1/t)       = r / (sqrt(1-c1) * t * (t + 1)),   r = c1/(1-c1)
+    // (identical in exact arithmetic; finite where the reference divides 0/0 for a zero vector).
+    //
+    // Factor-major sweep: step j applies factor j, x <- K x - Lj_j (v_j . x) v_j, to every pending row i > j.
+    //  * pending rows are held as y = x / K^j (all pending rows have had the same number of factors applied),
+    //    which turns the update into y <- y - (Lj_j / K)(v_j . y) v_j: one FMA per element; a row is multiplied
+    //    by K^i once, when it becomes final;
+    //  * |y|^2 follows from scalars already known, |y'|^2 = |y|^2 - 2 e d + e^2 |v_j|^2 (d = v_j . y,
+    //    e = (Lj_j / K) d), so the |v|^2 that Lj needs never costs a second reduction;
+    //  * a row is owned by one warp for the whole sweep; when its last factor has been applied the owner
+    //    publishes it (row, |v|^2, Lj/K, then an mbarrier arrive by every lane) and the other warps pick it up
+    //    as factor i with a blocking mbarrier wait: no block-wide barrier and no spinning warps competing
+    //    with the owner of the next row for issue slots.
+    const double Kd = o.K;
+    const float r_f = (float)(o.c1 / (1.0 - o.c1)), a_f = (float)o.M;
+    auto publish_scalars = [&](int i, float nv) {                   // lane 0: |v_i|^2 and Lj_i / K
+        const float t = sqrtf(fmaf(r_f, nv, 1.0f));
+        nv_s[i] = nv;
+        lj_s[i] = __fdividef(r_f, a_f * t * (t + 1.0f)) * invK;
+    };
+
+    if (RMAX > 0) {
+        // ---------------- register sweep: warp w owns rows first_stale + w + r * UPD_WARPS ----------------
+        constexpr int R = RMAX > 0 ? RMAX : 1;
+        const int base = first_stale + warp;
+        float4 y[R][NVB];
+        float ny[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = base + r * UPD_WARPS;
+            const bool on = i < live;
+            ny[r] = on ? nv_s[i] : 0.f;
+#pragma unroll
+            for (int it = 0; it < NVB; ++it) {
+                const int q = lane + 32 * it;
+                y[r][it] = (on && q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)i * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (on && q < nq) reinterpret_cast<float4*>(VPb + ((size_t)i * 2 + 1) * ns)[q] = y[r][it];   // pc_i at its (new) position
+            }
+        }
+        int my_last = -1;                                            // my largest row
+        if (base < live) my_last = base + ((live - 1 - base) / UPD_WARPS) * UPD_WARPS;
+        auto publish = [&](const float4 (&row)[NVB], int i, float nyv, double kp) {   // warp-collective: y_i K^i is the final v_i
+            const float kf = (float)kp;
+            float4* srow = reinterpret_cast<float4*>(rows_s + (size_t)i * ns);
+            float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
+            float4* dst2 = reinterpret_cast<float4*>(VPb + (size_t)i * 2 * ns);
+            if (lane == 0) publish_scalars(i, nyv * kf * kf);
+            float4 x[NVB];
+#pragma unroll
+            for (int it = 0; it < NVB; ++it) {
+                const int q = lane + 32 * it;
+                x[it] = make_float4(row[it].x * kf, row[it].y * kf, row[it].z * kf, row[it].w * kf);
+                if (q < nq) srow[q] = x[it];
+            }
+            __syncwarp();                                            // orders the lanes' stores before lane 0's release
+            if (lane == 0) mbar_arrive(&rowbar[i]);                  // ONE arrive: 32 arrives on one mbarrier serialise (~27 cycles each)
+            if (o.dbg && lane == 0 && i < 32) o.dbg[i] = clock64();
+            // the copy to HBM goes after the arrive: a release has to wait for every earlier store of the thread, and
+            // a store to HBM takes an L2 round trip that the next step of the sweep must not sit behind
+#pragma unroll
+            for (int it = 0; it < NVB; ++it) {
+                const int q = lane + 32 * it;
+                if (q < nq) { dst[q] = x[it]; dst2[q] = x[it]; }
+            }
+        };
+        if (first_stale == 0 && warp == 0) publish(y[0], 0, ny[0], 1.0);   // row 0 has no factors (v_0 = pc_0)
+        double kp = 1.0;                                             // K^(j+1) inside step j
+        for (int j = 0; j + 1 < live; ++j) {
+            kp *= Kd;
+            if (j >= my_last) break;                                 // all my rows are final
+            if (j >= first_stale) mbar_wait(&rowbar[j], 0);
+            const float4* vj = reinterpret_cast<const float4*>(rows_s + (size_t)j * ns);
+            const float ljk = lj_s[j], nvj = nv_s[j];
+            float4 a4[NVB];
+#pragma unroll
+            for (int it = 0; it < NVB; ++it) {
+                const int q = lane + 32 * it;
+                a4[it] = (q < nq) ? vj[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // the row that becomes final in this step goes first and alone: the next step waits for it
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (base + r * UPD_WARPS == j + 1) {
+                    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        d0 = fmaf(a4[it].x, y[r][it].x, d0); d1 = fmaf(a4[it].y, y[r][it].y, d1);
+                        d0 = fmaf(a4[it].z, y[r][it].z, d0); d1 = fmaf(a4[it].w, y[r][it].w, d1);
+                    }
+                    const float d = warp_sum(d0 + d1);
+                    const float e = ljk * d;
+                    ny[r] = fmaxf(fmaf(e, fmaf(e, nvj, -2.0f * d), ny[r]), 0.f);
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        y[r][it].x = fmaf(-e, a4[it].x, y[r][it].x); y[r][it].y = fmaf(-e, a4[it].y, y[r][it].y);
+                        y[r][it].z = fmaf(-e, a4[it].z, y[r][it].z); y[r][it].w = fmaf(-e, a4[it].w, y[r][it].w);
+                    }
+                    publish(y[r], j + 1, ny[r], kp);
+                }
+            }
+            // the other pending rows of this warp: independent dot products, reduced together
+            float d[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = base + r * UPD_WARPS;
+                float d0 = 0.f, d1 = 0.f;
+                if (i > j + 1 && i < live) {
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        d0 = fmaf(a4[it].x, y[r][it].x, d0); d1 = fmaf(a4[it].y, y[r][it].y, d1);
+                        d0 = fmaf(a4[it].z, y[r][it].z, d0); d1 = fmaf(a4[it].w, y[r][it].w, d1);
+                    }
+                }
+                d[r] = d0 + d1;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = base + r * UPD_WARPS;
+                if (i > j + 1 && i < live) {                          // warp-uniform: finished rows cost nothing
+#pragma unroll
+                    for (int ofs = 16; ofs > 0; ofs >>= 1) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = base + r * UPD_WARPS;
+                if (i > j + 1 && i < live) {
+                    const float e = ljk * d[r];
+                    ny[r] = fmaxf(fmaf(e, fmaf(e, nvj, -2.0f * d[r]), ny[r]), 0.f);
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        y[r][it].x = fmaf(-e, a4[it].x, y[r][it].x); y[r][it].y = fmaf(-e, a4[it].y, y[r][it].y);
+                        y[r][it].z = fmaf(-e, a4[it].z, y[r][it].z); y[r][it].w = fmaf(-e, a4[it].w, y[r][it].w);
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- streaming sweep: pending rows stay in shared memory (or HBM/L2) ----------------
+        const int pend = live - first_stale;
+        const int act_warps = min(nwarps, pend);
+        for (int i = first_stale + warp; i < live; i += nwarps) {    // pc_i at its (new) position in the mirror
+            const float4* src = reinterpret_cast<const float4*>(row_ptr(i));
+            float4* dst2 = reinterpret_cast<float4*>(VPb + ((size_t)i * 2 + 1) * ns);
+            for (int q = lane; q < nq; q += 32) dst2[q] = ld_row4<SMEM>(src + q);
+        }
+        auto publish = [&](int i, float nyv, double kp) {            // warp-collective: y_i K^i is the final v_i
+            const float kf = (float)kp;
+            float4* row = reinterpret_cast<float4*>(row_ptr(i));
+            float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
+            float4* dst2 = reinterpret_cast<float4*>(VPb + (size_t)i * 2 * ns);
+            if (lane == 0) publish_scalars(i, nyv * kf * kf);
+            for (int q = lane; q < nq; q += 32) {
+                float4 x = ld_row4<SMEM>(row + q);
+                x.x *= kf; x.y *= kf; x.z *= kf; x.w *= kf;
+                row[q] = x;
+            }
+            if (!SMEM) __threadfence();
+            __syncwarp();                                            // orders the lanes' stores before lane 0's release
+            if (lane == 0) mbar_arrive(&rowbar[i]);
+            for (int q = lane; q < nq; q += 32) {                    // copies to HBM after the release (see the register sweep)
+                const float4 x = ld_row4<SMEM>(row + q);
+                if (SMEM) dst[q] = x;
+                dst2[q] = x;
+            }
+        };
+        if (warp < act_warps) {
+            int i0 = first_stale + warp;                             // my first row that is not final yet
+            if (first_stale == 0 && warp == 0) publish(0, nv_s[0], 1.0);   // row 0 has no factors (v_0 = pc_0)
+            double kp = 1.0;                                         // K^(j+1) inside step j
+            for (int j = 0; j + 1 < live; ++j) {
+                kp *= Kd;
+                while (i0 <= j) i0 += act_warps;
+                if (i0 >= live) break;
+                if (j >= first_stale) mbar_wait(&rowbar[j], 0);
+                const float4* vj = reinterpret_cast<const float4*>(row_ptr(j));
+                const float ljk = lj_s[j], nvj = nv_s[j];
+                for (int i = i0; i < live; i += act_warps) {
+                    __syncwarp();                                    // lane 0's |y_i|^2 of the previous step
+                    float4* vi = reinterpret_cast<float4*>(row_ptr(i));
+                    float d0 = 0.f, d1 = 0.f;
+                    const float nyi = nv_s[i];
+                    for (int q = lane; q < nq; q += 32) {
+                        const float4 av = ld_row4<SMEM>(vj + q), c = ld_row4<SMEM>(vi + q);
+                        d0 = fmaf(av.x, c.x, d0); d1 = fmaf(av.y, c.y, d1);
+                        d0 = fmaf(av.z, c.z, d0); d1 = fmaf(av.w, c.w, d1);
+                    }
+                    const float d = warp_sum(d0 + d1);
+                    const float e = ljk * d;
+                    const float ny_new = fmaxf(fmaf(e, fmaf(e, nvj, -2.0f * d), nyi), 0.f);
+                    for (int q = lane; q < nq; q += 32) {
+                        const float4 av = ld_row4<SMEM>(vj + q);
+                        float4 c = ld_row4<SMEM>(vi + q);
+                        c.x = fmaf(-e, av.x, c.x); c.y = fmaf(-e, av.y, c.y);
+                        c.z = fmaf(-e, av.z, c.z); c.w = fmaf(-e, av.w, c.w);
+                        vi[q] = c;
+                    }
+                    if (i == j + 1) publish(i, ny_new, kp);
+                    else if (lane == 0) nv_s[i] = ny_new;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    UPD_STAMP(5);
+    if (a.dbg && threadIdx.x == 0) { a.dbg[10] = first_stale; a.dbg[11] = live; }
+    for (int i = first_stale + tid; i < live; i += nthr) {           // FP64 scalar state of the recomputed rows
+        const int slot = order[i];
+        const double nv = (double)nv_s[i], r = o.c1 / (1.0 - o.c1), am = o.M;
+        const double t = sqrt(1.0 + r * nv);
+        const double nj = am * r / (t + 1.0), lj = r / (am * t * (t + 1.0));
+        Njd[slot] = nj; Ljd[slot] = lj; Njf[slot] = (float)nj; Njsb[i] = (float)nj;
+    }
+    // ---- population-success step size (lmcma.cpp:393-419), counters (lmcma.cpp:189, 423) ----
+    if (tid == nthr - 1) {
+        unsigned long long S = 0;
+        if (a.payload_mode) {
+            for (int k = 0; k < a.n_slices; ++k) {
+                const float* pay = a.slices + (size_t)k * a.slice_stride + (size_t)b * a.inst_stride + ns;
+                S += ((unsigned long long)__float_as_uint(__ldcg(pay + 1)) << 32) | __float_as_uint(__ldcg(pay));
+            }
+        } else {
+            S = atomicExch(o.S_count + b, 0ull);
+        }
+        if (itr > 0) {
+            const double lam = (double)o.lambda;
+            const unsigned long long L = (unsigned long long)o.lambda;
+            const unsigned long long sum_cur = L * (L - 1ull) / 2ull + S;       // ranks of this generation in the merged order
+            const unsigned long long sum_prev = L * (2ull * L - 1ull) - sum_cur;
+            const double mean_cur = (double)sum_cur / lam, mean_prev = (double)sum_prev / lam;
+            const double success = (mean_prev - mean_cur) / lam;
+            const double snew = (1.0 - o.cs) * sc0.s + o.cs * (success - o.target);
+            scp->s = snew;
+            scp->sigma = sigma_old * exp(snew);
+        }
+        scp->itr = itr + 1;
+        scp->live = live;
+        scp->counteval = sc0.counteval + o.lambda;
+    }
+    UPD_STAMP(6);
+}
+
+// rebuild the sequence-ordered mirror from the slot-indexed state (after create / a state setter): grid = (m, B)
+__global__ void __launch_bounds__(128) k_pack_pairs(OptDev o) {
+    const int i = blockIdx.x, b = blockIdx.y, nq = o.ns >> 2;
+    const int slot = o.t[(size_t)b * o.m + i];
+    const float4* v = reinterpret_cast<const float4*>(o.V + ((size_t)b * o.m + slot) * o.ns);
+    const float4* p = reinterpret_cast<const float4*>(o.P + ((size_t)b * o.m + slot) * o.ns);
+    float4* dv = reinterpret_cast<float4*>(o.VPs + ((size_t)b * o.m + i) * 2 * o.ns);
+    float4* dp = dv + nq;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) { dv[q] = v[q]; dp[q] = p[q]; }
+    if (threadIdx.x == 0) o.Njs[(size_t)b * o.m + i] = o.Njf[(size_t)b * o.m + slot];
+}
+
+}  // namespace lmcma

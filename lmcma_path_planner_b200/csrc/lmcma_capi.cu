@@ -138,11 +138,14 @@ struct lmcma_b200_opt {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool have_run_timing = false;
     // sample launch config
-    int smp_threads = 128, smp_kc = 1, smp_nv = 1, smp_rb = 1;
+    int smp_threads = 128, smp_kc = 1, smp_nv = 1, smp_rb = 1, smp_stages = 2;
+    bool smp_wide = false; int smp_R = 1, smp_CW = 1, smp_qpw = 32, smp_RBW = 1;
+    bool mirror_dirty = true;          // the sequence-ordered pair mirror must be rebuilt (k_pack_pairs) before sampling
     size_t smp_smem = 0;
     int cost_tpt = 128;
-    int upd_threads = 512, upd_cap_rows = 0;
-    size_t upd_smem = 0;
+    int upd_nvb = 4, upd_rmax = 0;
+    bool upd_rows_in_smem = true;
+    size_t upd_smem = 0, rank_smem = 0;
     size_t cost_smem = 0;
 };
 
@@ -185,25 +188,70 @@ int pick_cost_tpt(int W, const float* start, const float* goal, int dims) {
 }
 
 template <int NV, int RB, int MAXT>
-int launch_sample_t(lmcma_b200_opt* o, cudaStream_t st) {
+int launch_sample_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
     auto kern = k_sample<NV, RB, MAXT>;
     if (o->smp_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_smem));
     const int rows_per_cta = (o->smp_threads / 32) * RB;
     const int ctas = (o->d.pop_count + rows_per_cta - 1) / rows_per_cta;
-    kern<<<dim3(ctas, o->d.B), o->smp_threads, o->smp_smem, st>>>(o->d, o->smp_kc);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ctas, o->d.B); cfg.blockDim = dim3(o->smp_threads); cfg.dynamicSmemBytes = o->smp_smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kern, o->d, o->smp_kc, o->smp_stages));
     g_launches++;
-    CU(cudaGetLastError());
     return 0;
 }
 
-int launch_sample(lmcma_b200_opt* o, cudaStream_t st) {
+template <int RBW, int MAXT>
+int launch_sample_wide_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
+    auto kern = k_sample_wide<RBW, MAXT>;
+    if (o->smp_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const int rows_per_cta = o->smp_R * RBW;
+    cfg.gridDim = dim3((o->d.pop_count + rows_per_cta - 1) / rows_per_cta, o->d.B); cfg.blockDim = dim3(32 * o->smp_R * o->smp_CW);
+    cfg.dynamicSmemBytes = o->smp_smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kern, o->d, o->smp_kc, o->smp_stages, o->smp_R, o->smp_CW, o->smp_qpw));
+    g_launches++;
+    return 0;
+}
+int launch_sample_wide(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
+    switch (o->smp_RBW) {
+        case 1: return launch_sample_wide_t<1, 1024>(o, pdl, st);
+        case 2: return launch_sample_wide_t<2, 1024>(o, pdl, st);
+        default: return launch_sample_wide_t<4, 512>(o, pdl, st);
+    }
+}
+
+// the sequence-ordered (v, pc) mirror k_sample streams from is maintained by k_update; after create or a state
+// setter it is rebuilt from the slot-indexed arrays
+int ensure_mirror(lmcma_b200_opt* o, cudaStream_t st) {
+    if (!o->mirror_dirty) return 0;
+    k_pack_pairs<<<dim3(o->d.m, o->d.B), 128, 0, st>>>(o->d);
+    g_launches++;
+    CU(cudaGetLastError());
+    o->mirror_dirty = false;
+    return 0;
+}
+
+// pdl: launched as a programmatic dependent of the kernel enqueued just before it on `st` (k_update)
+int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false) {
+    if (o->mirror_dirty) { int rc = ensure_mirror(o, st); if (rc) return rc; pdl = false; }
+    if (o->smp_wide) return launch_sample_wide(o, pdl, st);
     switch (o->smp_nv) {
-        case 1: return launch_sample_t<1, 4, 512>(o, st);
-        case 2: return launch_sample_t<2, 4, 512>(o, st);
-        case 4: return launch_sample_t<4, 2, 512>(o, st);
-        case 8: return launch_sample_t<8, 1, 512>(o, st);
-        case 12: return launch_sample_t<12, 1, 256>(o, st);
-        case 16: return launch_sample_t<16, 1, 256>(o, st);
+        case 1: return launch_sample_t<1, 4, 512>(o, pdl, st);
+        case 2: return launch_sample_t<2, 4, 512>(o, pdl, st);
+        case 4: return launch_sample_t<4, 2, 512>(o, pdl, st);
+        case 8: return launch_sample_t<8, 1, 512>(o, pdl, st);
+        case 12: return launch_sample_t<12, 1, 256>(o, pdl, st);
+        case 16: return launch_sample_t<16, 1, 256>(o, pdl, st);
     }
     return fail(LMCMA_B200_ERR_ARG, "unsupported n for k_sample (nv=%d)", o->smp_nv);
 }
@@ -226,51 +274,103 @@ int configure_sample(lmcma_b200_opt* o) {
         while (threads > 64) {
             const int rows_per_cta = (threads / 32) * o->smp_rb;
             const long long ctas = (long long)((o->d.pop_count + rows_per_cta - 1) / rows_per_cta) * o->d.B;
-            if (ctas >= o->props->sm_count) break;
+            if (ctas * 4 >= (long long)o->props->sm_count * 3) break;   // bigger tiles re-read the pairs less often
             threads >>= 1;
         }
     o->smp_threads = threads;
     const size_t pair_bytes = (size_t)2 * o->d.ns * sizeof(float);
-    int kc = (int)std::max<size_t>(1, (size_t)env_int("LMCMA_B200_SAMPLE_STAGE_KB", 32) * 1024 / pair_bytes);
-    kc = std::min(kc, o->d.m);
+    // pairs per stage: one group of 8 when it fits (else 4 / 2 / 1); as many stages as the live pairs need, within
+    // ~160 KB, so that for the common shapes every pair is requested up front and nothing is re-issued
+    const size_t budget = (size_t)env_int("LMCMA_B200_SAMPLE_SMEM_KB", 160) * 1024;
+    int kc = (int)(budget / 2 / pair_bytes);
+    kc = kc >= 8 ? 8 : (kc >= 4 ? 4 : (kc >= 2 ? 2 : 1));
     o->smp_kc = kc;
-    o->smp_smem = 2 * kc * pair_bytes + 64 + (size_t)o->d.m * sizeof(float);
+    const int max_chunks = (o->d.m + kc - 1) / kc;
+    o->smp_stages = (int)std::max<size_t>(2, std::min<size_t>(std::min(max_chunks, SAMPLE_MAX_STAGES), budget / (kc * pair_bytes)));
+    o->smp_smem = (size_t)o->smp_stages * kc * pair_bytes + SAMPLE_MAX_STAGES * 8 + (size_t)(2 * o->d.m + 16) * sizeof(float);
+    // one large population: split every row over CW column-warps (k_sample_wide) for occupancy
+    o->smp_wide = false;
+    if (o->d.pop_count >= 256 && nq > 32 && !env_int("LMCMA_B200_SAMPLE_NARROW", 0)) {
+        o->smp_wide = true;
+        o->smp_CW = (nq + 31) / 32;
+        o->smp_qpw = (nq + o->smp_CW - 1) / o->smp_CW;
+        // rows per warp: 2 (4 for very large populations); row-groups per CTA so that the grid still covers the SMs
+        o->smp_RBW = env_int("LMCMA_B200_SAMPLE_RBW", o->d.pop_count >= 1024 ? 4 : 2);
+        if (o->smp_RBW != 1 && o->smp_RBW != 2) o->smp_RBW = 4;
+        int R = std::max(1, std::min(15, (o->smp_RBW == 4 ? 16 : 32) / o->smp_CW));
+        const int forced_R = env_int("LMCMA_B200_SAMPLE_R", 0);
+        if (forced_R >= 1 && forced_R <= R) R = forced_R;
+        else
+            while (R > 1 && (long long)((o->d.pop_count + R * o->smp_RBW - 1) / (R * o->smp_RBW)) * o->d.B * 4 < (long long)o->props->sm_count * 3) R >>= 1;
+        o->smp_R = R;
+        o->smp_smem += (size_t)o->smp_stages * ((kc + SAMPLE_G - 1) / SAMPLE_G) * o->smp_R * o->smp_CW * o->smp_RBW * SAMPLE_G * sizeof(float);
+    }
     if (o->smp_smem > o->props->smem_optin) return fail(LMCMA_B200_ERR_ARG, "k_sample needs %zu B shared memory", o->smp_smem);
     return 0;
 }
 
-int launch_rank(lmcma_b200_opt* o, const float* f_all, cudaStream_t st) {
-    k_rank<<<dim3((o->d.pop_count + 31) / 32, o->d.B), 256, 0, st>>>(o->d, f_all);
-    g_launches++;
-    CU(cudaGetLastError());
-    return 0;
-}
-int launch_recombine(lmcma_b200_opt* o, cudaStream_t st) {
-    const int nq = o->d.ns / 4;
-    k_recombine<<<dim3((nq + 127) / 128, o->d.RS, o->d.B), 512, 0, st>>>(o->d);
-    g_launches++;
-    CU(cudaGetLastError());
-    return 0;
-}
-int launch_update(lmcma_b200_opt* o, const float* slices, int n_slices, long long slice_stride, long long inst_stride,
-                  const float* f_all, int payload_mode, cudaStream_t st) {
-    k_update<<<o->d.B, o->upd_threads, o->upd_smem, st>>>(o->d, slices, n_slices, slice_stride, inst_stride, f_all,
-                                                          payload_mode, o->upd_cap_rows);
+// ranks + recombination partial sums (k_rank.cuh); RANK_PACK is the split-population stage
+int launch_rank(lmcma_b200_opt* o, const float* f_all, int mode, float* payload, cudaStream_t st) {
+    auto kern = k_rank<1024>;
+    if (o->rank_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->rank_smem));
+    kern<<<dim3(o->d.RS, o->d.B), 1024, o->rank_smem, st>>>(o->d, f_all, mode, payload);
     g_launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
+template <int NVB, int RMAX, bool SMEM>
+int launch_update_t(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream_t st) {
+    auto kern = k_update<NVB, RMAX, SMEM>;
+    if (o->upd_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->upd_smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(o->d.B); cfg.blockDim = dim3(UPD_THREADS); cfg.dynamicSmemBytes = o->upd_smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kern, o->d, a));
+    g_launches++;
+    return 0;
+}
+
+// the serial part of update() (k_update.cuh).  pdl: launched as a programmatic dependent of the kernel enqueued just
+// before it on `st` (k_rank), so that its prologue overlaps that kernel
+int launch_update(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream_t st) {
+    if (o->upd_nvb == 4) {
+        if (o->upd_rmax == 3) return launch_update_t<4, 3, true>(o, a, pdl, st);
+        if (o->upd_rmax == 5) return launch_update_t<4, 5, true>(o, a, pdl, st);
+        return o->upd_rows_in_smem ? launch_update_t<4, 0, true>(o, a, pdl, st) : launch_update_t<4, 0, false>(o, a, pdl, st);
+    }
+    return o->upd_rows_in_smem ? launch_update_t<16, 0, true>(o, a, pdl, st) : launch_update_t<16, 0, false>(o, a, pdl, st);
+}
+
+UpdateArgs update_args_local(lmcma_b200_opt* o) {
+    UpdateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f_all = o->d.fit;
+    a.slices = o->d.partial; a.n_slices = o->d.RS; a.slice_stride = o->d.ns; a.inst_stride = (long long)o->d.RS * o->d.ns;
+    return a;
+}
+
 int configure_update(lmcma_b200_opt* o) {
-    // one warp per pending row where possible; pending rows live in shared memory while they fit
-    o->upd_threads = std::min(1024, std::max(64, 32 * o->d.m));
-    const size_t row_bytes = (size_t)o->d.ns * sizeof(float);
-    const size_t fixed = (size_t)o->d.m * 16 + 256;
-    const size_t budget = std::min<size_t>(o->props->smem_optin, 200 * 1024);
-    o->upd_cap_rows = (int)std::min<size_t>(o->d.m, budget > fixed ? (budget - fixed) / row_bytes : 0);
-    o->upd_smem = (size_t)o->upd_cap_rows * row_bytes + fixed;
-    if (o->upd_smem > 48 * 1024)
-        CU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->upd_smem));
+    const int nq = o->d.ns / 4;
+    if (nq > 512) return fail(LMCMA_B200_ERR_ARG, "n = %d too large (max 2048)", o->d.n);
+    o->upd_nvb = nq <= 128 ? 4 : 16;
+    o->rank_smem = (size_t)2 * TELL_FTILE * 4 + (size_t)3 * TELL_MAX_ROWS * 4 + (size_t)7 * 128 * 16;
+    const size_t fixed = (((size_t)o->d.m * 28 + 8 + 127) & ~(size_t)127) + (size_t)2048 * (UPD_GROUPS - 1);
+    const size_t rows = (size_t)o->d.m * o->d.ns * sizeof(float);
+    const size_t budget = o->props->smem_optin - 2048;            // static shared + slack
+    o->upd_rows_in_smem = fixed + rows <= budget;
+    o->upd_smem = fixed + (o->upd_rows_in_smem ? rows : 0);
+    if (o->upd_smem > budget) return fail(LMCMA_B200_ERR_ARG, "k_update needs %zu B shared memory (m = %d too large)", o->upd_smem, o->d.m);
+    // pending rows in registers when they fit: m <= 8 warps x RMAX rows of <= 128 float4 columns
+    o->upd_rmax = 0;
+    if (o->upd_nvb == 4 && o->upd_rows_in_smem && !env_int("LMCMA_B200_UPDATE_STREAMING", 0)) {
+        if (o->d.m <= UPD_WARPS * 3) o->upd_rmax = 3;
+        else if (o->d.m <= UPD_WARPS * 5) o->upd_rmax = 5;
+    }
     return 0;
 }
 
@@ -296,15 +396,14 @@ int host_rng_and_sample(lmcma_b200_opt* o, cudaStream_t st) {
         CU(cudaMemcpyAsync(o->d.Z, o->z_host.data(), o->z_host.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));   // z_host is pageable and reused
     }
-    return launch_sample(o, st);
+    return launch_sample(o, st, o->cfg.rng != LMCMA_B200_RNG_HANSEN);
 }
 
 // update() + sample() after the fitness of a generation is in d.fit
 int generation_tail(lmcma_b200_opt* o, cudaStream_t st) {
     int rc;
-    if ((rc = launch_rank(o, o->d.fit, st))) return rc;
-    if ((rc = launch_recombine(o, st))) return rc;
-    if ((rc = launch_update(o, o->d.partial, o->d.RS, o->d.ns, (long long)o->d.RS * o->d.ns, o->d.fit, 0, st))) return rc;
+    if ((rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st))) return rc;
+    if ((rc = launch_update(o, update_args_local(o), true, st))) return rc;
     o->x_cache_valid = false;
     o->sample_idx = 0;
     if (o->cfg.rng == LMCMA_B200_RNG_INJECT && !o->pending_z) { o->needs_sample = true; return 0; }
@@ -319,14 +418,14 @@ int ensure_graph(lmcma_b200_opt* o) {
     int rc = cost_args_for(o, &ca);
     if (rc) return rc;
     cudaStream_t st = o->stream;
+    if ((rc = ensure_mirror(o, st))) return rc;
     cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
-    if (!rc) rc = launch_rank(o, o->d.fit, st);
-    if (!rc) rc = launch_recombine(o, st);
-    if (!rc) rc = launch_update(o, o->d.partial, o->d.RS, o->d.ns, (long long)o->d.RS * o->d.ns, o->d.fit, 0, st);
-    if (!rc) rc = launch_sample(o, st);
+    if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st);
+    if (!rc) rc = launch_update(o, update_args_local(o), true, st);
+    if (!rc) rc = launch_sample(o, st, true);
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     g_launches.store(before);   // capture enqueues nothing
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -667,26 +766,34 @@ int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const doub
     DM(d.ncoll, B * pc); DM(d.nsamp, B * pc);
     DM(d.xmean, B * ns); DM(d.pc, B * ns);
     DM(d.V, B * m * ns); DM(d.P, B * m * ns);
-    DM(d.Nj, B * m); DM(d.Lj, B * m); DM(d.Njf, B * m);
+    DM(d.Nj, B * m); DM(d.Lj, B * m); DM(d.Njf, B * m); DM(d.Njs, B * m);
+    DM(d.VPs, B * m * 2 * ns);
     DM(d.t, B * m); DM(d.vec, B * m);
-    DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B);
-    d.RS = std::max(1, std::min(256, (d.pop_count + 31) / 32));
+    DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B); DM(d.done_count, B);
+    {   // row slices of k_tell's phase A: 32 rows per slice, at most 256 slices
+        const int rows_per = std::max(32, (d.pop_count + 255) / 256);
+        if (rows_per > TELL_MAX_ROWS) { lmcma_b200_destroy(o); return fail(LMCMA_B200_ERR_ARG, "population too large (max %d rows per handle)", 256 * TELL_MAX_ROWS); }
+        d.RS = (d.pop_count + rows_per - 1) / rows_per;
+    }
+    if (getenv("LMCMA_B200_DBG")) DM(d.dbg, 64);
     DM(d.partial, B * d.RS * ns);
 
     std::vector<float> wf(o->weights.begin(), o->weights.end());
     DM(o->d_w, d.mu);
     CU(cudaMemcpy(o->d_w, wf.data(), d.mu * sizeof(float), cudaMemcpyHostToDevice));
     d.w = o->d_w;
-    if (lo) {
-        o->lo_f.assign(lo, lo + d.n);
-        DM(o->d_lo, d.n);
-        CU(cudaMemcpy(o->d_lo, o->lo_f.data(), d.n * sizeof(float), cudaMemcpyHostToDevice));
+    if (lo) {   // padded to the row stride so that the kernels clamp whole float4 columns
+        o->lo_f.assign(d.ns, -std::numeric_limits<float>::max());
+        for (int k = 0; k < d.n; ++k) o->lo_f[k] = (float)lo[k];
+        DM(o->d_lo, d.ns);
+        CU(cudaMemcpy(o->d_lo, o->lo_f.data(), d.ns * sizeof(float), cudaMemcpyHostToDevice));
         d.lo = o->d_lo;
     }
     if (hi) {
-        o->hi_f.assign(hi, hi + d.n);
-        DM(o->d_hi, d.n);
-        CU(cudaMemcpy(o->d_hi, o->hi_f.data(), d.n * sizeof(float), cudaMemcpyHostToDevice));
+        o->hi_f.assign(d.ns, std::numeric_limits<float>::max());
+        for (int k = 0; k < d.n; ++k) o->hi_f[k] = (float)hi[k];
+        DM(o->d_hi, d.ns);
+        CU(cudaMemcpy(o->d_hi, o->hi_f.data(), d.ns * sizeof(float), cudaMemcpyHostToDevice));
         d.hi = o->d_hi;
     }
     // initial mean (lmcma.cpp:158-163)
@@ -722,7 +829,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     if (o->stream) cudaStreamSynchronize(o->stream);
     OptDev& d = o->d;
     void* ptrs[] = {d.X, d.Z, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
-                    d.Nj, d.Lj, d.Njf, d.t, d.vec, d.sc, d.best_x, d.S_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
+                    d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
     if (o->ev0) cudaEventDestroy(o->ev0);
@@ -867,7 +974,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
         if ((rc = ensure_graph(o))) return rc;
         for (int g = 0; g < generations; ++g) {
             CU(cudaGraphLaunch(o->graph_exec, o->stream));
-            g_launches += 5;
+            g_launches += 4;
         }
     } else {
         if (o->cfg.rng == LMCMA_B200_RNG_INJECT && generations > 1)
@@ -900,8 +1007,8 @@ int lmcma_b200_last_run_ms(lmcma_b200_opt* o, float* ms) {
     return 0;
 }
 
-int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms5) {
-    ARG(o && ms5 && generations >= 1, "bad argument");
+int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms4) {
+    ARG(o && ms4 && generations >= 1, "bad argument");
     if (!o->map) return fail(LMCMA_B200_ERR_STATE, "no cost attached");
     if (o->cfg.rng != LMCMA_B200_RNG_PHILOX) return fail(LMCMA_B200_ERR_STATE, "profile_kernels needs the PHILOX rng");
     CU(cudaSetDevice(o->cfg.device));
@@ -909,31 +1016,62 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
     int rc = cost_args_for(o, &ca);
     if (rc) return rc;
     cudaStream_t st = o->stream;
-    std::vector<cudaEvent_t> ev((size_t)generations * 6);
+    std::vector<cudaEvent_t> ev((size_t)generations * 5);
     for (auto& e : ev) CU(cudaEventCreate(&e));
     for (int g = 0; g < generations && !rc; ++g) {
-        cudaEvent_t* e = &ev[(size_t)g * 6];
+        cudaEvent_t* e = &ev[(size_t)g * 5];
         cudaEventRecord(e[0], st);
         rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
         cudaEventRecord(e[1], st);
-        if (!rc) rc = launch_rank(o, o->d.fit, st);
+        if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st);
         cudaEventRecord(e[2], st);
-        if (!rc) rc = launch_recombine(o, st);
+        if (!rc) rc = launch_update(o, update_args_local(o), false, st);   // serialised here so that the events separate the kernels
         cudaEventRecord(e[3], st);
-        if (!rc) rc = launch_update(o, o->d.partial, o->d.RS, o->d.ns, (long long)o->d.RS * o->d.ns, o->d.fit, 0, st);
-        cudaEventRecord(e[4], st);
         if (!rc) rc = launch_sample(o, st);
-        cudaEventRecord(e[5], st);
+        cudaEventRecord(e[4], st);
     }
     cudaError_t se = cudaStreamSynchronize(st);
     if (!rc && se != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "profile run: %s", cudaGetErrorString(se));
-    for (int k = 0; k < 5; ++k) ms5[k] = 0.f;
+    if (!rc && getenv("LMCMA_B200_UPDATE_DBG")) {   // debug: timeline of k_update
+        long long* dbg = nullptr;
+        if (cudaMalloc(&dbg, 16 * sizeof(long long)) == cudaSuccess) {
+            cudaMemset(dbg, 0, 16 * sizeof(long long));
+            UpdateArgs ua = update_args_local(o);
+            ua.dbg = dbg;
+            launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+            launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st);
+            launch_update(o, ua, true, st);
+            launch_sample(o, st, true);
+            cudaStreamSynchronize(st);
+            long long h[16];
+            cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            static const char* names[] = {"start", "bookkeeping", "prologue done", "k_rank done", "mean", "sweep", "end"};
+            fprintf(stderr, "k_update timeline (ns since start; first_stale=%lld live=%lld):", h[10], h[11]);
+            for (int k = 1; k < 7; ++k) fprintf(stderr, " %s=%lld", names[k], h[k] - h[0]);
+            fprintf(stderr, "\n");
+            cudaFree(dbg);
+        }
+    }
+    if (!rc && o->d.dbg) {
+        long long h[64];
+        cudaMemcpy(h, o->d.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "k_update publish clocks (cycles between consecutive rows):");
+        for (int k = 1; k < 32; ++k) fprintf(stderr, " %lld", h[k] - h[k - 1]);
+        fprintf(stderr, "\nk_sample timeline (CTA 0, ns):");
+        static const char* nm[] = {"start", "griddep", "order", "z ready", "first pairs", "loop done", "end"};
+        for (int k = 1; k < 7; ++k) fprintf(stderr, " %s=%lld", nm[k], h[32 + k] - h[32]);
+        fprintf(stderr, " | chunk waits:");
+        for (int k = 7; k < 12; ++k) fprintf(stderr, " %lld", h[32 + k] - h[32]);
+        fprintf(stderr, " dots done=%lld exchanged=%lld", h[32 + 15] - h[32], h[32 + 16] - h[32]);
+        fprintf(stderr, "\n");
+    }
+    for (int k = 0; k < 4; ++k) ms4[k] = 0.f;
     if (!rc)
         for (int g = 0; g < generations; ++g)
-            for (int k = 0; k < 5; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 float ms = 0.f;
-                cudaEventElapsedTime(&ms, ev[(size_t)g * 6 + k], ev[(size_t)g * 6 + k + 1]);
-                ms5[k] += ms / generations;
+                cudaEventElapsedTime(&ms, ev[(size_t)g * 5 + k], ev[(size_t)g * 5 + k + 1]);
+                ms4[k] += ms / generations;
             }
     for (auto& e : ev) cudaEventDestroy(e);
     o->x_cache_valid = false;
@@ -1076,6 +1214,7 @@ int lmcma_b200_set_f64(lmcma_b200_opt* o, int32_t which, const double* in, int64
         }
         case LMCMA_B200_F64_NJ: case LMCMA_B200_F64_LJ: {
             ARG(count == (int64_t)(B * d.m), "count");
+            o->mirror_dirty = true;
             CU(cudaMemcpyAsync(which == LMCMA_B200_F64_NJ ? d.Nj : d.Lj, in, B * d.m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
             if (which == LMCMA_B200_F64_NJ) {
                 std::vector<float> f(in, in + B * d.m);
@@ -1100,6 +1239,7 @@ int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_
             return h2d_rows(d.pc, in, B, w, p, o->stream);
         case LMCMA_B200_F32_V: case LMCMA_B200_F32_P:
             ARG(count == (int64_t)(B * d.m * d.n), "count");
+            o->mirror_dirty = true;
             return h2d_rows(which == LMCMA_B200_F32_V ? d.V : d.P, in, B * d.m, w, p, o->stream);
         case LMCMA_B200_F32_X:
             ARG(count == (int64_t)(B * d.pop_count * d.n), "count");
@@ -1122,6 +1262,7 @@ int lmcma_b200_set_i32(lmcma_b200_opt* o, int32_t which, const int32_t* in, int6
     switch (which) {
         case LMCMA_B200_I32_T: case LMCMA_B200_I32_VEC:
             ARG(count == (int64_t)(B * d.m), "count");
+            o->mirror_dirty = true;
             CU(cudaMemcpyAsync(which == LMCMA_B200_I32_T ? d.t : d.vec, in, B * d.m * sizeof(int), cudaMemcpyHostToDevice, o->stream));
             CU(cudaStreamSynchronize(o->stream));
             return 0;
@@ -1171,13 +1312,7 @@ int lmcma_b200_mg_rank(lmcma_b200_opt* o, const float* f_all_dev, float* payload
     cudaStream_t st = stream ? (cudaStream_t)stream : o->stream;
     // keep the gathered fitness: k_update needs it for prev_fit / best tracking
     CU(cudaMemcpyAsync(o->d.fit, f_all_dev, (size_t)o->d.lambda * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    int rc;
-    if ((rc = launch_rank(o, o->d.fit, st))) return rc;
-    if ((rc = launch_recombine(o, st))) return rc;
-    k_pack_payload<<<dim3((o->d.ns + 127) / 128, o->d.B), 128, 0, st>>>(o->d, payload_dev);
-    g_launches++;
-    CU(cudaGetLastError());
-    return 0;
+    return launch_rank(o, o->d.fit, RANK_PACK, payload_dev, st);
 }
 
 int lmcma_b200_mg_update(lmcma_b200_opt* o, const float* payload_all_dev, int32_t world, void* stream) {
@@ -1185,11 +1320,15 @@ int lmcma_b200_mg_update(lmcma_b200_opt* o, const float* payload_all_dev, int32_
     CU(cudaSetDevice(o->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : o->stream;
     const long long pf = o->d.ns + 4;
-    int rc = launch_update(o, payload_all_dev, world, (long long)o->d.B * pf, pf, o->d.fit, 1, st);
+    UpdateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.f_all = o->d.fit; a.slices = payload_all_dev; a.n_slices = world;
+    a.slice_stride = (long long)o->d.B * pf; a.inst_stride = pf; a.payload_mode = 1;
+    int rc = launch_update(o, a, false, st);
     if (rc) return rc;
     o->x_cache_valid = false;
     if (o->cfg.rng != LMCMA_B200_RNG_PHILOX) return fail(LMCMA_B200_ERR_STATE, "split-population mode needs the PHILOX rng");
-    return launch_sample(o, st);
+    return launch_sample(o, st, true);
 }
 
 // ---- host-side reference pieces ------------------------------------------------------------------

@@ -202,9 +202,9 @@ class Optimizer:
         return ms.value
 
     def profile_kernels(self, generations):
-        ms = np.zeros(5, np.float32)
+        ms = np.zeros(4, np.float32)
         K.check(K.lib().lmcma_b200_profile_kernels(self._h, int(generations), K.fptr(ms)))
-        return dict(zip(("cost", "rank", "recombine", "update", "sample"), (float(v) for v in ms)))
+        return dict(zip(("cost", "rank", "update", "sample"), (float(v) for v in ms)))
 
     def best(self):
         x = np.zeros((self.batch, self.n), np.float32)

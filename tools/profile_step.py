@@ -16,7 +16,7 @@ cmap = L.CostMap(dist, storage)
 opt = L.Optimizer(2 * bench.W, x0=x0, lam=bench.LAM, m=bench.M, lo=lo, hi=hi, sigma0=bench.SIGMA0, seed=1000)
 opt.attach_cost(cmap, [start], [goal], bench.W, L.LONGSAFE, 1e4)
 for g in range(warm):
-    opt.profile_kernels(1)          # un-graphed launches: 5 kernels per generation
+    opt.profile_kernels(1)          # un-graphed launches
 pk = opt.profile_kernels(5)
 print("per-kernel ms (L2 warm, events):", {k: round(v, 5) for k, v in pk.items()})
 print("mean samples/trajectory:", float(opt.get("nsamp").mean()), "sigma:", float(opt.get("sigma")[0]),
