@@ -3,8 +3,8 @@
 trajectory-cost evals/s + LM-CMA generations/s) on the C2 workload: one 2-D query on a 4096x4096 synthetic
 occupancy grid, 200 waypoints (n = 400), lambda = 1024, m = 2*sqrt(n) = 40.
 
-A "step" is ONE LM-CMA generation = k_cost (lambda trajectory evaluations) -> k_rank -> k_recombine ->
-k_update -> k_sample, replayed from a CUDA graph; `value` = trajectory evaluations per second with everything
+A "step" is ONE LM-CMA generation = k_cost (lambda trajectory evaluations) -> k_rank -> k_update -> k_sample,
+replayed from a CUDA graph; `value` = trajectory evaluations per second with everything
 resident in HBM; L2 is flushed (256 MiB write) before every timed step.  N > 1: every rank optimises its own
 independent query on its own GPU (weak scaling, no data-path collective: SURVEY.md section 8e).
 
@@ -29,6 +29,11 @@ WORKLOAD = {"workload": "C2: 2-D 4096x4096 synthetic occupancy grid (seed 42, 20
             "map": "4096x4096 f32 sign-tagged reciprocal clearance (64 MiB)", "n": 400, "lambda": 1024, "m": 40,
             "waypoints": 200}
 W, LAM, M, SIGMA0 = 200, 1024, 40, 32.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_cost launch of this workload, from the committed
+# `ncu --set full` capture (the map stays L2-resident between generations, so DRAM traffic is far BELOW the
+# algorithmic bytes: the kernel is bound by issue slots / L1 gather rate, not by HBM)
+NCU_DRAM_BYTES_PER_LAUNCH = 2.39e6
+NCU_SOURCE = "profiles/r1d_full.md (k_cost<2,0,0>: dram_read 2.39 MB, dram_write 0)"
 
 
 def peaks():
@@ -221,7 +226,8 @@ def run_b200(args):
                                      "note": "back-to-back graph replays, map L2-resident (deployment mode)"},
             "kernel_ms": per_kernel,
             "roofline": {"kernel": "k_cost", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_SOURCE,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": cost_ms,
                          "note": "bytes = lambda*(4n + S*4 + 8), S = mean map samples per trajectory; duration = CUDA events "
                                  "around k_cost on the launching stream, L2 flushed before each generation"},

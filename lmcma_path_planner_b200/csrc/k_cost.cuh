@@ -22,12 +22,13 @@ __device__ __forceinline__ int substeps_of(float linf) {
 }
 
 template <int DIMS, int STORAGE, bool TRACE>
-__global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
+__global__ void __launch_bounds__(256, 8) k_cost(MapDev mp, CostArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = a.W, NSEG = W + 1;
     float4* segA = reinterpret_cast<float4*>(smem_raw);          // 2-D {Ax, Ay, dx, dy}   3-D {Ax, Ay, Az, dx}
-    float4* segB = segA + NSEG;                                  // 2-D {invK, scale, -, -} 3-D {dy, dz, invK, scale}
-    int* off = reinterpret_cast<int*>(segB + NSEG);              // NSEG + 1 exclusive sample offsets
+    float4* segB = segA + NSEG;                                  // 2-D {invK, scale, K, first sample} 3-D {dy, dz, invK, scale}
+    int2* segC = reinterpret_cast<int2*>(segB + NSEG);           // 3-D {K, first sample} (NSEG entries, unused in 2-D)
+    int* off = reinterpret_cast<int*>(segC + NSEG);              // NSEG + 1 exclusive sample offsets
     float* lut = reinterpret_cast<float*>(off + NSEG + 1);       // 256 (U8 only)
     __shared__ float red_f[2][8];
     __shared__ int red_i[8];
@@ -70,8 +71,8 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
 #pragma unroll
             for (int c = 0; c < DIMS; ++c) { A[c] = -1.0e9f; D[c] = 0.f; }
         }
-        if (DIMS == 2) { segA[s] = make_float4(A[0], A[1], D[0], D[1]); segB[s] = make_float4(invK, len * invK, 0.f, 0.f); }
-        else { segA[s] = make_float4(A[0], A[1], A[2], D[0]); segB[s] = make_float4(D[1], D[2], invK, len * invK); }
+        if (DIMS == 2) { segA[s] = make_float4(A[0], A[1], D[0], D[1]); segB[s] = make_float4(invK, len * invK, __int_as_float(K), 0.f); }
+        else { segA[s] = make_float4(A[0], A[1], A[2], D[0]); segB[s] = make_float4(D[1], D[2], invK, len * invK); segC[s].x = K; }
         off[s + 1] = K + 1;                                      // samples of this segment (rewritten below)
         my_cnt += K + 1;
     }
@@ -86,10 +87,16 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
     int base = incl - my_cnt, T = 0;
     for (int w2 = 0; w2 < nwarps; ++w2) { const int v = warp_tot[w2]; if (w2 < warp) base += v; T += v; }
     if (tid == 0) off[0] = 0;
-    for (int s = s_begin; s < s_end; ++s) { base += off[s + 1]; off[s + 1] = base; }
+    for (int s = s_begin; s < s_end; ++s) {
+        if (DIMS == 2) segB[s].w = __int_as_float(base); else segC[s].y = base;   // first sample of the segment
+        base += off[s + 1]; off[s + 1] = base;
+    }
     __syncthreads();
 
-    // ---- phase 2: consecutive samples on consecutive lanes (<= 1 cell apart -> few lines per warp load) ----
+    // ---- phase 2: consecutive samples on consecutive lanes (<= 1 cell apart -> few lines per warp load).  The
+    //      segment of every lane's sample comes from ONE warp-wide step: the 32 next segment-end offsets are
+    //      loaded one per lane, the ends that fall inside this 32-sample block are OR-reduced into a bit mask
+    //      (redux.sync), and a lane's segment is the warp's first segment + popc(mask bits up to the lane) ----
     const int nblk = (T + 31) >> 5;
     const int blk0 = (int)(((long long)warp * nblk) / nwarps), blk1 = (int)(((long long)(warp + 1) * nblk) / nwarps);
     float clr_acc = 0.f; int coll = 0;
@@ -100,19 +107,23 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
         int s_warp = lo;
         const unsigned nxm1 = (unsigned)(mp.nx - 1), nym1 = (unsigned)(mp.ny - 1), nzm1 = (unsigned)(mp.nz - 1);
         const int last = NSEG - 1;
+        const float ng_coll = -mp.g_coll;
         for (int blk = blk0; blk < blk1; ++blk) {
-            const int t = (blk << 5) + lane;
-            const bool valid = t < T;
-            const int tt = valid ? t : T - 1;
-            int s = s_warp;
-            int cur = off[s], nxt = off[s + 1];                  // warp-uniform (broadcast) loads
-            while (tt >= nxt) { ++s; cur = nxt; nxt = off[s + 1]; }
-            s_warp = __shfl_sync(0xffffffffu, s, 31);
-            const int K = nxt - cur - 1, k = tt - cur;
+            const int t0 = blk << 5;
+            const int e_i = s_warp + 1 + lane;
+            const unsigned rel = (unsigned)(off[min(e_i, NSEG)] - t0);          // > 0: segment s_warp contains t0
+            const unsigned mask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+            const int adv = __popc(__ballot_sync(0xffffffffu, rel <= 32u && e_i <= NSEG));
+            const int tl = min(lane, T - 1 - t0);                // lanes past the last sample repeat it with weight 0
+            const bool valid = tl == lane;
+            const int s = s_warp + __popc(mask & (0xffffffffu >> (31 - tl)));
+            s_warp += adv;
             const float4 ra = segA[s];
-            float invK, scale, dx, dy, dz = 0.f, az = 0.f;
-            if (DIMS == 2) { const float2 rb = *reinterpret_cast<const float2*>(&segB[s]); invK = rb.x; scale = rb.y; dx = ra.z; dy = ra.w; }
-            else { const float4 rb = segB[s]; dx = ra.w; dy = rb.x; dz = rb.y; invK = rb.z; scale = rb.w; az = ra.z; }
+            const float4 rb = segB[s];
+            float invK, scale, dx, dy, dz = 0.f, az = 0.f; int K, cur;
+            if (DIMS == 2) { invK = rb.x; scale = rb.y; K = __float_as_int(rb.z); cur = __float_as_int(rb.w); dx = ra.z; dy = ra.w; }
+            else { const int2 rc = segC[s]; dx = ra.w; dy = rb.x; dz = rb.y; invK = rb.z; scale = rb.w; az = ra.z; K = rc.x; cur = rc.y; }
+            const int k = t0 + tl - cur;
             const float tk = __fmul_rn((float)k, invK);
             // round-half-even conversion == (int)rintf(q); saturates for huge |q| (-> fails the unsigned test)
             const int ix = __float2int_rn(__fadd_rn(ra.x, __fmul_rn(tk, dx)));
@@ -125,13 +136,14 @@ __global__ void __launch_bounds__(256) k_cost(MapDev mp, CostArgs a) {
             }
             const unsigned adr = inb ? brick_offset<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, mp.nbx, mp.nby) : 0u;
             float g = (STORAGE == 0) ? __ldg(mp.g32 + adr) : lut[__ldg(mp.q8 + adr)];   // branch-free: cell 0 when outside
-            g = inb ? g : -mp.g_coll;
-            float wgt = (k == 0 || k == K) ? 0.5f : 1.0f;
-            wgt = valid ? wgt : 0.f;
-            clr_acc = fmaf(fabsf(g) * wgt, scale, clr_acc);
+            g = inb ? g : ng_coll;
+            const bool endpt = (k == 0) || (k == K);
+            float sw = endpt ? 0.5f * scale : scale;             // trapezoid weight x len/K
+            sw = valid ? sw : 0.f;
+            clr_acc = fmaf(fabsf(g), sw, clr_acc);
             coll += (valid && g < 0.f && (k < K || s == last)) ? 1 : 0;
             if (TRACE) {
-                if (valid && t < a.max_cells) a.cells[t] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
+                if (valid && (long long)(t0 + lane) < a.max_cells) a.cells[t0 + lane] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
             }
         }
     }

@@ -3,7 +3,7 @@
 // grid = (RS, B): RS row slices per optimiser instance.  Every CTA computes the ranks of its slice's
 // candidates by counting (myqsort/compare, lmcma.cpp:84-104: stable ascending order, ties keep the lower id,
 // -0 == +0, NaN last) together with the pair count S of the merged 2*lambda ranking of the step-size rule,
-// and the slice's weighted partial sum of (x - xmean).  k_update (k_update.cuh) folds the partials.
+// and the slice's weighted partial sum of d = x - xmean (OptDev::D).  k_update (k_update.cuh) folds the partials.
 // Split-population mode (RANK_PACK): the last CTA of an instance to finish — fence + atomic ticket, no CTA
 // ever waits on another — folds the partials into the all-gather payload.
 #pragma once
@@ -38,12 +38,6 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
     const float* cur = f_all + (size_t)b * lambda;
     const float* prev = o.prev_fit + (size_t)b * lambda;
     if (tid == 0) sh_S = 0ull;
-    // requested now, used after the ranking: float(xmean) of this thread's columns (first column tile)
-    float4 m4_first = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((tid & 127) < (o.ns >> 2)) {
-        const double* xm = o.xmean + (size_t)b * o.ns + 4 * (tid & 127);
-        m4_first = make_float4((float)xm[0], (float)xm[1], (float)xm[2], (float)xm[3]);
-    }
 
     // threads per row: a power of two <= 32 so that a row's partial counts fold with warp shuffles
     int tpr = 32;
@@ -129,18 +123,13 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
     __syncthreads();
     const int nsel = sh_nsel;
 
-    // ---- weighted partial sums of (x - xmean): 128 float4 columns x (nthr/128) row groups ----
+    // ---- weighted partial sums of d = x - xmean: 128 float4 columns x (nthr/128) row groups ----
     const int nq = o.ns >> 2, ngrp = nthr >> 7, tq = tid & 127, g = tid >> 7;
     float* part = o.partial + ((size_t)b * o.RS + rs) * o.ns;
     for (int q0 = 0; q0 < nq; q0 += 128) {
         const int q = q0 + tq;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < nq) {
-            float4 m4 = m4_first;
-            if (q0 > 0) {
-                const double* xm = o.xmean + (size_t)b * o.ns + 4 * q;
-                m4 = make_float4((float)xm[0], (float)xm[1], (float)xm[2], (float)xm[3]);
-            }
             for (int k = g; k < nsel; k += 4 * ngrp) {               // up to 4 rows in flight per thread
                 float w[4]; float4 x[4];
 #pragma unroll
@@ -148,14 +137,14 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
                     const int kk = k + u * ngrp;
                     const bool on = kk < nsel;
                     w[u] = on ? sel_w[kk] : 0.f;
-                    x[u] = on ? reinterpret_cast<const float4*>(o.X + ((size_t)b * o.pop_count + sel_row[kk]) * o.ns)[q] : m4;
+                    x[u] = on ? reinterpret_cast<const float4*>(o.D + ((size_t)b * o.pop_count + sel_row[kk]) * o.ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    acc.x = fmaf(w[u], x[u].x - m4.x, acc.x);
-                    acc.y = fmaf(w[u], x[u].y - m4.y, acc.y);
-                    acc.z = fmaf(w[u], x[u].z - m4.z, acc.z);
-                    acc.w = fmaf(w[u], x[u].w - m4.w, acc.w);
+                    acc.x = fmaf(w[u], x[u].x, acc.x);
+                    acc.y = fmaf(w[u], x[u].y, acc.y);
+                    acc.z = fmaf(w[u], x[u].z, acc.z);
+                    acc.w = fmaf(w[u], x[u].w, acc.w);
                 }
             }
         }

@@ -44,23 +44,31 @@ __device__ __forceinline__ float reduce_scatter8(const float (&v)[SAMPLE_G], int
 // ------------------------------------------------------------------------------------------------
 
 // x = xmean + sigma * Az in FP64, clamp lo then hi (lmcma.cpp:307-310, 222-229); lo / hi are padded to ns with
-// -FLT_MAX / +FLT_MAX, the padding lanes of X are forced to 0
-__device__ __forceinline__ float4 sample_finish(const OptDev& o, const double* __restrict__ xm, double sigma, float4 az, int q) {
+// -FLT_MAX / +FLT_MAX, the padding lanes are forced to 0.  Writes the candidate (FP32) and its offset from the mean
+// d = x - xmean, formed in FP64 and rounded once (see OptDev::D).
+__device__ __forceinline__ void sample_finish(const OptDev& o, const double* __restrict__ xm, double sigma, float4 az, int q,
+                                              float* __restrict__ xrow, float* __restrict__ drow) {
     const double2 m01 = reinterpret_cast<const double2*>(xm)[2 * q];
     const double2 m23 = reinterpret_cast<const double2*>(xm)[2 * q + 1];
     float4 lo4 = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f), hi4 = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f);
     if (o.lo) lo4 = reinterpret_cast<const float4*>(o.lo)[q];
     if (o.hi) hi4 = reinterpret_cast<const float4*>(o.hi)[q];
-    float4 x;
-    x.x = fminf(fmaxf((float)(m01.x + sigma * (double)az.x), lo4.x), hi4.x);
-    x.y = fminf(fmaxf((float)(m01.y + sigma * (double)az.y), lo4.y), hi4.y);
-    x.z = fminf(fmaxf((float)(m23.x + sigma * (double)az.z), lo4.z), hi4.z);
-    x.w = fminf(fmaxf((float)(m23.y + sigma * (double)az.w), lo4.w), hi4.w);
+    const double mm[4] = {m01.x, m01.y, m23.x, m23.y};
+    const float aa[4] = {az.x, az.y, az.z, az.w}, ll[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, hh[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+    float xx[4], dd[4];
     const int e = q * 4;
-    if (e + 1 >= o.n) x.y = 0.f;
-    if (e + 2 >= o.n) x.z = 0.f;
-    if (e + 3 >= o.n) x.w = 0.f;
-    return x;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double x64 = mm[c] + sigma * (double)aa[c];
+        float xf = (float)x64;
+        if (xf < ll[c]) { xf = ll[c]; x64 = (double)ll[c]; }    // max(x, lo) then min(x, hi), lmcma.cpp:222-229
+        if (xf > hh[c]) { xf = hh[c]; x64 = (double)hh[c]; }
+        const bool pad = e + c >= o.n;
+        xx[c] = pad ? 0.f : xf;
+        dd[c] = pad ? 0.f : (float)(x64 - mm[c]);
+    }
+    reinterpret_cast<float4*>(xrow)[q] = make_float4(xx[0], xx[1], xx[2], xx[3]);
+    reinterpret_cast<float4*>(drow)[q] = make_float4(dd[0], dd[1], dd[2], dd[3]);
 }
 
 constexpr int SAMPLE_MAX_STAGES = 8;
@@ -217,10 +225,11 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
         const int row = row0 + r;
         if (row >= o.pop_count) continue;
         float* xrow = o.X + ((size_t)b * o.pop_count + row) * ns;
+        float* drow = o.D + ((size_t)b * o.pop_count + row) * ns;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int q = lane + 32 * i;
-            if (q < nq) reinterpret_cast<float4*>(xrow)[q] = sample_finish(o, xm, sc.sigma, az[r][i], q);
+            if (q < nq) sample_finish(o, xm, sc.sigma, az[r][i], q, xrow, drow);
         }
     }
 }
@@ -395,8 +404,8 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
     for (int r = 0; r < RBW; ++r) {
         const int row = row0 + r;
         if (qon && row < o.pop_count) {
-            float* xrow = o.X + ((size_t)b * o.pop_count + row) * ns;
-            reinterpret_cast<float4*>(xrow)[q] = sample_finish(o, o.xmean + (size_t)b * ns, sc.sigma, az[r], q);
+            const size_t roff2 = ((size_t)b * o.pop_count + row) * ns;
+            sample_finish(o, o.xmean + (size_t)b * ns, sc.sigma, az[r], q, o.X + roff2, o.D + roff2);
         }
     }
     SMP_STAMP(6);

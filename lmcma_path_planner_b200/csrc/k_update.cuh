@@ -43,12 +43,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = o.m, ns = o.ns, nq = ns >> 2;
     float* lj_s = reinterpret_cast<float*>(smem_raw);             // m: Lj / K in sequence order
-    float* nv_s = lj_s + m;                                       // m: |v|^2 (final rows) / |y|^2 (pending rows)
+    float* nv_s = lj_s + m;                                       // m: |v|^2 of the recomputed rows
     int* order = reinterpret_cast<int*>(nv_s + m);                // m: slot order
     int* stamp = order + m;                                       // m: generation stamp per SLOT
     float* ljslot = reinterpret_cast<float*>(stamp + m);          // m: Lj by slot (prefetched)
     unsigned long long* rowbar = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)m * 20 + 7) & ~(size_t)7));   // m mbarriers: row i is final
-    float4* red4 = reinterpret_cast<float4*>(smem_raw + (((size_t)m * 28 + 8 + 127) & ~(size_t)127));                      // 128 float4 scratch
+    unsigned long long* scalbar = rowbar + m;                      // m mbarriers: |v_i|^2 and Lj_i / K are published
+    float4* red4 = reinterpret_cast<float4*>(smem_raw + (((size_t)m * 36 + 8 + 127) & ~(size_t)127));                      // 128 float4 scratch
     float* rows_s = reinterpret_cast<float*>(red4 + 128 * (UPD_GROUPS - 1));                                                                  // m x ns (SMEM)
     __shared__ unsigned long long sh_key;
     __shared__ __align__(8) unsigned long long sh_bar;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     UPD_STAMP(0);
     // =============================== prologue: independent of k_rank ===============================
     const Scalars sc0 = *scp;
-    for (int i = tid; i < m; i += nthr) { order[i] = tg[i]; stamp[i] = vg[i]; ljslot[i] = (float)Ljd[i]; mbar_init(&rowbar[i], 1); }
+    for (int i = tid; i < m; i += nthr) { order[i] = tg[i]; stamp[i] = vg[i]; ljslot[i] = (float)Ljd[i]; mbar_init(&rowbar[i], 1); mbar_init(&scalbar[i], 1); }
     if (tid == 0) { sh_key = ~0ull; if (SMEM) mbar_init(&sh_bar, 1); }
     fence_barrier_init();
     __syncthreads();
@@ -182,19 +183,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         if (take && tid == 0) { scp->best_f = (double)bf; scp->best_local = local ? 1 : 0; }
     }
-    // |v_j|^2 of the final rows and |pc_i|^2 of the pending ones (all but the newest)
-    auto row_norm = [&](int i) {                                     // warp-collective
-        const float4* v = reinterpret_cast<const float4*>(row_ptr(i));
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int it = 0; it < NVB; ++it) {
-            const int q = lane + 32 * it;
-            if (q < nq) { const float4 x = ld_row4<SMEM>(v + q); s0 = fmaf(x.x, x.x, s0); s1 = fmaf(x.y, x.y, s1); s0 = fmaf(x.z, x.z, s0); s1 = fmaf(x.w, x.w, s1); }
-        }
-        const float tot = warp_sum(s0 + s1);
-        if (lane == 0) nv_s[i] = tot;
-    };
-    for (int i = warp; i + 1 < live; i += nwarps) row_norm(i);
     UPD_STAMP(2);
 
     // =============================== needs k_rank's partial sums ===============================
@@ -246,8 +234,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 double xn[4]; float pn[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const double xold_f = (double)(float)xo[c];      // the partials are relative to float(xmean)
-                    const double shift = (xold_f - xo[c]) + (double)d[c];   // new mean - old mean
+                    const double shift = (double)d[c];               // new mean - old mean = sum_i w_i (x_i - xmean)
                     xn[c] = xo[c] + shift;
                     pn[c] = (float)((1.0 - o.cc) * (double)po[c] + coef * shift);
                 }
@@ -262,7 +249,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
     }
     if (!SMEM) __threadfence();
-    if (warp == 0) row_norm(live - 1);
     __syncthreads();
     UPD_STAMP(4);
 
@@ -276,8 +262,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     //  * pending rows are held as y = x / K^j (all pending rows have had the same number of factors applied),
     //    which turns the update into y <- y - (Lj_j / K)(v_j . y) v_j: one FMA per element; a row is multiplied
     //    by K^i once, when it becomes final;
-    //  * |y|^2 follows from scalars already known, |y'|^2 = |y|^2 - 2 e d + e^2 |v_j|^2 (d = v_j . y,
-    //    e = (Lj_j / K) d), so the |v|^2 that Lj needs never costs a second reduction;
+    //  * |v_i|^2 (which Lj_i needs) is a real reduction over the finished row, as in the reference (lmcma.cpp:383-384) —
+    //    a scalar recurrence |y'|^2 = |y|^2 - 2 e d + e^2 |v_j|^2 cancels catastrophically once the evolution paths
+    //    are nearly collinear with the stored directions — but it is taken AFTER the row has been handed over:
+    //    the consumers need Lj_i only after their own dot products, so it is off the chain;
     //  * a row is owned by one warp for the whole sweep; when its last factor has been applied the owner
     //    publishes it (row, |v|^2, Lj/K, then an mbarrier arrive by every lane) and the other warps pick it up
     //    as factor i with a blocking mbarrier wait: no block-wide barrier and no spinning warps competing
@@ -295,12 +283,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         constexpr int R = RMAX > 0 ? RMAX : 1;
         const int base = first_stale + warp;
         float4 y[R][NVB];
-        float ny[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = base + r * UPD_WARPS;
             const bool on = i < live;
-            ny[r] = on ? nv_s[i] : 0.f;
 #pragma unroll
             for (int it = 0; it < NVB; ++it) {
                 const int q = lane + 32 * it;
@@ -310,22 +296,29 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         int my_last = -1;                                            // my largest row
         if (base < live) my_last = base + ((live - 1 - base) / UPD_WARPS) * UPD_WARPS;
-        auto publish = [&](const float4 (&row)[NVB], int i, float nyv, double kp) {   // warp-collective: y_i K^i is the final v_i
+        auto publish = [&](const float4 (&row)[NVB], int i, double kp) {   // warp-collective: y_i K^i is the final v_i
             const float kf = (float)kp;
             float4* srow = reinterpret_cast<float4*>(rows_s + (size_t)i * ns);
             float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
             float4* dst2 = reinterpret_cast<float4*>(VPb + (size_t)i * 2 * ns);
-            if (lane == 0) publish_scalars(i, nyv * kf * kf);
             float4 x[NVB];
 #pragma unroll
             for (int it = 0; it < NVB; ++it) {
                 const int q = lane + 32 * it;
-                x[it] = make_float4(row[it].x * kf, row[it].y * kf, row[it].z * kf, row[it].w * kf);
+                const float2 k2 = make_float2(kf, kf), l = fmul2(lo2(row[it]), k2), h = fmul2(hi2(row[it]), k2);
+                x[it] = make_float4(l.x, l.y, h.x, h.y);
                 if (q < nq) srow[q] = x[it];
             }
             __syncwarp();                                            // orders the lanes' stores before lane 0's release
             if (lane == 0) mbar_arrive(&rowbar[i]);                  // ONE arrive: 32 arrives on one mbarrier serialise (~27 cycles each)
-            if (o.dbg && lane == 0 && i < 32) o.dbg[i] = clock64();
+            float2 nn = make_float2(0.f, 0.f);                       // |v_i|^2: after the hand-over, off the chain
+#pragma unroll
+            for (int it = 0; it < NVB; ++it) { nn = ffma2(lo2(x[it]), lo2(x[it]), nn); nn = ffma2(hi2(x[it]), hi2(x[it]), nn); }
+            const float nv = warp_sum(nn.x + nn.y);
+            if (lane == 0) {
+                publish_scalars(i, nv);
+                mbar_arrive(&scalbar[i]);
+            }
             // the copy to HBM goes after the arrive: a release has to wait for every earlier store of the thread, and
             // a store to HBM takes an L2 round trip that the next step of the sweep must not sit behind
 #pragma unroll
@@ -334,14 +327,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 if (q < nq) { dst[q] = x[it]; dst2[q] = x[it]; }
             }
         };
-        if (first_stale == 0 && warp == 0) publish(y[0], 0, ny[0], 1.0);   // row 0 has no factors (v_0 = pc_0)
+        if (first_stale == 0 && warp == 0) publish(y[0], 0, 1.0);   // row 0 has no factors (v_0 = pc_0)
         double kp = 1.0;                                             // K^(j+1) inside step j
         for (int j = 0; j + 1 < live; ++j) {
             kp *= Kd;
             if (j >= my_last) break;                                 // all my rows are final
             if (j >= first_stale) mbar_wait(&rowbar[j], 0);
             const float4* vj = reinterpret_cast<const float4*>(rows_s + (size_t)j * ns);
-            const float ljk = lj_s[j], nvj = nv_s[j];
             float4 a4[NVB];
 #pragma unroll
             for (int it = 0; it < NVB; ++it) {
@@ -352,21 +344,19 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (base + r * UPD_WARPS == j + 1) {
-                    float d0 = 0.f, d1 = 0.f;
+                    float2 dd = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(y[r][it]), dd); dd = ffma2(hi2(a4[it]), hi2(y[r][it]), dd); }
+                    const float d = warp_sum(dd.x + dd.y);
+                    if (j >= first_stale) mbar_wait(&scalbar[j], 0);   // Lj_j / K, |v_j|^2: published right after the row (long done)
+                    const float e = lj_s[j] * d;
+                    const float2 me = make_float2(-e, -e);
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) {
-                        d0 = fmaf(a4[it].x, y[r][it].x, d0); d1 = fmaf(a4[it].y, y[r][it].y, d1);
-                        d0 = fmaf(a4[it].z, y[r][it].z, d0); d1 = fmaf(a4[it].w, y[r][it].w, d1);
+                        const float2 l = ffma2(me, lo2(a4[it]), lo2(y[r][it])), h = ffma2(me, hi2(a4[it]), hi2(y[r][it]));
+                        y[r][it] = make_float4(l.x, l.y, h.x, h.y);
                     }
-                    const float d = warp_sum(d0 + d1);
-                    const float e = ljk * d;
-                    ny[r] = fmaxf(fmaf(e, fmaf(e, nvj, -2.0f * d), ny[r]), 0.f);
-#pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        y[r][it].x = fmaf(-e, a4[it].x, y[r][it].x); y[r][it].y = fmaf(-e, a4[it].y, y[r][it].y);
-                        y[r][it].z = fmaf(-e, a4[it].z, y[r][it].z); y[r][it].w = fmaf(-e, a4[it].w, y[r][it].w);
-                    }
-                    publish(y[r], j + 1, ny[r], kp);
+                    publish(y[r], j + 1, kp);
                 }
             }
             // the other pending rows of this warp: independent dot products, reduced together
@@ -374,15 +364,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int i = base + r * UPD_WARPS;
-                float d0 = 0.f, d1 = 0.f;
+                float2 dd = make_float2(0.f, 0.f);
                 if (i > j + 1 && i < live) {
 #pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        d0 = fmaf(a4[it].x, y[r][it].x, d0); d1 = fmaf(a4[it].y, y[r][it].y, d1);
-                        d0 = fmaf(a4[it].z, y[r][it].z, d0); d1 = fmaf(a4[it].w, y[r][it].w, d1);
-                    }
+                    for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(y[r][it]), dd); dd = ffma2(hi2(a4[it]), hi2(y[r][it]), dd); }
                 }
-                d[r] = d0 + d1;
+                d[r] = dd.x + dd.y;
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -392,16 +379,18 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     for (int ofs = 16; ofs > 0; ofs >>= 1) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
                 }
             }
+            if (j >= first_stale) mbar_wait(&scalbar[j], 0);
+            const float ljk = lj_s[j];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int i = base + r * UPD_WARPS;
                 if (i > j + 1 && i < live) {
                     const float e = ljk * d[r];
-                    ny[r] = fmaxf(fmaf(e, fmaf(e, nvj, -2.0f * d[r]), ny[r]), 0.f);
+                    const float2 me = make_float2(-e, -e);
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) {
-                        y[r][it].x = fmaf(-e, a4[it].x, y[r][it].x); y[r][it].y = fmaf(-e, a4[it].y, y[r][it].y);
-                        y[r][it].z = fmaf(-e, a4[it].z, y[r][it].z); y[r][it].w = fmaf(-e, a4[it].w, y[r][it].w);
+                        const float2 l = ffma2(me, lo2(a4[it]), lo2(y[r][it])), h = ffma2(me, hi2(a4[it]), hi2(y[r][it]));
+                        y[r][it] = make_float4(l.x, l.y, h.x, h.y);
                     }
                 }
             }
@@ -415,17 +404,20 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             float4* dst2 = reinterpret_cast<float4*>(VPb + ((size_t)i * 2 + 1) * ns);
             for (int q = lane; q < nq; q += 32) dst2[q] = ld_row4<SMEM>(src + q);
         }
-        auto publish = [&](int i, float nyv, double kp) {            // warp-collective: y_i K^i is the final v_i
+        auto publish = [&](int i, double kp) {                       // warp-collective: y_i K^i is the final v_i
             const float kf = (float)kp;
             float4* row = reinterpret_cast<float4*>(row_ptr(i));
             float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
             float4* dst2 = reinterpret_cast<float4*>(VPb + (size_t)i * 2 * ns);
-            if (lane == 0) publish_scalars(i, nyv * kf * kf);
+            float nn = 0.f;
             for (int q = lane; q < nq; q += 32) {
                 float4 x = ld_row4<SMEM>(row + q);
                 x.x *= kf; x.y *= kf; x.z *= kf; x.w *= kf;
                 row[q] = x;
+                nn += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
             }
+            nn = warp_sum(nn);
+            if (lane == 0) publish_scalars(i, nn);
             if (!SMEM) __threadfence();
             __syncwarp();                                            // orders the lanes' stores before lane 0's release
             if (lane == 0) mbar_arrive(&rowbar[i]);
@@ -437,7 +429,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         };
         if (warp < act_warps) {
             int i0 = first_stale + warp;                             // my first row that is not final yet
-            if (first_stale == 0 && warp == 0) publish(0, nv_s[0], 1.0);   // row 0 has no factors (v_0 = pc_0)
+            if (first_stale == 0 && warp == 0) publish(0, 1.0);      // row 0 has no factors (v_0 = pc_0)
             double kp = 1.0;                                         // K^(j+1) inside step j
             for (int j = 0; j + 1 < live; ++j) {
                 kp *= Kd;
@@ -445,12 +437,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 if (i0 >= live) break;
                 if (j >= first_stale) mbar_wait(&rowbar[j], 0);
                 const float4* vj = reinterpret_cast<const float4*>(row_ptr(j));
-                const float ljk = lj_s[j], nvj = nv_s[j];
+                const float ljk = lj_s[j];
                 for (int i = i0; i < live; i += act_warps) {
-                    __syncwarp();                                    // lane 0's |y_i|^2 of the previous step
                     float4* vi = reinterpret_cast<float4*>(row_ptr(i));
                     float d0 = 0.f, d1 = 0.f;
-                    const float nyi = nv_s[i];
                     for (int q = lane; q < nq; q += 32) {
                         const float4 av = ld_row4<SMEM>(vj + q), c = ld_row4<SMEM>(vi + q);
                         d0 = fmaf(av.x, c.x, d0); d1 = fmaf(av.y, c.y, d1);
@@ -458,7 +448,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     }
                     const float d = warp_sum(d0 + d1);
                     const float e = ljk * d;
-                    const float ny_new = fmaxf(fmaf(e, fmaf(e, nvj, -2.0f * d), nyi), 0.f);
                     for (int q = lane; q < nq; q += 32) {
                         const float4 av = ld_row4<SMEM>(vj + q);
                         float4 c = ld_row4<SMEM>(vi + q);
@@ -466,8 +455,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                         c.z = fmaf(-e, av.z, c.z); c.w = fmaf(-e, av.w, c.w);
                         vi[q] = c;
                     }
-                    if (i == j + 1) publish(i, ny_new, kp);
-                    else if (lane == 0) nv_s[i] = ny_new;
+                    if (i == j + 1) publish(i, kp);
                 }
             }
         }

@@ -156,7 +156,7 @@ namespace {
 
 template <int DIMS, int STORAGE, bool TRACE>
 int launch_cost_t(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, cudaStream_t st) {
-    const size_t smem = (size_t)32 * (a.W + 1) + sizeof(int) * (a.W + 2) + (STORAGE == 1 ? 1024 : 0);
+    const size_t smem = (size_t)40 * (a.W + 1) + sizeof(int) * (a.W + 2) + (STORAGE == 1 ? 1024 : 0);
     auto kern = k_cost<DIMS, STORAGE, TRACE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(rows, B), tpt, smem, st>>>(mp, a);
@@ -359,7 +359,7 @@ int configure_update(lmcma_b200_opt* o) {
     if (nq > 512) return fail(LMCMA_B200_ERR_ARG, "n = %d too large (max 2048)", o->d.n);
     o->upd_nvb = nq <= 128 ? 4 : 16;
     o->rank_smem = (size_t)2 * TELL_FTILE * 4 + (size_t)3 * TELL_MAX_ROWS * 4 + (size_t)7 * 128 * 16;
-    const size_t fixed = (((size_t)o->d.m * 28 + 8 + 127) & ~(size_t)127) + (size_t)2048 * (UPD_GROUPS - 1);
+    const size_t fixed = (((size_t)o->d.m * 36 + 8 + 127) & ~(size_t)127) + (size_t)2048 * (UPD_GROUPS - 1);
     const size_t rows = (size_t)o->d.m * o->d.ns * sizeof(float);
     const size_t budget = o->props->smem_optin - 2048;            // static shared + slack
     o->upd_rows_in_smem = fixed + rows <= budget;
@@ -760,6 +760,7 @@ int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const doub
 
     const size_t B = d.B, ns = d.ns, lam = d.lambda, pc = d.pop_count, m = d.m;
     DM(d.X, B * pc * ns);
+    DM(d.D, B * pc * ns);
     if (cfg->rng != LMCMA_B200_RNG_PHILOX || cfg->record_z) DM(d.Z, B * pc * ns);
     DM(d.fit, B * lam); DM(d.fit_sorted, B * lam); DM(d.prev_fit, B * lam);
     DM(d.rank, B * lam); DM(d.arindex, B * lam);
@@ -828,7 +829,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     cudaSetDevice(o->cfg.device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     OptDev& d = o->d;
-    void* ptrs[] = {d.X, d.Z, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
+    void* ptrs[] = {d.X, d.D, d.Z, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
                     d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
@@ -1055,9 +1056,7 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
     if (!rc && o->d.dbg) {
         long long h[64];
         cudaMemcpy(h, o->d.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "k_update publish clocks (cycles between consecutive rows):");
-        for (int k = 1; k < 32; ++k) fprintf(stderr, " %lld", h[k] - h[k - 1]);
-        fprintf(stderr, "\nk_sample timeline (CTA 0, ns):");
+        fprintf(stderr, "k_sample timeline (CTA 0, ns):");
         static const char* nm[] = {"start", "griddep", "order", "z ready", "first pairs", "loop done", "end"};
         for (int k = 1; k < 7; ++k) fprintf(stderr, " %s=%lld", nm[k], h[32 + k] - h[32]);
         fprintf(stderr, " | chunk waits:");
@@ -1241,10 +1240,23 @@ int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_
             ARG(count == (int64_t)(B * d.m * d.n), "count");
             o->mirror_dirty = true;
             return h2d_rows(which == LMCMA_B200_F32_V ? d.V : d.P, in, B * d.m, w, p, o->stream);
-        case LMCMA_B200_F32_X:
+        case LMCMA_B200_F32_X: {
             ARG(count == (int64_t)(B * d.pop_count * d.n), "count");
             o->x_cache_valid = false;
+            // keep the offsets d = x - xmean consistent with the overwritten candidates
+            std::vector<double> xm(B * d.n);
+            int rc = d2h_rows(xm.data(), d.xmean, B, d.n * sizeof(double), d.ns * sizeof(double), o->stream);
+            if (rc) return rc;
+            std::vector<float> dd((size_t)count);
+            for (size_t b = 0; b < B; ++b)
+                for (size_t r = 0; r < (size_t)d.pop_count; ++r)
+                    for (int k = 0; k < d.n; ++k) {
+                        const size_t idx = (b * d.pop_count + r) * d.n + k;
+                        dd[idx] = (float)((double)in[idx] - xm[b * d.n + k]);
+                    }
+            if ((rc = h2d_rows(d.D, dd.data(), B * d.pop_count, w, p, o->stream))) return rc;
             return h2d_rows(d.X, in, B * d.pop_count, w, p, o->stream);
+        }
         case LMCMA_B200_F32_PREV_FIT:
             ARG(count == (int64_t)(B * d.lambda), "count");
             CU(cudaMemcpyAsync(d.prev_fit, in, B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, o->stream));

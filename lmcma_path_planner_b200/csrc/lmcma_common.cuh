@@ -38,6 +38,8 @@ struct OptDev {
     // population
     float* X;          // B x pop_count x ns
     float* Z;          // B x pop_count x ns (INJECT / record_z) or null
+    float* D;          // B x pop_count x ns  x - xmean, formed in FP64 and rounded once: FP32 X cannot resolve a step
+                       //                     below ulp(x) (sigma / |x| < 6e-8), the recombination must not depend on it
     float* fit;        // B x lambda   fitness as evaluated / told (all rows, global order)
     float* fit_sorted; // B x lambda
     float* prev_fit;   // B x lambda   previous generation (any order)
@@ -113,6 +115,24 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Packed FP32 (Blackwell FFMA2 / FMUL2: two IEEE fp32 operations per lane per issue slot, each component rounded
+// exactly like the scalar instruction).  The FMA-bound inner loops are issue-slot bound, so this halves their cost.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
 __device__ __forceinline__ float canon_fitness(float f) { return (f != f) ? __int_as_float(0x7f800000) : f; }
 
 // mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) wrappers

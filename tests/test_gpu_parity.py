@@ -420,8 +420,40 @@ def test_cpp_facade_demo_converges_like_the_reference(tmp_path):
     assert rows[0] == "x,y,z," and len(rows) == 1001
 
 
-def test_cpp_planner_driver_writes_a_collision_free_path(tmp_path):
+def test_cpp_planner_driver_improves_on_the_straight_line(tmp_path):
+    """plan() mirrors optimal_palnning_without_setting_path (planner.cpp:694-775) on the two-bar map: the returned
+    path is the one that achieved the returned cost (re-evaluated through the host-buffer entry point), it beats
+    the straight line LM-CMA starts from, and it is written one state per line (printAsMatrix convention)."""
     r = _example(["plan", "path.txt", "300"], tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
+    fields = r.stdout.split()
+    assert float(fields[fields.index("best") + 2]) < float(fields[fields.index("initial") + 2])
     pts = np.loadtxt(tmp_path / "path.txt")
     assert pts.shape == (22, 2) and tuple(pts[0]) == (99.0, 0.0) and tuple(pts[-1]) == (0.0, 99.0)
+
+
+def test_long_free_run_stays_finite_and_tracks_the_oracle(po):
+    """Regression for two FP32 hazards found on the C2 workload once sigma has collapsed (evolution paths nearly
+    collinear with the stored directions, steps below ulp(x)): the recombination works on offsets formed in FP64
+    (OptDev::D), and |v|^2 is a real reduction over the finished row (a scalar recurrence cancels catastrophically).
+    The device runs fused generations; the FP64 oracle is fed the device's deviates and fitness."""
+    W, lam, m = 100, 256, 28
+    dist, start, goal = maps.config2_map(size=1024, n_rects=128, seed=42, clamp=64.0)
+    lo, hi = maps.box_bounds((1024, 1024), W)
+    x0 = maps.straight_line(start, goal, W)
+    cm = L.CostMap(dist, "f32")
+    dev = L.Optimizer(2 * W, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=8.0, seed=5, record_z=True)
+    dev.attach_cost(cm, [start], [goal], W, L.LONGSAFE, 1e4)
+    ora = po.OracleLMCMA(2 * W, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma=8.0, seed=1, Z0=dev.get("Z")[0].astype(np.float64))
+    worst = 0.0
+    for g in range(260):
+        Xd, Xo = dev.get("X")[0], ora.array("X")
+        assert np.isfinite(Xd).all(), g
+        if g < 40:
+            worst = max(worst, float(np.abs(Xd - Xo).max()))
+        dev.run(1)
+        ora.tell_all(dev.get("fit")[0].astype(np.float64), dev.get("Z")[0].astype(np.float64))
+    assert worst < 5e-2, worst                                   # cells; same ranks -> same sigma, FP32 drift only
+    assert np.isfinite(dev.get("V")[0]).all() and np.isfinite(dev.get("xmean")[0]).all()
+    sd, so = float(dev.get("sigma")[0]), ora.doubles()["sigma"]
+    assert abs(sd - so) <= 1e-6 * so                             # sigma depends on the (shared) fitness ranks only
