@@ -439,12 +439,14 @@ int ensure_graph(lmcma_b200_opt* o) {
 
 // dense <-> pitched copies
 int d2h_rows(void* dst, const void* src, size_t rows, size_t width_bytes, size_t src_pitch_bytes, cudaStream_t st) {
-    CU(cudaMemcpy2DAsync(dst, width_bytes, src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, st));
+    if (width_bytes == src_pitch_bytes) CU(cudaMemcpyAsync(dst, src, rows * width_bytes, cudaMemcpyDeviceToHost, st));   // dense: one 1-D copy
+    else CU(cudaMemcpy2DAsync(dst, width_bytes, src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return 0;
 }
 int h2d_rows(void* dst, const void* src, size_t rows, size_t width_bytes, size_t dst_pitch_bytes, cudaStream_t st) {
-    CU(cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, width_bytes, width_bytes, rows, cudaMemcpyHostToDevice, st));
+    if (width_bytes == dst_pitch_bytes) CU(cudaMemcpyAsync(dst, src, rows * width_bytes, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, width_bytes, width_bytes, rows, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
     return 0;
 }
