@@ -124,6 +124,12 @@ typedef struct {
  * Builds the first population unless rng == INJECT (then the first inject_z does). */
 int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const double* lo, const double* hi,
                       lmcma_b200_opt** opt_out);
+/* Same with the reference's `covariance` constructor argument (lmcma.hpp:131-133): a fixed n x n symmetric positive
+ * definite prior (e.g. lmcma_b200_covariance).  It is factored once (cholesky, lmcma.cpp:165-169, 844-855) and every
+ * deviate vector becomes z <- L z before computeAz (sampleStandardNormal + applyCovL, lmcma.cpp:212-218, 857-864):
+ * on the device one FP32 contraction [batch * pop_count x n] x [n x n] per generation.  covariance == NULL -> no prior. */
+int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0, const double* lo, const double* hi,
+                                 const double* covariance, lmcma_b200_opt** opt_out);
 int lmcma_b200_destroy(lmcma_b200_opt* opt);
 
 /* run this handle's work on the caller's stream (void* cudaStream_t; NULL -> the handle's own
@@ -238,6 +244,9 @@ int lmcma_b200_hansen_uniform(int64_t seed, int64_t count, double* out);
 /* Smoothness prior (covariance(), lmcma.cpp:769-810): host-side, heap-allocated (the reference's stack
  * arrays overflow for n >~ 720).  out: (dims*waypoints)^2 doubles, row-major. */
 int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out);
+/* cholesky() (lmcma.cpp:844-855): lower factor of a symmetric positive definite n x n matrix, row-major, zero above
+ * the diagonal (the reference takes Eigen's LLT; this is plain Cholesky-Banachiewicz in FP64). */
+int lmcma_b200_cholesky(int32_t n, const double* C, double* L_out);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,7 @@ static const Weights kLongSafe = {1.0f, 1000.0f};
 //  * pointer arguments are read in init() and COPIED (the reference keeps borrowing lo/hi on every
 //    sample(), lmcma.cpp:222-229);
 //  * inseed < 1 means seed 1, not wall-clock (lmcma.cpp:40-45), so runs are reproducible;
-//  * a `covariance` prior is rejected on this path instead of being ignored;
+//  * a `covariance` prior is factored on the host (plain Cholesky instead of Eigen's LLT) and applied on the device;
 //  * arithmetic on the device is FP32 for the bulk arrays (FP64 for sigma, s, xmean, Nj, Lj).
 // ---------------------------------------------------------------------------------------------------
 class LMCMA {
@@ -64,13 +64,12 @@ public:
     LMCMA& operator=(const LMCMA&) = delete;
 
     void init(int N) {
-        if (cov_) throw Error(LMCMA_B200_ERR_ARG, "lmcma_b200: the covariance prior (applyCovL) is not on the device path yet");
         lmcma_b200_destroy(h_);
         h_ = 0;
         lmcma_b200_config cfg = lmcma_b200_config();
         cfg.n = N; cfg.lambda = lambda_; cfg.m = m_; cfg.batch = 1; cfg.sigma0 = sigma_;
         cfg.seed = seed_ < 1 ? 1 : seed_; cfg.rng = LMCMA_B200_RNG_HANSEN; cfg.device = device_;
-        check(lmcma_b200_create(&cfg, x0_, lo_, hi_, &h_));
+        check(lmcma_b200_create_with_prior(&cfg, x0_, lo_, hi_, cov_, &h_));
         n_ = N; counteval = 0; BestF = DBL_MAX;
     }
     void getNextParameterVector(double* params, int N) { check(lmcma_b200_ask_one(handle(), params, N)); }

@@ -55,6 +55,7 @@ SIGNATURES = {
     "lmcma_b200_cost_evaluate_dev": (C.c_int, [_vp, C.POINTER(Objective), C.POINTER(Endpoints), _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "lmcma_b200_cost_trace": (C.c_int, [_vp, C.POINTER(Objective), C.POINTER(Endpoints), _pf, _pl, _i64, _pl]),
     "lmcma_b200_create": (C.c_int, [C.POINTER(Config), _pd, _pd, _pd, C.POINTER(_vp)]),
+    "lmcma_b200_create_with_prior": (C.c_int, [C.POINTER(Config), _pd, _pd, _pd, _pd, C.POINTER(_vp)]),
     "lmcma_b200_destroy": (C.c_int, [_vp]),
     "lmcma_b200_set_stream": (C.c_int, [_vp, _vp]),
     "lmcma_b200_shape": (C.c_int, [_vp, _pi]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "lmcma_b200_hansen_gauss": (C.c_int, [_i64, _i64, _i64, _pd]),
     "lmcma_b200_hansen_uniform": (C.c_int, [_i64, _i64, _pd]),
     "lmcma_b200_covariance": (C.c_int, [_i32, _i32, _pd]),
+    "lmcma_b200_cholesky": (C.c_int, [_i32, _pd, _pd]),
 }
 
 _lib = None

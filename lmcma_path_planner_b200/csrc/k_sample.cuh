@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
             const int q = lane + 32 * i;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rv && q < nq) {
-                if (o.rng_mode == 0) {
+                if (o.Zc) {                                          // prior: k_prior has already formed L z
+                    v = reinterpret_cast<const float4*>(o.Zc + roff)[q];
+                } else if (o.rng_mode == 0) {
                     v = philox_normal4((unsigned)q, (unsigned)(o.pop_offset + row), (unsigned)sc.itr, (unsigned)b, o.seed);
                     const int e = q * 4;
                     if (e + 1 >= o.n) v.y = 0.f;
@@ -305,7 +307,9 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
         const size_t roff = ((size_t)b * o.pop_count + (row < o.pop_count ? row : 0)) * ns;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (on) {
-            if (o.rng_mode == 0) {
+            if (o.Zc) {                                              // prior: k_prior has already formed L z
+                v = reinterpret_cast<const float4*>(o.Zc + roff)[q];
+            } else if (o.rng_mode == 0) {
                 v = philox_normal4((unsigned)q, (unsigned)(o.pop_offset + row), (unsigned)sc.itr, (unsigned)b, o.seed);
                 const int e = q * 4;
                 if (e + 1 >= o.n) v.y = 0.f;

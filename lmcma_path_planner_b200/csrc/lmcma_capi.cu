@@ -140,6 +140,7 @@ struct lmcma_b200_opt {
     // sample launch config
     int smp_threads = 128, smp_kc = 1, smp_nv = 1, smp_rb = 1, smp_stages = 2;
     bool smp_wide = false; int smp_R = 1, smp_CW = 1, smp_qpw = 32, smp_RBW = 1;
+    float* d_Lf = nullptr;             // lower Cholesky factor of the smoothness prior (n x ns FP32) or null
     bool mirror_dirty = true;          // the sequence-ordered pair mirror must be rebuilt (k_pack_pairs) before sampling
     size_t smp_smem = 0;
     int cost_tpt = 128;
@@ -244,6 +245,18 @@ int ensure_mirror(lmcma_b200_opt* o, cudaStream_t st) {
 // pdl: launched as a programmatic dependent of the kernel enqueued just before it on `st` (k_update)
 int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false) {
     if (o->mirror_dirty) { int rc = ensure_mirror(o, st); if (rc) return rc; pdl = false; }
+    if (o->d_Lf) {   // smoothness prior: z <- L z for the whole population before computeAz (lmcma.cpp:216-217)
+        const OptDev& d = o->d;
+        if (o->cfg.rng == LMCMA_B200_RNG_PHILOX) {
+            k_gauss<<<dim3((d.ns / 4 + 127) / 128, d.pop_count, d.B), 128, 0, st>>>(d);
+            g_launches++;
+        }
+        const int rows = d.B * d.pop_count;
+        k_prior<<<dim3((d.ns + 63) / 64, (rows + 63) / 64), 256, 0, st>>>(d.Z, o->d_Lf, d.Zc, rows, d.n, d.ns);
+        g_launches++;
+        CU(cudaGetLastError());
+        pdl = false;
+    }
     if (o->smp_wide) return launch_sample_wide(o, pdl, st);
     switch (o->smp_nv) {
         case 1: return launch_sample_t<1, 4, 512>(o, pdl, st);
@@ -709,6 +722,11 @@ int lmcma_b200_cost_trace(lmcma_b200_map* m, const lmcma_b200_objective* obj, co
 // =================================================================================================
 int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const double* lo, const double* hi,
                       lmcma_b200_opt** out) {
+    return lmcma_b200_create_with_prior(cfg, x0, lo, hi, nullptr, out);
+}
+
+int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0, const double* lo, const double* hi,
+                                 const double* covariance, lmcma_b200_opt** out) {
     ARG(cfg && out, "null pointer");
     ARG(cfg->n >= 1, "n must be >= 1");
     ARG(cfg->batch >= 1, "batch must be >= 1");
@@ -763,7 +781,18 @@ int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const doub
     const size_t B = d.B, ns = d.ns, lam = d.lambda, pc = d.pop_count, m = d.m;
     DM(d.X, B * pc * ns);
     DM(d.D, B * pc * ns);
-    if (cfg->rng != LMCMA_B200_RNG_PHILOX || cfg->record_z) DM(d.Z, B * pc * ns);
+    if (cfg->rng != LMCMA_B200_RNG_PHILOX || cfg->record_z || covariance) DM(d.Z, B * pc * ns);
+    if (covariance) {   // CMABase::init factors the prior once (cholesky, lmcma.cpp:165-169)
+        std::vector<double> Ld((size_t)d.n * d.n);
+        if (!cholesky_lower(covariance, d.n, Ld.data())) { lmcma_b200_destroy(o); return fail(LMCMA_B200_ERR_ARG, "covariance prior is not symmetric positive definite"); }
+        std::vector<float> Lf((size_t)d.n * ns, 0.f);
+        for (int i = 0; i < d.n; ++i)
+            for (int k = 0; k <= i; ++k) Lf[(size_t)i * ns + k] = (float)Ld[(size_t)i * d.n + k];
+        DM(o->d_Lf, (size_t)d.n * ns);
+        CU(cudaMemcpy(o->d_Lf, Lf.data(), Lf.size() * sizeof(float), cudaMemcpyHostToDevice));
+        d.Lf = o->d_Lf;
+        DM(d.Zc, B * pc * ns);
+    }
     DM(d.fit, B * lam); DM(d.fit_sorted, B * lam); DM(d.prev_fit, B * lam);
     DM(d.rank, B * lam); DM(d.arindex, B * lam);
     DM(d.ncoll, B * pc); DM(d.nsamp, B * pc);
@@ -831,7 +860,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     cudaSetDevice(o->cfg.device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     OptDev& d = o->d;
-    void* ptrs[] = {d.X, d.D, d.Z, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
+    void* ptrs[] = {d.X, d.D, d.Z, d.Zc, o->d_Lf, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
                     d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
@@ -977,7 +1006,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
         if ((rc = ensure_graph(o))) return rc;
         for (int g = 0; g < generations; ++g) {
             CU(cudaGraphLaunch(o->graph_exec, o->stream));
-            g_launches += 4;
+            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0);
         }
     } else {
         if (o->cfg.rng == LMCMA_B200_RNG_INJECT && generations > 1)
@@ -1362,6 +1391,12 @@ int lmcma_b200_hansen_uniform(int64_t seed, int64_t count, double* out) {
 int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out) {
     ARG(out && dims >= 1 && waypoints >= 1, "bad argument");
     if (!smoothness_covariance(dims, waypoints, out)) return fail(LMCMA_B200_ERR_ARG, "singular finite-difference block");
+    return 0;
+}
+
+int lmcma_b200_cholesky(int32_t n, const double* Cm, double* L_out) {
+    ARG(Cm && L_out && n >= 1, "bad argument");
+    if (!cholesky_lower(Cm, n, L_out)) return fail(LMCMA_B200_ERR_ARG, "matrix is not symmetric positive definite");
     return 0;
 }
 

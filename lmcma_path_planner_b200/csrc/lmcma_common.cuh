@@ -38,6 +38,8 @@ struct OptDev {
     // population
     float* X;          // B x pop_count x ns
     float* Z;          // B x pop_count x ns (INJECT / record_z) or null
+    float* Zc;         // B x pop_count x ns  L z (smoothness prior, k_prior.cuh) or null: what computeAz sees
+    const float* Lf;   // n x ns lower Cholesky factor of the prior (FP32) or null
     float* D;          // B x pop_count x ns  x - xmean, formed in FP64 and rounded once: FP32 X cannot resolve a step
                        //                     below ulp(x) (sigma / |x| < 6e-8), the recombination must not depend on it
     float* fit;        // B x lambda   fitness as evaluated / told (all rows, global order)

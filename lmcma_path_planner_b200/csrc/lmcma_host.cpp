@@ -60,4 +60,20 @@ bool smoothness_covariance(int dims, int waypoints, double* out) {
     return true;
 }
 
+bool cholesky_lower(const double* C, int n, double* L) {
+    std::memset(L, 0, sizeof(double) * static_cast<size_t>(n) * n);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {                      // Cholesky-Banachiewicz, row by row
+            double s = C[static_cast<size_t>(i) * n + j];
+            for (int k = 0; k < j; ++k) s -= L[static_cast<size_t>(i) * n + k] * L[static_cast<size_t>(j) * n + k];
+            if (i == j) {
+                if (!(s > 0.0)) return false;
+                L[static_cast<size_t>(i) * n + i] = std::sqrt(s);
+            } else {
+                L[static_cast<size_t>(i) * n + j] = s / L[static_cast<size_t>(j) * n + j];
+            }
+        }
+    return true;
+}
+
 }  // namespace lmcma

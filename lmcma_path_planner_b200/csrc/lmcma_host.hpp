@@ -63,4 +63,8 @@ private:
 // Returns false if a block is singular.
 bool smoothness_covariance(int dims, int waypoints, double* out);
 
+// Lower Cholesky factor of a symmetric positive definite n x n matrix (cholesky(), lmcma.cpp:844-855, which takes
+// Eigen's LLT): L row-major, zero above the diagonal.  Returns false if C is not positive definite.
+bool cholesky_lower(const double* C, int n, double* L);
+
 }  // namespace lmcma

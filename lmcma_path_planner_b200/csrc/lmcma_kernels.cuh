@@ -4,3 +4,4 @@
 #include "k_rank.cuh"
 #include "k_sample.cuh"
 #include "k_update.cuh"
+#include "k_prior.cuh"

@@ -106,7 +106,7 @@ class Optimizer:
     """B independent LM-CMA instances of one shape on one device."""
 
     def __init__(self, n, x0=None, lam=0, m=0, batch=1, lo=None, hi=None, sigma0=1.0, seed=1, rng="philox",
-                 device=0, record_z=False, pop_offset=0, pop_count=0):
+                 device=0, record_z=False, pop_offset=0, pop_count=0, covariance=None):
         cfg = K.Config()
         cfg.n, cfg.lambda_, cfg.m, cfg.batch = int(n), int(lam), int(m), int(batch)
         cfg.sigma0, cfg.seed = float(sigma0), int(seed)
@@ -116,10 +116,11 @@ class Optimizer:
         x0a = None if x0 is None else K.f64c(np.broadcast_to(np.asarray(x0, np.float64), (batch, n)) if np.ndim(x0) == 1 else x0)
         loa = None if lo is None else K.f64c(lo)
         hia = None if hi is None else K.f64c(hi)
+        cva = None if covariance is None else K.f64c(np.asarray(covariance, np.float64).reshape(n, n))
         h = C.c_void_p()
-        K.check(K.lib().lmcma_b200_create(C.byref(cfg), None if x0a is None else K.dptr(x0a),
-                                         None if loa is None else K.dptr(loa), None if hia is None else K.dptr(hia),
-                                         C.byref(h)))
+        K.check(K.lib().lmcma_b200_create_with_prior(C.byref(cfg), None if x0a is None else K.dptr(x0a),
+                                                    None if loa is None else K.dptr(loa), None if hia is None else K.dptr(hia),
+                                                    None if cva is None else K.dptr(cva), C.byref(h)))
         self._h = h
         shp = np.zeros(8, np.int32)
         K.check(K.lib().lmcma_b200_shape(h, K.iptr(shp)))
@@ -273,14 +274,12 @@ class LMCMA:
     """The reference's class shape (lmcma.hpp:131-138).  Differences, all deliberate:
     arrays are copied at construction (the reference borrows the pointers, lmcma.cpp:109-110);
     ``inseed < 1`` means seed 1, not wall-clock (lmcma.cpp:40-45), so runs are reproducible;
-    ``covariance`` is not supported on this path yet and raises."""
+    ``covariance`` (n x n, symmetric positive definite) enables the smoothness-prior sampling path."""
 
     def __init__(self, initialParams, lambda_=0, loBounds=None, hiBounds=None, sigma=1.0, covariance=None,
                  inseed=0, verbose=False, m=0, device=0):
-        if covariance is not None:
-            raise NotImplementedError("smoothness-prior sampling (applyCovL, lmcma.cpp:857-864) is not on the device path yet")
         self._args = dict(x0=initialParams, lam=lambda_, m=m, lo=loBounds, hi=hiBounds, sigma0=sigma,
-                          seed=max(1, int(inseed)), device=device)
+                          seed=max(1, int(inseed)), device=device, covariance=covariance)
         self.verbose = verbose
         self.counteval = 0
         self.BestF = np.finfo(np.float64).max

@@ -137,3 +137,17 @@ def test_cpp_example_fails_loudly_without_a_gpu(tmp_path):
     import subprocess
     r = subprocess.run([EXAMPLE, "demo"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert r.returncode == 3 and "lmcma_b200" in r.stderr
+
+
+def test_cholesky_matches_numpy_and_rejects_indefinite(golden):
+    """cholesky() of the reference (lmcma.cpp:844-855) restated on the host: L L^T = C for the smoothness prior."""
+    cov = np.array(golden["covariance_2_10_shim_pinned"]).reshape(20, 20)
+    Lm = np.zeros((20, 20))
+    assert K.lib().lmcma_b200_cholesky(20, K.dptr(K.f64c(cov)), K.dptr(Lm)) == 0
+    assert np.allclose(Lm, np.linalg.cholesky(cov), rtol=1e-12, atol=1e-15)
+    assert np.all(np.triu(Lm, 1) == 0)
+    bad = np.eye(3); bad[2, 2] = -1.0
+    assert K.lib().lmcma_b200_cholesky(3, K.dptr(K.f64c(bad)), K.dptr(np.zeros((3, 3)))) == K.ERR_ARG
+    ours = np.zeros(400)
+    assert K.lib().lmcma_b200_covariance(2, 10, K.dptr(ours)) == 0
+    assert np.allclose(ours, golden["covariance_2_10_shim_pinned"], rtol=1e-9, atol=1e-12)

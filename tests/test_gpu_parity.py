@@ -457,3 +457,31 @@ def test_long_free_run_stays_finite_and_tracks_the_oracle(po):
     assert np.isfinite(dev.get("V")[0]).all() and np.isfinite(dev.get("xmean")[0]).all()
     sd, so = float(dev.get("sigma")[0]), ora.doubles()["sigma"]
     assert abs(sd - so) <= 1e-6 * so                             # sigma depends on the (shared) fitness ranks only
+
+
+def test_smoothness_prior_sampling_matches_the_reference(golden):
+    """The covariance-prior path (cholesky + applyCovL before computeAz, lmcma.cpp:165-169, 216-217, 844-864) against
+    the compiled reference (Eigen stand-in: shim-pinned): same Hansen stream, prior = covariance(2, 10).  The first
+    population is x0 + sigma L z exactly; later generations are compared free-running over a short window."""
+    g = golden["run_prior_shim_pinned"]
+    cov = np.array(golden["covariance_2_10_shim_pinned"]).reshape(20, 20)
+    opt = L.LMCMA(np.array(g["x0"]), lambda_=g["lambda"], sigma=g["sigma0"], covariance=cov, inseed=1)
+    opt.init(20)
+    for gen in range(4):
+        ref = g["gens"][gen]
+        for i in range(g["lambda"]):
+            xi = opt.getNextParameterVector()
+            tol = 2e-5 if gen == 0 else 2e-3
+            assert np.allclose(xi, np.array(ref["X"][i]), rtol=tol, atol=tol), (gen, i, np.abs(xi - np.array(ref["X"][i])).max())
+            opt.setEvaluationFeedback(ref["f"][i])      # the reference's fitness: identical ranks on both sides
+        assert abs(opt._opt.get("sigma")[0] - g["sigma"][gen + 1]) < 1e-9 * g["sigma"][gen + 1]
+    # throughput mode: device Philox deviates through the same contraction, large population (tiled kernel, wide sampler)
+    n, lam = 400, 512
+    big = np.zeros(n * n)
+    from lmcma_path_planner_b200 import _capi as K
+    assert K.lib().lmcma_b200_covariance(2, 200, K.dptr(big)) == 0
+    big = big.reshape(n, n)
+    dev = L.Optimizer(n, x0=np.zeros(n), lam=lam, sigma0=1.0, seed=3, record_z=True, covariance=big)
+    Z, X = dev.get("Z")[0].astype(np.float64), dev.get("X")[0].astype(np.float64)
+    want = Z @ np.linalg.cholesky(big).T                          # no pairs yet: x = x0 + sigma * L z
+    assert np.abs(X - want).max() < 1e-5 * max(1.0, np.abs(want).max())
