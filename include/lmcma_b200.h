@@ -64,6 +64,14 @@ int lmcma_b200_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t
  * c_min: floor on the clearance used in the state cost 1/clearance (planner.cpp:667). */
 int lmcma_b200_map_create(int device, int dims, const int32_t* shape_xyz, const float* dist_host,
                           int storage, float u8_scale, float c_min, lmcma_b200_map** map_out);
+/* Occupancy grid (1 = obstacle; row-major [ny][nx] / [nz][ny][nx]) -> exact Euclidean distance field in cells, on the
+ * device (separable, integer-exact; k_edt.cuh).  Replaces the reference's ways of obtaining EDT_Matrix from a map:
+ * the in-file 8SSEDT on a fixed 100 x 100 grid (planner.cpp:403-490) and dynamicEDT3D (planner.cpp:81-87, 305-307).
+ * clamp > 0 limits the distance (dynamicEDT3D's maxdist); clamp <= 0 leaves it unbounded. */
+int lmcma_b200_edt(int device, int dims, const int32_t* shape_xyz, const uint8_t* occ_host, float clamp, float* dist_host_out);
+/* map_create fed by an occupancy grid: distance transform + conversion to the map storage, all on the device */
+int lmcma_b200_map_create_from_occupancy(int device, int dims, const int32_t* shape_xyz, const uint8_t* occ_host, float clamp,
+                                         int storage, float u8_scale, float c_min, lmcma_b200_map** map_out);
 int lmcma_b200_map_destroy(lmcma_b200_map* map);
 /* the distance field the evaluator effectively uses, back on the host (identity for F32 storage) */
 int lmcma_b200_map_dequantized(const lmcma_b200_map* map, float* dist_host_out);
@@ -247,6 +255,18 @@ int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out);
 /* cholesky() (lmcma.cpp:844-855): lower factor of a symmetric positive definite n x n matrix, row-major, zero above
  * the diagonal (the reference takes Eigen's LLT; this is plain Cholesky-Banachiewicz in FP64). */
 int lmcma_b200_cholesky(int32_t n, const double* C, double* L_out);
+
+/* ---------------------------------------------------------------- map ingest (host-side file parsing) ---------- */
+/* All three: pass out == NULL to query the size first.
+ * BMP (24/32-bit, uncompressed): occupancy with the reference's rule g < 128 -> obstacle (Signed_Distance_Fields_test,
+ * planner.cpp:505-523); rows top to bottom, occ_out[y * width + x]. */
+int lmcma_b200_load_bmp(const char* path, uint8_t* occ_out, int64_t capacity, int32_t* width, int32_t* height);
+/* binvox run-length voxel grid (format as read by binvox2bt.cpp:164-285; files under .../files/mesh_files):
+ * occ_out[(z * ny + y) * nx + x], shape_xyz = {nx, ny, nz}; translate / scale from the header (nullable). */
+int lmcma_b200_load_binvox(const char* path, uint8_t* occ_out, int64_t capacity, int32_t* shape_xyz, double* translate_xyz,
+                           double* scale);
+/* comma-separated matrix, one row per line: the file populate_EDT_Matrix_old reads into EDT_Matrix (planner.cpp:777-818) */
+int lmcma_b200_load_text_matrix(const char* path, double* out, int64_t capacity, int32_t* rows, int32_t* cols);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,12 @@ SIGNATURES = {
     "lmcma_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "lmcma_b200_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), _pl, _pl, C.POINTER(C.c_int)]),
     "lmcma_b200_map_create": (C.c_int, [C.c_int, C.c_int, _pi, _pf, C.c_int, C.c_float, C.c_float, C.POINTER(_vp)]),
+    "lmcma_b200_edt": (C.c_int, [C.c_int, C.c_int, _pi, C.POINTER(C.c_uint8), C.c_float, _pf]),
+    "lmcma_b200_map_create_from_occupancy": (C.c_int, [C.c_int, C.c_int, _pi, C.POINTER(C.c_uint8), C.c_float, C.c_int, C.c_float,
+                                                     C.c_float, C.POINTER(_vp)]),
+    "lmcma_b200_load_bmp": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint8), _i64, _pi, _pi]),
+    "lmcma_b200_load_binvox": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint8), _i64, _pi, _pd, _pd]),
+    "lmcma_b200_load_text_matrix": (C.c_int, [C.c_char_p, _pd, _i64, _pi, _pi]),
     "lmcma_b200_map_destroy": (C.c_int, [_vp]),
     "lmcma_b200_map_dequantized": (C.c_int, [_vp, _pf]),
     "lmcma_b200_map_set_l2_persist": (C.c_int, [_vp, C.c_int]),

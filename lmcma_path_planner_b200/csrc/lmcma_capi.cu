@@ -59,6 +59,21 @@ int dmalloc(T** p, size_t count) {
         if (rc__) return rc__;                      \
     } while (0)
 
+}  // namespace
+namespace lmcma {
+// error reporting for the other translation units of the library (lmcma_ingest.cpp)
+int set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace lmcma
+namespace {
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -493,9 +508,10 @@ int lmcma_b200_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t
 // =================================================================================================
 // cost map
 // =================================================================================================
-int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const float* dist, int storage, float u8_scale,
-                          float c_min, lmcma_b200_map** out) {
-    ARG(out && shape && dist, "null pointer");
+// handle + device buffers + LUT of a cost map (no contents yet)
+extern "C" int lmcma_b200_map_destroy(lmcma_b200_map* m);
+static int map_alloc(int device, int dims, const int32_t* shape, int storage, float u8_scale, float c_min, lmcma_b200_map** out) {
+    ARG(out && shape, "null pointer");
     ARG(dims == 2 || dims == 3, "dims must be 2 or 3");
     ARG(storage == LMCMA_B200_MAP_F32 || storage == LMCMA_B200_MAP_U8, "unknown storage");
     ARG(c_min > 0.f, "c_min must be > 0");
@@ -510,9 +526,6 @@ int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const floa
     m->dev.dims = dims; m->dev.nx = shape[0]; m->dev.ny = shape[1]; m->dev.nz = dims == 3 ? shape[2] : 1;
     m->dev.storage = storage; m->dev.g_coll = 1.0f / c_min;
     m->cells = (size_t)m->dev.nx * m->dev.ny * m->dev.nz;
-    CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    // the transform E -> stored representation (values + bricked layout, lmcma_layout.hpp) is a one-off
-    // host pass on the upload path, not the hot path
     const BrickShape bs = dims == 2 ? (storage == 0 ? brick_shape<2, 0>() : brick_shape<2, 1>())
                                     : (storage == 0 ? brick_shape<3, 0>() : brick_shape<3, 1>());
     const unsigned nbx = (m->dev.nx + bs.bx - 1) / bs.bx, nby = (m->dev.ny + bs.by - 1) / bs.by,
@@ -520,41 +533,132 @@ int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const floa
     m->dev.nbx = nbx; m->dev.nby = nby;
     m->stored = (size_t)nbx * nby * nbz * bs.bx * bs.by * bs.bz;
     if (m->stored >= ((size_t)1 << 32)) { delete m; return fail(LMCMA_B200_ERR_ARG, "map too large: %zu stored cells (limit 2^32)", m->stored); }
-    auto offset_of = [&](unsigned x, unsigned y, unsigned z) -> size_t {
-        if (dims == 2) return storage == 0 ? brick_offset<2, 0>(x, y, z, nbx, nby) : brick_offset<2, 1>(x, y, z, nbx, nby);
-        return storage == 0 ? brick_offset<3, 0>(x, y, z, nbx, nby) : brick_offset<3, 1>(x, y, z, nbx, nby);
-    };
-    if (storage == LMCMA_B200_MAP_F32) {
-        std::vector<float> g(m->stored, -m->dev.g_coll);          // padding cells are never addressed
-        for (int z = 0; z < m->dev.nz; ++z)
-            for (int y = 0; y < m->dev.ny; ++y)
-                for (int x = 0; x < m->dev.nx; ++x) {
-                    const float e = dist[((size_t)z * m->dev.ny + y) * m->dev.nx + x];
-                    g[offset_of(x, y, z)] = (e > 0.f) ? 1.0f / std::max(e, c_min) : -m->dev.g_coll;
-                }
-        DM(m->d_g32, m->stored);
-        CU(cudaMemcpy(m->d_g32, g.data(), m->stored * sizeof(float), cudaMemcpyHostToDevice));
-        m->dev.g32 = m->d_g32;
-    } else {
-        std::vector<unsigned char> q(m->stored, 0);
-        for (int z = 0; z < m->dev.nz; ++z)
-            for (int y = 0; y < m->dev.ny; ++y)
-                for (int x = 0; x < m->dev.nx; ++x) {
-                    const float e = dist[((size_t)z * m->dev.ny + y) * m->dev.nx + x];
-                    int v = 0;
-                    if (e > 0.f) { v = (int)std::floor(e / u8_scale); v = std::min(255, std::max(1, v)); }
-                    q[offset_of(x, y, z)] = (unsigned char)v;
-                }
-        float lut[256];
-        lut[0] = -m->dev.g_coll;
-        for (int v = 1; v < 256; ++v) lut[v] = 1.0f / std::max((float)v * u8_scale, c_min);
-        DM(m->d_q8, m->stored);
-        DM(m->d_lut, 256);
-        CU(cudaMemcpy(m->d_q8, q.data(), m->stored, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(m->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    rc = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    if (!rc && storage == LMCMA_B200_MAP_F32) { rc = dmalloc(&m->d_g32, m->stored); m->dev.g32 = m->d_g32; }   // padding cells are never addressed
+    if (!rc && storage == LMCMA_B200_MAP_U8) {
+        rc = dmalloc(&m->d_q8, m->stored);
+        if (!rc) rc = dmalloc(&m->d_lut, 256);
+        if (!rc) {
+            float lut[256];
+            lut[0] = -m->dev.g_coll;
+            for (int v = 1; v < 256; ++v) lut[v] = 1.0f / std::max((float)v * u8_scale, c_min);
+            e = cudaMemcpy(m->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
+        }
         m->dev.q8 = m->d_q8; m->dev.lut = m->d_lut;
     }
-    DM(m->d_ends, 6);
+    if (!rc) rc = dmalloc(&m->d_ends, 6);
+    if (rc) { lmcma_b200_map_destroy(m); return rc; }
+    *out = m;
+    return 0;
+}
+
+// row-major distance field on the device -> the bricked storage (values + layout, lmcma_layout.hpp)
+static int map_fill_from_dist_dev(lmcma_b200_map* m, const float* d_dist, cudaStream_t st) {
+    const MapDev& d = m->dev;
+    const unsigned blocks = (unsigned)((m->cells + 255) / 256);
+    if (d.dims == 2) {
+        if (m->storage == 0) k_brick<2, 0><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
+        else k_brick<2, 1><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
+    } else {
+        if (m->storage == 0) k_brick<3, 0><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
+        else k_brick<3, 1><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
+    }
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// exact Euclidean distance transform on the device (k_edt.cuh): d_occ (1 = obstacle) -> d_dist, both row-major [z][y][x]
+static int edt_device(int dims, const int32_t* shape, const unsigned char* d_occ, float clamp, float* d_dist, cudaStream_t st) {
+    const int nx = shape[0], ny = shape[1], nz = dims == 3 ? shape[2] : 1;
+    ARG(nx <= 32767 && ny <= 32767 && nz <= 32767, "axis longer than 32767 cells");
+    const size_t cells = (size_t)nx * ny * nz;
+    int *d2 = nullptr, *s = nullptr, *t = nullptr, *gh = nullptr;
+    int rc = dmalloc(&d2, cells);
+    if (!rc) rc = dmalloc(&s, cells);
+    if (!rc) rc = dmalloc(&t, cells);
+    if (!rc) rc = dmalloc(&gh, cells);
+    if (!rc) {
+        const long long nlines = (long long)ny * nz;
+        k_edt_x<<<(unsigned)((nlines + 7) / 8), 256, 0, st>>>(d_occ, d2, nx, nlines);
+        g_launches++;
+        if (ny > 1) {
+            const long long lines = (long long)nx * nz;
+            k_edt_axis<<<(unsigned)((lines + 127) / 128), 128, 0, st>>>(d2, ny, nx, nx, nz, (long long)nx * ny, s, t, gh);
+            g_launches++;
+        }
+        if (nz > 1) {
+            const long long lines = (long long)nx * ny;
+            k_edt_axis<<<(unsigned)((lines + 127) / 128), 128, 0, st>>>(d2, nz, (long long)nx * ny, nx * ny, 1, 0, s, t, gh);
+            g_launches++;
+        }
+        k_edt_finish<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(d2, d_dist, (long long)cells, clamp);
+        g_launches++;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "distance transform: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d2); cudaFree(s); cudaFree(t); cudaFree(gh);
+    return rc;
+}
+
+int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const float* dist, int storage, float u8_scale,
+                          float c_min, lmcma_b200_map** out) {
+    ARG(dist, "null pointer");
+    lmcma_b200_map* m = nullptr;
+    int rc = map_alloc(device, dims, shape, storage, u8_scale, c_min, &m);
+    if (rc) return rc;
+    float* d_dist = nullptr;
+    rc = dmalloc(&d_dist, m->cells);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(d_dist, dist, m->cells * sizeof(float), cudaMemcpyHostToDevice, m->stream);
+        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = map_fill_from_dist_dev(m, d_dist, m->stream);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(m->stream); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "map upload: %s", cudaGetErrorString(e)); }
+    cudaFree(d_dist);
+    if (rc) { lmcma_b200_map_destroy(m); return rc; }
+    *out = m;
+    return 0;
+}
+
+int lmcma_b200_edt(int device, int dims, const int32_t* shape, const uint8_t* occ_host, float clamp, float* dist_host_out) {
+    ARG(shape && occ_host && dist_host_out, "null pointer");
+    ARG(dims == 2 || dims == 3, "dims must be 2 or 3");
+    for (int c = 0; c < dims; ++c) ARG(shape[c] >= 1, "bad shape");
+    DeviceProps* props;
+    int rc = query_props(device, &props);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    const size_t cells = (size_t)shape[0] * shape[1] * (dims == 3 ? shape[2] : 1);
+    unsigned char* d_occ = nullptr; float* d_dist = nullptr;
+    rc = dmalloc(&d_occ, cells);
+    if (!rc) rc = dmalloc(&d_dist, cells);
+    if (!rc) { cudaError_t e = cudaMemcpy(d_occ, occ_host, cells, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
+    if (!rc) rc = edt_device(dims, shape, d_occ, clamp, d_dist, 0);
+    if (!rc) { cudaError_t e = cudaMemcpy(dist_host_out, d_dist, cells * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
+    cudaFree(d_occ); cudaFree(d_dist);
+    return rc;
+}
+
+int lmcma_b200_map_create_from_occupancy(int device, int dims, const int32_t* shape, const uint8_t* occ_host, float clamp, int storage,
+                                         float u8_scale, float c_min, lmcma_b200_map** out) {
+    ARG(occ_host, "null pointer");
+    lmcma_b200_map* m = nullptr;
+    int rc = map_alloc(device, dims, shape, storage, u8_scale, c_min, &m);
+    if (rc) return rc;
+    unsigned char* d_occ = nullptr; float* d_dist = nullptr;
+    rc = dmalloc(&d_occ, m->cells);
+    if (!rc) rc = dmalloc(&d_dist, m->cells);
+    if (!rc) { cudaError_t e = cudaMemcpy(d_occ, occ_host, m->cells, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
+    if (!rc) rc = edt_device(dims, shape, d_occ, clamp, d_dist, m->stream);
+    if (!rc) rc = map_fill_from_dist_dev(m, d_dist, m->stream);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(m->stream); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "map build: %s", cudaGetErrorString(e)); }
+    cudaFree(d_occ); cudaFree(d_dist);
+    if (rc) { lmcma_b200_map_destroy(m); return rc; }
     *out = m;
     return 0;
 }

@@ -5,3 +5,4 @@
 #include "k_sample.cuh"
 #include "k_update.cuh"
 #include "k_prior.cuh"
+#include "k_edt.cuh"

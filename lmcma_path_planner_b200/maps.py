@@ -113,3 +113,50 @@ def random_queries(dist, count, seed, min_sep):
                 starts.append(a[i][::-1].astype(np.float32))
                 goals.append(b[i][::-1].astype(np.float32))
     return np.array(starts), np.array(goals)
+
+
+# ---- the library's map ingest / distance transform entry points (include/lmcma_b200.h) ----
+def load_bmp(path):
+    """Occupancy (1 = obstacle, the reference's g < 128 rule) of a 24/32-bit BMP as uint8 [height, width]."""
+    import ctypes as C
+    from . import _capi as K
+    w, h = C.c_int32(0), C.c_int32(0)
+    K.check(K.lib().lmcma_b200_load_bmp(path.encode(), None, 0, C.byref(w), C.byref(h)))
+    occ = np.zeros((h.value, w.value), np.uint8)
+    K.check(K.lib().lmcma_b200_load_bmp(path.encode(), occ.ctypes.data_as(C.POINTER(C.c_uint8)), occ.size, C.byref(w), C.byref(h)))
+    return occ
+
+
+def load_binvox(path):
+    """Dense voxel occupancy [nz, ny, nx] (uint8) + header (translate, scale) of a binvox file."""
+    import ctypes as C
+    from . import _capi as K
+    shp = np.zeros(3, np.int32)
+    tr = np.zeros(3, np.float64)
+    sc = C.c_double(0)
+    K.check(K.lib().lmcma_b200_load_binvox(path.encode(), None, 0, K.iptr(shp), K.dptr(tr), C.byref(sc)))
+    occ = np.zeros((int(shp[2]), int(shp[1]), int(shp[0])), np.uint8)
+    K.check(K.lib().lmcma_b200_load_binvox(path.encode(), occ.ctypes.data_as(C.POINTER(C.c_uint8)), occ.size, K.iptr(shp), K.dptr(tr),
+                                         C.byref(sc)))
+    return occ, tr, sc.value
+
+
+def load_text_matrix(path):
+    import ctypes as C
+    from . import _capi as K
+    r, c = C.c_int32(0), C.c_int32(0)
+    K.check(K.lib().lmcma_b200_load_text_matrix(path.encode(), None, 0, C.byref(r), C.byref(c)))
+    out = np.zeros((r.value, c.value), np.float64)
+    K.check(K.lib().lmcma_b200_load_text_matrix(path.encode(), K.dptr(out), out.size, C.byref(r), C.byref(c)))
+    return out
+
+
+def edt_device(occ, clamp=0.0, device=0):
+    """Exact Euclidean distance transform on the GPU (k_edt.cuh): occupancy (non-zero = obstacle) -> float32 distances."""
+    import ctypes as C
+    from . import _capi as K
+    o = np.ascontiguousarray(np.asarray(occ) != 0, np.uint8)
+    shp = np.array(o.shape[::-1], np.int32)
+    out = np.zeros(o.shape, np.float32)
+    K.check(K.lib().lmcma_b200_edt(device, o.ndim, K.iptr(shp), o.ctypes.data_as(C.POINTER(C.c_uint8)), float(clamp), K.fptr(out)))
+    return out

@@ -53,6 +53,22 @@ class CostMap:
         self._h = h
         self.bytes_per_cell = 4 if self.storage == K.MAP_F32 else 1
 
+    @classmethod
+    def from_occupancy(cls, occ, clamp=0.0, storage="f32", u8_scale=0.25, c_min=0.5, device=0):
+        """Occupancy grid (non-zero = obstacle) -> distance transform + map storage, all on the device."""
+        o = np.ascontiguousarray(np.asarray(occ) != 0, np.uint8)
+        self = cls.__new__(cls)
+        self.dims, self.shape = o.ndim, o.shape
+        self.storage = {"f32": K.MAP_F32, "u8": K.MAP_U8}[storage]
+        self.c_min, self.device = float(c_min), device
+        shp = np.array(o.shape[::-1], np.int32)
+        h = C.c_void_p()
+        K.check(K.lib().lmcma_b200_map_create_from_occupancy(device, o.ndim, K.iptr(shp), o.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                             float(clamp), self.storage, float(u8_scale), float(c_min), C.byref(h)))
+        self._h = h
+        self.bytes_per_cell = 4 if self.storage == K.MAP_F32 else 1
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             K.lib().lmcma_b200_map_destroy(self._h)

@@ -485,3 +485,37 @@ def test_smoothness_prior_sampling_matches_the_reference(golden):
     Z, X = dev.get("Z")[0].astype(np.float64), dev.get("X")[0].astype(np.float64)
     want = Z @ np.linalg.cholesky(big).T                          # no pairs yet: x = x0 + sigma * L z
     assert np.abs(X - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+
+
+# ------------------------------------------------------------------------------------------------
+# distance transform on the device
+# ------------------------------------------------------------------------------------------------
+def test_edt_device_is_exact(po, golden_maps):
+    """k_edt against scipy's exact EDT (bit-equal: integer squared distances, one FP64 sqrt rounded to FP32) on the
+    reference's 100 x 100 maps, random 2-D / 3-D grids with odd sizes, and the clamp; the 8SSEDT the reference uses
+    (planner.cpp:403-490) is only approximate, so it is compared with a tolerance of one cell."""
+    rng = np.random.default_rng(2)
+    cases = [golden_maps["problem1"], golden_maps["two_bars"], (rng.random((37, 53)) < 0.05), (rng.random((130, 257)) < 0.002),
+             (rng.random((9, 21, 34)) < 0.03), (rng.random((40, 33, 65)) < 0.001)]
+    for occ in cases:
+        want = po.edt_exact(np.asarray(occ, np.uint8))
+        got = maps.edt_device(occ)
+        assert np.array_equal(got, want), (np.asarray(occ).shape, float(np.abs(got - want).max()))
+    occ = cases[3]
+    assert np.array_equal(maps.edt_device(occ, clamp=7.5), np.minimum(po.edt_exact(np.asarray(occ, np.uint8)), np.float32(7.5)))
+    sd = po.ssedt8_signed(golden_maps["problem1"])                        # int(sqrt(d1)) - int(sqrt(d2)) of the reference
+    ours = np.floor(maps.edt_device(golden_maps["problem1"])) - np.floor(maps.edt_device(1 - golden_maps["problem1"]))
+    assert np.abs(ours - sd).max() <= 1
+
+
+def test_map_from_occupancy_equals_map_from_distance_field(po):
+    """distance transform + bricking on the device == host EDT + lmcma_b200_map_create: identical costs and collisions."""
+    rng = np.random.default_rng(4)
+    occ = maps.random_boxes_occupancy((200, 300), 12, 5, 30, seed=9, border=2, clear=[((20.0, 20.0), 12.0), ((280.0, 180.0), 12.0)])
+    W, start, goal = 30, (20.0, 20.0), (280.0, 180.0)
+    lo, hi = maps.box_bounds((300, 200), W)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 64, 9.0, lo, hi)
+    for storage in ("f32", "u8"):
+        a = L.CostMap(maps.distance_field(occ, 40.0), storage).evaluate(X, start, goal, W)
+        b = L.CostMap.from_occupancy(occ, 40.0, storage).evaluate(X, start, goal, W)
+        assert np.array_equal(a["ncoll"], b["ncoll"]) and np.array_equal(a["f"], b["f"])
