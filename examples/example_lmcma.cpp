@@ -3,6 +3,9 @@
 //
 //   example_lmcma demo  [seed]                    two-Gaussian test function, reference ask/tell protocol,
 //                                                 writes path_to_min.csv like the reference demo
+//   example_lmcma planfile <map.bmp|map.binvox> <start> <goal> <out.txt> [generations] [waypoints] [lambda]
+//                                                 start / goal as x,y or x,y,z (cells): load the map (g < 128 rule /
+//                                                 binvox voxels), distance transform + planning on the device
 //   example_lmcma plan  [out.txt] [generations]   one 2-D query (99,0)->(0,99) on the reference's hard-coded
 //                                                 two-bar 100x100 map, fused on-device planner; the path is
 //                                                 written one state per line (OMPL printAsMatrix convention)
@@ -10,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <fstream>
+#include <string>
 #include <vector>
 
 #include "lmcma_b200.hpp"
@@ -95,10 +100,68 @@ int plan(const char* out_path, int generations) {
     return (std::fabs(best - f) <= 1e-5f * std::fabs(f) && best < f0) ? 0 : 1;
 }
 
+int parse_point(const char* s, float* p) {
+    int n = 0;
+    char* end = const_cast<char*>(s);
+    while (*end && n < 3) {
+        p[n++] = std::strtof(end, &end);
+        if (*end == ',') ++end;
+    }
+    return n;
+}
+
+// a map file -> occupancy -> distance field + planner, everything after the file parser on the device
+int planfile(int argc, char** argv) {
+    if (argc < 6) { std::fprintf(stderr, "usage: example_lmcma planfile <map.bmp|map.binvox> <start> <goal> <out.txt> [generations] [waypoints] [lambda]\n"); return 2; }
+    const std::string map_path = argv[2];
+    float start[3] = {0, 0, 0}, goal[3] = {0, 0, 0};
+    const int ds = parse_point(argv[3], start), dg = parse_point(argv[4], goal);
+    const bool is_vox = map_path.size() > 7 && map_path.compare(map_path.size() - 7, 7, ".binvox") == 0;
+    int32_t shape[3] = {1, 1, 1};
+    std::vector<uint8_t> occ;
+    int dims = 2;
+    if (is_vox) {
+        dims = 3;
+        lmcma_b200::check(lmcma_b200_load_binvox(map_path.c_str(), 0, 0, shape, 0, 0));
+        occ.resize((size_t)shape[0] * shape[1] * shape[2]);
+        lmcma_b200::check(lmcma_b200_load_binvox(map_path.c_str(), occ.data(), (int64_t)occ.size(), shape, 0, 0));
+    } else {
+        lmcma_b200::check(lmcma_b200_load_bmp(map_path.c_str(), 0, 0, &shape[0], &shape[1]));
+        occ.resize((size_t)shape[0] * shape[1]);
+        lmcma_b200::check(lmcma_b200_load_bmp(map_path.c_str(), occ.data(), (int64_t)occ.size(), &shape[0], &shape[1]));
+    }
+    if (ds != dims || dg != dims) { std::fprintf(stderr, "start / goal need %d coordinates\n", dims); return 2; }
+    lmcma_b200_map* mh = 0;
+    lmcma_b200::check(lmcma_b200_map_create_from_occupancy(0, dims, shape, occ.data(), 64.0f, LMCMA_B200_MAP_F32, 0.25f, 0.5f, &mh));
+    lmcma_b200::CostMap map(mh, dims);
+    lmcma_b200::PlanOptions po;
+    po.generations = argc >= 7 ? std::atoi(argv[6]) : 300;
+    po.waypoints = argc >= 8 ? std::atoi(argv[7]) : 20;
+    po.lambda = argc >= 9 ? std::atoi(argv[8]) : 256;
+    po.sigma0 = 0.08 * std::max(shape[0], std::max(shape[1], shape[2]));
+    std::vector<float> path;
+    const float best = lmcma_b200::plan(map, shape, start, goal, po, &path);
+    float f = 0.f; int32_t ncoll = -1;
+    map.evaluate(path.data(), 1, po.waypoints, start, goal, po.weights, po.w_col, &f, &ncoll);
+    std::FILE* fh = std::fopen(argv[5], "w");
+    if (!fh) return 2;
+    for (int w = -1; w <= po.waypoints; ++w) {
+        for (int d = 0; d < dims; ++d) {
+            const float v = w < 0 ? start[d] : (w == po.waypoints ? goal[d] : path[d * po.waypoints + w]);
+            std::fprintf(fh, d ? " %g" : "%g", v);
+        }
+        std::fprintf(fh, "\n");
+    }
+    std::fclose(fh);
+    std::printf("map %dx%dx%d best cost %.4f re-evaluated %.4f collisions %d\n", shape[0], shape[1], shape[2], best, f, ncoll);
+    return std::fabs(best - f) <= 1e-5f * std::fabs(f) ? 0 : 1;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     try {
+        if (argc >= 2 && !std::strcmp(argv[1], "planfile")) return planfile(argc, argv);
         if (argc >= 2 && !std::strcmp(argv[1], "plan"))
             return plan(argc >= 3 ? argv[2] : "path.txt", argc >= 4 ? std::atoi(argv[3]) : 300);
         return demo(argc >= 3 ? std::atoi(argv[2]) : 1);

@@ -115,6 +115,7 @@ public:
         : dims_(dims), h_(0) {
         check(lmcma_b200_map_create(device, dims, shape_xyz, dist, storage, u8_scale, c_min, &h_));
     }
+    CostMap(lmcma_b200_map* adopted, int dims) : dims_(dims), h_(adopted) {}   // e.g. from lmcma_b200_map_create_from_occupancy
     ~CostMap() { lmcma_b200_map_destroy(h_); }
     CostMap(const CostMap&) = delete;
     CostMap& operator=(const CostMap&) = delete;

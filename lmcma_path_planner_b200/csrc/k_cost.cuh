@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256, 8) k_cost(MapDev mp, CostArgs a) {
     __shared__ int red_i[8];
     __shared__ int warp_tot[8];
 
+    griddep_launch_dependents();          // k_rank may become resident as this grid drains; it waits for completion
     const int row = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const float* x = a.X + ((size_t)b * a.inst_rows + row) * a.ld;

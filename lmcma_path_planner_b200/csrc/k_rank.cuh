@@ -179,7 +179,11 @@ template <int MAXT>
 __global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict__ f_all, int mode, float* __restrict__ payload) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int sh_last;
-    griddep_launch_dependents();          // k_update's prologue does not depend on this kernel (see k_update.cuh)
+    // Launched as a programmatic dependent of k_cost inside the fused generation.  The trigger for k_update comes AFTER
+    // this kernel's own wait: k_update's prologue reads the fitness, so it may only start once k_cost has completed
+    // (its prologue does not depend on THIS kernel, see k_update.cuh).
+    griddep_wait();
+    griddep_launch_dependents();
     const int b = blockIdx.y;
     tell_phase_a(o, f_all, b, blockIdx.x, smem_raw);
     if (mode != RANK_PACK) return;

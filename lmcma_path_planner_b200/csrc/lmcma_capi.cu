@@ -338,12 +338,19 @@ int configure_sample(lmcma_b200_opt* o) {
 }
 
 // ranks + recombination partial sums (k_rank.cuh); RANK_PACK is the split-population stage
-int launch_rank(lmcma_b200_opt* o, const float* f_all, int mode, float* payload, cudaStream_t st) {
+// pdl: launched as a programmatic dependent of the kernel enqueued just before it on `st` (k_cost)
+int launch_rank(lmcma_b200_opt* o, const float* f_all, int mode, float* payload, cudaStream_t st, bool pdl = false) {
     auto kern = k_rank<1024>;
     if (o->rank_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->rank_smem));
-    kern<<<dim3(o->d.RS, o->d.B), 1024, o->rank_smem, st>>>(o->d, f_all, mode, payload);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(o->d.RS, o->d.B); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = o->rank_smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kern, o->d, f_all, mode, payload));
     g_launches++;
-    CU(cudaGetLastError());
     return 0;
 }
 
@@ -451,7 +458,7 @@ int ensure_graph(lmcma_b200_opt* o) {
     const long long before = g_launches.load();
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
-    if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st);
+    if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st, true);
     if (!rc) rc = launch_update(o, update_args_local(o), true, st);
     if (!rc) rc = launch_sample(o, st, true);
     cudaError_t e = cudaStreamEndCapture(st, &graph);

@@ -519,3 +519,19 @@ def test_map_from_occupancy_equals_map_from_distance_field(po):
         a = L.CostMap(maps.distance_field(occ, 40.0), storage).evaluate(X, start, goal, W)
         b = L.CostMap.from_occupancy(occ, 40.0, storage).evaluate(X, start, goal, W)
         assert np.array_equal(a["ncoll"], b["ncoll"]) and np.array_equal(a["f"], b["f"])
+
+
+def test_cpp_planner_driver_from_a_map_file(tmp_path):
+    """File -> occupancy (g < 128) -> distance transform -> LM-CMA planning -> printAsMatrix-style path, in C++."""
+    import struct
+    occ = maps.two_bars_occupancy()
+    rgb = np.where(occ[:, :, None] > 0, 0, 255).astype(np.uint8).repeat(3, axis=2)
+    h, w, _ = rgb.shape
+    stride = (w * 3 + 3) & ~3
+    data = b"".join(rgb[y, :, ::-1].tobytes() + b"\0" * (stride - w * 3) for y in range(h - 1, -1, -1))
+    hdr = b"BM" + struct.pack("<IHHI", 54 + len(data), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, h, 1, 24, 0, len(data), 2835, 2835, 0, 0)
+    (tmp_path / "bars.bmp").write_bytes(hdr + data)
+    r = _example(["planfile", "bars.bmp", "99,0", "0,99", "p.txt", "200", "20", "128"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    pts = np.loadtxt(tmp_path / "p.txt")
+    assert pts.shape == (22, 2) and tuple(pts[0]) == (99.0, 0.0) and tuple(pts[-1]) == (0.0, 99.0)
