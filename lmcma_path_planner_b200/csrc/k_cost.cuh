@@ -22,14 +22,15 @@ __device__ __forceinline__ int substeps_of(float linf) {
 }
 
 template <int DIMS, int STORAGE, bool TRACE>
-__global__ void __launch_bounds__(256, 8) k_cost(MapDev mp, CostArgs a) {
+// 7 warps per CTA, 7 CTAs per SM: 40 registers per thread with every trajectory of a 1024-wide population resident at once
+__global__ void __launch_bounds__(224, 7) k_cost(MapDev mp, CostArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = a.W, NSEG = W + 1;
     float4* segA = reinterpret_cast<float4*>(smem_raw);          // 2-D {Ax, Ay, dx, dy}   3-D {Ax, Ay, Az, dx}
     float4* segB = segA + NSEG;                                  // 2-D {invK, scale, K, first sample} 3-D {dy, dz, invK, scale}
     int2* segC = reinterpret_cast<int2*>(segB + NSEG);           // 3-D {K, first sample} (NSEG entries, unused in 2-D)
-    int* off = reinterpret_cast<int*>(segC + NSEG);              // NSEG + 1 exclusive sample offsets
-    float* lut = reinterpret_cast<float*>(off + NSEG + 1);       // 256 (U8 only)
+    int* off = reinterpret_cast<int*>(segC + NSEG);              // NSEG + 1 exclusive sample offsets + 32 x T padding
+    float* lut = reinterpret_cast<float*>(off + NSEG + 1 + 32);  // 256 (U8 only)
     __shared__ float red_f[2][8];
     __shared__ int red_i[8];
     __shared__ int warp_tot[8];
@@ -92,12 +93,15 @@ __global__ void __launch_bounds__(256, 8) k_cost(MapDev mp, CostArgs a) {
         if (DIMS == 2) segB[s].w = __int_as_float(base); else segC[s].y = base;   // first sample of the segment
         base += off[s + 1]; off[s + 1] = base;
     }
+    if (tid < 32) off[NSEG + 1 + tid] = T;                       // padding read by the 32-wide end-offset loads
     __syncthreads();
 
     // ---- phase 2: consecutive samples on consecutive lanes (<= 1 cell apart -> few lines per warp load).  The
     //      segment of every lane's sample comes from ONE warp-wide step: the 32 next segment-end offsets are
     //      loaded one per lane, the ends that fall inside this 32-sample block are OR-reduced into a bit mask
-    //      (redux.sync), and a lane's segment is the warp's first segment + popc(mask bits up to the lane) ----
+    //      (redux.sync), and a lane's segment is the warp's first segment + popc(mask bits below the lane).
+    //      The loop is issue-slot bound (the map is L2-resident), so it is kept to ~50 instructions per block:
+    //      no per-lane search, bounds / tail handling hoisted to warp-uniform rare paths ----
     const int nblk = (T + 31) >> 5;
     const int blk0 = (int)(((long long)warp * nblk) / nwarps), blk1 = (int)(((long long)(warp + 1) * nblk) / nwarps);
     float clr_acc = 0.f; int coll = 0;
@@ -107,18 +111,22 @@ __global__ void __launch_bounds__(256, 8) k_cost(MapDev mp, CostArgs a) {
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= tfirst) lo = mid; else hi = mid - 1; }
         int s_warp = lo;
         const unsigned nxm1 = (unsigned)(mp.nx - 1), nym1 = (unsigned)(mp.ny - 1), nzm1 = (unsigned)(mp.nz - 1);
+        const unsigned nbx = mp.nbx, nby = mp.nby;
         const int last = NSEG - 1;
         const float ng_coll = -mp.g_coll;
-        for (int blk = blk0; blk < blk1; ++blk) {
+        const float* __restrict__ g32 = mp.g32;
+        const unsigned char* __restrict__ q8 = mp.q8;
+        // one 32-sample block; TAIL = the trajectory's last block, where lanes past the last sample repeat it with weight 0
+        auto block = [&](const int blk, const bool TAIL) {
             const int t0 = blk << 5;
-            const int e_i = s_warp + 1 + lane;
-            const unsigned rel = (unsigned)(off[min(e_i, NSEG)] - t0);          // > 0: segment s_warp contains t0
-            const unsigned mask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-            const int adv = __popc(__ballot_sync(0xffffffffu, rel <= 32u && e_i <= NSEG));
-            const int tl = min(lane, T - 1 - t0);                // lanes past the last sample repeat it with weight 0
-            const bool valid = tl == lane;
-            const int s = s_warp + __popc(mask & (0xffffffffu >> (31 - tl)));
-            s_warp += adv;
+            // segment ends at t0 + 1 .. t0 + 32 -> bits 0 .. 31 (off[] is padded with T beyond NSEG; shl clamps >= 32 to 0)
+            const unsigned rel1 = (unsigned)(off[s_warp + 1 + lane] - t0 - 1);
+            unsigned bit;
+            asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(rel1));
+            const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
+            const int tl = TAIL ? min(lane, T - 1 - t0) : lane;
+            const int s = s_warp + __popc(mask & ((1u << tl) - 1u));   // ends at or before this lane's sample
+            s_warp += __popc(mask);
             const float4 ra = segA[s];
             const float4 rb = segB[s];
             float invK, scale, dx, dy, dz = 0.f, az = 0.f; int K, cur;
@@ -135,18 +143,24 @@ __global__ void __launch_bounds__(256, 8) k_cost(MapDev mp, CostArgs a) {
                 iz = __float2int_rn(__fadd_rn(az, __fmul_rn(tk, dz)));
                 inb = inb && ((unsigned)iz <= nzm1);
             }
-            const unsigned adr = inb ? brick_offset<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, mp.nbx, mp.nby) : 0u;
-            float g = (STORAGE == 0) ? __ldg(mp.g32 + adr) : lut[__ldg(mp.q8 + adr)];   // branch-free: cell 0 when outside
-            g = inb ? g : ng_coll;
+            unsigned adr = brick_offset<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, nbx, nby);
+            const bool all_in = __all_sync(0xffffffffu, inb);    // the box bounds keep candidates inside: almost always true
+            if (!all_in) adr = inb ? adr : 0u;
+            float g = (STORAGE == 0) ? __ldg(g32 + adr) : lut[__ldg(q8 + adr)];
+            if (!all_in) g = inb ? g : ng_coll;                   // a sample outside the map is a collision
             const bool endpt = (k == 0) || (k == K);
             float sw = endpt ? 0.5f * scale : scale;             // trapezoid weight x len/K
-            sw = valid ? sw : 0.f;
+            bool counted = (k < K) || (s == last);               // every distinct poly-line sample once
+            if (TAIL) { const bool valid = tl == lane; sw = valid ? sw : 0.f; counted = counted && valid; }
             clr_acc = fmaf(fabsf(g), sw, clr_acc);
-            coll += (valid && g < 0.f && (k < K || s == last)) ? 1 : 0;
+            coll += (counted && g < 0.f) ? 1 : 0;
             if (TRACE) {
-                if (valid && (long long)(t0 + lane) < a.max_cells) a.cells[t0 + lane] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
+                if ((!TAIL || tl == lane) && (long long)(t0 + lane) < a.max_cells) a.cells[t0 + lane] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
             }
-        }
+        };
+        const int blk_full_end = min(blk1, nblk - 1);            // the trajectory's last block may be partial
+        for (int blk = blk0; blk < blk_full_end; ++blk) block(blk, false);
+        if (blk1 == nblk) block(nblk - 1, true);
     }
 
     // ---- phase 3: block reduction ----

@@ -172,7 +172,7 @@ namespace {
 
 template <int DIMS, int STORAGE, bool TRACE>
 int launch_cost_t(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, cudaStream_t st) {
-    const size_t smem = (size_t)40 * (a.W + 1) + sizeof(int) * (a.W + 2) + (STORAGE == 1 ? 1024 : 0);
+    const size_t smem = (size_t)40 * (a.W + 1) + sizeof(int) * (a.W + 2 + 32) + (STORAGE == 1 ? 1024 : 0);
     auto kern = k_cost<DIMS, STORAGE, TRACE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(rows, B), tpt, smem, st>>>(mp, a);
@@ -193,14 +193,14 @@ int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, b
 
 int pick_cost_tpt(int W, const float* start, const float* goal, int dims) {
     const int forced = env_int("LMCMA_B200_COST_TPT", 0);
-    if (forced >= 32 && forced <= 256 && (forced & (forced - 1)) == 0) return forced;
+    if (forced >= 32 && forced <= 224 && forced % 32 == 0) return forced;
     float linf = 0.f;
     if (start && goal)
         for (int c = 0; c < dims; ++c) linf = std::max(linf, std::fabs(goal[c] - start[c]));
     const double est = 2.0 * (W + 1) + linf;     // expected samples per trajectory
     int tpt = 32;
     while (tpt < 256 && est / tpt > 24.0) tpt <<= 1;
-    return tpt;
+    return tpt == 256 ? 224 : tpt;               // k_cost is built for at most 7 warps (register budget, see k_cost.cuh)
 }
 
 template <int NV, int RB, int MAXT>
