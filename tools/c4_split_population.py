@@ -1,0 +1,60 @@
+"""C4 mechanics over real NCCL (BASELINE.json configs[3], scaled): one LM-CMA population split over the ranks of a
+torchrun launch, 3-D voxel cost map, two tiny all-gathers per generation (lambda fitness scalars, then one
+(n + 4)-float payload per rank).  Rank 0 also runs the unsplit optimiser and checks that the split run tracks it.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      tools/c4_split_population.py [size] [waypoints] [lambda] [generations]
+"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+import lmcma_path_planner_b200 as L
+from lmcma_path_planner_b200 import maps, parallel
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 500
+lam = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
+gens = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+n = 3 * W
+m = int(2 * np.sqrt(n))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dmap, start, goal = maps.config4_map(size=size, n_boxes=max(64, 4096 * size ** 3 // 512 ** 3), seed=43)
+cmap = L.CostMap(dmap, "u8", u8_scale=0.25, device=local)
+lo, hi = maps.box_bounds((size, size, size), W)
+x0 = maps.straight_line(start, goal, W)
+kw = dict(x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=8.0 * size / 512, seed=43, device=local)
+part = L.Optimizer(n, pop_offset=rank * lam // world, pop_count=lam // world, **kw)
+part.attach_cost(cmap, [start], [goal], W, L.LONGSAFE, 1e4)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+part.set_stream(stream.cuda_stream)
+sp = parallel.SplitPopulation(parallel.DeviceBackend(part, stream.cuda_stream), dist, torch.device("cuda", local))
+whole = None
+if rank == 0:
+    whole = L.Optimizer(n, **kw)
+    whole.attach_cost(cmap, [start], [goal], W, L.LONGSAFE, 1e4)
+sp.run(3)
+torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+e0.record(stream)
+sp.run(gens)
+e1.record(stream)
+torch.cuda.synchronize()
+t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+ms = float(t.item())
+if rank == 0:
+    whole.run(3 + gens)
+    whole.sync()
+    sw, ss = float(whole.get("sigma")[0]), float(part.get("sigma")[0])
+    dx = float(np.abs(whole.get("xmean") - part.get("xmean")).max())
+    print("C4 split population: %d^3 u8 map, n=%d, lambda=%d over %d GPU(s), m=%d: %.3f ms/generation, %.3g evals/s" %
+          (size, n, lam, world, m, ms / gens, lam * gens / (ms * 1e-3)))
+    print("split vs unsplit after %d generations: sigma %.6g vs %.6g, max |xmean diff| %.3g cells" % (3 + gens, ss, sw, dx))
+    assert abs(ss - sw) <= 0.05 * sw and dx < 1.0, "split-population run does not track the unsplit optimiser"
+dist.barrier()
+dist.destroy_process_group()
