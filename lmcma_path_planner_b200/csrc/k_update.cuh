@@ -36,10 +36,12 @@ template <bool SMEM> __device__ __forceinline__ float4 ld_row4(const float4* p) 
 
 // NVB  = float4 column slots per lane (ns <= 128 * NVB)
 // RMAX = pending rows a warp can hold in registers (m <= UPD_WARPS * RMAX); 0 = streaming sweep (rows stay in
-//        shared memory, or in HBM/L2 when SMEM is false: shapes whose rows fit neither registers nor smem)
+//        shared memory, or in HBM/L2 when SMEM is false); -1 = no sweep here: the recompute is done by the Gram-matrix
+//        kernels (k_gram.cuh) for shapes whose rows fit neither registers nor shared memory; this kernel then only
+//        hands them {first_stale, live}
 template <int NVB, int RMAX, bool SMEM>
 __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs a) {
-    static_assert(RMAX == 0 || SMEM, "the register sweep publishes finished rows through shared memory");
+    static_assert(RMAX <= 0 || SMEM, "the register sweep publishes finished rows through shared memory");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = o.m, ns = o.ns, nq = ns >> 2;
     float* lj_s = reinterpret_cast<float*>(smem_raw);             // m: Lj / K in sequence order
@@ -159,7 +161,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         if (lane == 0) { am_v[warp] = bf; am_i[warp] = bi; }
     }
-    if (!SMEM) {                                                     // rows stay in HBM/L2: pending rows start as pc_j
+    if (RMAX < 0) {
+        if (tid == 0) o.gram_hdr[b] = make_int2(first_stale, live);
+    } else if (!SMEM) {                                              // rows stay in HBM/L2: pending rows start as pc_j
         for (int i = first_stale + warp; i + 1 < live; i += nwarps) {
             const float4* src = reinterpret_cast<const float4*>(Pb + (size_t)order[i] * ns);
             float4* dst = reinterpret_cast<float4*>(row_ptr(i));
@@ -278,7 +282,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         lj_s[i] = __fdividef(r_f, a_f * t * (t + 1.0f)) * invK;
     };
 
-    if (RMAX > 0) {
+    if (RMAX < 0) {
+        // the Gram-matrix kernels take it from here (they also write Nj / Lj)
+    } else if (RMAX > 0) {
         // ---------------- register sweep: warp w owns rows first_stale + w + r * UPD_WARPS ----------------
         constexpr int R = RMAX > 0 ? RMAX : 1;
         const int base = first_stale + warp;
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     __syncthreads();
     UPD_STAMP(5);
     if (a.dbg && threadIdx.x == 0) { a.dbg[10] = first_stale; a.dbg[11] = live; }
-    for (int i = first_stale + tid; i < live; i += nthr) {           // FP64 scalar state of the recomputed rows
+    for (int i = first_stale + tid; i < live && RMAX >= 0; i += nthr) {   // FP64 scalar state of the recomputed rows
         const int slot = order[i];
         const double nv = (double)nv_s[i], r = o.c1 / (1.0 - o.c1), am = o.M;
         const double t = sqrt(1.0 + r * nv);

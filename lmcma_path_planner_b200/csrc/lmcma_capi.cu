@@ -50,6 +50,9 @@ int dmalloc(T** p, size_t count) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
     if (e != cudaSuccess) return fail(LMCMA_B200_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
     e = cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T));
+    // the memset is asynchronous on the legacy stream, which the library's non-blocking streams do not wait for: without
+    // this wait it can land AFTER a copy / kernel that one of those streams issues into the new buffer
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -160,6 +163,7 @@ struct lmcma_b200_opt {
     size_t smp_smem = 0;
     int cost_tpt = 128;
     int upd_nvb = 4, upd_rmax = 0;
+    bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
     bool upd_rows_in_smem = true;
     size_t upd_smem = 0, rank_smem = 0;
     size_t cost_smem = 0;
@@ -193,14 +197,14 @@ int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, b
 
 int pick_cost_tpt(int W, const float* start, const float* goal, int dims) {
     const int forced = env_int("LMCMA_B200_COST_TPT", 0);
-    if (forced >= 32 && forced <= 224 && forced % 32 == 0) return forced;
+    if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
     float linf = 0.f;
     if (start && goal)
         for (int c = 0; c < dims; ++c) linf = std::max(linf, std::fabs(goal[c] - start[c]));
     const double est = 2.0 * (W + 1) + linf;     // expected samples per trajectory
     int tpt = 32;
     while (tpt < 256 && est / tpt > 24.0) tpt <<= 1;
-    return tpt == 256 ? 224 : tpt;               // k_cost is built for at most 7 warps (register budget, see k_cost.cuh)
+    return tpt;                                  // k_cost is built for at most 8 warps (COST_MAX_WARPS)
 }
 
 template <int NV, int RB, int MAXT>
@@ -373,6 +377,19 @@ int launch_update_t(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream
 // the serial part of update() (k_update.cuh).  pdl: launched as a programmatic dependent of the kernel enqueued just
 // before it on `st` (k_rank), so that its prologue overlaps that kernel
 int launch_update(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream_t st) {
+    if (o->upd_gram) {
+        int rc = o->upd_nvb == 4 ? launch_update_t<4, -1, false>(o, a, pdl, st) : launch_update_t<16, -1, false>(o, a, pdl, st);
+        if (rc) return rc;
+        const OptDev& d = o->d;
+        const int tiles = (d.m + GRAM_TILE - 1) / GRAM_TILE;
+        k_gram<<<dim3(tiles, tiles, d.B), 256, 0, st>>>(d);
+        if (o->coef_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_coef, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->coef_smem));
+        k_coef<<<d.B, 1024, o->coef_smem, st>>>(d);
+        k_combine<<<dim3((d.ns / 4 + 127) / 128, (d.m + 7) / 8, d.B), 128, 0, st>>>(d);
+        g_launches += 3;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (o->upd_nvb == 4) {
         if (o->upd_rmax == 3) return launch_update_t<4, 3, true>(o, a, pdl, st);
         if (o->upd_rmax == 5) return launch_update_t<4, 5, true>(o, a, pdl, st);
@@ -400,9 +417,14 @@ int configure_update(lmcma_b200_opt* o) {
     o->upd_rows_in_smem = fixed + rows <= budget;
     o->upd_smem = fixed + (o->upd_rows_in_smem ? rows : 0);
     if (o->upd_smem > budget) return fail(LMCMA_B200_ERR_ARG, "k_update needs %zu B shared memory (m = %d too large)", o->upd_smem, o->d.m);
+    // rows that fit neither the registers nor the shared memory of one SM: Gram-matrix recompute (k_gram.cuh)
+    o->coef_smem = (size_t)3 * o->d.m * (o->d.m | 1) * sizeof(double) + (size_t)2 * o->d.m * sizeof(double);
+    o->upd_gram = (!o->upd_rows_in_smem || env_int("LMCMA_B200_UPDATE_GRAM", 0)) && o->d.m <= 128 && o->coef_smem <= budget &&
+                  !env_int("LMCMA_B200_UPDATE_STREAMING", 0);
+    if (o->upd_gram) { o->upd_rows_in_smem = false; o->upd_smem = fixed; }
     // pending rows in registers when they fit: m <= 8 warps x RMAX rows of <= 128 float4 columns
     o->upd_rmax = 0;
-    if (o->upd_nvb == 4 && o->upd_rows_in_smem && !env_int("LMCMA_B200_UPDATE_STREAMING", 0)) {
+    if (o->upd_nvb == 4 && o->upd_rows_in_smem && !o->upd_gram && !env_int("LMCMA_B200_UPDATE_STREAMING", 0)) {
         if (o->d.m <= UPD_WARPS * 3) o->upd_rmax = 3;
         else if (o->d.m <= UPD_WARPS * 5) o->upd_rmax = 5;
     }
@@ -538,6 +560,11 @@ static int map_alloc(int device, int dims, const int32_t* shape, int storage, fl
     const unsigned nbx = (m->dev.nx + bs.bx - 1) / bs.bx, nby = (m->dev.ny + bs.by - 1) / bs.by,
                    nbz = (m->dev.nz + bs.bz - 1) / bs.bz;
     m->dev.nbx = nbx; m->dev.nby = nby;
+    if (dims == 2) { m->dev.py = storage == 0 ? brick_pitch_y<2, 0>(nbx) : brick_pitch_y<2, 1>(nbx); m->dev.pz = 0; }
+    else {
+        m->dev.py = storage == 0 ? brick_pitch_y<3, 0>(nbx) : brick_pitch_y<3, 1>(nbx);
+        m->dev.pz = storage == 0 ? brick_pitch_z<3, 0>(nbx, nby) : brick_pitch_z<3, 1>(nbx, nby);
+    }
     m->stored = (size_t)nbx * nby * nbz * bs.bx * bs.by * bs.bz;
     if (m->stored >= ((size_t)1 << 32)) { delete m; return fail(LMCMA_B200_ERR_ARG, "map too large: %zu stored cells (limit 2^32)", m->stored); }
     rc = 0;
@@ -808,6 +835,7 @@ int lmcma_b200_cost_trace(lmcma_b200_map* m, const lmcma_b200_objective* obj, co
     CU(cudaMemcpy(dX, x_host, n * sizeof(float), cudaMemcpyHostToDevice));
     float e6[6] = {ends->start[0], ends->start[1], ends->start[2], ends->goal[0], ends->goal[1], ends->goal[2]};
     CU(cudaMemcpy(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(cudaStreamLegacy));   // the kernel runs on the map's non-blocking stream
     CostArgs a;
     memset(&a, 0, sizeof(a));
     a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
@@ -953,6 +981,11 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
 
     rc = configure_sample(o);
     if (!rc) rc = configure_update(o);
+    if (!rc && o->upd_gram) {
+        rc = dmalloc(&d.G, B * m * m);
+        if (!rc) rc = dmalloc(&d.Cf, B * m * m);
+        if (!rc) rc = dmalloc(&d.gram_hdr, B);
+    }
     if (rc) { lmcma_b200_destroy(o); return rc; }
     o->f_host.assign(B * lam, 0.f);
     // first population (LMCMA::init -> sample(), lmcma.cpp:298)
@@ -972,7 +1005,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     if (o->stream) cudaStreamSynchronize(o->stream);
     OptDev& d = o->d;
     void* ptrs[] = {d.X, d.D, d.Z, d.Zc, o->d_Lf, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
-                    d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
+                    d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
     if (o->ev0) cudaEventDestroy(o->ev0);
@@ -1117,7 +1150,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
         if ((rc = ensure_graph(o))) return rc;
         for (int g = 0; g < generations; ++g) {
             CU(cudaGraphLaunch(o->graph_exec, o->stream));
-            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0);
+            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0);
         }
     } else {
         if (o->cfg.rng == LMCMA_B200_RNG_INJECT && generations > 1)

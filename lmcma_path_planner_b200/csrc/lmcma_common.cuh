@@ -61,6 +61,10 @@ struct OptDev {
     // chunk of consecutive pairs is ONE contiguous block (one bulk async copy instead of one per row)
     float* VPs;        // B x m x 2 x ns
     float* Njs;        // B x m   Nj in sequence order
+    // Gram-matrix recompute (k_gram.cuh), allocated only for shapes that take it
+    double* G;         // B x m x m
+    double* Cf;        // B x m x m
+    int2* gram_hdr;    // B : {first_stale, live} handed from k_update to k_gram / k_coef / k_combine
     int* t;            // B x m   slot order, oldest -> newest
     int* vec;          // B x m   generation stamp per slot
     Scalars* sc;       // B
@@ -80,6 +84,7 @@ struct OptDev {
 struct MapDev {
     int dims, nx, ny, nz;
     unsigned nbx, nby;         // bricks per row / per column (lmcma_layout.hpp)
+    unsigned py, pz;           // brick_pitch_y / brick_pitch_z of the layout (constant-bank operands of the sample loop)
     int storage;               // 0 = F32 sign-tagged reciprocal clearance, 1 = U8 quantised distance
     const float* g32;
     const unsigned char* q8;

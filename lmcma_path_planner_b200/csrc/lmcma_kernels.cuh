@@ -6,3 +6,4 @@
 #include "k_update.cuh"
 #include "k_prior.cuh"
 #include "k_edt.cuh"
+#include "k_gram.cuh"

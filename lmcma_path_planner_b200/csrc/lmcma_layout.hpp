@@ -6,6 +6,13 @@
 //   2-D f32: brick  8 x 4      cells        2-D u8: brick 16 x 8     cells
 //   3-D f32: brick  4 x 4 x 2  cells        3-D u8: brick  8 x 4 x 4 cells
 //
+// Inside a brick the cells are ordered x-major: index = (x_in * BY + y_in) * BZ + z_in.  Two reasons:
+//  * the x term of the offset is then just `ix << log2(BY * BZ)` (its low bits are the in-brick column, its high
+//    bits the brick column), and the y / z terms are one multiply-add each: `iy * BZ + (iy >> log2 BY) * py` with
+//    `py = brick_row_pitch - BY * BZ` — 3 integer instructions per 2-D sample on the hot path instead of 9;
+//  * a 32-byte sector (the unit L2 -> L1 moves) is a 2 x 4 (f32) / 4 x 8 (u8) tile instead of a 1-cell-high strip, so
+//    a diagonal run of samples touches about half as many sectors.
+//
 // The logical (row-major) cell index ((z*ny + y)*nx + x) stays the API-visible index (lmcma_b200_cost_trace).
 #pragma once
 #include <stddef.h>
@@ -27,18 +34,39 @@ LMCMA_HD BrickShape brick_shape() {
     return STORAGE == 0 ? BrickShape{4, 4, 2} : BrickShape{8, 4, 4};
 }
 
-// element offset of cell (ix, iy, iz) in the bricked array; nbx / nby = bricks per row / per column.
-// Cells are row-major inside a brick (a handful of shifts and masks on the hot path); 32-bit offsets:
-// a map holds fewer than 2^32 stored elements (checked at upload).
+// log2 of the brick extents
+template <int DIMS, int STORAGE> struct BrickLog2 {
+    static constexpr int X = DIMS == 2 ? (STORAGE == 0 ? 3 : 4) : (STORAGE == 0 ? 2 : 3);
+    static constexpr int Y = DIMS == 2 ? (STORAGE == 0 ? 2 : 3) : 2;
+    static constexpr int Z = DIMS == 2 ? 0 : (STORAGE == 0 ? 1 : 2);
+};
+
+// the two pitch constants of brick_offset (host: computed per call; device hot path: hoisted out of the sample loop)
+template <int DIMS, int STORAGE>
+LMCMA_HD unsigned brick_pitch_y(unsigned nbx) {
+    typedef BrickLog2<DIMS, STORAGE> L;
+    return (nbx << (L::X + L::Y + L::Z)) - (1u << (L::Y + L::Z));
+}
+template <int DIMS, int STORAGE>
+LMCMA_HD unsigned brick_pitch_z(unsigned nbx, unsigned nby) {
+    typedef BrickLog2<DIMS, STORAGE> L;
+    return ((nbx * nby) << (L::X + L::Y + L::Z)) - (1u << L::Z);
+}
+
+// element offset of cell (ix, iy, iz) given the hoisted pitches; 32-bit offsets: a map holds fewer than 2^32 stored
+// elements (checked at upload)
+template <int DIMS, int STORAGE>
+LMCMA_HD unsigned brick_offset_p(unsigned ix, unsigned iy, unsigned iz, unsigned py, unsigned pz) {
+    typedef BrickLog2<DIMS, STORAGE> L;
+    unsigned o = (ix << (L::Y + L::Z)) + (iy << L::Z) + (iy >> L::Y) * py;
+    if (DIMS == 3) o += iz + (iz >> L::Z) * pz;
+    return o;
+}
+
+// nbx / nby = bricks per row / per column
 template <int DIMS, int STORAGE>
 LMCMA_HD unsigned brick_offset(unsigned ix, unsigned iy, unsigned iz, unsigned nbx, unsigned nby) {
-    if (DIMS == 2) {
-        if (STORAGE == 0) return (((iy >> 2) * nbx + (ix >> 3)) << 5) | ((iy & 3u) << 3) | (ix & 7u);
-        return (((iy >> 3) * nbx + (ix >> 4)) << 7) | ((iy & 7u) << 4) | (ix & 15u);
-    } else {
-        if (STORAGE == 0) return ((((iz >> 1) * nby + (iy >> 2)) * nbx + (ix >> 2)) << 5) | ((iz & 1u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
-        return ((((iz >> 2) * nby + (iy >> 2)) * nbx + (ix >> 3)) << 7) | ((iz & 3u) << 5) | ((iy & 3u) << 3) | (ix & 7u);
-    }
+    return brick_offset_p<DIMS, STORAGE>(ix, iy, iz, brick_pitch_y<DIMS, STORAGE>(nbx), brick_pitch_z<DIMS, STORAGE>(nbx, nby));
 }
 
 }  // namespace lmcma

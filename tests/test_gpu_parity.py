@@ -535,3 +535,13 @@ def test_cpp_planner_driver_from_a_map_file(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     pts = np.loadtxt(tmp_path / "p.txt")
     assert pts.shape == (22, 2) and tuple(pts[0]) == (99.0, 0.0) and tuple(pts[-1]) == (0.0, 99.0)
+
+
+def test_lmcma_teacher_forced_gram_path(po, monkeypatch):
+    """The Gram-matrix recompute (k_gram / k_coef / k_combine): forced on the C2-like shape so that slot recycling
+    (itr >= m, first_stale > 0) is exercised, then on the C4 row length where it is the default (m * n = 115 K floats
+    fit neither registers nor shared memory), past the point where all 77 slots are live."""
+    monkeypatch.setenv("LMCMA_B200_UPDATE_GRAM", "1")
+    _teacher_forced(po, 400, 128, 40, 50, seed=3, sigma=0.5)
+    monkeypatch.delenv("LMCMA_B200_UPDATE_GRAM")
+    _teacher_forced(po, 1500, 32, 77, 84, seed=4, sigma=0.3)
