@@ -9,15 +9,22 @@ namespace lmcma {
 // ValidityChecker::isValid/clearance planner.cpp:591-631, ClearanceObjective::stateCost :655-669,
 // weights :677-690).  One CTA per trajectory.
 // Phase 1: one thread per segment: record {A, B-A, 1/K, len/K, first sample} into shared memory, block scan of the
-//   sample counts, and the two END samples of the segment (k = 0, k = K) fetched here — see below.
-// Phase 2: the flattened sample sequence is cut into 32-sample blocks, a contiguous run of blocks per warp,
-//   consecutive samples on consecutive lanes: they are <= 1 cell apart, and the map is stored in 128-byte bricks
-//   (lmcma_layout.hpp), so one warp load touches a handful of lines instead of 32 (the L1 wavefront rate, not
-//   DRAM, bounds a row-major gather).  Every sample is accumulated with the INTERIOR trapezoid weight len/K and
-//   counted as a potential collision; phase 1's end samples then take back half a weight at k = 0 and k = K and the
-//   doubly counted joint (k = K of every segment but the last) — that keeps weights, end-point tests and K itself
-//   out of the 32-sample loop.  The loop is software-pipelined: the loads of two blocks are in flight while the
-//   previous two are accumulated (the kernel was stalled on the load-to-use latency, not on issue slots).
+//   sample counts.
+// Phase 2: the flattened sample sequence is cut into 32-sample blocks, consecutive samples on consecutive lanes: they
+//   are <= 1 cell apart, and the map is stored in 128-byte bricks (lmcma_layout.hpp), so one warp load touches a
+//   handful of lines instead of 32 (the L1 wavefront rate, not DRAM, bounds a row-major gather).
+//   2a — per-block records {bit mask of the segment ends inside the block, first segment}, written by the segment
+//   threads (a segment names itself first segment of the blocks that start inside it and sets its end bit); a lane's
+//   segment is then first + popc(mask below the lane): no per-lane search, no warp reduction, and no dependency
+//   between blocks in the loop.  Trajectories longer than the record stage (CostArgs::cb blocks) take several rounds.
+//   2b — the loop, a contiguous run of blocks per warp (drawing chunks from a shared counter was measured slower:
+//   the draw costs more than the imbalance it removes).  Every sample is accumulated with the INTERIOR trapezoid weight len/K and counted as a potential collision;
+//   phase 2c then takes back half a weight at k = 0 and k = K of every segment and the doubly counted joint (k = K of
+//   every segment but the last) — that keeps weights, end-point tests and K itself out of the loop.  The loop is
+//   software-pipelined: three block loads are in flight while the oldest one is accumulated (the kernel is bound by
+//   the load-to-use latency and the L1 line rate, not by DRAM).
+//   2c — the end samples, one thread per segment, after the loop: their lines were just touched (L1 / L2 hits), and
+//   warps that finish the loop early do this instead of waiting at the barrier.
 //   Trajectories whose waypoints all lie inside the map (always, for candidates clamped by the optimiser's box
 //   bounds) take a loop without bounds tests; others take the CHECK variant (out of the map = collision).
 // Phase 3: block reduction.
@@ -41,11 +48,12 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     typedef typename RawCell<STORAGE>::type raw_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = a.W, NSEG = W + 1;
-    float4* segA = reinterpret_cast<float4*>(smem_raw);          // 2-D {Ax, Ay, dx, dy}   3-D {Ax, Ay, Az, dx}
-    float4* segB = segA + NSEG;                                  // 2-D {invK, len/K, first sample, -} 3-D {dy, dz, invK, len/K}
-    int* segC = reinterpret_cast<int*>(segB + NSEG);             // 3-D first sample (NSEG entries, unused in 2-D)
-    int* off = segC + NSEG;                                      // NSEG + 1 exclusive sample offsets + 32 x T padding
-    float* lut = reinterpret_cast<float*>(off + NSEG + 1 + 32);  // 256 (U8 only)
+    // segment s: rec[2s] = 2-D {Ax, Ay, dx, dy} / 3-D {Ax, Ay, Az, dx};  rec[2s+1] = 2-D {invK, len/K, first sample, -} / 3-D {dy, dz, invK, len/K}
+    float4* rec = reinterpret_cast<float4*>(smem_raw);
+    uint2* blkrec = reinterpret_cast<uint2*>(rec + 2 * NSEG);    // a.cb per-block records {segment-end mask, first segment}
+    int* segC = reinterpret_cast<int*>(blkrec + a.cb);           // 3-D first sample (NSEG entries, unused in 2-D)
+    int* off = segC + NSEG;                                      // NSEG + 1 exclusive sample offsets
+    float* lut = reinterpret_cast<float*>(off + NSEG + 1);       // 256 (U8 only)
     __shared__ float red_f[3][COST_MAX_WARPS];
     __shared__ int red_i[COST_MAX_WARPS];
     __shared__ int warp_tot[COST_MAX_WARPS];
@@ -89,17 +97,9 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     const int s_begin = min(NSEG, tid * spt), s_end = min(NSEG, s_begin + spt);
     float len_acc = 0.f; int my_cnt = 0;
     bool safe = true;                                            // every waypoint of my segments inside the map
-    // end samples of the thread's most recent segment, taken back from the sums once their loads have landed
-    raw_t e0 = 0, eK = 0; bool e0_out = false, eK_out = false, eK_joint = false; float e_half = 0.f;
-    float corr_clr = 0.f; int corr_coll = 0;
-    auto take_back = [&]() {
-        const float g0 = e0_out ? ng_coll : value_of(e0), gK = eK_out ? ng_coll : value_of(eK);
-        corr_clr = fmaf(e_half, fabsf(g0) + fabsf(gK), corr_clr);
-        corr_coll += (eK_joint && gK < 0.f) ? 1 : 0;
-    };
+    const raw_t idle = (raw_t)(STORAGE == 1 ? 1 : 0);             // a free cell
     if (STORAGE == 1) __syncthreads();                           // the lut
     for (int s = s_begin; s < s_end; ++s) {
-        if (s > s_begin) take_back();
         float A[3], D[3]; float linf = 0.f, l2 = 0.f; bool bad = false;
         A[2] = 0.f; D[2] = 0.f;
 #pragma unroll
@@ -130,18 +130,10 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
             for (int c = 0; c < DIMS; ++c) { A[c] = -1.0e9f; D[c] = 0.f; }
         }
         const float scale = len * invK;
-        if (DIMS == 2) { segA[s] = make_float4(A[0], A[1], D[0], D[1]); segB[s] = make_float4(invK, scale, 0.f, 0.f); }
-        else { segA[s] = make_float4(A[0], A[1], A[2], D[0]); segB[s] = make_float4(D[1], D[2], invK, scale); }
+        if (DIMS == 2) { rec[2 * s] = make_float4(A[0], A[1], D[0], D[1]); rec[2 * s + 1] = make_float4(invK, scale, 0.f, 0.f); }
+        else { rec[2 * s] = make_float4(A[0], A[1], A[2], D[0]); rec[2 * s + 1] = make_float4(D[1], D[2], invK, scale); }
         off[s + 1] = K + 1;                                      // samples of this segment (rewritten below)
         my_cnt += K + 1;
-        // the two end samples (k = 0 and k = K), by the same arithmetic as the sample loop
-        int ix, iy, iz;
-        e0_out = !cell_of(__fmul_rn(0.f, invK), A[0], A[1], A[2], D[0], D[1], D[2], ix, iy, iz);
-        e0 = load_raw(e0_out ? 0u : brick_offset_p<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, py, pz));
-        eK_out = !cell_of(__fmul_rn((float)K, invK), A[0], A[1], A[2], D[0], D[1], D[2], ix, iy, iz);
-        eK = load_raw(eK_out ? 0u : brick_offset_p<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, py, pz));
-        e_half = 0.5f * scale;
-        eK_joint = s != last;
     }
     int incl = my_cnt;                                           // block-wide exclusive scan of my_cnt
 #pragma unroll
@@ -155,91 +147,114 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     for (int w2 = 0; w2 < nwarps; ++w2) { const int v = warp_tot[w2]; if (w2 < warp) base += v; T += v; }
     if (tid == 0) off[0] = 0;
     for (int s = s_begin; s < s_end; ++s) {
-        if (DIMS == 2) segB[s].z = __int_as_float(base); else segC[s] = base;   // first sample of the segment
+        if (DIMS == 2) rec[2 * s + 1].z = __int_as_float(base); else segC[s] = base;   // first sample of the segment
         base += off[s + 1]; off[s + 1] = base;
     }
-    if (tid < 32) off[NSEG + 1 + tid] = T;                       // padding read by the 32-wide end-offset loads
     __syncthreads();
 
-    // ---- phase 2: consecutive samples on consecutive lanes (<= 1 cell apart -> few lines per warp load).  The
-    //      segment of every lane's sample comes from ONE warp-wide step: the 32 next segment-end offsets are
-    //      loaded one per lane, the ends that fall inside this 32-sample block are OR-reduced into a bit mask
-    //      (redux.sync), and a lane's segment is the warp's first segment + popc(mask bits below the lane) ----
-    const unsigned nblk = (unsigned)(T + 31) >> 5;
-    const int blk0 = (int)(((unsigned)warp * nblk) / (unsigned)nwarps), blk1 = (int)(((unsigned)(warp + 1) * nblk) / (unsigned)nwarps);
+    // ---- phase 2 ----
+    const int nblk = (int)((unsigned)(T + 31) >> 5);
+    const unsigned below = (1u << lane) - 1u;
     float clr_acc = 0.f; int coll = 0;
-    if (blk0 < blk1) {
-        int lo = 0, hi = NSEG - 1;                               // warp-uniform: last s with off[s] <= first sample
-        const int tfirst = blk0 << 5;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= tfirst) lo = mid; else hi = mid - 1; }
-        int s_warp = lo;
-        const unsigned below = (1u << lane) - 1u;
-        // one 32-sample block: address + load issue.  TAIL = the trajectory's last block, where the lanes past the last
-        // sample contribute nothing (weight 0, not a collision).  CHECK = bounds tests (a sample outside the map is a collision)
-        auto fetch = [&](const int blk, const bool TAIL, const bool CHECK, raw_t& raw, float& wgt, bool& outside) {
-            const int t0 = blk << 5;
-            // segment ends at t0 + 1 .. t0 + 32 -> bits 0 .. 31 (off[] is padded with T beyond NSEG; shl clamps >= 32 to 0)
-            const unsigned rel1 = (unsigned)(off[s_warp + 1 + lane] - t0 - 1);
-            unsigned bit;
-            asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(rel1));
-            const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
-            const bool dead = TAIL && (t0 + lane >= T);
-            const int tl = TAIL ? min(lane, T - 1 - t0) : lane;
-            const int s = s_warp + __popc(mask & (TAIL ? ((1u << tl) - 1u) : below));   // ends at or before this lane's sample
-            s_warp += __popc(mask);
-            const float4 ra = segA[s];
-            const float4 rb = segB[s];
-            float invK, scale, ax = ra.x, ay = ra.y, az = 0.f, dx, dy, dz = 0.f; int cur;
-            if (DIMS == 2) { invK = rb.x; scale = rb.y; cur = __float_as_int(rb.z); dx = ra.z; dy = ra.w; }
-            else { dx = ra.w; dy = rb.x; dz = rb.y; invK = rb.z; scale = rb.w; az = ra.z; cur = segC[s]; }
-            const int k = t0 + tl - cur;
-            int ix, iy, iz;
-            const bool inb = cell_of(__fmul_rn((float)k, invK), ax, ay, az, dx, dy, dz, ix, iy, iz);
-            unsigned adr = brick_offset_p<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, py, pz);
-            if (CHECK) adr = inb ? adr : 0u;
-            raw = load_raw(adr);
-            outside = CHECK && !inb;
-            wgt = dead ? 0.f : scale;
-            if (TRACE) {
-                if (!dead && (long long)(t0 + lane) < a.max_cells) a.cells[t0 + lane] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
-            }
-        };
-        // |g| x weight into the clearance sum; a collision is the sign bit of g (obstacle cells and out-of-map samples
-        // are negative, never -0)
-        auto accumulate = [&](raw_t raw, float wgt, bool outside, const bool CHECK) {
-            float g = value_of(raw);
-            if (CHECK) g = outside ? ng_coll : g;
-            clr_acc = fmaf(fabsf(g), wgt, clr_acc);
-            coll += (int)(__float_as_uint(g) >> 31);
-        };
-        auto run = [&](const bool CHECK) {
-            const int blk_full_end = min(blk1, (int)nblk - 1);   // the trajectory's last block may be partial
-            const raw_t idle = (raw_t)(STORAGE == 1 ? 1 : 0);     // a free cell: nothing in flight yet (weight 0, no collision)
-            raw_t p0 = idle, p1 = idle; float w0 = 0.f, w1 = 0.f; bool o0 = false, o1 = false;   // the two blocks in flight
-            int blk = blk0;
-            for (; blk + 1 < blk_full_end; blk += 2) {
-                raw_t r0, r1; float v0, v1; bool q0, q1;
-                fetch(blk, false, CHECK, r0, v0, q0);
-                fetch(blk + 1, false, CHECK, r1, v1, q1);
-                accumulate(p0, w0, o0, CHECK);
-                accumulate(p1, w1, o1, CHECK);
-                p0 = r0; w0 = v0; o0 = q0; p1 = r1; w1 = v1; o1 = q1;
-            }
-            // at most one full block and the partial last block remain
-            raw_t r0 = idle, r1 = idle; float v0 = 0.f, v1 = 0.f; bool q0 = false, q1 = false;
-            if (blk < blk_full_end) fetch(blk, false, CHECK, r0, v0, q0);
-            if (blk1 == (int)nblk) {
-                fetch((int)nblk - 1, true, CHECK, r1, v1, q1);
-                if ((int)((nblk - 1) << 5) + lane >= T) { r1 = idle; q1 = false; }   // lanes past the last sample
-            }
-            accumulate(p0, w0, o0, CHECK);
-            accumulate(p1, w1, o1, CHECK);
-            accumulate(r0, v0, q0, CHECK);
-            accumulate(r1, v1, q1, CHECK);
-        };
-        if (all_safe) run(false); else run(true);
+    // one 32-sample block: address + load issue.  bp = the block's record, tl = this lane's sample index (TAIL: clamped
+    // to the last sample).  TAIL = the trajectory's last block, where the lanes past the last sample contribute nothing.
+    // CHECK = bounds tests (a sample outside the map is a collision)
+    auto fetch = [&](const uint2* bp, const int tl, const bool TAIL, const bool dead, const bool CHECK, raw_t& raw, float& wgt, bool& outside) {
+        const uint2 br = *bp;
+        const unsigned bel = TAIL ? ((1u << (tl & 31)) - 1u) : below;
+        const int s = (int)br.y + __popc(br.x & bel);             // segment ends before this lane's sample
+        const float4 ra = rec[2 * s];
+        const float4 rb = rec[2 * s + 1];
+        float invK, scale, ax = ra.x, ay = ra.y, az = 0.f, dx, dy, dz = 0.f; int cur;
+        if (DIMS == 2) { invK = rb.x; scale = rb.y; cur = __float_as_int(rb.z); dx = ra.z; dy = ra.w; }
+        else { dx = ra.w; dy = rb.x; dz = rb.y; invK = rb.z; scale = rb.w; az = ra.z; cur = segC[s]; }
+        const int k = tl - cur;
+        int ix, iy, iz;
+        const bool inb = cell_of(__fmul_rn((float)k, invK), ax, ay, az, dx, dy, dz, ix, iy, iz);
+        unsigned adr = brick_offset_p<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, py, pz);
+        if (CHECK) adr = inb ? adr : 0u;
+        raw = load_raw(adr);
+        outside = CHECK && !inb;
+        wgt = scale;
+        if (TAIL && dead) { raw = idle; outside = false; wgt = 0.f; }
+        if (TRACE) {
+            if (!dead && (long long)tl < a.max_cells) a.cells[tl] = inb ? ((long long)iz * mp.ny + iy) * mp.nx + ix : -1;
+        }
+    };
+    // |g| x weight into the clearance sum; a collision is the sign bit of g (obstacle cells and out-of-map samples
+    // are negative, never -0)
+    auto accumulate = [&](raw_t raw, float wgt, bool outside, const bool CHECK) {
+        float g = value_of(raw);
+        if (CHECK) g = outside ? ng_coll : g;
+        clr_acc = fmaf(fabsf(g), wgt, clr_acc);
+        coll += (int)(__float_as_uint(g) >> 31);
+    };
+    raw_t p0 = idle, p1 = idle, p2 = idle; float w0 = 0.f, w1 = 0.f, w2 = 0.f; bool o0 = false, o1 = false, o2 = false;   // in flight
+    // blocks [lb0, lb1) of the round that starts at block c0; the pipeline keeps running across calls
+    auto run = [&](const int c0, const int lb0, const int lb1, const bool CHECK) {
+        const bool has_tail = (c0 + lb1 == nblk);                 // the trajectory's last block may be partial
+        const uint2* bp = blkrec + lb0;
+        const uint2* const bp_full = blkrec + (has_tail ? lb1 - 1 : lb1);
+        int tl = ((c0 + lb0) << 5) + lane;
+#pragma unroll 1
+        for (; bp + 2 < bp_full; bp += 3, tl += 96) {             // three blocks in flight, the oldest is accumulated
+            raw_t r; float v; bool q;
+            fetch(bp, tl, false, false, CHECK, r, v, q);          accumulate(p0, w0, o0, CHECK); p0 = r; w0 = v; o0 = q;
+            fetch(bp + 1, tl + 32, false, false, CHECK, r, v, q); accumulate(p1, w1, o1, CHECK); p1 = r; w1 = v; o1 = q;
+            fetch(bp + 2, tl + 64, false, false, CHECK, r, v, q); accumulate(p2, w2, o2, CHECK); p2 = r; w2 = v; o2 = q;
+        }
+#pragma unroll 1
+        for (; bp < bp_full; ++bp, tl += 32) {
+            raw_t r; float v; bool q;
+            fetch(bp, tl, false, false, CHECK, r, v, q); accumulate(p0, w0, o0, CHECK);
+            p0 = p1; w0 = w1; o0 = o1; p1 = p2; w1 = w2; o1 = o2; p2 = r; w2 = v; o2 = q;
+        }
+        if (has_tail) {
+            raw_t r; float v; bool q;
+            fetch(bp, min(tl, T - 1), true, tl >= T, CHECK, r, v, q); accumulate(p0, w0, o0, CHECK);
+            p0 = p1; w0 = w1; o0 = o1; p1 = p2; w1 = w2; o1 = o2; p2 = r; w2 = v; o2 = q;
+        }
+    };
+    for (int c0 = 0; c0 < nblk; c0 += a.cb) {
+        const int nb = min(a.cb, nblk - c0);
+        // 2a: block records of this round.  Segment s covers samples [off[s], off[s+1]): it is the first segment of
+        // every block that starts inside it, and its last sample sets one end bit
+        for (int lb = tid; lb < nb; lb += nthr) blkrec[lb].x = 0u;
+        __syncthreads();
+        const int r_lo = c0 << 5, r_hi = (c0 + nb) << 5;          // samples of this round
+        for (int sg = s_begin; sg < s_end; ++sg) {
+            const int f0 = off[sg], f1 = off[sg + 1];
+            for (int blk = max((f0 + 31) >> 5, c0); blk < c0 + nb && (blk << 5) < f1; ++blk) blkrec[blk - c0].y = (unsigned)sg;
+            const int e = f1 - 1;
+            if (e >= r_lo && e < r_hi) atomicOr(&blkrec[(e >> 5) - c0].x, 1u << (e & 31));
+        }
+        __syncthreads();
+        // 2b: a contiguous run of blocks per warp
+        const int lb0 = (int)(((unsigned)warp * (unsigned)nb) / (unsigned)nwarps), lb1 = (int)(((unsigned)(warp + 1) * (unsigned)nb) / (unsigned)nwarps);
+        if (lb0 < lb1) { if (all_safe) run(c0, lb0, lb1, false); else run(c0, lb0, lb1, true); }
+        if (c0 + a.cb < nblk) __syncthreads();                    // the stage is rebuilt
     }
-    if (s_begin < s_end) take_back();
+    if (all_safe) { accumulate(p0, w0, o0, false); accumulate(p1, w1, o1, false); accumulate(p2, w2, o2, false); }
+    else { accumulate(p0, w0, o0, true); accumulate(p1, w1, o1, true); accumulate(p2, w2, o2, true); }
+
+    // ---- 2c: the end samples (k = 0 and k = K) of my segments, by the same arithmetic as the sample loop ----
+    float corr_clr = 0.f; int corr_coll = 0;
+    for (int sg = s_begin; sg < s_end; ++sg) {
+        const float4 ra = rec[2 * sg];
+        const float4 rb = rec[2 * sg + 1];
+        float invK, scale, ax = ra.x, ay = ra.y, az = 0.f, dx, dy, dz = 0.f;
+        if (DIMS == 2) { invK = rb.x; scale = rb.y; dx = ra.z; dy = ra.w; }
+        else { dx = ra.w; dy = rb.x; dz = rb.y; invK = rb.z; scale = rb.w; az = ra.z; }
+        const int K = off[sg + 1] - off[sg] - 1;
+        int ix, iy, iz;
+        const bool in0 = cell_of(__fmul_rn(0.f, invK), ax, ay, az, dx, dy, dz, ix, iy, iz);
+        const raw_t e0 = load_raw(in0 ? brick_offset_p<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, py, pz) : 0u);
+        const bool inK = cell_of(__fmul_rn((float)K, invK), ax, ay, az, dx, dy, dz, ix, iy, iz);
+        const raw_t eK = load_raw(inK ? brick_offset_p<DIMS, STORAGE>((unsigned)ix, (unsigned)iy, (unsigned)iz, py, pz) : 0u);
+        const float g0 = in0 ? value_of(e0) : ng_coll, gK = inK ? value_of(eK) : ng_coll;
+        corr_clr = fmaf(0.5f * scale, fabsf(g0) + fabsf(gK), corr_clr);
+        corr_coll += (sg != last && gK < 0.f) ? 1 : 0;
+    }
 
     // ---- phase 3: block reduction ----
     len_acc = warp_sum(len_acc);

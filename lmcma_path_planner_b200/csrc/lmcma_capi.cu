@@ -161,7 +161,7 @@ struct lmcma_b200_opt {
     float* d_Lf = nullptr;             // lower Cholesky factor of the smoothness prior (n x ns FP32) or null
     bool mirror_dirty = true;          // the sequence-ordered pair mirror must be rebuilt (k_pack_pairs) before sampling
     size_t smp_smem = 0;
-    int cost_tpt = 128;
+    CostShape cost_shape;
     int upd_nvb = 4, upd_rmax = 0;
     bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
     bool upd_rows_in_smem = true;
@@ -175,36 +175,48 @@ struct lmcma_b200_opt {
 namespace {
 
 template <int DIMS, int STORAGE, bool TRACE>
-int launch_cost_t(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, cudaStream_t st) {
-    const size_t smem = (size_t)40 * (a.W + 1) + sizeof(int) * (a.W + 2 + 32) + (STORAGE == 1 ? 1024 : 0);
+int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostShape shape, cudaStream_t st) {
+    CostArgs a = a0;
+    a.cb = shape.cb;
+    // segment records 36 B, sample offsets, per-block records 8 B (k_cost.cuh), 256-entry table (u8 storage)
+    const size_t smem = (size_t)36 * (a.W + 1) + sizeof(int) * (a.W + 2) + 28 + (size_t)8 * shape.cb + (STORAGE == 1 ? 1024 : 0);
     auto kern = k_cost<DIMS, STORAGE, TRACE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(rows, B), tpt, smem, st>>>(mp, a);
+    kern<<<dim3(rows, B), shape.tpt, smem, st>>>(mp, a);
     g_launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, int tpt, bool trace, cudaStream_t st) {
+int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, CostShape shape, bool trace, cudaStream_t st) {
     if (rows <= 0 || B <= 0) return 0;
     if (trace) {
-        if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, tpt, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, tpt, st);
-        return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, tpt, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, tpt, st);
+        if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, shape, st);
+        return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, shape, st);
     }
-    if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false>(mp, a, rows, B, tpt, st) : launch_cost_t<2, 1, false>(mp, a, rows, B, tpt, st);
-    return mp.storage == 0 ? launch_cost_t<3, 0, false>(mp, a, rows, B, tpt, st) : launch_cost_t<3, 1, false>(mp, a, rows, B, tpt, st);
+    if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false>(mp, a, rows, B, shape, st);
+    return mp.storage == 0 ? launch_cost_t<3, 0, false>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false>(mp, a, rows, B, shape, st);
 }
 
-int pick_cost_tpt(int W, const float* start, const float* goal, int dims) {
-    const int forced = env_int("LMCMA_B200_COST_TPT", 0);
-    if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+// CTA width and per-block record capacity of k_cost from the expected samples per trajectory
+CostShape pick_cost_shape(int W, const float* start, const float* goal, int dims) {
     float linf = 0.f;
     if (start && goal)
         for (int c = 0; c < dims; ++c) linf = std::max(linf, std::fabs(goal[c] - start[c]));
     const double est = 2.0 * (W + 1) + linf;     // expected samples per trajectory
-    int tpt = 32;
-    while (tpt < 256 && est / tpt > 24.0) tpt <<= 1;
-    return tpt;                                  // k_cost is built for at most 8 warps (COST_MAX_WARPS)
+    CostShape sh;
+    sh.tpt = 32;
+    // enough lanes for the samples, and a thread per segment (phase 1 is a chain of dependent loads per segment);
+    // k_cost is built for at most 8 warps (COST_MAX_WARPS)
+    while (sh.tpt < 256 && (est / sh.tpt > 24.0 || W + 1 > sh.tpt)) sh.tpt <<= 1;
+    const int forced = env_int("LMCMA_B200_COST_TPT", 0);
+    if (forced >= 32 && forced <= 256 && forced % 32 == 0) sh.tpt = forced;
+    // 32-sample blocks whose records are staged at once (longer trajectories take several rounds): ~3x the estimate
+    sh.cb = 64;
+    while (sh.cb < 2048 && sh.cb * 32.0 < 3.0 * est) sh.cb <<= 1;
+    const int forced_cb = env_int("LMCMA_B200_COST_CB", 0);
+    if (forced_cb >= 8 && forced_cb <= 4096) sh.cb = forced_cb;
+    return sh;
 }
 
 template <int NV, int RB, int MAXT>
@@ -479,7 +491,7 @@ int ensure_graph(lmcma_b200_opt* o) {
     cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+    rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
     if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st, true);
     if (!rc) rc = launch_update(o, update_args_local(o), true, st);
     if (!rc) rc = launch_sample(o, st, true);
@@ -790,7 +802,7 @@ int lmcma_b200_cost_evaluate_dev(lmcma_b200_map* m, const lmcma_b200_objective* 
     a.X = X_dev; a.ld = ld; a.inst_rows = count; a.ends = m->d_ends; a.ends_per_instance = 0;
     a.f = f_dev; a.f_stride = count; a.f_offset = 0; a.ncoll = ncoll_dev; a.nsamp = nsamp_dev;
     if ((rc = apply_l2_window(m, st))) return rc;
-    return launch_cost(m->dev, a, count, 1, pick_cost_tpt(a.W, ends->start, ends->goal, m->dev.dims), false, st);
+    return launch_cost(m->dev, a, count, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims), false, st);
 }
 
 int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
@@ -841,7 +853,7 @@ int lmcma_b200_cost_trace(lmcma_b200_map* m, const lmcma_b200_objective* obj, co
     a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
     a.X = dX; a.ld = (long long)n; a.inst_rows = 1; a.ends = m->d_ends; a.ends_per_instance = 0;
     a.f = df; a.f_stride = 1; a.nsamp = dns; a.cells = dcells; a.max_cells = max_cells;
-    rc = launch_cost(m->dev, a, 1, 1, pick_cost_tpt(a.W, ends->start, ends->goal, m->dev.dims), true, m->stream);
+    rc = launch_cost(m->dev, a, 1, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims), true, m->stream);
     if (!rc) {
         cudaError_t e = cudaStreamSynchronize(m->stream);
         if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "trace kernel: %s", cudaGetErrorString(e));
@@ -1132,7 +1144,7 @@ int lmcma_b200_attach_cost(lmcma_b200_opt* o, lmcma_b200_map* map, const lmcma_b
         for (int c = 0; c < 3; ++c) { e6[b * 6 + c] = ends[b].start[c]; e6[b * 6 + 3 + c] = ends[b].goal[c]; }
     if (!o->d_ends) DM(o->d_ends, (size_t)o->d.B * 6);
     CU(cudaMemcpy(o->d_ends, e6.data(), e6.size() * sizeof(float), cudaMemcpyHostToDevice));
-    o->cost_tpt = pick_cost_tpt(obj->waypoints, ends[0].start, ends[0].goal, map->dev.dims);
+    o->cost_shape = pick_cost_shape(obj->waypoints, ends[0].start, ends[0].goal, map->dev.dims);
     if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
     return 0;
 }
@@ -1158,7 +1170,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
         CostArgs ca;
         if ((rc = cost_args_for(o, &ca))) return rc;
         for (int g = 0; g < generations; ++g) {
-            if ((rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, o->stream))) return rc;
+            if ((rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, o->stream))) return rc;
             if ((rc = generation_tail(o, o->stream))) return rc;
         }
     }
@@ -1197,7 +1209,7 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
     for (int g = 0; g < generations && !rc; ++g) {
         cudaEvent_t* e = &ev[(size_t)g * 5];
         cudaEventRecord(e[0], st);
-        rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+        rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
         cudaEventRecord(e[1], st);
         if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st);
         cudaEventRecord(e[2], st);
@@ -1214,7 +1226,7 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
             cudaMemset(dbg, 0, 16 * sizeof(long long));
             UpdateArgs ua = update_args_local(o);
             ua.dbg = dbg;
-            launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+            launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
             launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st);
             launch_update(o, ua, true, st);
             launch_sample(o, st, true);
@@ -1489,7 +1501,7 @@ int lmcma_b200_mg_evaluate(lmcma_b200_opt* o, float* f_local_dev, void* stream) 
     ca.f = f_local_dev; ca.f_stride = o->d.pop_count; ca.f_offset = 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : o->stream;
     if ((rc = apply_l2_window(o->map, st))) return rc;
-    return launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_tpt, false, st);
+    return launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
 }
 
 int lmcma_b200_mg_rank(lmcma_b200_opt* o, const float* f_all_dev, float* payload_dev, void* stream) {

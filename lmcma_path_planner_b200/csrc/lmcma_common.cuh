@@ -107,7 +107,10 @@ struct CostArgs {
     int* nsamp;
     long long* cells;          // trace mode (nullable)
     long long max_cells;
+    int cb;                    // capacity of the per-block record stage (32-sample blocks), set by the launcher
 };
+
+struct CostShape { int tpt = 128, cb = 256; };   // launch shape of k_cost: threads per trajectory, block-record capacity
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
