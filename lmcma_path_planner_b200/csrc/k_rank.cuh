@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict
     griddep_wait();
     griddep_launch_dependents();
     const int b = blockIdx.y;
+    // the hand-over flags of this generation's k_update -> k_sample (both start after this grid has completed)
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i <= o.m; i += blockDim.x) o.progress[(size_t)b * (o.m + 1) + i] = 0;
     tell_phase_a(o, f_all, b, blockIdx.x, smem_raw);
     if (mode != RANK_PACK) return;
     __threadfence();

@@ -246,8 +246,13 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
 // and group.  4x..16x more resident warps per SM than the warp-per-row kernel.
 // grid = (ceil(pop_count / (R * RBW)), B), block = 32 * R * CW.
 // ------------------------------------------------------------------------------------------------
+//
+// progressive != 0 (one query, fused generation): the kernel is released while k_update is still in its triangular
+// sweep and consumes the pairs as k_update publishes them (OptDev::progress, gpu-scope release / acquire), one chunk
+// per round, so that only the last chunk's work is left when the sweep ends.  Requires one stage per chunk.
 template <int RBW, int MAXT>
-__global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nstages, int R, int CW, int qpw /* float4 columns per warp */) {
+__global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nstages, int R, int CW, int qpw /* float4 columns per warp */,
+                                                       int progressive) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
 #define SMP_STAMP(k) do { if (o.dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) o.dbg[32 + k] = gtime(); } while (0)
     SMP_STAMP(0);
@@ -264,7 +269,22 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
         for (int s2 = 0; s2 < nstages; ++s2) mbar_init(&bars[s2], 1);
         fence_barrier_init();
     }
-    griddep_wait();                            // every input is k_update's output
+    const int* flags = o.progress + (size_t)b * (o.m + 1);
+    // bounded spin on a hand-over flag; if it never comes (a launch that did not pair this kernel with a publishing
+    // k_update) fall back to waiting for the whole predecessor grid, after which everything is final anyway
+    auto wait_flag = [&](const int* f) {
+        for (int spin = 0; spin < (1 << 22); ++spin) {
+            if (ld_acquire_gpu(f) != 0) return;
+            __nanosleep(32);
+        }
+        griddep_wait();
+    };
+    if (!progressive) {
+        griddep_wait();                        // every input is k_update's output
+    } else {
+        if (threadIdx.x == 0) wait_flag(flags);                 // scalars + mean
+        __syncthreads();
+    }
     SMP_STAMP(1);
     const float* vps = o.VPs + (size_t)b * o.m * 2 * ns;
     // one bulk async copy per chunk of consecutive pairs; sized by m, not by the live count, so that the first
@@ -277,7 +297,7 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
         bulk_g2s(stage_base + st * stage_floats, vps + (size_t)k0 * 2 * ns, bytes, &bars[st]);
     };
     const int max_chunks = (o.m + kc - 1) / kc;
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0 && !progressive)
         for (int c = 0; c < max_chunks && c < nstages; ++c) issue(c);
     const Scalars sc = o.sc[b];
     const int live = sc.live;
@@ -285,11 +305,45 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
     SMP_STAMP(2);
     const float Mf = (float)o.M, Minv = 1.0f / Mf;
     const int live8 = (live + SAMPLE_G - 1) & ~(SAMPLE_G - 1);
-    for (int k = threadIdx.x; k < live8; k += blockDim.x) {
-        float sc8 = Minv;                                       // M^-((k mod 8) + 1)
-        for (int c = 0; c < (k & 7); ++c) sc8 *= Minv;
-        nj_s[k] = (k < live) ? o.Njs[(size_t)b * o.m + k] * sc8 : 0.f;
-    }
+    if (!progressive)
+        for (int k = threadIdx.x; k < live8; k += blockDim.x) {
+            float sc8 = Minv;                                       // M^-((k mod 8) + 1)
+            for (int c = 0; c < (k & 7); ++c) sc8 *= Minv;
+            nj_s[k] = (k < live) ? o.Njs[(size_t)b * o.m + k] * sc8 : 0.f;
+        }
+    // progressive (warp 0, all lanes): chunk c = pairs [c kc, c kc + cnt) — poll their flags, stage Nj, request the copy
+    int next_issue = 0;                                         // warp 0: chunks [0, next_issue) have been requested
+    auto chunk_ready = [&](int c) -> bool {
+        const int k0 = c * kc, cnt = min(kc, live - k0);
+        int f = 1;
+        if (lane < cnt) f = ld_acquire_gpu(flags + 1 + k0 + lane);
+        return __all_sync(0xffffffffu, f != 0);
+    };
+    auto request_chunk = [&](int c) {                           // flags are set
+        const int k0 = c * kc, cnt = min(kc, live - k0);
+        if (lane < SAMPLE_G && lane < ((cnt + SAMPLE_G - 1) & ~(SAMPLE_G - 1))) {
+            float sc8 = Minv;
+            for (int c2 = 0; c2 < (lane & 7); ++c2) sc8 *= Minv;
+            nj_s[k0 + lane] = (lane < cnt) ? o.Njs[(size_t)b * o.m + k0 + lane] * sc8 : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async_all();                            // the rows were written through the generic proxy (by k_update)
+            const int st = c % nstages;
+            const unsigned bytes = (unsigned)(cnt * 2 * ns * sizeof(float));
+            mbar_expect_tx(&bars[st], bytes);
+            bulk_g2s(stage_base + st * stage_floats, vps + (size_t)k0 * 2 * ns, bytes, &bars[st]);
+        }
+    };
+    auto provide_chunk = [&](int c) {                           // warp 0: make sure chunk c is on its way, then run ahead
+        while (next_issue <= c) {
+            bool ok = false;
+            for (int spin = 0; spin < (1 << 22) && !ok; ++spin) { ok = chunk_ready(next_issue); if (!ok) __nanosleep(32); }
+            if (!ok) griddep_wait();                            // see wait_flag
+            request_chunk(next_issue++);
+        }
+        while (next_issue < nchunks && chunk_ready(next_issue)) request_chunk(next_issue++);
+    };
     float M8 = 1.0f;
 #pragma unroll
     for (int c = 0; c < SAMPLE_G; ++c) M8 *= Mf;
@@ -328,13 +382,18 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
     // first (all against the ORIGINAL z: no ordering between pairs), the partial sums are exchanged ONCE, then the
     // ordered recurrence runs over the round's pairs: one named barrier per round instead of one per group.
     const int gpc = (kc + SAMPLE_G - 1) / SAMPLE_G;             // groups per chunk
-    for (int c0 = 0; c0 < nchunks; c0 += nstages) {
-        const int c1 = min(nchunks, c0 + nstages);
+    const int round = progressive ? 1 : nstages;                // chunks per round
+    for (int c0 = 0; c0 < nchunks; c0 += round) {
+        const int c1 = min(nchunks, c0 + round);
         float* dp0 = dpart + (size_t)rl * CW * RBW * SAMPLE_G;
         const size_t grp_stride = (size_t)R * CW * RBW * SAMPLE_G;
-        int grp = 0;
+        // progressive: no block-wide barrier between rounds, so the exchange buffer alternates (a warp can be one
+        // round ahead of its row-group, never two: the named barrier below)
+        const int grp0 = progressive ? (c0 & 1) * gpc : 0;
+        int grp = grp0;
         for (int c = c0; c < c1; ++c) {
             const int st = c % nstages;
+            if (progressive && warp == 0) provide_chunk(c);
             mbar_wait(&bars[st], (unsigned)((c / nstages) & 1));
             if (c == 0) SMP_STAMP(4);
             if (c < 8) SMP_STAMP(7 + c);
@@ -362,7 +421,7 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
         if (CW > 1) named_bar_sync(1 + rl, CW * 32);            // the CW warps of this row-group (ids 1..15: R <= 15)
         else __syncwarp();
         SMP_STAMP(16);
-        grp = 0;
+        grp = grp0;
         for (int c = c0; c < c1; ++c) {
             const int st = c % nstages;
             const float* sb = stage_base + st * stage_floats;
@@ -396,7 +455,7 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
                 for (int r = 0; r < RBW; ++r) az[r] = make_float4(acc[r].x * mg, acc[r].y * mg, acc[r].z * mg, acc[r].w * mg);
             }
         }
-        if (c1 < nchunks) {                                     // next round: every warp is done with all stages
+        if (c1 < nchunks && !progressive) {                     // next round: every warp is done with all stages
             __syncthreads();
             if (threadIdx.x == 0)
                 for (int c = c1; c < max_chunks && c < c1 + nstages; ++c) issue(c);
@@ -412,6 +471,7 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
             sample_finish(o, o.xmean + (size_t)b * ns, sc.sigma, az[r], q, o.X + roff2, o.D + roff2);
         }
     }
+    if (progressive) griddep_wait();                            // stream order: this grid ends after k_update has
     SMP_STAMP(6);
 #undef SMP_STAMP
 }

@@ -28,6 +28,8 @@ struct UpdateArgs {
     long long slice_stride, inst_stride;
     int payload_mode;          // slices are all-gather payloads (S rides in the 2 floats after ns)
     long long* dbg;            // optional: globaltimer stamps (LMCMA_B200_UPDATE_DBG)
+    int progressive;           // publish OptDev::progress flags as the outputs become final: k_sample (launched as a
+                               // programmatic dependent) consumes the pairs while the sweep is still producing them
 };
 
 #define UPD_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[k] = gtime(); } while (0)
@@ -72,7 +74,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     float* Njsb = o.Njs + (size_t)b * m;
     const float* fa = a.f_all + (size_t)b * o.lambda;
 
-    griddep_launch_dependents();          // k_sample may be scheduled; it waits for this grid before reading anything
+    // classic: k_sample may be scheduled right away; it waits for this grid to complete before reading anything.
+    // progressive: it is released after this kernel's own wait (k_rank has reset the hand-over flags by then)
+    if (!a.progressive) griddep_launch_dependents();
+    int* flags = o.progress + (size_t)b * (m + 1);
     UPD_STAMP(0);
     // =============================== prologue: independent of k_rank ===============================
     const Scalars sc0 = *scp;
@@ -191,7 +196,35 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 
     // =============================== needs k_rank's partial sums ===============================
     griddep_wait();
+    if (a.progressive) griddep_launch_dependents();
     UPD_STAMP(3);
+    // ---- population-success step size (lmcma.cpp:393-419), counters (lmcma.cpp:189, 423): needs only k_rank's pair
+    //      count, so it goes first (the progressive hand-over publishes the scalars before the sweep) ----
+    if (tid == nthr - 1) {
+        unsigned long long S = 0;
+        if (a.payload_mode) {
+            for (int k = 0; k < a.n_slices; ++k) {
+                const float* pay = a.slices + (size_t)k * a.slice_stride + (size_t)b * a.inst_stride + ns;
+                S += ((unsigned long long)__float_as_uint(__ldcg(pay + 1)) << 32) | __float_as_uint(__ldcg(pay));
+            }
+        } else {
+            S = atomicExch(o.S_count + b, 0ull);
+        }
+        if (itr > 0) {
+            const double lam = (double)o.lambda;
+            const unsigned long long L = (unsigned long long)o.lambda;
+            const unsigned long long sum_cur = L * (L - 1ull) / 2ull + S;       // ranks of this generation in the merged order
+            const unsigned long long sum_prev = L * (2ull * L - 1ull) - sum_cur;
+            const double mean_cur = (double)sum_cur / lam, mean_prev = (double)sum_prev / lam;
+            const double success = (mean_prev - mean_cur) / lam;
+            const double snew = (1.0 - o.cs) * sc0.s + o.cs * (success - o.target);
+            scp->s = snew;
+            scp->sigma = sigma_old * exp(snew);
+        }
+        scp->itr = itr + 1;
+        scp->live = live;
+        scp->counteval = sc0.counteval + o.lambda;
+    }
     // prev_fit (lmcma.cpp:420-421): k_rank has finished reading the previous generation's values
     for (int j = tid; j < o.lambda; j += nthr) o.prev_fit[(size_t)b * o.lambda + j] = canon_fitness(__ldcg(fa + j));
 
@@ -255,6 +288,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     if (!SMEM) __threadfence();
     __syncthreads();
     UPD_STAMP(4);
+    if (a.progressive) {
+        // scalars and mean are final; so are the pairs in front of the first stale position (untouched this generation)
+        for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);
+        if (tid == 0) st_release_gpu(flags, 1);
+    }
 
     // ---- recompute v from the first stale position (lmcma.cpp:373-390) ----
     // Closed forms of lmcma.cpp:386-389 with t = sqrt(1 + c1/(1-c1) |v|^2), rewritten without cancellation:
@@ -331,6 +369,14 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             for (int it = 0; it < NVB; ++it) {
                 const int q = lane + 32 * it;
                 if (q < nq) { dst[q] = x[it]; dst2[q] = x[it]; }
+            }
+            if (a.progressive) {                                     // pair i of the mirror and Njs[i] are final
+                __syncwarp();
+                if (lane == 0) {
+                    const double r = o.c1 / (1.0 - o.c1), t = sqrt(1.0 + r * (double)nv);
+                    Njsb[i] = (float)(o.M * r / (t + 1.0));          // the value the epilogue stores, too
+                    st_release_gpu(flags + 1 + i, 1);
+                }
             }
         };
         if (first_stale == 0 && warp == 0) publish(y[0], 0, 1.0);   // row 0 has no factors (v_0 = pc_0)
@@ -475,32 +521,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         const double t = sqrt(1.0 + r * nv);
         const double nj = am * r / (t + 1.0), lj = r / (am * t * (t + 1.0));
         Njd[slot] = nj; Ljd[slot] = lj; Njf[slot] = (float)nj; Njsb[i] = (float)nj;
-    }
-    // ---- population-success step size (lmcma.cpp:393-419), counters (lmcma.cpp:189, 423) ----
-    if (tid == nthr - 1) {
-        unsigned long long S = 0;
-        if (a.payload_mode) {
-            for (int k = 0; k < a.n_slices; ++k) {
-                const float* pay = a.slices + (size_t)k * a.slice_stride + (size_t)b * a.inst_stride + ns;
-                S += ((unsigned long long)__float_as_uint(__ldcg(pay + 1)) << 32) | __float_as_uint(__ldcg(pay));
-            }
-        } else {
-            S = atomicExch(o.S_count + b, 0ull);
-        }
-        if (itr > 0) {
-            const double lam = (double)o.lambda;
-            const unsigned long long L = (unsigned long long)o.lambda;
-            const unsigned long long sum_cur = L * (L - 1ull) / 2ull + S;       // ranks of this generation in the merged order
-            const unsigned long long sum_prev = L * (2ull * L - 1ull) - sum_cur;
-            const double mean_cur = (double)sum_cur / lam, mean_prev = (double)sum_prev / lam;
-            const double success = (mean_prev - mean_cur) / lam;
-            const double snew = (1.0 - o.cs) * sc0.s + o.cs * (success - o.target);
-            scp->s = snew;
-            scp->sigma = sigma_old * exp(snew);
-        }
-        scp->itr = itr + 1;
-        scp->live = live;
-        scp->counteval = sc0.counteval + o.lambda;
     }
     UPD_STAMP(6);
 }

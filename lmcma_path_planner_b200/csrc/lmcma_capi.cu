@@ -162,6 +162,7 @@ struct lmcma_b200_opt {
     bool mirror_dirty = true;          // the sequence-ordered pair mirror must be rebuilt (k_pack_pairs) before sampling
     size_t smp_smem = 0;
     CostShape cost_shape;
+    bool progressive = false;   // k_update -> k_sample hand-over inside the fused generation (k_update.cuh)
     int upd_nvb = 4, upd_rmax = 0;
     bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
     bool upd_rows_in_smem = true;
@@ -238,7 +239,7 @@ int launch_sample_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
 }
 
 template <int RBW, int MAXT>
-int launch_sample_wide_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
+int launch_sample_wide_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st, int progressive) {
     auto kern = k_sample_wide<RBW, MAXT>;
     if (o->smp_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_smem));
     cudaLaunchConfig_t cfg;
@@ -250,15 +251,15 @@ int launch_sample_wide_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    CU(cudaLaunchKernelEx(&cfg, kern, o->d, o->smp_kc, o->smp_stages, o->smp_R, o->smp_CW, o->smp_qpw));
+    CU(cudaLaunchKernelEx(&cfg, kern, o->d, o->smp_kc, o->smp_stages, o->smp_R, o->smp_CW, o->smp_qpw, progressive));
     g_launches++;
     return 0;
 }
-int launch_sample_wide(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
+int launch_sample_wide(lmcma_b200_opt* o, bool pdl, cudaStream_t st, int progressive) {
     switch (o->smp_RBW) {
-        case 1: return launch_sample_wide_t<1, 1024>(o, pdl, st);
-        case 2: return launch_sample_wide_t<2, 1024>(o, pdl, st);
-        default: return launch_sample_wide_t<4, 512>(o, pdl, st);
+        case 1: return launch_sample_wide_t<1, 1024>(o, pdl, st, progressive);
+        case 2: return launch_sample_wide_t<2, 1024>(o, pdl, st, progressive);
+        default: return launch_sample_wide_t<4, 512>(o, pdl, st, progressive);
     }
 }
 
@@ -274,7 +275,8 @@ int ensure_mirror(lmcma_b200_opt* o, cudaStream_t st) {
 }
 
 // pdl: launched as a programmatic dependent of the kernel enqueued just before it on `st` (k_update)
-int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false) {
+// progressive: that k_update was launched with UpdateArgs::progressive (only meaningful with pdl)
+int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false, bool progressive = false) {
     if (o->mirror_dirty) { int rc = ensure_mirror(o, st); if (rc) return rc; pdl = false; }
     if (o->d_Lf) {   // smoothness prior: z <- L z for the whole population before computeAz (lmcma.cpp:216-217)
         const OptDev& d = o->d;
@@ -288,7 +290,7 @@ int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false) {
         CU(cudaGetLastError());
         pdl = false;
     }
-    if (o->smp_wide) return launch_sample_wide(o, pdl, st);
+    if (o->smp_wide) return launch_sample_wide(o, pdl, st, (pdl && progressive && o->progressive) ? 1 : 0);
     switch (o->smp_nv) {
         case 1: return launch_sample_t<1, 4, 512>(o, pdl, st);
         case 2: return launch_sample_t<2, 4, 512>(o, pdl, st);
@@ -455,7 +457,7 @@ int cost_args_for(lmcma_b200_opt* o, CostArgs* a) {
 }
 
 // generate / stage deviates on the host for HANSEN mode, then sample
-int host_rng_and_sample(lmcma_b200_opt* o, cudaStream_t st) {
+int host_rng_and_sample(lmcma_b200_opt* o, cudaStream_t st, bool progressive = false) {
     if (o->cfg.rng == LMCMA_B200_RNG_HANSEN) {
         const size_t rows = (size_t)o->d.pop_count;
         o->z_host.assign(rows * o->d.ns, 0.f);
@@ -465,19 +467,23 @@ int host_rng_and_sample(lmcma_b200_opt* o, cudaStream_t st) {
         CU(cudaMemcpyAsync(o->d.Z, o->z_host.data(), o->z_host.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));   // z_host is pageable and reused
     }
-    return launch_sample(o, st, o->cfg.rng != LMCMA_B200_RNG_HANSEN);
+    return launch_sample(o, st, o->cfg.rng != LMCMA_B200_RNG_HANSEN, progressive);
 }
 
 // update() + sample() after the fitness of a generation is in d.fit
 int generation_tail(lmcma_b200_opt* o, cudaStream_t st) {
     int rc;
     if ((rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st))) return rc;
-    if ((rc = launch_update(o, update_args_local(o), true, st))) return rc;
+    // device RNG: k_sample follows k_update directly and can take its outputs as they become final
+    const bool prog = o->progressive && o->cfg.rng == LMCMA_B200_RNG_PHILOX && !o->mirror_dirty;
+    UpdateArgs ua = update_args_local(o);
+    ua.progressive = prog ? 1 : 0;
+    if ((rc = launch_update(o, ua, true, st))) return rc;
     o->x_cache_valid = false;
     o->sample_idx = 0;
     if (o->cfg.rng == LMCMA_B200_RNG_INJECT && !o->pending_z) { o->needs_sample = true; return 0; }
     o->pending_z = false;
-    return host_rng_and_sample(o, st);
+    return host_rng_and_sample(o, st, prog);
 }
 
 int ensure_graph(lmcma_b200_opt* o) {
@@ -493,8 +499,10 @@ int ensure_graph(lmcma_b200_opt* o) {
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
     if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st, true);
-    if (!rc) rc = launch_update(o, update_args_local(o), true, st);
-    if (!rc) rc = launch_sample(o, st, true);
+    UpdateArgs ua = update_args_local(o);
+    ua.progressive = o->progressive ? 1 : 0;                 // ensure_mirror above: the mirror is clean
+    if (!rc) rc = launch_update(o, ua, true, st);
+    if (!rc) rc = launch_sample(o, st, true, o->progressive);
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     g_launches.store(before);   // capture enqueues nothing
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -952,7 +960,7 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     DM(d.Nj, B * m); DM(d.Lj, B * m); DM(d.Njf, B * m); DM(d.Njs, B * m);
     DM(d.VPs, B * m * 2 * ns);
     DM(d.t, B * m); DM(d.vec, B * m);
-    DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B); DM(d.done_count, B);
+    DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B); DM(d.done_count, B); DM(d.progress, B * (m + 1));
     {   // row slices of k_tell's phase A: 32 rows per slice, at most 256 slices
         const int rows_per = std::max(32, (d.pop_count + 255) / 256);
         if (rows_per > TELL_MAX_ROWS) { lmcma_b200_destroy(o); return fail(LMCMA_B200_ERR_ARG, "population too large (max %d rows per handle)", 256 * TELL_MAX_ROWS); }
@@ -993,6 +1001,11 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
 
     rc = configure_sample(o);
     if (!rc) rc = configure_update(o);
+    // one query with a wide sampler and the register sweep: k_sample consumes the direction pairs while k_update's sweep
+    // is still producing them (k_update.cuh / k_sample.cuh "progressive")
+    o->progressive = !rc && B == 1 && o->smp_wide && o->upd_rmax > 0 && !o->upd_gram && !o->d_Lf && o->smp_kc == 8 &&
+                     o->smp_stages >= (m + o->smp_kc - 1) / o->smp_kc && cfg->rng == LMCMA_B200_RNG_PHILOX &&
+                     env_int("LMCMA_B200_PROGRESSIVE", 1) != 0;
     if (!rc && o->upd_gram) {
         rc = dmalloc(&d.G, B * m * m);
         if (!rc) rc = dmalloc(&d.Cf, B * m * m);
@@ -1017,7 +1030,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     if (o->stream) cudaStreamSynchronize(o->stream);
     OptDev& d = o->d;
     void* ptrs[] = {d.X, d.D, d.Z, d.Zc, o->d_Lf, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
-                    d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
+                    d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.progress, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
     if (o->ev0) cudaEventDestroy(o->ev0);

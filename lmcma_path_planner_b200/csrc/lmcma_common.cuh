@@ -65,6 +65,9 @@ struct OptDev {
     double* G;         // B x m x m
     double* Cf;        // B x m x m
     int2* gram_hdr;    // B : {first_stale, live} handed from k_update to k_gram / k_coef / k_combine
+    // progressive hand-over k_update -> k_sample inside one generation (see k_update.cuh): [0] = scalars and mean are
+    // final, [1 + i] = pair i of the sequence-ordered mirror (and Njs[i]) is final.  Reset by k_rank.
+    int* progress;     // B x (m + 1)
     int* t;            // B x m   slot order, oldest -> newest
     int* vec;          // B x m   generation stamp per slot
     Scalars* sc;       // B
@@ -177,6 +180,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// gpu-scope release / acquire on a flag in global memory, and the generic -> async proxy fence a bulk async copy of
+// data published that way needs
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ long long gtime() {
     long long t;
