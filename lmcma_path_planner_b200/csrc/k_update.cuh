@@ -28,6 +28,7 @@ struct UpdateArgs {
     long long slice_stride, inst_stride;
     int payload_mode;          // slices are all-gather payloads (S rides in the 2 floats after ns)
     long long* dbg;            // optional: globaltimer stamps (LMCMA_B200_UPDATE_DBG)
+    int blocked;               // register sweep: a warp owns R CONSECUTIVE rows (else rows w, w + 16, ...)
     int progressive;           // publish OptDev::progress flags as the outputs become final: k_sample (launched as a
                                // programmatic dependent) consumes the pairs while the sweep is still producing them
 };
@@ -325,11 +326,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     } else if (RMAX > 0) {
         // ---------------- register sweep: warp w owns rows first_stale + w + r * UPD_WARPS ----------------
         constexpr int R = RMAX > 0 ? RMAX : 1;
-        const int base = first_stale + warp;
+        const int rstride = a.blocked ? 1 : UPD_WARPS;
+        const int base = first_stale + (a.blocked ? warp * R : warp);
         float4 y[R][NVB];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = base + r * UPD_WARPS;
+            const int i = base + r * rstride;
             const bool on = i < live;
 #pragma unroll
             for (int it = 0; it < NVB; ++it) {
@@ -339,7 +341,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             }
         }
         int my_last = -1;                                            // my largest row
-        if (base < live) my_last = base + ((live - 1 - base) / UPD_WARPS) * UPD_WARPS;
+#pragma unroll
+        for (int r = 0; r < R; ++r) if (base + r * rstride < live) my_last = base + r * rstride;
         auto publish = [&](const float4 (&row)[NVB], int i, double kp) {   // warp-collective: y_i K^i is the final v_i
             const float kf = (float)kp;
             float4* srow = reinterpret_cast<float4*>(rows_s + (size_t)i * ns);
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             // the row that becomes final in this step goes first and alone: the next step waits for it
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (base + r * UPD_WARPS == j + 1) {
+                if (base + r * rstride == j + 1) {
                     float2 dd = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(y[r][it]), dd); dd = ffma2(hi2(a4[it]), hi2(y[r][it]), dd); }
@@ -411,39 +414,36 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     publish(y[r], j + 1, kp);
                 }
             }
-            // the other pending rows of this warp: independent dot products, reduced together
+            // the other pending rows of this warp.  Straight-line code over all R rows — a finished (or absent) row rides
+            // along with a zero coefficient — so that the R dot-product chains and the R x 5 shuffle rounds interleave:
+            // with a (warp-uniform) branch per row the rounds of one row could not overlap the next row's, and the
+            // latency of this block, not its issue slots, is what paces the sweep
+            bool on[R];
             float d[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int i = base + r * UPD_WARPS;
-                float2 dd = make_float2(0.f, 0.f);
-                if (i > j + 1 && i < live) {
+                const int i = base + r * rstride;
+                on[r] = i > j + 1 && i < live;
+                float2 d0 = make_float2(0.f, 0.f), d1 = d0;
 #pragma unroll
-                    for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(y[r][it]), dd); dd = ffma2(hi2(a4[it]), hi2(y[r][it]), dd); }
-                }
-                d[r] = dd.x + dd.y;
+                for (int it = 0; it < NVB; ++it) { d0 = ffma2(lo2(a4[it]), lo2(y[r][it]), d0); d1 = ffma2(hi2(a4[it]), hi2(y[r][it]), d1); }
+                d[r] = (d0.x + d0.y) + (d1.x + d1.y);
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int i = base + r * UPD_WARPS;
-                if (i > j + 1 && i < live) {                          // warp-uniform: finished rows cost nothing
+            for (int ofs = 16; ofs > 0; ofs >>= 1) {
 #pragma unroll
-                    for (int ofs = 16; ofs > 0; ofs >>= 1) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
-                }
+                for (int r = 0; r < R; ++r) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
             }
             if (j >= first_stale) mbar_wait(&scalbar[j], 0);
             const float ljk = lj_s[j];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int i = base + r * UPD_WARPS;
-                if (i > j + 1 && i < live) {
-                    const float e = ljk * d[r];
-                    const float2 me = make_float2(-e, -e);
+                const float e = on[r] ? ljk * d[r] : 0.f;             // 0: y - 0 * a = y, bit for bit
+                const float2 me = make_float2(-e, -e);
 #pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        const float2 l = ffma2(me, lo2(a4[it]), lo2(y[r][it])), h = ffma2(me, hi2(a4[it]), hi2(y[r][it]));
-                        y[r][it] = make_float4(l.x, l.y, h.x, h.y);
-                    }
+                for (int it = 0; it < NVB; ++it) {
+                    const float2 l = ffma2(me, lo2(a4[it]), lo2(y[r][it])), h = ffma2(me, hi2(a4[it]), hi2(y[r][it]));
+                    y[r][it] = make_float4(l.x, l.y, h.x, h.y);
                 }
             }
         }

@@ -417,6 +417,7 @@ UpdateArgs update_args_local(lmcma_b200_opt* o) {
     memset(&a, 0, sizeof(a));
     a.f_all = o->d.fit;
     a.slices = o->d.partial; a.n_slices = o->d.RS; a.slice_stride = o->d.ns; a.inst_stride = (long long)o->d.RS * o->d.ns;
+    a.blocked = env_int("LMCMA_B200_UPDATE_BLOCKED", 0);
     return a;
 }
 
@@ -1235,8 +1236,8 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
     if (!rc && se != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "profile run: %s", cudaGetErrorString(se));
     if (!rc && getenv("LMCMA_B200_UPDATE_DBG")) {   // debug: timeline of k_update
         long long* dbg = nullptr;
-        if (cudaMalloc(&dbg, 16 * sizeof(long long)) == cudaSuccess) {
-            cudaMemset(dbg, 0, 16 * sizeof(long long));
+        if (cudaMalloc(&dbg, 64 * sizeof(long long)) == cudaSuccess) {
+            cudaMemset(dbg, 0, 64 * sizeof(long long));
             UpdateArgs ua = update_args_local(o);
             ua.dbg = dbg;
             launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
@@ -1244,7 +1245,7 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
             launch_update(o, ua, true, st);
             launch_sample(o, st, true);
             cudaStreamSynchronize(st);
-            long long h[16];
+            long long h[64];
             cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
             static const char* names[] = {"start", "bookkeeping", "prologue done", "k_rank done", "mean", "sweep", "end"};
             fprintf(stderr, "k_update timeline (ns since start; first_stale=%lld live=%lld):", h[10], h[11]);

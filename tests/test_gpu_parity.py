@@ -545,3 +545,23 @@ def test_lmcma_teacher_forced_gram_path(po, monkeypatch):
     _teacher_forced(po, 400, 128, 40, 50, seed=3, sigma=0.5)
     monkeypatch.delenv("LMCMA_B200_UPDATE_GRAM")
     _teacher_forced(po, 1500, 32, 77, 84, seed=4, sigma=0.3)
+
+
+def test_progressive_hand_over_is_bit_identical_to_the_serial_order(po, monkeypatch):
+    """k_sample consuming the direction pairs while k_update's sweep is still publishing them (release / acquire flags,
+    k_update.cuh "progressive") must not change a single bit relative to running the two kernels back to back: same
+    operations in the same order, only earlier.  Fused generations past the point where slots are recycled."""
+    W, lam, m = 100, 512, 24
+    dist, start, goal = maps.config2_map(size=1024, n_rects=128, seed=42, clamp=64.0)
+    lo, hi = maps.box_bounds((1024, 1024), W)
+    x0 = maps.straight_line(start, goal, W)
+    cm = L.CostMap(dist, "f32")
+    state = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LMCMA_B200_PROGRESSIVE", mode)
+        dev = L.Optimizer(2 * W, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=8.0, seed=11)
+        dev.attach_cost(cm, [start], [goal], W, L.LONGSAFE, 1e4)
+        dev.run(70)
+        state[mode] = {k: dev.get(k).copy() for k in ("X", "xmean", "V", "P", "sigma", "fit", "t")}
+    for k in state["1"]:
+        assert np.array_equal(state["1"][k], state["0"][k]), k
