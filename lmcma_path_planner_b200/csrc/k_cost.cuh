@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     int* segC = reinterpret_cast<int*>(blkrec + a.cb);           // 3-D first sample (NSEG entries, unused in 2-D)
     int* off = segC + NSEG;                                      // NSEG + 1 exclusive sample offsets
     float* lut = reinterpret_cast<float*>(off + NSEG + 1);       // 256 (U8 only)
+    float* xs = reinterpret_cast<float*>((reinterpret_cast<size_t>(lut + (STORAGE == 1 ? 256 : 0)) + 15) & ~(size_t)15);   // the candidate row
     __shared__ float red_f[3][COST_MAX_WARPS];
     __shared__ int red_i[COST_MAX_WARPS];
     __shared__ int warp_tot[COST_MAX_WARPS];
@@ -64,6 +65,17 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     const float* x = a.X + ((size_t)b * a.inst_rows + row) * a.ld;
     const float* en = a.ends + (a.ends_per_instance ? (size_t)b * 6 : 0);
     if (STORAGE == 1) for (int i = tid; i < 256; i += nthr) lut[i] = mp.lut[i];
+    // the candidate row, read ONCE and coalesced (it may live in pinned host memory: lmcma_b200_cost_evaluate hands a
+    // page-locked caller buffer to the kernel directly, and the row then crosses PCIe while other CTAs compute)
+    {
+        const int nflt = DIMS * W;
+        if ((reinterpret_cast<size_t>(x) & 15) == 0 && (nflt & 3) == 0) {
+            for (int i = tid; i < (nflt >> 2); i += nthr) reinterpret_cast<float4*>(xs)[i] = reinterpret_cast<const float4*>(x)[i];
+        } else {
+            for (int i = tid; i < nflt; i += nthr) xs[i] = x[i];
+        }
+    }
+    __syncthreads();                                             // xs (and the lut)
 
     const unsigned nxm1 = (unsigned)(mp.nx - 1), nym1 = (unsigned)(mp.ny - 1), nzm1 = (unsigned)(mp.nz - 1);
     const float fx1 = (float)(mp.nx - 1), fy1 = (float)(mp.ny - 1), fz1 = (float)(mp.nz - 1);
@@ -98,14 +110,13 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     float len_acc = 0.f; int my_cnt = 0;
     bool safe = true;                                            // every waypoint of my segments inside the map
     const raw_t idle = (raw_t)(STORAGE == 1 ? 1 : 0);             // a free cell
-    if (STORAGE == 1) __syncthreads();                           // the lut
     for (int s = s_begin; s < s_end; ++s) {
         float A[3], D[3]; float linf = 0.f, l2 = 0.f; bool bad = false;
         A[2] = 0.f; D[2] = 0.f;
 #pragma unroll
         for (int c = 0; c < DIMS; ++c) {
-            A[c] = (s == 0) ? en[c] : x[c * W + s - 1];
-            const float Bc = (s == W) ? en[3 + c] : x[c * W + s];
+            A[c] = (s == 0) ? en[c] : xs[c * W + s - 1];
+            const float Bc = (s == W) ? en[3 + c] : xs[c * W + s];
             const float hi_c = c == 0 ? fx1 : (c == 1 ? fy1 : fz1);
             safe = safe && (A[c] >= 0.f) && (A[c] <= hi_c) && (Bc >= 0.f) && (Bc <= hi_c);
             D[c] = __fsub_rn(Bc, A[c]);

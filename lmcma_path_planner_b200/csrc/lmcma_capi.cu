@@ -180,7 +180,9 @@ int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostSha
     CostArgs a = a0;
     a.cb = shape.cb;
     // segment records 36 B, sample offsets, per-block records 8 B (k_cost.cuh), 256-entry table (u8 storage)
-    const size_t smem = (size_t)36 * (a.W + 1) + sizeof(int) * (a.W + 2) + 28 + (size_t)8 * shape.cb + (STORAGE == 1 ? 1024 : 0);
+    // + the candidate row (16-byte aligned)
+    const size_t smem = (size_t)36 * (a.W + 1) + sizeof(int) * (a.W + 2) + 28 + (size_t)8 * shape.cb + (STORAGE == 1 ? 1024 : 0) +
+                        sizeof(float) * DIMS * (size_t)a.W + 16;
     auto kern = k_cost<DIMS, STORAGE, TRACE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(rows, B), shape.tpt, smem, st>>>(mp, a);
@@ -515,6 +517,16 @@ int ensure_graph(lmcma_b200_opt* o) {
     return 0;
 }
 
+// device-side alias of a page-locked host buffer (unified addressing), or null for pageable / foreign memory
+void* mapped_device_pointer(const void* host, int device) {
+    cudaPointerAttributes at;
+    memset(&at, 0, sizeof(at));
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    (void)device;
+    return at.devicePointer;
+}
+
 // dense <-> pitched copies
 int d2h_rows(void* dst, const void* src, size_t rows, size_t width_bytes, size_t src_pitch_bytes, cudaStream_t st) {
     if (width_bytes == src_pitch_bytes) CU(cudaMemcpyAsync(dst, src, rows * width_bytes, cudaMemcpyDeviceToHost, st));   // dense: one 1-D copy
@@ -822,23 +834,42 @@ int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj,
     if (count == 0) return 0;
     CU(cudaSetDevice(m->device));
     const size_t n = (size_t)m->dev.dims * obj->waypoints;
-    if (m->d_X_cap < (size_t)count * n) {
-        cudaFree(m->d_X); m->d_X = nullptr; m->d_X_cap = 0;
-        DM(m->d_X, (size_t)count * n);
-        m->d_X_cap = (size_t)count * n;
+    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister) are handed to the kernel as they are: every CTA reads
+    // its own candidate row across PCIe once, coalesced, while other CTAs compute (instead of a serial H2D copy in front
+    // of the kernel), and the three results per trajectory are stored straight into the caller's arrays.  Pageable
+    // buffers are staged through device memory.  LMCMA_B200_ZEROCOPY=0 forces staging.
+    const bool zc = env_int("LMCMA_B200_ZEROCOPY", 1) != 0;
+    const float* X_dev = zc ? static_cast<const float*>(mapped_device_pointer(X_host, m->device)) : nullptr;
+    float* f_dev = zc ? static_cast<float*>(mapped_device_pointer(f_host, m->device)) : nullptr;
+    int32_t* nc_dev = (zc && ncoll_host) ? static_cast<int32_t*>(mapped_device_pointer(ncoll_host, m->device)) : nullptr;
+    int32_t* ns_dev = (zc && nsamp_host) ? static_cast<int32_t*>(mapped_device_pointer(nsamp_host, m->device)) : nullptr;
+    const bool out_direct = f_dev && (!ncoll_host || nc_dev) && (!nsamp_host || ns_dev);
+    if (!X_dev) {
+        if (m->d_X_cap < (size_t)count * n) {
+            cudaFree(m->d_X); m->d_X = nullptr; m->d_X_cap = 0;
+            DM(m->d_X, (size_t)count * n);
+            m->d_X_cap = (size_t)count * n;
+        }
+        CU(cudaMemcpyAsync(m->d_X, X_host, (size_t)count * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        X_dev = m->d_X;
     }
-    if (m->d_out_cap < (size_t)count) {
-        cudaFree(m->d_f); cudaFree(m->d_nc); cudaFree(m->d_ns);
-        m->d_f = nullptr; m->d_nc = nullptr; m->d_ns = nullptr; m->d_out_cap = 0;
-        DM(m->d_f, count); DM(m->d_nc, count); DM(m->d_ns, count);
-        m->d_out_cap = count;
+    if (!out_direct) {
+        if (m->d_out_cap < (size_t)count) {
+            cudaFree(m->d_f); cudaFree(m->d_nc); cudaFree(m->d_ns);
+            m->d_f = nullptr; m->d_nc = nullptr; m->d_ns = nullptr; m->d_out_cap = 0;
+            DM(m->d_f, count); DM(m->d_nc, count); DM(m->d_ns, count);
+            m->d_out_cap = count;
+        }
+        f_dev = m->d_f; nc_dev = m->d_nc; ns_dev = m->d_ns;
     }
-    CU(cudaMemcpyAsync(m->d_X, X_host, (size_t)count * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-    rc = lmcma_b200_cost_evaluate_dev(m, obj, ends, m->d_X, (int64_t)n, count, m->d_f, m->d_nc, m->d_ns, m->stream);
+    rc = lmcma_b200_cost_evaluate_dev(m, obj, ends, X_dev, (int64_t)n, count, f_dev, ncoll_host ? nc_dev : nullptr,
+                                      nsamp_host ? ns_dev : nullptr, m->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(f_host, m->d_f, count * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-    if (ncoll_host) CU(cudaMemcpyAsync(ncoll_host, m->d_nc, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    if (nsamp_host) CU(cudaMemcpyAsync(nsamp_host, m->d_ns, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (!out_direct) {
+        CU(cudaMemcpyAsync(f_host, m->d_f, count * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+        if (ncoll_host) CU(cudaMemcpyAsync(ncoll_host, m->d_nc, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        if (nsamp_host) CU(cudaMemcpyAsync(nsamp_host, m->d_ns, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    }
     CU(cudaStreamSynchronize(m->stream));
     return 0;
 }

@@ -565,3 +565,31 @@ def test_progressive_hand_over_is_bit_identical_to_the_serial_order(po, monkeypa
         state[mode] = {k: dev.get(k).copy() for k in ("X", "xmean", "V", "P", "sigma", "fit", "t")}
     for k in state["1"]:
         assert np.array_equal(state["1"][k], state["0"][k]), k
+
+
+def test_cost_evaluate_page_locked_buffers_match_staged(po, golden_maps, monkeypatch):
+    """lmcma_b200_cost_evaluate hands page-locked caller buffers to the kernel directly (candidates read across PCIe
+    by the CTAs, results stored into the caller's arrays); pageable buffers are staged.  Same bits either way."""
+    import ctypes as C
+    import torch
+    from lmcma_path_planner_b200 import _capi as K
+    from lmcma_path_planner_b200.optimizer import _endpoints, _objective
+    dist = po.edt_exact(golden_maps["problem1"])
+    W, start, goal = 23, (99.0, 0.0), (0.0, 99.0)                # n = 46: rows are not 16-byte aligned
+    lo, hi = maps.box_bounds((100, 100), W)
+    rng = np.random.default_rng(5)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 300, 9.0, lo - 4.0, hi + 4.0)   # some samples leave the map
+    cm = L.CostMap(dist, "f32")
+    ref = cm.evaluate(X, start, goal, W)                          # pageable numpy buffers: staged
+    Xp = torch.from_numpy(X.copy()).pin_memory().numpy()
+    fp = torch.zeros(300, dtype=torch.float32).pin_memory().numpy()
+    ncp = torch.zeros(300, dtype=torch.int32).pin_memory().numpy()
+    nsp = torch.zeros(300, dtype=torch.int32).pin_memory().numpy()
+    obj, ends = _objective(W, L.LONGSAFE, 1e4), _endpoints(start, goal)
+    for zc in ("1", "0"):
+        monkeypatch.setenv("LMCMA_B200_ZEROCOPY", zc)
+        fp[:] = 0; ncp[:] = 0; nsp[:] = 0
+        K.check(K.lib().lmcma_b200_cost_evaluate(cm._h, C.byref(obj), C.byref(ends), K.fptr(Xp), 300, K.fptr(fp), K.iptr(ncp), K.iptr(nsp)))
+        assert np.array_equal(fp, ref["f"]) and np.array_equal(ncp, ref["ncoll"]) and np.array_equal(nsp, ref["nsamp"]), zc
+    orc = po.CostProblem(dist, start, goal, W).evaluate(X)
+    assert np.array_equal(ref["ncoll"], orc["ncoll"]) and rel_err(ref["f"], orc["f"]) < COST_RTOL
