@@ -237,12 +237,38 @@ def run_b200(args):
                             "(H2D f; update+sample), pinned host buffers, wall clock around synchronous calls"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        out["e2e"]["path"] += "; page-locked buffers are read / written by k_cost directly (no staging copy)"
+        if world == 1:
+            out["roofline_batched_queries"] = batched_cost_roofline(dist, cmap, lo, hi, peak, local)
         out["cpu_baseline"] = cpu_baseline(dist, start, goal, lo, hi, x0, budget_s=12.0)
         print(json.dumps(out))
     if dist_pg is not None:
         dist_pg.barrier()
         dist_pg.destroy_process_group()
     return out
+
+
+def batched_cost_roofline(dist, cmap, lo, hi, peak, local, queries=256, lam=64, gens=12):
+    """Explanatory extra (not the headline workload): the same k_cost on a C3-shaped batch — `queries` independent
+    start/goal queries x lambda 64 on the C2 map — where many waves of CTAs overlap the per-trajectory phases that a
+    single 1024-trajectory query runs in lock-step.  Same algorithmic-bytes definition, CUDA events around k_cost."""
+    import lmcma_path_planner_b200 as L
+    from lmcma_path_planner_b200 import maps
+    starts, goals = maps.random_queries(dist, queries, seed=7, min_sep=1024)
+    x0b = np.stack([maps.straight_line(starts[q], goals[q], W) for q in range(queries)])
+    opt = L.Optimizer(2 * W, x0=x0b, lam=lam, m=M, batch=queries, lo=lo, hi=hi, sigma0=SIGMA0, seed=7, device=local)
+    opt.attach_cost(cmap, starts, goals, W, L.LONGSAFE, 1e4)
+    opt.run(5)
+    cost_ms, nsamp = 0.0, 0.0
+    for _ in range(gens):
+        cost_ms += opt.profile_kernels(1)["cost"] / gens
+        nsamp += float(opt.get("nsamp").mean()) / gens
+    nbytes = queries * lam * (4 * 2 * W + nsamp * cmap.bytes_per_cell + 8)
+    achieved = nbytes / (cost_ms * 1e-3) / 1e9
+    return {"kernel": "k_cost", "workload": "%d queries x lambda %d (C3-shaped batch, one launch), L2 warm" % (queries, lam),
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "algorithmic_bytes_per_launch": nbytes, "launch_ms": cost_ms, "mean_samples_per_trajectory": nsamp,
+            "samples_per_s": queries * lam * nsamp / (cost_ms * 1e-3)}
 
 
 def cpu_baseline(dist, start, goal, lo, hi, x0, budget_s, steps=None, warmup=0):

@@ -14,6 +14,7 @@
 //    REGISTERS by the warp that owns them and only finished rows pass through shared memory.
 #pragma once
 #include "lmcma_common.cuh"
+#include <type_traits>
 
 namespace lmcma {
 
@@ -28,7 +29,8 @@ struct UpdateArgs {
     long long slice_stride, inst_stride;
     int payload_mode;          // slices are all-gather payloads (S rides in the 2 floats after ns)
     long long* dbg;            // optional: globaltimer stamps (LMCMA_B200_UPDATE_DBG)
-    int blocked;               // register sweep: a warp owns R CONSECUTIVE rows (else rows w, w + 16, ...)
+    int blocked;               // register sweep: a warp owns R CONSECUTIVE rows (else rows w, w + sweep_warps, ...)
+    int sweep_warps;           // register sweep: warps that own rows (<= UPD_WARPS; every warp pays a fixed cost per step)
     int progressive;           // publish OptDev::progress flags as the outputs become final: k_sample (launched as a
                                // programmatic dependent) consumes the pairs while the sweep is still producing them
 };
@@ -326,8 +328,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     } else if (RMAX > 0) {
         // ---------------- register sweep: warp w owns rows first_stale + w + r * UPD_WARPS ----------------
         constexpr int R = RMAX > 0 ? RMAX : 1;
-        const int rstride = a.blocked ? 1 : UPD_WARPS;
-        const int base = first_stale + (a.blocked ? warp * R : warp);
+        const int sw = a.sweep_warps;
+        const int rstride = a.blocked ? 1 : sw;
+        const int base = warp < sw ? first_stale + (a.blocked ? warp * R : warp) : live;   // warps >= sw own nothing
         float4 y[R][NVB];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -414,36 +417,48 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     publish(y[r], j + 1, kp);
                 }
             }
-            // the other pending rows of this warp.  Straight-line code over all R rows — a finished (or absent) row rides
-            // along with a zero coefficient — so that the R dot-product chains and the R x 5 shuffle rounds interleave:
-            // with a (warp-uniform) branch per row the rounds of one row could not overlap the next row's, and the
-            // latency of this block, not its issue slots, is what paces the sweep
-            bool on[R];
-            float d[R];
+            // the other pending rows of this warp: always a suffix r >= r0 of its rows (they finish in index order).
+            // One straight-line block per r0, so that the dot-product chains and the 5 shuffle rounds of the rows
+            // interleave (a branch per row would serialise their latencies) and finished rows cost no issue slots —
+            // the single SM of this CTA is issue-bound in this loop (ncu: ~200 warp instructions per warp and step)
+            int r0 = 0;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int i = base + r * rstride;
-                on[r] = i > j + 1 && i < live;
-                float2 d0 = make_float2(0.f, 0.f), d1 = d0;
+            for (int r = 0; r < R; ++r) r0 += (base + r * rstride <= j + 1) ? 1 : 0;
+            auto others = [&](auto r0c) {
+                constexpr int R0 = decltype(r0c)::value;
+                float d[R];
 #pragma unroll
-                for (int it = 0; it < NVB; ++it) { d0 = ffma2(lo2(a4[it]), lo2(y[r][it]), d0); d1 = ffma2(hi2(a4[it]), hi2(y[r][it]), d1); }
-                d[r] = (d0.x + d0.y) + (d1.x + d1.y);
-            }
+                for (int r = R0; r < R; ++r) {
+                    float2 d0 = make_float2(0.f, 0.f), d1 = d0;
 #pragma unroll
-            for (int ofs = 16; ofs > 0; ofs >>= 1) {
+                    for (int it = 0; it < NVB; ++it) { d0 = ffma2(lo2(a4[it]), lo2(y[r][it]), d0); d1 = ffma2(hi2(a4[it]), hi2(y[r][it]), d1); }
+                    d[r] = (d0.x + d0.y) + (d1.x + d1.y);
+                }
 #pragma unroll
-                for (int r = 0; r < R; ++r) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
-            }
-            if (j >= first_stale) mbar_wait(&scalbar[j], 0);
-            const float ljk = lj_s[j];
+                for (int ofs = 16; ofs > 0; ofs >>= 1) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float e = on[r] ? ljk * d[r] : 0.f;             // 0: y - 0 * a = y, bit for bit
-                const float2 me = make_float2(-e, -e);
+                    for (int r = R0; r < R; ++r) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
+                }
+                if (j >= first_stale) mbar_wait(&scalbar[j], 0);
+                const float ljk = lj_s[j];
 #pragma unroll
-                for (int it = 0; it < NVB; ++it) {
-                    const float2 l = ffma2(me, lo2(a4[it]), lo2(y[r][it])), h = ffma2(me, hi2(a4[it]), hi2(y[r][it]));
-                    y[r][it] = make_float4(l.x, l.y, h.x, h.y);
+                for (int r = R0; r < R; ++r) {
+                    const float e = (base + r * rstride < live) ? ljk * d[r] : 0.f;   // an absent row rides along: y - 0 * a = y
+                    const float2 me = make_float2(-e, -e);
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        const float2 l = ffma2(me, lo2(a4[it]), lo2(y[r][it])), h = ffma2(me, hi2(a4[it]), hi2(y[r][it]));
+                        y[r][it] = make_float4(l.x, l.y, h.x, h.y);
+                    }
+                }
+            };
+            if (r0 < R && base + r0 * rstride < live) {
+                switch (r0) {
+                    case 0: others(std::integral_constant<int, 0>()); break;
+                    case 1: others(std::integral_constant<int, (R > 1 ? 1 : 0)>()); break;
+                    case 2: others(std::integral_constant<int, (R > 2 ? 2 : 0)>()); break;
+                    case 3: others(std::integral_constant<int, (R > 3 ? 3 : 0)>()); break;
+                    default: others(std::integral_constant<int, (R > 4 ? 4 : 0)>()); break;
                 }
             }
         }

@@ -163,7 +163,7 @@ struct lmcma_b200_opt {
     size_t smp_smem = 0;
     CostShape cost_shape;
     bool progressive = false;   // k_update -> k_sample hand-over inside the fused generation (k_update.cuh)
-    int upd_nvb = 4, upd_rmax = 0;
+    int upd_nvb = 4, upd_rmax = 0, upd_sweep_warps = 16;
     bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
     bool upd_rows_in_smem = true;
     size_t upd_smem = 0, rank_smem = 0;
@@ -392,7 +392,9 @@ int launch_update_t(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream
 
 // the serial part of update() (k_update.cuh).  pdl: launched as a programmatic dependent of the kernel enqueued just
 // before it on `st` (k_rank), so that its prologue overlaps that kernel
-int launch_update(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream_t st) {
+int launch_update(lmcma_b200_opt* o, const UpdateArgs& a_in, bool pdl, cudaStream_t st) {
+    UpdateArgs a = a_in;
+    if (a.sweep_warps <= 0) a.sweep_warps = o->upd_sweep_warps;     // callers that build UpdateArgs from scratch
     if (o->upd_gram) {
         int rc = o->upd_nvb == 4 ? launch_update_t<4, -1, false>(o, a, pdl, st) : launch_update_t<16, -1, false>(o, a, pdl, st);
         if (rc) return rc;
@@ -420,6 +422,7 @@ UpdateArgs update_args_local(lmcma_b200_opt* o) {
     a.f_all = o->d.fit;
     a.slices = o->d.partial; a.n_slices = o->d.RS; a.slice_stride = o->d.ns; a.inst_stride = (long long)o->d.RS * o->d.ns;
     a.blocked = env_int("LMCMA_B200_UPDATE_BLOCKED", 0);
+    a.sweep_warps = o->upd_sweep_warps;
     return a;
 }
 
@@ -442,8 +445,11 @@ int configure_update(lmcma_b200_opt* o) {
     // pending rows in registers when they fit: m <= 8 warps x RMAX rows of <= 128 float4 columns
     o->upd_rmax = 0;
     if (o->upd_nvb == 4 && o->upd_rows_in_smem && !o->upd_gram && !env_int("LMCMA_B200_UPDATE_STREAMING", 0)) {
-        if (o->d.m <= UPD_WARPS * 3) o->upd_rmax = 3;
-        else if (o->d.m <= UPD_WARPS * 5) o->upd_rmax = 5;
+        o->upd_sweep_warps = UPD_WARPS;
+        const int forced_sw = env_int("LMCMA_B200_UPDATE_SWEEP_WARPS", 0);
+        if (forced_sw >= 1 && forced_sw <= UPD_WARPS) o->upd_sweep_warps = forced_sw;
+        if (o->d.m <= o->upd_sweep_warps * 3) o->upd_rmax = 3;
+        else if (o->d.m <= o->upd_sweep_warps * 5) o->upd_rmax = 5;
     }
     return 0;
 }
