@@ -95,7 +95,9 @@ typedef struct {
 /* Batched trajectory cost: replaces per-state ValidityChecker::isValid / clearance /
  * ClearanceObjective::stateCost (planner.cpp:591-669) + OMPL's path integration.
  * X_host: count x n FP32 candidates, dense.  Outputs (each may be NULL except f): fitness,
- * number of colliding samples (bit-exact contract) and number of map samples visited. */
+ * number of colliding samples (bit-exact contract) and number of map samples visited.
+ * Page-locked buffers (cudaHostAlloc / cudaHostRegister) are read and written by the kernel
+ * directly (no staging copy); pageable buffers are staged through device memory. */
 int lmcma_b200_cost_evaluate(lmcma_b200_map* map, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
                              const float* X_host, int32_t count, float* f_host, int32_t* ncoll_host,
                              int32_t* nsamp_host);
