@@ -593,3 +593,23 @@ def test_cost_evaluate_page_locked_buffers_match_staged(po, golden_maps, monkeyp
         assert np.array_equal(fp, ref["f"]) and np.array_equal(ncp, ref["ncoll"]) and np.array_equal(nsp, ref["nsamp"]), zc
     orc = po.CostProblem(dist, start, goal, W).evaluate(X)
     assert np.array_equal(ref["ncoll"], orc["ncoll"]) and rel_err(ref["f"], orc["f"]) < COST_RTOL
+
+
+def test_cost_long_trajectories_and_staged_rounds(po, monkeypatch):
+    """More segments than threads (W = 600: three segments per thread), and the per-block record stage forced small so
+    that every trajectory takes many rounds of block records (k_cost phase 2a / 2b); both storages, bit-exact counts."""
+    dist, start, goal = maps.config2_map(size=512, n_rects=48, seed=3, clamp=64.0)
+    W = 600
+    rng = np.random.default_rng(8)
+    lo, hi = maps.box_bounds((512, 512), W)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 64, 6.0, lo - 3.0, hi + 3.0)
+    for cb in ("0", "8"):
+        monkeypatch.setenv("LMCMA_B200_COST_CB", cb)
+        for storage in ("f32", "u8"):
+            cm = L.CostMap(dist, storage, u8_scale=0.25)
+            dd = dist if storage == "f32" else cm.dequantized()
+            ref = po.CostProblem(dd, start, goal, W).evaluate(X)
+            got = cm.evaluate(X, start, goal, W)
+            assert np.array_equal(got["ncoll"], ref["ncoll"]), (cb, storage)
+            assert np.array_equal(got["nsamp"], ref["nsamp"]), (cb, storage)
+            assert rel_err(got["f"], ref["f"]) < COST_RTOL, (cb, storage)
