@@ -1211,6 +1211,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
     CU(cudaEventRecord(o->ev0, o->stream));
     if (o->cfg.rng == LMCMA_B200_RNG_PHILOX) {
         if ((rc = ensure_graph(o))) return rc;
+        if ((rc = ensure_mirror(o, o->stream))) return rc;       // a state setter since the last run: the graph's sampler reads the mirror
         for (int g = 0; g < generations; ++g) {
             CU(cudaGraphLaunch(o->graph_exec, o->stream));
             g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0);
