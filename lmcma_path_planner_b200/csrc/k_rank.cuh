@@ -11,7 +11,7 @@
 
 namespace lmcma {
 
-enum { RANK_PLAIN = 0, RANK_PACK = 1 };
+enum { RANK_PLAIN = 0, RANK_PACK = 1, RANK_KEEP_FLAGS = 2 };   // bit 1: the hand-over flags belong to a concurrently running k_update
 
 constexpr int TELL_FTILE = 4096;       // fitness values staged per shared-memory tile
 constexpr int TELL_MAX_ROWS = 256;     // rows per slice upper bound (rows_per = max(32, ceil(pop/256)))
@@ -35,6 +35,8 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
     __shared__ int sh_nsel;
     __shared__ unsigned long long sh_S;
 
+#define RNK_STAMP(k) do { if (o.dbg && threadIdx.x == 0 && blockIdx.x == 0 && b == 0) o.dbg[16 + (k)] = gtime(); } while (0)
+    RNK_STAMP(0);
     const float* cur = f_all + (size_t)b * lambda;
     const float* prev = o.prev_fit + (size_t)b * lambda;
     if (tid == 0) sh_S = 0ull;
@@ -101,6 +103,7 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
         }
     }
     __syncthreads();
+    RNK_STAMP(1);
     if (tid == 0 && sh_S) atomicAdd(o.S_count + b, sh_S);
 
     // ---- compact the selected rows (rank < mu) in row order: deterministic summation order ----
@@ -121,6 +124,7 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
         if (lane == 0) sh_nsel = nsel;
     }
     __syncthreads();
+    RNK_STAMP(2);
     const int nsel = sh_nsel;
 
     // ---- weighted partial sums of d = x - xmean: 128 float4 columns x (nthr/128) row groups ----
@@ -148,6 +152,7 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
                 }
             }
         }
+        RNK_STAMP(3);
         if (g > 0) red[(g - 1) * 128 + tq] = acc;
         __syncthreads();
         if (g == 0 && q < nq) {
@@ -156,6 +161,8 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
         }
         __syncthreads();
     }
+    RNK_STAMP(4);
+#undef RNK_STAMP
 }
 
 // A_PACK tail (split mode): fold the RS local partials and the local S count into the all-gather payload
@@ -183,12 +190,24 @@ __global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict
     // this kernel's own wait: k_update's prologue reads the fitness, so it may only start once k_cost has completed
     // (its prologue does not depend on THIS kernel, see k_update.cuh).
     griddep_wait();
-    griddep_launch_dependents();
+    // overlapped generation (RANK_KEEP_FLAGS): the dependent is k_sample, whose 128 CTAs would share SMs with this grid and
+    // slow the ranks k_update is waiting for; it is released when this CTA is done instead (env LMCMA_B200_RANK_LATE=0: early)
+    const bool late_release = (mode & RANK_KEEP_FLAGS) && !(mode & 4);
+    if (!late_release) griddep_launch_dependents();
     const int b = blockIdx.y;
     // the hand-over flags of this generation's k_update -> k_sample (both start after this grid has completed)
-    if (blockIdx.x == 0) for (int i = threadIdx.x; i <= o.m; i += blockDim.x) o.progress[(size_t)b * (o.m + 1) + i] = 0;
+    if (blockIdx.x == 0 && !(mode & RANK_KEEP_FLAGS)) for (int i = threadIdx.x; i < o.m + 2; i += blockDim.x) o.progress[(size_t)b * (o.m + 2) + i] = 0;
     tell_phase_a(o, f_all, b, blockIdx.x, smem_raw);
-    if (mode != RANK_PACK) return;
+    // one ticket per CTA once its ranks / partial sums are stored: the overlapped generation's k_update (not a stream
+    // successor of this grid) waits for RS of them; every k_update resets the counter
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(o.rank_ticket + b, 1u);
+        if (o.dbg && b == 0 && blockIdx.x == gridDim.x - 1) o.dbg[21] = gtime();
+    }
+    if (late_release) griddep_launch_dependents();
+    if (!(mode & RANK_PACK)) return;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {

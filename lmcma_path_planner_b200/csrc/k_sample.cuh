@@ -269,20 +269,23 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
         for (int s2 = 0; s2 < nstages; ++s2) mbar_init(&bars[s2], 1);
         fence_barrier_init();
     }
-    const int* flags = o.progress + (size_t)b * (o.m + 1);
+    const int* flags = o.progress + (size_t)b * (o.m + 2);
     // bounded spin on a hand-over flag; if it never comes (a launch that did not pair this kernel with a publishing
     // k_update) fall back to waiting for the whole predecessor grid, after which everything is final anyway
+    // progressive == 2 (overlapped generation): k_update is NOT a stream predecessor (it runs on a side branch of the graph,
+    // concurrently with k_cost / k_rank), so there is no grid to fall back to: spin long, then fail loudly
     auto wait_flag = [&](const int* f) {
-        for (int spin = 0; spin < (1 << 22); ++spin) {
+        for (long long spin = 0; spin < (progressive == 2 ? (1ll << 26) : (1ll << 22)); ++spin) {
             if (ld_acquire_gpu(f) != 0) return;
             __nanosleep(32);
         }
+        if (progressive == 2) __trap();
         griddep_wait();
     };
     if (!progressive) {
         griddep_wait();                        // every input is k_update's output
     } else {
-        if (threadIdx.x == 0) wait_flag(flags);                 // scalars + mean
+        if (threadIdx.x == 0) wait_flag(progressive == 2 ? flags + o.m + 1 : flags);   // (early) scalars
         __syncthreads();
     }
     SMP_STAMP(1);
@@ -338,8 +341,8 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
     auto provide_chunk = [&](int c) {                           // warp 0: make sure chunk c is on its way, then run ahead
         while (next_issue <= c) {
             bool ok = false;
-            for (int spin = 0; spin < (1 << 22) && !ok; ++spin) { ok = chunk_ready(next_issue); if (!ok) __nanosleep(32); }
-            if (!ok) griddep_wait();                            // see wait_flag
+            for (long long spin = 0; spin < (progressive == 2 ? (1ll << 26) : (1ll << 22)) && !ok; ++spin) { ok = chunk_ready(next_issue); if (!ok) __nanosleep(32); }
+            if (!ok) { if (progressive == 2) __trap(); griddep_wait(); }   // see wait_flag
             request_chunk(next_issue++);
         }
         while (next_issue < nchunks && chunk_ready(next_issue)) request_chunk(next_issue++);
@@ -463,12 +466,18 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
     }
     (void)gpc;
     SMP_STAMP(5);
+    double sigma = sc.sigma;
+    if (progressive == 2) {                                     // step size and mean arrive after k_rank, late in k_update
+        if (threadIdx.x == 0) wait_flag(flags);
+        __syncthreads();
+        sigma = __ldcg(&o.sc[b].sigma);
+    }
 #pragma unroll
     for (int r = 0; r < RBW; ++r) {
         const int row = row0 + r;
         if (qon && row < o.pop_count) {
             const size_t roff2 = ((size_t)b * o.pop_count + row) * ns;
-            sample_finish(o, o.xmean + (size_t)b * ns, sc.sigma, az[r], q, o.X + roff2, o.D + roff2);
+            sample_finish(o, o.xmean + (size_t)b * ns, sigma, az[r], q, o.X + roff2, o.D + roff2);
         }
     }
     if (progressive) griddep_wait();                            // stream order: this grid ends after k_update has

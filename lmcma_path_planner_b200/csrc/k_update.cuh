@@ -31,6 +31,11 @@ struct UpdateArgs {
     long long* dbg;            // optional: globaltimer stamps (LMCMA_B200_UPDATE_DBG)
     int blocked;               // register sweep: a warp owns R CONSECUTIVE rows (else rows w, w + sweep_warps, ...)
     int sweep_warps;           // register sweep: warps that own rows (<= UPD_WARPS; every warp pays a fixed cost per step)
+    int overlap;               // fused single-query generation: this kernel runs on a side branch of the graph, CONCURRENTLY
+                               // with k_cost and k_rank.  Everything that does not depend on this generation's fitness —
+                               // bookkeeping, and the sweep over every pending row but the newest — comes first; then it
+                               // waits for k_rank's tickets, forms the mean / new evolution path and finishes the newest
+                               // row.  Implies `progressive` (k_sample is released by k_rank and follows the flags)
     int progressive;           // publish OptDev::progress flags as the outputs become final: k_sample (launched as a
                                // programmatic dependent) consumes the pairs while the sweep is still producing them
 };
@@ -44,8 +49,9 @@ template <bool SMEM> __device__ __forceinline__ float4 ld_row4(const float4* p) 
 //        shared memory, or in HBM/L2 when SMEM is false); -1 = no sweep here: the recompute is done by the Gram-matrix
 //        kernels (k_gram.cuh) for shapes whose rows fit neither registers nor shared memory; this kernel then only
 //        hands them {first_stale, live}
-template <int NVB, int RMAX, bool SMEM>
+template <int NVB, int RMAX, bool SMEM, bool OVERLAP>
 __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs a) {
+    static_assert(!OVERLAP || (RMAX > 0 && SMEM), "the overlapped generation uses the register sweep");
     static_assert(RMAX <= 0 || SMEM, "the register sweep publishes finished rows through shared memory");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = o.m, ns = o.ns, nq = ns >> 2;
@@ -80,7 +86,14 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     // classic: k_sample may be scheduled right away; it waits for this grid to complete before reading anything.
     // progressive: it is released after this kernel's own wait (k_rank has reset the hand-over flags by then)
     if (!a.progressive) griddep_launch_dependents();
-    int* flags = o.progress + (size_t)b * (m + 1);
+    int* flags = o.progress + (size_t)b * (m + 2);                 // [0] scalars + mean, [1 + i] pair i, [m + 1] early scalars (itr, live)
+    if (OVERLAP) {
+        // the previous generation's sampler has completed (graph order): reset its flags, then tell k_gate that this CTA
+        // holds its SM (k_cost is released only then and fills the other SMs)
+        for (int i = tid; i < m + 2; i += nthr) flags[i] = 0;
+        __syncthreads();
+        if (tid == 0) { __threadfence(); st_release_gpu(o.resident + b, 1); }
+    }
     UPD_STAMP(0);
     // =============================== prologue: independent of k_rank ===============================
     const Scalars sc0 = *scp;
@@ -127,6 +140,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     __syncthreads();
     const int live = min(itr + 1, m);
     const int slot_new = order[live - 1];
+    if (OVERLAP && tid == 0) {                                     // what the sampler needs to start on the finished pairs
+        scp->itr = itr + 1; scp->live = live;
+        st_release_gpu(flags + m + 1, 1);
+    }
     if (first_stale == 1) first_stale = 0;                           // lmcma.cpp:373-374
     UPD_STAMP(1);
 
@@ -152,7 +169,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     }
 
     // ---- best-so-far: first occurrence of the minimum in evaluation order; strict improvement, or the very first
-    //      evaluation (lmcma.cpp:192-198).  The fitness is k_cost's output, complete before k_rank started ----
+    //      evaluation (lmcma.cpp:192-198).  The fitness is k_cost's output (block-collective) ----
+    auto best_so_far = [&]() {
     {
         float bf = __int_as_float(0x7f800000); int bi = 0x7fffffff;
         for (int j0 = 0; j0 < o.lambda; j0 += 4 * nthr) {            // 4 loads in flight per thread
@@ -169,18 +187,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         if (lane == 0) { am_v[warp] = bf; am_i[warp] = bi; }
     }
-    if (RMAX < 0) {
-        if (tid == 0) o.gram_hdr[b] = make_int2(first_stale, live);
-    } else if (!SMEM) {                                              // rows stay in HBM/L2: pending rows start as pc_j
-        for (int i = first_stale + warp; i + 1 < live; i += nwarps) {
-            const float4* src = reinterpret_cast<const float4*>(Pb + (size_t)order[i] * ns);
-            float4* dst = reinterpret_cast<float4*>(row_ptr(i));
-            for (int q = lane; q < nq; q += 32) dst[q] = __ldcg(src + q);
-        }
-        __threadfence();
-    } else if (live > 1) {
-        mbar_wait(&sh_bar, 0);
-    }
     __syncthreads();
     {
         float bf = am_v[0]; int bi = am_i[0];
@@ -195,12 +201,26 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         if (take && tid == 0) { scp->best_f = (double)bf; scp->best_local = local ? 1 : 0; }
     }
+    };
+    if (RMAX < 0) {
+        if (tid == 0) o.gram_hdr[b] = make_int2(first_stale, live);
+    } else if (!SMEM) {                                              // rows stay in HBM/L2: pending rows start as pc_j
+        for (int i = first_stale + warp; i + 1 < live; i += nwarps) {
+            const float4* src = reinterpret_cast<const float4*>(Pb + (size_t)order[i] * ns);
+            float4* dst = reinterpret_cast<float4*>(row_ptr(i));
+            for (int q = lane; q < nq; q += 32) dst[q] = __ldcg(src + q);
+        }
+        __threadfence();
+    } else if (live > 1) {
+        mbar_wait(&sh_bar, 0);
+    }
+    if (OVERLAP) __syncthreads(); else best_so_far();              // overlap: k_cost is still running
     UPD_STAMP(2);
 
     // =============================== needs k_rank's partial sums ===============================
-    griddep_wait();
-    if (a.progressive) griddep_launch_dependents();
+    auto post_rank = [&]() {                                         // block-collective
     UPD_STAMP(3);
+    if (tid == 0) o.rank_ticket[b] = 0u;                             // k_rank's CTAs of this generation have all drawn one
     // ---- population-success step size (lmcma.cpp:393-419), counters (lmcma.cpp:189, 423): needs only k_rank's pair
     //      count, so it goes first (the progressive hand-over publishes the scalars before the sweep) ----
     if (tid == nthr - 1) {
@@ -292,9 +312,18 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     __syncthreads();
     UPD_STAMP(4);
     if (a.progressive) {
-        // scalars and mean are final; so are the pairs in front of the first stale position (untouched this generation)
-        for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);
+        // scalars and mean are final; so are the pairs in front of the first stale position (untouched this generation;
+        // overlap mode has published those before its sweep)
+        if (!OVERLAP) for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);
         if (tid == 0) st_release_gpu(flags, 1);
+    }
+    };
+    if (!OVERLAP) {
+        griddep_wait();
+        if (a.progressive) griddep_launch_dependents();
+        post_rank();
+    } else {
+        for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);   // untouched pairs: final already
     }
 
     // ---- recompute v from the first stale position (lmcma.cpp:373-390) ----
@@ -330,12 +359,14 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         constexpr int R = RMAX > 0 ? RMAX : 1;
         const int sw = a.sweep_warps;
         const int rstride = a.blocked ? 1 : sw;
-        const int base = warp < sw ? first_stale + (a.blocked ? warp * R : warp) : live;   // warps >= sw own nothing
+        // overlap: the newest row (this generation's evolution path) does not exist yet; it is finished after the sweep
+        const int hi = OVERLAP ? live - 1 : live;
+        const int base = warp < sw ? first_stale + (a.blocked ? warp * R : warp) : hi;     // warps >= sw own nothing
         float4 y[R][NVB];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = base + r * rstride;
-            const bool on = i < live;
+            const bool on = i < hi;
 #pragma unroll
             for (int it = 0; it < NVB; ++it) {
                 const int q = lane + 32 * it;
@@ -345,7 +376,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         int my_last = -1;                                            // my largest row
 #pragma unroll
-        for (int r = 0; r < R; ++r) if (base + r * rstride < live) my_last = base + r * rstride;
+        for (int r = 0; r < R; ++r) if (base + r * rstride < hi) my_last = base + r * rstride;
         auto publish = [&](const float4 (&row)[NVB], int i, double kp) {   // warp-collective: y_i K^i is the final v_i
             const float kf = (float)kp;
             float4* srow = reinterpret_cast<float4*>(rows_s + (size_t)i * ns);
@@ -385,9 +416,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 }
             }
         };
-        if (first_stale == 0 && warp == 0) publish(y[0], 0, 1.0);   // row 0 has no factors (v_0 = pc_0)
+        if (first_stale == 0 && warp == 0 && hi > 0) publish(y[0], 0, 1.0);   // row 0 has no factors (v_0 = pc_0)
         double kp = 1.0;                                             // K^(j+1) inside step j
-        for (int j = 0; j + 1 < live; ++j) {
+        for (int j = 0; j + 1 < hi; ++j) {
             kp *= Kd;
             if (j >= my_last) break;                                 // all my rows are final
             if (j >= first_stale) mbar_wait(&rowbar[j], 0);
@@ -443,7 +474,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 const float ljk = lj_s[j];
 #pragma unroll
                 for (int r = R0; r < R; ++r) {
-                    const float e = (base + r * rstride < live) ? ljk * d[r] : 0.f;   // an absent row rides along: y - 0 * a = y
+                    const float e = (base + r * rstride < hi) ? ljk * d[r] : 0.f;   // an absent row rides along: y - 0 * a = y
                     const float2 me = make_float2(-e, -e);
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) {
@@ -452,7 +483,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     }
                 }
             };
-            if (r0 < R && base + r0 * rstride < live) {
+            if (r0 < R && base + r0 * rstride < hi) {
                 switch (r0) {
                     case 0: others(std::integral_constant<int, 0>()); break;
                     case 1: others(std::integral_constant<int, (R > 1 ? 1 : 0)>()); break;
@@ -460,6 +491,68 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     case 3: others(std::integral_constant<int, (R > 3 ? 3 : 0)>()); break;
                     default: others(std::integral_constant<int, (R > 4 ? 4 : 0)>()); break;
                 }
+            }
+        }
+        if (OVERLAP) {
+            // ---------------- overlap: every older row is final; now the part that needs this generation's ranks ----------------
+            __syncthreads();
+            UPD_STAMP(7);
+            if (tid == 0) {                                          // k_rank: one ticket per CTA after its last store (k_rank.cuh)
+                const unsigned need = (unsigned)o.RS;
+                // plain polling by one thread (this wait is on the critical path); the fence is the acquire for the ranks /
+                // partial sums behind the tickets
+                for (long long spin = 0; *reinterpret_cast<const volatile int*>(o.rank_ticket + b) != (int)need; ++spin)
+                    if (spin > (1ll << 28)) __trap();                // a mis-built graph: fail loudly instead of hanging
+                __threadfence();
+            }
+            __syncthreads();
+            UPD_STAMP(8);
+            best_so_far();
+            post_rank();                                             // mean, step size, the new evolution path -> rows_s[live - 1]
+            if (warp == 0) {
+                // the newest row: factors 0 .. live-2 in order, with the same arithmetic as the sweep (every factor but the
+                // last by the pending-row form, the last by the final-step form), then published like any other row
+                float4 yn[NVB];
+#pragma unroll
+                for (int it = 0; it < NVB; ++it) {
+                    const int q = lane + 32 * it;
+                    yn[it] = (q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < nq) reinterpret_cast<float4*>(VPb + ((size_t)(live - 1) * 2 + 1) * ns)[q] = yn[it];   // pc at its position
+                }
+                double kn = 1.0;
+                for (int j = 0; j + 1 < live; ++j) {
+                    kn *= Kd;
+                    const float4* vj = reinterpret_cast<const float4*>(rows_s + (size_t)j * ns);
+                    float4 a4[NVB];
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        const int q = lane + 32 * it;
+                        a4[it] = (q < nq) ? vj[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    float d;
+                    if (j + 2 < live) {
+                        float2 d0 = make_float2(0.f, 0.f), d1 = d0;
+#pragma unroll
+                        for (int it = 0; it < NVB; ++it) { d0 = ffma2(lo2(a4[it]), lo2(yn[it]), d0); d1 = ffma2(hi2(a4[it]), hi2(yn[it]), d1); }
+                        d = (d0.x + d0.y) + (d1.x + d1.y);
+                    } else {
+                        float2 dd = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(yn[it]), dd); dd = ffma2(hi2(a4[it]), hi2(yn[it]), dd); }
+                        d = dd.x + dd.y;
+                    }
+#pragma unroll
+                    for (int ofs = 16; ofs > 0; ofs >>= 1) d += __shfl_xor_sync(0xffffffffu, d, ofs);
+                    const float e = lj_s[j] * d;
+                    const float2 me = make_float2(-e, -e);
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        const float2 l = ffma2(me, lo2(a4[it]), lo2(yn[it])), h = ffma2(me, hi2(a4[it]), hi2(yn[it]));
+                        yn[it] = make_float4(l.x, l.y, h.x, h.y);
+                    }
+                }
+                publish(yn, live - 1, kn);
+                UPD_STAMP(9);
             }
         }
     } else {
@@ -538,6 +631,18 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         Njd[slot] = nj; Ljd[slot] = lj; Njf[slot] = (float)nj; Njsb[i] = (float)nj;
     }
     UPD_STAMP(6);
+}
+
+// overlapped generation: k_cost must not be released before every k_update CTA holds its SM (a full SM: 512 threads x 128
+// registers), otherwise k_cost's single wave takes every SM and k_update starts when k_cost ends.  One thread per instance.
+__global__ void k_gate(OptDev o) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= o.B) return;
+    for (long long spin = 0; ld_acquire_gpu(o.resident + b) == 0; ++spin) {
+        __nanosleep(64);
+        if (spin > (1ll << 26)) __trap();
+    }
+    o.resident[b] = 0;
 }
 
 // rebuild the sequence-ordered mirror from the slot-indexed state (after create / a state setter): grid = (m, B)

@@ -163,6 +163,10 @@ struct lmcma_b200_opt {
     size_t smp_smem = 0;
     CostShape cost_shape;
     bool progressive = false;   // k_update -> k_sample hand-over inside the fused generation (k_update.cuh)
+    bool overlap = false;       // fused generation with k_update on a side branch, concurrent with k_cost / k_rank (k_update.cuh)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    long long* graph_dbg = nullptr;   // LMCMA_B200_GRAPH_DBG: k_update's timeline inside the fused generation, printed by lmcma_b200_sync
     int upd_nvb = 4, upd_rmax = 0, upd_sweep_warps = 16;
     bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
     bool upd_rows_in_smem = true;
@@ -278,7 +282,7 @@ int ensure_mirror(lmcma_b200_opt* o, cudaStream_t st) {
 
 // pdl: launched as a programmatic dependent of the kernel enqueued just before it on `st` (k_update)
 // progressive: that k_update was launched with UpdateArgs::progressive (only meaningful with pdl)
-int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false, bool progressive = false) {
+int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false, bool progressive = false, int progressive_mode = 1) {
     if (o->mirror_dirty) { int rc = ensure_mirror(o, st); if (rc) return rc; pdl = false; }
     if (o->d_Lf) {   // smoothness prior: z <- L z for the whole population before computeAz (lmcma.cpp:216-217)
         const OptDev& d = o->d;
@@ -292,7 +296,7 @@ int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false, bool pro
         CU(cudaGetLastError());
         pdl = false;
     }
-    if (o->smp_wide) return launch_sample_wide(o, pdl, st, (pdl && progressive && o->progressive) ? 1 : 0);
+    if (o->smp_wide) return launch_sample_wide(o, pdl, st, (pdl && progressive && o->progressive) ? progressive_mode : 0);
     switch (o->smp_nv) {
         case 1: return launch_sample_t<1, 4, 512>(o, pdl, st);
         case 2: return launch_sample_t<2, 4, 512>(o, pdl, st);
@@ -374,9 +378,9 @@ int launch_rank(lmcma_b200_opt* o, const float* f_all, int mode, float* payload,
     return 0;
 }
 
-template <int NVB, int RMAX, bool SMEM>
+template <int NVB, int RMAX, bool SMEM, bool OVERLAP = false>
 int launch_update_t(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream_t st) {
-    auto kern = k_update<NVB, RMAX, SMEM>;
+    auto kern = k_update<NVB, RMAX, SMEM, OVERLAP>;
     if (o->upd_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->upd_smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -409,6 +413,11 @@ int launch_update(lmcma_b200_opt* o, const UpdateArgs& a_in, bool pdl, cudaStrea
         return 0;
     }
     if (o->upd_nvb == 4) {
+        if (a.overlap) {                                         // the overlapped generation (ensure_graph): register sweep only
+            if (o->upd_rmax == 3) return launch_update_t<4, 3, true, true>(o, a, pdl, st);
+            if (o->upd_rmax == 5) return launch_update_t<4, 5, true, true>(o, a, pdl, st);
+            return fail(LMCMA_B200_ERR_STATE, "overlapped generation without the register sweep");
+        }
         if (o->upd_rmax == 3) return launch_update_t<4, 3, true>(o, a, pdl, st);
         if (o->upd_rmax == 5) return launch_update_t<4, 5, true>(o, a, pdl, st);
         return o->upd_rows_in_smem ? launch_update_t<4, 0, true>(o, a, pdl, st) : launch_update_t<4, 0, false>(o, a, pdl, st);
@@ -505,13 +514,30 @@ int ensure_graph(lmcma_b200_opt* o) {
     if ((rc = ensure_mirror(o, st))) return rc;
     cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
+    if (env_int("LMCMA_B200_GRAPH_DBG", 0) && !o->graph_dbg && cudaMalloc(&o->graph_dbg, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(o->graph_dbg, 0, 64 * sizeof(long long)); cudaDeviceSynchronize(); }
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
-    if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st, true);
     UpdateArgs ua = update_args_local(o);
     ua.progressive = o->progressive ? 1 : 0;                 // ensure_mirror above: the mirror is clean
-    if (!rc) rc = launch_update(o, ua, true, st);
-    if (!rc) rc = launch_sample(o, st, true, o->progressive);
+    ua.dbg = o->graph_dbg;
+    if (o->overlap) {
+        // side branch: k_update starts with the graph; main branch: k_gate (waits until k_update holds its SM) -> k_cost ->
+        // k_rank -> k_sample (released by k_rank, follows k_update's flags); join before the graph ends
+        ua.overlap = 1;
+        rc = 0;
+        if (cudaEventRecord(o->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(o->side_stream, o->ev_fork, 0) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph fork failed");
+        if (!rc) rc = launch_update(o, ua, false, o->side_stream);
+        if (!rc && cudaEventRecord(o->ev_join, o->side_stream) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph join record failed");
+        if (!rc) { k_gate<<<(o->d.B + 31) / 32, 32, 0, st>>>(o->d); g_launches++; }
+        if (!rc) rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
+        if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN | RANK_KEEP_FLAGS | (env_int("LMCMA_B200_RANK_LATE", 1) ? 0 : 4), nullptr, st, true);
+        if (!rc) rc = launch_sample(o, st, true, true, 2);
+        if (!rc && cudaStreamWaitEvent(st, o->ev_join, 0) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph join failed");
+    } else {
+        rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
+        if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st, true);
+        if (!rc) rc = launch_update(o, ua, true, st);
+        if (!rc) rc = launch_sample(o, st, true, o->progressive);
+    }
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     g_launches.store(before);   // capture enqueues nothing
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -998,7 +1024,7 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     DM(d.Nj, B * m); DM(d.Lj, B * m); DM(d.Njf, B * m); DM(d.Njs, B * m);
     DM(d.VPs, B * m * 2 * ns);
     DM(d.t, B * m); DM(d.vec, B * m);
-    DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B); DM(d.done_count, B); DM(d.progress, B * (m + 1));
+    DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B); DM(d.done_count, B); DM(d.progress, B * (m + 2)); DM(d.rank_ticket, B); DM(d.resident, B);
     {   // row slices of k_tell's phase A: 32 rows per slice, at most 256 slices
         const int rows_per = std::max(32, (d.pop_count + 255) / 256);
         if (rows_per > TELL_MAX_ROWS) { lmcma_b200_destroy(o); return fail(LMCMA_B200_ERR_ARG, "population too large (max %d rows per handle)", 256 * TELL_MAX_ROWS); }
@@ -1044,6 +1070,13 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     o->progressive = !rc && B == 1 && o->smp_wide && o->upd_rmax > 0 && !o->upd_gram && !o->d_Lf && o->smp_kc == 8 &&
                      o->smp_stages >= (m + o->smp_kc - 1) / o->smp_kc && cfg->rng == LMCMA_B200_RNG_PHILOX &&
                      env_int("LMCMA_B200_PROGRESSIVE", 1) != 0;
+    o->overlap = o->progressive && env_int("LMCMA_B200_OVERLAP", 1) != 0;
+    if (o->overlap) {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&o->side_stream, cudaStreamNonBlocking);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming);
+        if (e2 != cudaSuccess) { cudaGetLastError(); o->overlap = false; }
+    }
     if (!rc && o->upd_gram) {
         rc = dmalloc(&d.G, B * m * m);
         if (!rc) rc = dmalloc(&d.Cf, B * m * m);
@@ -1068,12 +1101,15 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     if (o->stream) cudaStreamSynchronize(o->stream);
     OptDev& d = o->d;
     void* ptrs[] = {d.X, d.D, d.Z, d.Zc, o->d_Lf, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
-                    d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.progress, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
+                    d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.progress, d.rank_ticket, d.resident, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
     if (o->ev0) cudaEventDestroy(o->ev0);
     if (o->ev1) cudaEventDestroy(o->ev1);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    if (o->side_stream) cudaStreamDestroy(o->side_stream);
+    if (o->ev_fork) cudaEventDestroy(o->ev_fork);
+    if (o->ev_join) cudaEventDestroy(o->ev_join);
     delete o;
     return 0;
 }
@@ -1214,7 +1250,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
         if ((rc = ensure_mirror(o, o->stream))) return rc;       // a state setter since the last run: the graph's sampler reads the mirror
         for (int g = 0; g < generations; ++g) {
             CU(cudaGraphLaunch(o->graph_exec, o->stream));
-            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0);
+            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0) + (o->overlap ? 1 : 0);
         }
     } else {
         if (o->cfg.rng == LMCMA_B200_RNG_INJECT && generations > 1)
@@ -1236,6 +1272,22 @@ int lmcma_b200_sync(lmcma_b200_opt* o) {
     ARG(o, "null handle");
     CU(cudaSetDevice(o->cfg.device));
     CU(cudaStreamSynchronize(o->stream));
+    if (o->graph_dbg) {
+        long long h[64];
+        cudaMemcpy(h, o->graph_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "fused generation, k_update (ns since its start): bookkeeping=%lld prologue=%lld sweep: warp 0 done=%lld, all done + ranks seen=%lld post start=%lld mean=%lld newest row=%lld tail=%lld end=%lld",
+                h[1] - h[0], h[2] - h[0], h[7] - h[0], h[8] - h[0], h[3] - h[0], h[4] - h[0], h[9] - h[0], h[5] - h[0], h[6] - h[0]);
+        if (o->d.dbg) {
+            long long g[64];
+            cudaMemcpy(g, o->d.dbg, sizeof(g), cudaMemcpyDeviceToHost);
+            fprintf(stderr, " | k_sample CTA 0: start=%lld flags=%lld loop done=%lld end=%lld", g[32] - h[0], g[33] - h[0], g[37] - h[0], g[38] - h[0]);
+            fprintf(stderr, " | k_rank CTA 0: start=%lld ranked=%lld compacted=%lld gathered=%lld stored=%lld", g[16] - h[0], g[17] - h[0], g[18] - h[0], g[19] - h[0], g[20] - h[0]);
+            fprintf(stderr, " last slice stored=%lld", g[21] - h[0]);
+            cudaMemset(o->d.dbg + 21, 0, sizeof(long long));
+            cudaDeviceSynchronize();
+        }
+        fprintf(stderr, "\n");
+    }
     return 0;
 }
 

@@ -66,8 +66,11 @@ struct OptDev {
     double* Cf;        // B x m x m
     int2* gram_hdr;    // B : {first_stale, live} handed from k_update to k_gram / k_coef / k_combine
     // progressive hand-over k_update -> k_sample inside one generation (see k_update.cuh): [0] = scalars and mean are
-    // final, [1 + i] = pair i of the sequence-ordered mirror (and Njs[i]) is final.  Reset by k_rank.
-    int* progress;     // B x (m + 1)
+    // final, [1 + i] = pair i of the sequence-ordered mirror (and Njs[i]) is final.  Reset by k_rank (by k_update itself
+    // in the overlapped generation).
+    int* progress;     // B x (m + 2): [0] scalars + mean, [1 + i] pair i, [m + 1] early scalars (itr, live) of the overlapped generation
+    unsigned* rank_ticket;   // B : one ticket per k_rank CTA after its last store; k_update waits for RS of them in the overlapped generation
+    int* resident;     // B : k_update (overlapped generation) holds its SM; k_gate releases k_cost
     int* t;            // B x m   slot order, oldest -> newest
     int* vec;          // B x m   generation stamp per slot
     Scalars* sc;       // B

@@ -547,7 +547,7 @@ def test_lmcma_teacher_forced_gram_path(po, monkeypatch):
     _teacher_forced(po, 1500, 32, 77, 84, seed=4, sigma=0.3)
 
 
-def test_progressive_hand_over_is_bit_identical_to_the_serial_order(po, monkeypatch):
+def test_progressive_and_overlapped_generations_are_bit_identical_to_the_serial_order(po, monkeypatch):
     """k_sample consuming the direction pairs while k_update's sweep is still publishing them (release / acquire flags,
     k_update.cuh "progressive") must not change a single bit relative to running the two kernels back to back: same
     operations in the same order, only earlier.  Fused generations past the point where slots are recycled."""
@@ -557,14 +557,19 @@ def test_progressive_hand_over_is_bit_identical_to_the_serial_order(po, monkeypa
     x0 = maps.straight_line(start, goal, W)
     cm = L.CostMap(dist, "f32")
     state = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("LMCMA_B200_PROGRESSIVE", mode)
+    # serial order / progressive hand-over / overlapped generation (k_update on a side branch of the graph, concurrent with
+    # k_cost and k_rank: everything that does not depend on this generation's fitness runs first)
+    for mode, (prog, ovl) in {"serial": ("0", "0"), "progressive": ("1", "0"), "overlapped": ("1", "1")}.items():
+        monkeypatch.setenv("LMCMA_B200_PROGRESSIVE", prog)
+        monkeypatch.setenv("LMCMA_B200_OVERLAP", ovl)
         dev = L.Optimizer(2 * W, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=8.0, seed=11)
         dev.attach_cost(cm, [start], [goal], W, L.LONGSAFE, 1e4)
         dev.run(70)
-        state[mode] = {k: dev.get(k).copy() for k in ("X", "xmean", "V", "P", "sigma", "fit", "t")}
-    for k in state["1"]:
-        assert np.array_equal(state["1"][k], state["0"][k]), k
+        state[mode] = {k: dev.get(k).copy() for k in ("X", "xmean", "V", "P", "sigma", "fit", "t", "vec", "Nj", "Lj")}
+        state[mode]["best_f"] = dev.best()[1].copy()
+    for mode in ("progressive", "overlapped"):
+        for k in state["serial"]:
+            assert np.array_equal(state[mode][k], state["serial"][k]), (mode, k)
 
 
 def test_cost_evaluate_page_locked_buffers_match_staged(po, golden_maps, monkeypatch):
