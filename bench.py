@@ -155,6 +155,8 @@ def run_b200(args):
     # per-kernel durations (CUDA events around every kernel), same flush policy as the timed region
     per_kernel = {}
     nsamp_k = []
+    for _ in range(3):                               # un-graphed launch path: first use loads these kernel variants
+        opt.profile_kernels(1)
     for _ in range(args.steps):
         flush.fill_(1)
         pk = opt.profile_kernels(1)
