@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     const float* x = a.X + ((size_t)b * a.inst_rows + row) * a.ld;
     const float* en = a.ends + (a.ends_per_instance ? (size_t)b * 6 : 0);
     if (STORAGE == 1) for (int i = tid; i < 256; i += nthr) lut[i] = mp.lut[i];
+    for (int lb = tid; lb < a.cb; lb += nthr) blkrec[lb].x = 0u;    // first round of block records (phase 2a), zeroed ahead of the barrier below
     // the candidate row, read ONCE and coalesced (it may live in pinned host memory: lmcma_b200_cost_evaluate hands a
     // page-locked caller buffer to the kernel directly, and the row then crosses PCIe while other CTAs compute)
     {
@@ -157,9 +158,17 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
     int base = incl - my_cnt, T = 0;
     for (int w2 = 0; w2 < nwarps; ++w2) { const int v = warp_tot[w2]; if (w2 < warp) base += v; T += v; }
     if (tid == 0) off[0] = 0;
+    const int nblk0 = min(a.cb, (int)((unsigned)(T + 31) >> 5));    // blocks of the first round
     for (int s = s_begin; s < s_end; ++s) {
         if (DIMS == 2) rec[2 * s + 1].z = __int_as_float(base); else segC[s] = base;   // first sample of the segment
+        const int f0 = base;
         base += off[s + 1]; off[s + 1] = base;
+        // phase 2a of the first round, from the registers at hand (no second pass over off[], no extra barrier): segment s
+        // covers samples [f0, base): it is the first segment of every block that starts inside it, and its last sample
+        // sets one end bit
+        for (int blk = (f0 + 31) >> 5; blk < nblk0 && (blk << 5) < base; ++blk) blkrec[blk].y = (unsigned)s;
+        const int e = base - 1;
+        if ((e >> 5) < nblk0) atomicOr(&blkrec[e >> 5].x, 1u << (e & 31));
     }
     __syncthreads();
 
@@ -230,16 +239,18 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, Cost
         const int nb = min(a.cb, nblk - c0);
         // 2a: block records of this round.  Segment s covers samples [off[s], off[s+1]): it is the first segment of
         // every block that starts inside it, and its last sample sets one end bit
-        for (int lb = tid; lb < nb; lb += nthr) blkrec[lb].x = 0u;
-        __syncthreads();
-        const int r_lo = c0 << 5, r_hi = (c0 + nb) << 5;          // samples of this round
-        for (int sg = s_begin; sg < s_end; ++sg) {
-            const int f0 = off[sg], f1 = off[sg + 1];
-            for (int blk = max((f0 + 31) >> 5, c0); blk < c0 + nb && (blk << 5) < f1; ++blk) blkrec[blk - c0].y = (unsigned)sg;
-            const int e = f1 - 1;
-            if (e >= r_lo && e < r_hi) atomicOr(&blkrec[(e >> 5) - c0].x, 1u << (e & 31));
+        if (c0 > 0) {                                             // the first round's records were written in phase 1
+            for (int lb = tid; lb < nb; lb += nthr) blkrec[lb].x = 0u;
+            __syncthreads();
+            const int r_lo = c0 << 5, r_hi = (c0 + nb) << 5;      // samples of this round
+            for (int sg = s_begin; sg < s_end; ++sg) {
+                const int f0 = off[sg], f1 = off[sg + 1];
+                for (int blk = max((f0 + 31) >> 5, c0); blk < c0 + nb && (blk << 5) < f1; ++blk) blkrec[blk - c0].y = (unsigned)sg;
+                const int e = f1 - 1;
+                if (e >= r_lo && e < r_hi) atomicOr(&blkrec[(e >> 5) - c0].x, 1u << (e & 31));
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // 2b: a contiguous run of blocks per warp
         const int lb0 = (int)(((unsigned)warp * (unsigned)nb) / (unsigned)nwarps), lb1 = (int)(((unsigned)(warp + 1) * (unsigned)nb) / (unsigned)nwarps);
         if (lb0 < lb1) { if (all_safe) run(c0, lb0, lb1, false); else run(c0, lb0, lb1, true); }
