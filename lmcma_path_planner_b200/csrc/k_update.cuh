@@ -170,15 +170,17 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 
     // ---- best-so-far: first occurrence of the minimum in evaluation order; strict improvement, or the very first
     //      evaluation (lmcma.cpp:192-198).  The fitness is k_cost's output (block-collective) ----
-    auto best_so_far = [&]() {
+    // w0 = first participating warp (0: the whole CTA, barrier 0; 1: warps 1.. while warp 0 is busy elsewhere, named barrier 1)
+    auto best_so_far = [&](const int w0) {
+    const int nt = nthr - 32 * w0, t = tid - 32 * w0;
     {
         float bf = __int_as_float(0x7f800000); int bi = 0x7fffffff;
-        for (int j0 = 0; j0 < o.lambda; j0 += 4 * nthr) {            // 4 loads in flight per thread
+        for (int j0 = 0; j0 < o.lambda; j0 += 4 * nt) {              // 4 loads in flight per thread
             float v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr + tid; v[u] = (j < o.lambda) ? canon_fitness(__ldcg(fa + j)) : __int_as_float(0x7f800000); }
+            for (int u = 0; u < 4; ++u) { const int j = j0 + u * nt + t; v[u] = (j < o.lambda) ? canon_fitness(__ldcg(fa + j)) : __int_as_float(0x7f800000); }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr + tid; if (j < o.lambda && (v[u] < bf || (v[u] == bf && j < bi))) { bf = v[u]; bi = j; } }
+            for (int u = 0; u < 4; ++u) { const int j = j0 + u * nt + t; if (j < o.lambda && (v[u] < bf || (v[u] == bf && j < bi))) { bf = v[u]; bi = j; } }
         }
 #pragma unroll
         for (int ofs = 16; ofs > 0; ofs >>= 1) {
@@ -187,10 +189,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         if (lane == 0) { am_v[warp] = bf; am_i[warp] = bi; }
     }
-    __syncthreads();
+    if (w0 == 0) __syncthreads(); else named_bar_sync(1, nt);
     {
-        float bf = am_v[0]; int bi = am_i[0];
-        for (int w2 = 1; w2 < nwarps; ++w2) if (am_v[w2] < bf || (am_v[w2] == bf && am_i[w2] < bi)) { bf = am_v[w2]; bi = am_i[w2]; }
+        float bf = am_v[w0]; int bi = am_i[w0];
+        for (int w2 = w0 + 1; w2 < nwarps; ++w2) if (am_v[w2] < bf || (am_v[w2] == bf && am_i[w2] < bi)) { bf = am_v[w2]; bi = am_i[w2]; }
         if (bi == 0x7fffffff) bi = 0;
         const bool take = ((double)bf < sc0.best_f) || (sc0.counteval == 0);
         const bool local = bi >= o.pop_offset && bi < o.pop_offset + o.pop_count;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             float4* dst = reinterpret_cast<float4*>(o.best_x + (size_t)b * ns);
             for (int q = lane; q < nq; q += 32) dst[q] = src[q];
         }
-        if (take && tid == 0) { scp->best_f = (double)bf; scp->best_local = local ? 1 : 0; }
+        if (take && t == 0) { scp->best_f = (double)bf; scp->best_local = local ? 1 : 0; }
     }
     };
     if (RMAX < 0) {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     } else if (live > 1) {
         mbar_wait(&sh_bar, 0);
     }
-    if (OVERLAP) __syncthreads(); else best_so_far();              // overlap: k_cost is still running
+    if (OVERLAP) __syncthreads(); else best_so_far(0);             // overlap: k_cost is still running
     UPD_STAMP(2);
 
     // =============================== needs k_rank's partial sums ===============================
@@ -507,19 +509,21 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             }
             __syncthreads();
             UPD_STAMP(8);
-            best_so_far();
             post_rank();                                             // mean, step size, the new evolution path -> rows_s[live - 1]
+            // warps 1.. track the best-so-far candidate (it reads X, which the sampler overwrites only after the newest pair
+            // below has been published) while warp 0 runs the newest row's chain
+            if (warp > 0) best_so_far(1);
+            float4 yn[NVB];
+            double kn = 1.0;
             if (warp == 0) {
                 // the newest row: factors 0 .. live-2 in order, with the same arithmetic as the sweep (every factor but the
                 // last by the pending-row form, the last by the final-step form), then published like any other row
-                float4 yn[NVB];
 #pragma unroll
                 for (int it = 0; it < NVB; ++it) {
                     const int q = lane + 32 * it;
                     yn[it] = (q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                     if (q < nq) reinterpret_cast<float4*>(VPb + ((size_t)(live - 1) * 2 + 1) * ns)[q] = yn[it];   // pc at its position
                 }
-                double kn = 1.0;
                 for (int j = 0; j + 1 < live; ++j) {
                     kn *= Kd;
                     const float4* vj = reinterpret_cast<const float4*>(rows_s + (size_t)j * ns);
@@ -551,6 +555,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                         yn[it] = make_float4(l.x, l.y, h.x, h.y);
                     }
                 }
+            }
+            __syncthreads();                                         // best-so-far has copied its row out of X
+            if (warp == 0) {
                 publish(yn, live - 1, kn);
                 UPD_STAMP(9);
             }
