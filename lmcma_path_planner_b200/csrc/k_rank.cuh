@@ -6,6 +6,9 @@
 // and the slice's weighted partial sum of d = x - xmean (OptDev::D).  k_update (k_update.cuh) folds the partials.
 // Split-population mode (RANK_PACK): the last CTA of an instance to finish — fence + atomic ticket, no CTA
 // ever waits on another — folds the partials into the all-gather payload.
+// Every CTA also adds one ticket to OptDev::rank_ticket after its last store: the overlapped generation's k_update is not
+// a stream successor of this grid and waits for RS tickets (RANK_KEEP_FLAGS: the hand-over flags are then k_update's to
+// reset, and the dependent grid — the sampler — is released when the CTA is done, not after the wait on k_cost).
 #pragma once
 #include "lmcma_common.cuh"
 

@@ -1,6 +1,6 @@
 // k_update.cuh — the serial part of LMCMA::update (lmcma.cpp:316-424): mean, evolution path, slot
 // bookkeeping, recomputation of the inverse-direction vectors (invAz, lmcma.cpp:449-463), population-success
-// step size, best-so-far.  One CTA of 8 warps per optimiser instance.
+// step size, best-so-far.  One CTA of 16 warps per optimiser instance.
 //
 // A single query is latency-bound (one generation moves a few MB), so this kernel is organised around
 // its dependency chain:
@@ -11,7 +11,13 @@
 //  * the triangular recompute runs factor-major (step j applies factor j to every pending row i > j: same
 //    per-row operation order as the reference's row-major loops, lmcma.cpp:375-390).  All ~live^2/2 row-steps
 //    run on this one SM, where shared-memory bandwidth is the scarce resource, so the pending rows are held in
-//    REGISTERS by the warp that owns them and only finished rows pass through shared memory.
+//    REGISTERS by the warp that owns them and only finished rows pass through shared memory;
+//  * progressive hand-over (UpdateArgs::progressive): the outputs are published with release stores as they become
+//    final and the sampler, released early, consumes the direction pairs while the sweep is still producing them;
+//  * overlapped generation (template parameter OVERLAP, one query): only the mean / step size / new evolution path
+//    and the NEWEST row depend on this generation's fitness, so the kernel runs on a side branch of the CUDA graph
+//    beside k_cost and k_rank — bookkeeping and the sweep over all older rows first, then a wait for k_rank's tickets,
+//    then the rest.  Same operations in the same order as the serial launch order, bit for bit.
 #pragma once
 #include "lmcma_common.cuh"
 #include <type_traits>
