@@ -540,11 +540,19 @@ int ensure_graph(lmcma_b200_opt* o) {
     }
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     g_launches.store(before);   // capture enqueues nothing
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&o->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    if (!rc && e == cudaSuccess) {
+        e = cudaGraphInstantiate(&o->graph_exec, graph, 0);
+        if (e != cudaSuccess) o->graph_exec = nullptr;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if ((rc || e != cudaSuccess) && o->overlap) {
+        // the forked graph could not be built here (capture / instantiation of the side branch): fall back to the linear one
+        cudaGetLastError();
+        o->overlap = false;
+        return ensure_graph(o);
+    }
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "graph capture / instantiate failed: %s", cudaGetErrorString(e));
     o->graph_built_for = st;
     return 0;
 }
@@ -1110,6 +1118,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     if (o->side_stream) cudaStreamDestroy(o->side_stream);
     if (o->ev_fork) cudaEventDestroy(o->ev_fork);
     if (o->ev_join) cudaEventDestroy(o->ev_join);
+    if (o->graph_dbg) cudaFree(o->graph_dbg);
     delete o;
     return 0;
 }
