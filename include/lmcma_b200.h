@@ -259,7 +259,7 @@ int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out);
 int lmcma_b200_cholesky(int32_t n, const double* C, double* L_out);
 
 /* ---------------------------------------------------------------- map ingest (host-side file parsing) ---------- */
-/* All three: pass out == NULL to query the size first.
+/* All four: pass out == NULL to query the size first.
  * BMP (24/32-bit, uncompressed): occupancy with the reference's rule g < 128 -> obstacle (Signed_Distance_Fields_test,
  * planner.cpp:505-523); rows top to bottom, occ_out[y * width + x]. */
 int lmcma_b200_load_bmp(const char* path, uint8_t* occ_out, int64_t capacity, int32_t* width, int32_t* height);
@@ -267,6 +267,11 @@ int lmcma_b200_load_bmp(const char* path, uint8_t* occ_out, int64_t capacity, in
  * occ_out[(z * ny + y) * nx + x], shape_xyz = {nx, ny, nz}; translate / scale from the header (nullable). */
 int lmcma_b200_load_binvox(const char* path, uint8_t* occ_out, int64_t capacity, int32_t* shape_xyz, double* translate_xyz,
                            double* scale);
+/* OctoMap binary tree (.bt: what binvox2bt.cpp:287-300 writes and planner.cpp:152-163 reads with OcTree::readBinary;
+ * files .../files/mesh_files/{Dude,room}.binvox.bt): dense occupancy of the bounding box of the occupied leaves,
+ * occ_out[(z * ny + y) * nx + x] (1 = occupied, 0 = free or unknown), pruned leaves expanded; origin_key_xyz = key of
+ * the first cell per axis (cell k spans [(k - 32768) res, (k - 32767) res)), res = leaf size (both nullable). */
+int lmcma_b200_load_bt(const char* path, uint8_t* occ_out, int64_t capacity, int32_t* shape_xyz, int32_t* origin_key_xyz, double* res);
 /* comma-separated matrix, one row per line: the file populate_EDT_Matrix_old reads into EDT_Matrix (planner.cpp:777-818) */
 int lmcma_b200_load_text_matrix(const char* path, double* out, int64_t capacity, int32_t* rows, int32_t* cols);
 

@@ -53,6 +53,7 @@ SIGNATURES = {
                                                      C.c_float, C.POINTER(_vp)]),
     "lmcma_b200_load_bmp": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint8), _i64, _pi, _pi]),
     "lmcma_b200_load_binvox": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint8), _i64, _pi, _pd, _pd]),
+    "lmcma_b200_load_bt": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint8), _i64, _pi, _pi, _pd]),
     "lmcma_b200_load_text_matrix": (C.c_int, [C.c_char_p, _pd, _i64, _pi, _pi]),
     "lmcma_b200_map_destroy": (C.c_int, [_vp]),
     "lmcma_b200_map_dequantized": (C.c_int, [_vp, _pf]),

@@ -121,6 +121,85 @@ int lmcma_b200_load_binvox(const char* path, uint8_t* occ_out, int64_t capacity,
     return 0;
 }
 
+// OctoMap binary tree (".bt", written by OcTree::writeBinary — binvox2bt.cpp:287-300 in the reference, read there by
+// planner.cpp:152-163).  Text header up to the line "data" ("id OcTree", "size <nodes>", "res <leaf size>"), then the tree
+// depth first: every inner node is 2 bytes = 8 x 2 bits, child i in bits (2i, 2i+1) of the little-endian bit order
+// std::bitset uses: 00 no child (unknown), 10 free leaf, 01 occupied leaf, 11 inner child (its own 2 bytes follow, in child
+// order).  Depth 16, child index = x | y << 1 | z << 2 of the key bit at that level; a leaf above the last level stands for
+// the whole pruned cube below it.  Key k of an axis is the cell [ (k - 32768) res, (k - 32767) res ).
+// Output: dense occupancy [z][y][x] over the bounding box of the OCCUPIED leaves (1 = occupied, 0 = free or unknown),
+// the key of its first cell per axis and the leaf size.
+namespace {
+struct BtLeaf { uint32_t key[3]; uint32_t size; };
+bool bt_walk(const std::vector<unsigned char>& raw, size_t* pos, uint32_t kx, uint32_t ky, uint32_t kz, int depth, std::vector<BtLeaf>* occ,
+             int64_t* nodes) {
+    if (*pos + 2 > raw.size()) return false;
+    const unsigned bits = (unsigned)raw[*pos] | ((unsigned)raw[*pos + 1] << 8);
+    *pos += 2;
+    ++*nodes;
+    const uint32_t half = 1u << (15 - depth);                  // children of a depth-`depth` node are cubes of `half` leaves
+    for (int i = 0; i < 8; ++i) {
+        const unsigned c = (bits >> (2 * i)) & 3u;              // bit 2i -> low bit
+        if (c == 0u) continue;
+        const uint32_t cx = kx + ((i & 1) ? half : 0u), cy = ky + ((i & 2) ? half : 0u), cz = kz + ((i & 4) ? half : 0u);
+        ++*nodes;
+        if (c == 2u) occ->push_back(BtLeaf{{cx, cy, cz}, half});   // bits (2i, 2i+1) = (0, 1): occupied leaf
+        else if (c == 3u) {                                        // inner child
+            --*nodes;                                              // counted when its own bytes are read
+            if (depth + 1 >= 16) return false;
+            if (!bt_walk(raw, pos, cx, cy, cz, depth + 1, occ, nodes)) return false;
+        }                                                          // c == 1: bits (1, 0): free leaf
+    }
+    return true;
+}
+}  // namespace
+
+int lmcma_b200_load_bt(const char* path, uint8_t* occ_out, int64_t capacity, int32_t* shape_xyz, int32_t* origin_key_xyz, double* res) {
+    if (!path || !shape_xyz) return set_error(LMCMA_B200_ERR_ARG, "null pointer");
+    std::vector<unsigned char> raw;
+    if (!read_file(path, &raw)) return set_error(LMCMA_B200_ERR_ARG, "cannot read %s", path);
+    size_t pos = 0;
+    auto line = [&]() -> std::string {
+        const size_t b = pos;
+        while (pos < raw.size() && raw[pos] != '\n') ++pos;
+        std::string l(raw.begin() + b, raw.begin() + pos);
+        if (pos < raw.size()) ++pos;
+        if (!l.empty() && l.back() == '\r') l.pop_back();
+        return l;
+    };
+    if (line().compare(0, 28, "# Octomap OcTree binary file") != 0) return set_error(LMCMA_B200_ERR_ARG, "%s: not an OctoMap binary tree", path);
+    double leaf = 0.0; long long size = -1; bool have_data = false, id_ok = false;
+    while (pos < raw.size()) {
+        const std::string l = line();
+        if (l == "data") { have_data = true; break; }
+        if (l.empty() || l[0] == '#') continue;
+        if (l.compare(0, 3, "id ") == 0) id_ok = l.substr(3) == "OcTree";
+        else if (l.compare(0, 5, "size ") == 0) size = atoll(l.c_str() + 5);
+        else if (l.compare(0, 4, "res ") == 0) leaf = atof(l.c_str() + 4);
+    }
+    if (!have_data || !id_ok || leaf <= 0.0) return set_error(LMCMA_B200_ERR_ARG, "%s: bad OcTree header", path);
+    std::vector<BtLeaf> occ;
+    int64_t nodes = 0;
+    if (size != 0 && !bt_walk(raw, &pos, 0u, 0u, 0u, 0, &occ, &nodes)) return set_error(LMCMA_B200_ERR_ARG, "%s: truncated or malformed tree data", path);
+    if (size > 0 && nodes != size) return set_error(LMCMA_B200_ERR_ARG, "%s: header says %lld nodes, the data holds %lld", path, size, (long long)nodes);
+    if (occ.empty()) return set_error(LMCMA_B200_ERR_ARG, "%s holds no occupied leaf", path);
+    uint32_t lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0u, 0u, 0u};
+    for (const BtLeaf& l : occ)
+        for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], l.key[c]); hi[c] = std::max(hi[c], l.key[c] + l.size); }
+    for (int c = 0; c < 3; ++c) shape_xyz[c] = (int32_t)(hi[c] - lo[c]);
+    if (origin_key_xyz) for (int c = 0; c < 3; ++c) origin_key_xyz[c] = (int32_t)lo[c];
+    if (res) *res = leaf;
+    if (!occ_out) return 0;                                     // size query
+    const int64_t nx = shape_xyz[0], ny = shape_xyz[1], nz = shape_xyz[2];
+    if (capacity < nx * ny * nz) return set_error(LMCMA_B200_ERR_ARG, "capacity %lld < %lld cells", (long long)capacity, (long long)(nx * ny * nz));
+    memset(occ_out, 0, (size_t)(nx * ny * nz));
+    for (const BtLeaf& l : occ)
+        for (uint32_t z = l.key[2] - lo[2]; z < l.key[2] - lo[2] + l.size; ++z)
+            for (uint32_t y = l.key[1] - lo[1]; y < l.key[1] - lo[1] + l.size; ++y)
+                memset(occ_out + ((size_t)z * ny + y) * nx + (l.key[0] - lo[0]), 1, l.size);
+    return 0;
+}
+
 int lmcma_b200_load_text_matrix(const char* path, double* out, int64_t capacity, int32_t* rows, int32_t* cols) {
     if (!path || !rows || !cols) return set_error(LMCMA_B200_ERR_ARG, "null pointer");
     std::ifstream f(path);

@@ -141,6 +141,21 @@ def load_binvox(path):
     return occ, tr, sc.value
 
 
+def load_bt(path):
+    """Dense occupancy [nz, ny, nx] (uint8, 1 = occupied) of the bounding box of the occupied leaves of an OctoMap binary
+    tree (.bt), the key of its first cell per axis (x, y, z) and the leaf size."""
+    import ctypes as C
+    from . import _capi as K
+    shp = np.zeros(3, np.int32)
+    org = np.zeros(3, np.int32)
+    res = C.c_double(0)
+    K.check(K.lib().lmcma_b200_load_bt(path.encode(), None, 0, K.iptr(shp), K.iptr(org), C.byref(res)))
+    occ = np.zeros((int(shp[2]), int(shp[1]), int(shp[0])), np.uint8)
+    K.check(K.lib().lmcma_b200_load_bt(path.encode(), occ.ctypes.data_as(C.POINTER(C.c_uint8)), occ.size, K.iptr(shp), K.iptr(org),
+                                     C.byref(res)))
+    return occ, org, res.value
+
+
 def load_text_matrix(path):
     import ctypes as C
     from . import _capi as K

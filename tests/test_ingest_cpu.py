@@ -1,6 +1,7 @@
 """Map ingest formats: host-side parsers of the C ABI against files written here and, where
 /root/reference exists, against the reference's own bundled files."""
 import os
+import re
 import struct
 
 import numpy as np
@@ -71,6 +72,73 @@ def test_text_matrix_loader(tmp_path):
         maps.load_text_matrix(p)
 
 
+def _write_bt(path, occ_keys, free_keys, res, depth=16):
+    """An OctoMap binary tree written here from sets of leaf keys: 2 bits per child (01 occupied, 10 free, 11 inner, 00
+    unknown; bit 2i first), inner nodes depth first, a node whose 8 children are equal leaves pruned into one leaf."""
+    def build(keys_occ, keys_free, level):                               # -> 'occ' | 'free' | None | [8 children]
+        if level == depth:
+            return "occ" if keys_occ else ("free" if keys_free else None)
+        if not keys_occ and not keys_free:
+            return None
+        bit = depth - 1 - level
+        kids = []
+        for i in range(8):
+            sel = lambda ks: [k for k in ks if ((k[0] >> bit) & 1, (k[1] >> bit) & 1, (k[2] >> bit) & 1) == (i & 1, (i >> 1) & 1, (i >> 2) & 1)]
+            kids.append(build(sel(keys_occ), sel(keys_free), level + 1))
+        if all(k == "occ" for k in kids):
+            return "occ"
+        if all(k == "free" for k in kids):
+            return "free"
+        return kids
+    out = bytearray()
+    count = [1]                                                          # the root
+    def emit(node):
+        bits = 0
+        for i, k in enumerate(node):
+            code = 0 if k is None else (2 if k == "occ" else (1 if k == "free" else 3))    # value of (bit 2i) | (bit 2i+1) << 1
+            bits |= code << (2 * i)
+            count[0] += k is not None
+        out.extend(struct.pack("<H", bits))
+        for k in node:
+            if isinstance(k, list):
+                emit(k)
+    root = build(list(occ_keys), list(free_keys), 0)
+    assert isinstance(root, list)
+    emit(root)
+    open(path, "wb").write(b"# Octomap OcTree binary file\n# comment\nid OcTree\nsize %d\nres %s\ndata\n" % (count[0], repr(res).encode())
+                           + bytes(out))
+
+
+def test_bt_loader_leaves_pruned_cubes_and_header(tmp_path):
+    rng = np.random.default_rng(3)
+    base = np.array([32768 - 5, 32768 + 8, 32768 + 16])                  # straddles the sign boundary of the x axis
+    cells = rng.random((11, 9, 14)) < 0.3                                # [z, y, x]
+    cells[0:4, 0:4, 8:12] = True                                         # key-aligned 4^3 cube: pruned two levels up
+    zz, yy, xx = np.nonzero(cells)
+    occ_keys = {(int(base[0] + x), int(base[1] + y), int(base[2] + z)) for x, y, z in zip(xx, yy, zz)}
+    free_keys = {(int(base[0] + x), int(base[1] + y), int(base[2] + 30)) for x in range(14) for y in range(9)} - occ_keys
+    p = str(tmp_path / "t.bt")
+    _write_bt(p, occ_keys, free_keys, 0.05)
+    occ, org, res = maps.load_bt(p)
+    lo = np.array([min(k[c] for k in occ_keys) for c in range(3)])
+    hi = np.array([max(k[c] for k in occ_keys) for c in range(3)]) + 1
+    assert res == 0.05 and org.tolist() == lo.tolist() and occ.shape == tuple((hi - lo)[::-1])
+    want = np.zeros(occ.shape, np.uint8)
+    for k in occ_keys:
+        want[k[2] - lo[2], k[1] - lo[1], k[0] - lo[0]] = 1
+    assert np.array_equal(occ, want)                                     # free leaves and unknown space are both 0
+    raw = open(p, "rb").read()
+    open(p, "wb").write(raw[:-3])                                        # truncated data
+    with pytest.raises(K.LmcmaError):
+        maps.load_bt(p)
+    open(p, "wb").write(raw.replace(b"id OcTree", b"id ColorOcTree"))    # other tree types are not binary-compatible
+    with pytest.raises(K.LmcmaError):
+        maps.load_bt(p)
+    open(p, "wb").write(re.sub(rb"size \d+", b"size 7", raw))             # node count does not match
+    with pytest.raises(K.LmcmaError):
+        maps.load_bt(p)
+
+
 @pytest.mark.skipif(not REFERENCE_PRESENT, reason="needs /root/reference (authoring container)")
 def test_reference_files(golden_maps):
     for name in ("problem1", "problem2"):
@@ -78,3 +146,21 @@ def test_reference_files(golden_maps):
     occ, tr, sc = maps.load_binvox(os.path.join(REF, "files", "mesh_files", "Dude.binvox"))
     assert occ.shape == (256, 256, 256)
     assert abs(occ.mean() - 0.0174) < 5e-4                               # 1.74 % occupied
+
+
+@pytest.mark.skipif(not REFERENCE_PRESENT, reason="needs /root/reference (authoring container)")
+@pytest.mark.parametrize("name", ["Dude", "room"])
+def test_reference_bt_equals_its_binvox_source(name):
+    """The bundled .bt files were made from the bundled .binvox files by binvox2bt.cpp:250-271: voxel (x, y, z) -> point
+    (float)(v res + t + 1e-6) -> key floor(p / res) + 32768, res = scale / depth.  Both loaders must agree cell for cell."""
+    d = os.path.join(REF, "files", "mesh_files")
+    occ, org, res = maps.load_bt(os.path.join(d, name + ".binvox.bt"))
+    vox, tr, sc = maps.load_binvox(os.path.join(d, name + ".binvox"))
+    assert abs(res - sc / vox.shape[2]) < 1e-6 * res                     # the header prints 5-6 significant digits
+    zz, yy, xx = np.nonzero(vox)
+    r = sc / vox.shape[2]
+    key = lambda v, t: np.floor((v * r + t + 0.000001).astype(np.float32).astype(np.float64) / res).astype(np.int64) + 32768
+    ix, iy, iz = key(xx, tr[0]) - org[0], key(yy, tr[1]) - org[1], key(zz, tr[2]) - org[2]
+    want = np.zeros_like(occ)
+    want[iz, iy, ix] = 1
+    assert np.array_equal(occ, want) and occ.sum() == vox.sum()
