@@ -176,17 +176,25 @@ def run_b200(args):
     from lmcma_path_planner_b200.optimizer import _endpoints, _objective
     obj, ends = _objective(W, L.LONGSAFE, 1e4), _endpoints(start, goal)
 
+    e2e_parts = [0.0, 0.0, 0.0]                                  # host wall clock inside ask_all / cost_evaluate / tell_all
+
     def e2e_step():
+        t0 = time.perf_counter()
         K.check(K.lib().lmcma_b200_ask_all(e2e_opt._h, K.fptr(Xh)))
+        t1 = time.perf_counter()
         K.check(K.lib().lmcma_b200_cost_evaluate(cmap._h, C.byref(obj), C.byref(ends), K.fptr(Xh), LAM, K.fptr(fh),
                                                 K.iptr(nch), K.iptr(nsh)))
+        t2 = time.perf_counter()
         K.check(K.lib().lmcma_b200_tell_all(e2e_opt._h, K.fptr(fh)))
+        t3 = time.perf_counter()
+        e2e_parts[0] += t1 - t0; e2e_parts[1] += t2 - t1; e2e_parts[2] += t3 - t2
         return float(fh[0])
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
     barrier()
     e2e_t = 0.0
+    e2e_parts[:] = [0.0, 0.0, 0.0]
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
@@ -235,6 +243,7 @@ def run_b200(args):
                                  "around k_cost on the launching stream, L2 flushed before each generation"},
             "e2e": {"value": world * LAM * args.steps / e2e_t, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_t / args.steps * 1e3,
+                    "calls_ms_rank0": {k: v / args.steps * 1e3 for k, v in zip(("ask_all", "cost_evaluate", "tell_all"), e2e_parts)},
                     "path": "lmcma_b200_ask_all (D2H X) -> lmcma_b200_cost_evaluate (H2D X, D2H f/flags) -> lmcma_b200_tell_all "
                             "(H2D f; update+sample), pinned host buffers, wall clock around synchronous calls"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,

@@ -112,15 +112,21 @@ int parse_point(const char* s, float* p) {
 
 // a map file -> occupancy -> distance field + planner, everything after the file parser on the device
 int planfile(int argc, char** argv) {
-    if (argc < 6) { std::fprintf(stderr, "usage: example_lmcma planfile <map.bmp|map.binvox> <start> <goal> <out.txt> [generations] [waypoints] [lambda]\n"); return 2; }
+    if (argc < 6) { std::fprintf(stderr, "usage: example_lmcma planfile <map.bmp|map.binvox|map.bt> <start> <goal> <out.txt> [generations] [waypoints] [lambda]\n"); return 2; }
     const std::string map_path = argv[2];
     float start[3] = {0, 0, 0}, goal[3] = {0, 0, 0};
     const int ds = parse_point(argv[3], start), dg = parse_point(argv[4], goal);
     const bool is_vox = map_path.size() > 7 && map_path.compare(map_path.size() - 7, 7, ".binvox") == 0;
+    const bool is_bt = map_path.size() > 3 && map_path.compare(map_path.size() - 3, 3, ".bt") == 0;
     int32_t shape[3] = {1, 1, 1};
     std::vector<uint8_t> occ;
     int dims = 2;
-    if (is_vox) {
+    if (is_bt) {                                                 // cell coordinates relative to the first occupied key per axis
+        dims = 3;
+        lmcma_b200::check(lmcma_b200_load_bt(map_path.c_str(), 0, 0, shape, 0, 0));
+        occ.resize((size_t)shape[0] * shape[1] * shape[2]);
+        lmcma_b200::check(lmcma_b200_load_bt(map_path.c_str(), occ.data(), (int64_t)occ.size(), shape, 0, 0));
+    } else if (is_vox) {
         dims = 3;
         lmcma_b200::check(lmcma_b200_load_binvox(map_path.c_str(), 0, 0, shape, 0, 0));
         occ.resize((size_t)shape[0] * shape[1] * shape[2]);

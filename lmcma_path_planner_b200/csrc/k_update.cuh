@@ -530,15 +530,27 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     yn[it] = (q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                     if (q < nq) reinterpret_cast<float4*>(VPb + ((size_t)(live - 1) * 2 + 1) * ns)[q] = yn[it];   // pc at its position
                 }
+                // every factor row is final and in shared memory by now: the next factor is fetched while this one's
+                // dot product is in the shuffle rounds (the loads would otherwise sit on the 39-step chain)
+                float4 a4[NVB];
+                float ljn = lj_s[0];
+#pragma unroll
+                for (int it = 0; it < NVB; ++it) {
+                    const int q = lane + 32 * it;
+                    a4[it] = (q < nq && live > 1) ? reinterpret_cast<const float4*>(rows_s)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll 2
                 for (int j = 0; j + 1 < live; ++j) {
                     kn *= Kd;
-                    const float4* vj = reinterpret_cast<const float4*>(rows_s + (size_t)j * ns);
-                    float4 a4[NVB];
+                    const float ljj = ljn;
+                    float4 an[NVB];
+                    const float4* vn = reinterpret_cast<const float4*>(rows_s + (size_t)(j + 1) * ns);   // row live-1 (the path itself) is read but unused
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) {
                         const int q = lane + 32 * it;
-                        a4[it] = (q < nq) ? vj[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        an[it] = (q < nq) ? vn[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                    ljn = lj_s[j + 1];
                     float d;
                     if (j + 2 < live) {
                         float2 d0 = make_float2(0.f, 0.f), d1 = d0;
@@ -553,12 +565,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     }
 #pragma unroll
                     for (int ofs = 16; ofs > 0; ofs >>= 1) d += __shfl_xor_sync(0xffffffffu, d, ofs);
-                    const float e = lj_s[j] * d;
+                    const float e = ljj * d;
                     const float2 me = make_float2(-e, -e);
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) {
                         const float2 l = ffma2(me, lo2(a4[it]), lo2(yn[it])), h = ffma2(me, hi2(a4[it]), hi2(yn[it]));
                         yn[it] = make_float4(l.x, l.y, h.x, h.y);
+                        a4[it] = an[it];
                     }
                 }
             }

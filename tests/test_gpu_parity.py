@@ -537,6 +537,23 @@ def test_cpp_planner_driver_from_a_map_file(tmp_path):
     assert pts.shape == (22, 2) and tuple(pts[0]) == (99.0, 0.0) and tuple(pts[-1]) == (0.0, 99.0)
 
 
+def test_cpp_planner_driver_from_an_octomap_tree(tmp_path):
+    """.bt (OcTree::writeBinary, what planner.cpp:152-163 reads) -> dense occupancy -> device EDT -> 3-D LM-CMA planning.
+    A ball on the straight line: the planned path must go around it (the driver re-evaluates it: no collisions)."""
+    from test_ingest_cpu import _write_bt
+    base = 32768 - 10
+    g = np.arange(40)
+    ball = (g[:, None, None] - 19.5) ** 2 + (g[None, :, None] - 19.5) ** 2 + (g[None, None, :] - 19.5) ** 2 <= 7.0 ** 2
+    occ = {(base + int(x), base + int(y), base + int(z)) for x, y, z in zip(*np.nonzero(ball))}
+    occ.update((base + x, base + y, base + z) for x in (0, 39) for y in (0, 39) for z in (0, 39))   # bounding box = 40^3
+    _write_bt(str(tmp_path / "ball.bt"), occ, set(), 0.1)
+    r = _example(["planfile", "ball.bt", "5,5,5", "34,34,34", "p.txt", "300", "12", "256"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "map 40x40x40" in r.stdout and "collisions 0" in r.stdout, r.stdout
+    pts = np.loadtxt(tmp_path / "p.txt")
+    assert pts.shape == (14, 3) and tuple(pts[0]) == (5.0, 5.0, 5.0) and tuple(pts[-1]) == (34.0, 34.0, 34.0)
+
+
 def test_lmcma_teacher_forced_gram_path(po, monkeypatch):
     """The Gram-matrix recompute (k_gram / k_coef / k_combine): forced on the C2-like shape so that slot recycling
     (itr >= m, first_stale > 0) is exercised, then on the C4 row length where it is the default (m * n = 115 K floats
