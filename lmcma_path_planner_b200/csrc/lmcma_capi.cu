@@ -127,6 +127,9 @@ struct lmcma_b200_map {
     float* d_X = nullptr; size_t d_X_cap = 0;
     float* d_f = nullptr; int* d_nc = nullptr; int* d_ns = nullptr; size_t d_out_cap = 0;
     float* d_ends = nullptr;
+    float ends_host[6] = {0, 0, 0, 0, 0, 0};   // what d_ends holds (cost_evaluate*: re-uploaded only when the query changes)
+    bool ends_valid = false;
+    cudaStream_t ends_stream = nullptr;
 };
 
 struct lmcma_b200_opt {
@@ -153,6 +156,10 @@ struct lmcma_b200_opt {
     // graph
     cudaGraphExec_t graph_exec = nullptr;
     cudaStream_t graph_built_for = nullptr;
+    cudaGraphExec_t tell_graph = nullptr;     // tell_all of one query: H2D fitness -> k_rank -> k_sample, k_update on a side branch
+    cudaStream_t tell_graph_for = nullptr;
+    bool tell_graph_failed = false;
+    float* f_pinned = nullptr;                // the graph's copy source (the caller's fitness array is copied here first)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool have_run_timing = false;
     // sample launch config
@@ -557,6 +564,40 @@ int ensure_graph(lmcma_b200_opt* o) {
     return 0;
 }
 
+// tell_all of one query as a forked graph (see lmcma_b200_tell_all); on failure the caller takes the stream-ordered path
+int ensure_tell_graph(lmcma_b200_opt* o) {
+    if (o->tell_graph && o->tell_graph_for == o->stream) return ensure_mirror(o, o->stream);
+    if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
+    cudaStream_t st = o->stream;
+    const OptDev& d = o->d;
+    int rc = ensure_mirror(o, st);
+    if (rc) return rc;
+    if (!o->f_pinned && cudaHostAlloc(&o->f_pinned, (size_t)d.B * d.lambda * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError(); o->f_pinned = nullptr; o->tell_graph_failed = true; return 0;
+    }
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches.load();
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    UpdateArgs ua = update_args_local(o);
+    ua.progressive = 1;
+    ua.overlap = 1;
+    bool ok = cudaEventRecord(o->ev_fork, st) == cudaSuccess && cudaStreamWaitEvent(o->side_stream, o->ev_fork, 0) == cudaSuccess;
+    if (ok) ok = launch_update(o, ua, false, o->side_stream) == 0;
+    if (ok) ok = cudaEventRecord(o->ev_join, o->side_stream) == cudaSuccess;
+    if (ok) ok = cudaMemcpyAsync(d.fit, o->f_pinned, (size_t)d.B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (ok) { k_gate<<<(d.B + 31) / 32, 32, 0, st>>>(d); ok = cudaGetLastError() == cudaSuccess; }   // k_update has reset the flags and holds its SM
+    if (ok) ok = launch_rank(o, d.fit, RANK_PLAIN | RANK_KEEP_FLAGS, nullptr, st, false) == 0;
+    if (ok) ok = launch_sample(o, st, true, true, 2) == 0;
+    if (ok) ok = cudaStreamWaitEvent(st, o->ev_join, 0) == cudaSuccess;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    g_launches.store(before);   // capture enqueues nothing
+    if (ok && e == cudaSuccess && cudaGraphInstantiate(&o->tell_graph, graph, 0) != cudaSuccess) o->tell_graph = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    if (!o->tell_graph) { cudaGetLastError(); o->tell_graph_failed = true; return 0; }
+    o->tell_graph_for = st;
+    return 0;
+}
+
 // device-side alias of a page-locked host buffer (unified addressing), or null for pageable / foreign memory
 void* mapped_device_pointer(const void* host, int device) {
     cudaPointerAttributes at;
@@ -856,7 +897,11 @@ int lmcma_b200_cost_evaluate_dev(lmcma_b200_map* m, const lmcma_b200_objective* 
     CU(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
     float e6[6] = {ends->start[0], ends->start[1], ends->start[2], ends->goal[0], ends->goal[1], ends->goal[2]};
-    CU(cudaMemcpyAsync(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice, st));
+    if (!m->ends_valid || m->ends_stream != st || memcmp(m->ends_host, e6, sizeof(e6)) != 0) {   // a planner asks about one query many times
+        CU(cudaMemcpyAsync(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice, st));
+        memcpy(m->ends_host, e6, sizeof(e6));
+        m->ends_valid = true; m->ends_stream = st;
+    }
     CostArgs a;
     memset(&a, 0, sizeof(a));
     a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
@@ -927,6 +972,7 @@ int lmcma_b200_cost_trace(lmcma_b200_map* m, const lmcma_b200_objective* obj, co
     CU(cudaMemcpy(dX, x_host, n * sizeof(float), cudaMemcpyHostToDevice));
     float e6[6] = {ends->start[0], ends->start[1], ends->start[2], ends->goal[0], ends->goal[1], ends->goal[2]};
     CU(cudaMemcpy(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice));
+    m->ends_valid = false;
     CU(cudaStreamSynchronize(cudaStreamLegacy));   // the kernel runs on the map's non-blocking stream
     CostArgs a;
     memset(&a, 0, sizeof(a));
@@ -1112,6 +1158,8 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
                     d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.progress, d.rank_ticket, d.resident, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
+    if (o->tell_graph) cudaGraphExecDestroy(o->tell_graph);
+    if (o->f_pinned) cudaFreeHost(o->f_pinned);
     if (o->ev0) cudaEventDestroy(o->ev0);
     if (o->ev1) cudaEventDestroy(o->ev1);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
@@ -1182,8 +1230,28 @@ int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
     if (o->d.pop_count != o->d.lambda) return fail(LMCMA_B200_ERR_STATE, "split-population handles use the mg_* entry points");
     CU(cudaSetDevice(o->cfg.device));
     const OptDev& d = o->d;
+    int rc;
+    if (o->overlap && !o->tell_graph_failed && env_int("LMCMA_B200_TELL_OVERLAP", 1) != 0) {
+        // One query (the conditions of the overlapped generation): everything in update() that does not
+        // depend on this generation's fitness — slot bookkeeping, the sweep over every pending row but the newest — runs on
+        // a side branch while the fitness crosses PCIe and k_rank runs; k_update then waits for k_rank's tickets and
+        // k_sample follows its hand-over flags.  Same kernels and arithmetic as the fused generation (bit-identical to the
+        // serial order), replayed as one CUDA graph: launched kernel by kernel, the fork / join costs more host time than
+        // the overlap saves.
+        if ((rc = ensure_tell_graph(o)) == 0 && o->tell_graph) {
+            memcpy(o->f_pinned, f, (size_t)d.B * d.lambda * sizeof(float));
+            CU(cudaGraphLaunch(o->tell_graph, o->stream));
+            g_launches += 4;                                     // k_update, k_gate, k_rank, k_sample
+            o->x_cache_valid = false;
+            o->sample_idx = 0;
+            o->pending_z = false;
+            CU(cudaStreamSynchronize(o->stream));
+            return 0;
+        }
+        if (rc) return rc;
+    }
     CU(cudaMemcpyAsync(d.fit, f, (size_t)d.B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, o->stream));
-    int rc = generation_tail(o, o->stream);
+    rc = generation_tail(o, o->stream);
     if (rc) return rc;
     CU(cudaStreamSynchronize(o->stream));
     return 0;

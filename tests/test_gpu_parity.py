@@ -587,6 +587,19 @@ def test_progressive_and_overlapped_generations_are_bit_identical_to_the_serial_
     for mode in ("progressive", "overlapped"):
         for k in state["serial"]:
             assert np.array_equal(state[mode][k], state["serial"][k]), (mode, k)
+    # the same through the host-buffer protocol: tell_all runs k_update's fitness-independent part on a side stream while
+    # the fitness is copied and ranked (LMCMA_B200_TELL_OVERLAP, default on) — same bits as the fused generations above
+    monkeypatch.setenv("LMCMA_B200_PROGRESSIVE", "1")
+    monkeypatch.setenv("LMCMA_B200_OVERLAP", "1")
+    for tell in ("1", "0"):
+        monkeypatch.setenv("LMCMA_B200_TELL_OVERLAP", tell)
+        dev = L.Optimizer(2 * W, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=8.0, seed=11)
+        for g in range(70):
+            r = cm.evaluate(dev.ask_all()[0], start, goal, W, L.LONGSAFE, 1e4)
+            dev.tell_all(r["f"])
+        for k in ("X", "xmean", "V", "P", "sigma", "t", "vec", "Nj", "Lj"):
+            assert np.array_equal(dev.get(k), state["serial"][k]), ("tell_all overlap " + tell, k)
+        assert np.array_equal(dev.best()[1], state["serial"]["best_f"])
 
 
 def test_cost_evaluate_page_locked_buffers_match_staged(po, golden_maps, monkeypatch):

@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -q > gpurun_out/s5_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/s5_pytest.log
+python -m pytest tests -m gpu -q -x > gpurun_out/s5_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/s5_pytest.log
 python bench.py --steps 300 --warmup 5 > gpurun_out/s5_bench.log 2> gpurun_out/s5_bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json
