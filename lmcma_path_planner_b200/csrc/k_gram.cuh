@@ -7,7 +7,7 @@
 //     v_j . x  =  coef(v_j)^T G coef(x).
 //   k_gram     G in FP64 from the FP32 rows, many CTAs (the only pass over the long rows besides the last one)
 //   k_coef     the recurrence x <- K x - Lj_j (v_j . x) v_j on coefficient vectors, FP64, one CTA per instance,
-//              same operation order as the reference; |v_j|^2 = c_j^T G c_j, Nj / Lj closed forms
+//              same factor order as the reference; |v_j|^2 = c_j^T G c_j, Nj / Lj closed forms
 //   k_combine  v_i = sum_k C[i][k] b_k for the recomputed rows, FP64 accumulation, many CTAs; also refreshes the
 //              sequence-ordered mirror k_sample streams from
 // All cancellation (|pc| ~ 10^3 collapsing to |v| ~ 10 once the paths are collinear) happens in FP64 here, so this
@@ -19,17 +19,20 @@ namespace lmcma {
 
 constexpr int GRAM_TILE = 16;
 constexpr int GRAM_KC = 64;        // columns staged per step
+constexpr int GRAM_KS = 8;         // column slices of a tile pair, one CTA each; OptDev::G holds the GRAM_KS partial matrices of an
+                                   // instance, k_coef adds them in slice order (no atomics: every rank of a split population
+                                   // must form the same bits)
 
 __device__ __forceinline__ const float* basis_row(const OptDev& o, int b, int i, int first_stale) {
     const int slot = o.t[(size_t)b * o.m + i];
     return (i < first_stale ? o.V : o.P) + ((size_t)b * o.m + slot) * o.ns;
 }
 
-// grid = (tiles_a, tiles_b, B) with tiles_b >= tiles_a used (upper triangle incl. diagonal), 256 threads = 16 x 16 dots
+// grid = (tiles_a, tiles_b, B * GRAM_KS) with tiles_b >= tiles_a used (upper triangle incl. diagonal), 256 threads = 16 x 16 dots
 __global__ void __launch_bounds__(256) k_gram(OptDev o) {
     __shared__ float As[GRAM_TILE][GRAM_KC + 1];
     __shared__ float Bs[GRAM_TILE][GRAM_KC + 1];
-    const int b = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
+    const int b = blockIdx.z / GRAM_KS, ks = blockIdx.z - b * GRAM_KS, ta = blockIdx.x, tb = blockIdx.y;
     if (tb < ta) return;
     const int2 hdr = o.gram_hdr[b];
     const int first_stale = hdr.x, live = hdr.y;
@@ -40,7 +43,9 @@ __global__ void __launch_bounds__(256) k_gram(OptDev o) {
     const float* arow = (a0 + lr < live) ? basis_row(o, b, a0 + lr, first_stale) : nullptr;
     const float* brow = (b0 + lr < live) ? basis_row(o, b, b0 + lr, first_stale) : nullptr;
     double acc0 = 0.0, acc1 = 0.0;
-    for (int c0 = 0; c0 < o.ns; c0 += GRAM_KC) {
+    const int steps = (o.ns + GRAM_KC - 1) / GRAM_KC, per = (steps + GRAM_KS - 1) / GRAM_KS;   // this slice: steps [ks per, (ks + 1) per)
+    const int c_end = min(o.ns, (ks + 1) * per * GRAM_KC);
+    for (int c0 = ks * per * GRAM_KC; c0 < c_end; c0 += GRAM_KC) {
         float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
         if (arow && c0 + lc < o.ns) av = *reinterpret_cast<const float4*>(arow + c0 + lc);
         if (brow && c0 + lc < o.ns) bv = *reinterpret_cast<const float4*>(brow + c0 + lc);
@@ -56,132 +61,153 @@ __global__ void __launch_bounds__(256) k_gram(OptDev o) {
     }
     const int ia = a0 + ty, ib = b0 + tx;
     if (ia < live && ib < live) {
-        double* G = o.G + (size_t)b * o.m * o.m;
+        double* G = o.G + ((size_t)b * GRAM_KS + ks) * o.m * o.m;
         const double g = acc0 + acc1;
         G[(size_t)ia * o.m + ib] = g;
         G[(size_t)ib * o.m + ia] = g;
     }
 }
 
-// one CTA per instance; dynamic shared memory: G, C, W as L x LP doubles (LP odd: conflict-free column access)
-__global__ void __launch_bounds__(1024) k_coef(OptDev o) {
+// one CTA per instance, 8 lanes per basis row.  Row i of C = coefficients of the current x_i; row i of U = G coef(x_i),
+// carried along with every update (x <- K x - e v_j  =>  U_i <- K U_i - e U_j), so that when a row becomes final its
+// W = G coef(v) is already there and v_j . x_i = coef(v_j) . U_i needs no pass over G: ONE phase and ONE barrier per factor.
+// What bounds this kernel is the FP64 pipe of its one SM (measured: ~6 G FP64 instructions / s whatever the layout), so
+// the count is kept minimal:
+//  * a pending row is held as y = x / K^j (every pending row has had the same j factors), which turns both updates into
+//    ONE fused multiply-add per element, y <- y - (Lj_j / K)(v_j . y) v_j, and drops the K c_i[i] term; a row is scaled back
+//    by K^i when it becomes final;
+//  * only the support is touched: coef(v_j) and coef(x_i) live on {0 .. j} (and i); U_i is a full row.
+// A pending row lives in the REGISTERS of its 8 lanes (lane `sub` holds the elements k = sub + 8 t, t < TMAX, of both
+// vectors, loops unrolled with block-uniform bounds); only final rows are in shared memory (U, C as L x LP doubles, read
+// as broadcasts by every pending row).  Earlier versions: all rows in shared memory with W_j = G c_j and |v_j|^2
+// recomputed in two more block-wide phases per factor (126 us for C4's 77 rows); registers without the scaling and the
+// support bounds (122 us, 5 FP64 instructions per element and factor over the padded row).
+template <int TMAX>
+__global__ void __launch_bounds__(64 * TMAX) k_coef(OptDev o) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int m = o.m;
     const int2 hdr = o.gram_hdr[b];
     const int first_stale = hdr.x, L = hdr.y;
     const int LP = m | 1;
-    double* Gs = reinterpret_cast<double*>(smem_raw);             // [L][LP]
-    double* Cs = Gs + (size_t)m * LP;                             // [L][LP]: row i = coefficients of the current x_i
-    double* Ws = Cs + (size_t)m * LP;                             // [L][LP]: row j = G coef(v_j)
-    double* lj_s = Ws + (size_t)m * LP;                           // [L]
+    double* Us = reinterpret_cast<double*>(smem_raw);             // [L][LP]: final rows only
+    double* Cs = Us + (size_t)m * LP;                             // [L][LP]: recomputed final rows only
+    double* lj_s = Cs + (size_t)m * LP;                           // [L]: Lj / K
     double* nv_s = lj_s + m;                                      // [L]
-    const double* G = o.G + (size_t)b * m * m;
+    const double* G = o.G + (size_t)b * GRAM_KS * m * m;
     const int* order = o.t + (size_t)b * m;
-    for (int e = tid; e < L * L; e += nthr) {
-        const int i = e / L, k = e - i * L;
-        Gs[i * LP + k] = G[(size_t)i * m + k];
-        Cs[i * LP + k] = (i == k) ? 1.0 : 0.0;
+    const int sub = tid & 7, i = tid >> 3;                        // this thread's row (8 aligned lanes of one warp per row)
+    const bool row_on = i < L;
+    const double Kd = o.K, invK = 1.0 / o.K, r = o.c1 / (1.0 - o.c1), am = o.M;
+    double c[TMAX], u[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+        const int k = sub + 8 * t;
+        double g = 0.0;
+        if (row_on && k < L) {
+#pragma unroll
+            for (int ks = 0; ks < GRAM_KS; ++ks) g += G[((size_t)ks * m + i) * m + k];   // the column slices of k_gram, in slice order
+        }
+        u[t] = g;                                                 // coef(x_i) = e_i: U_i = row i of G
+        c[t] = (row_on && k == i) ? 1.0 : 0.0;
+        if (row_on && i < first_stale && k < L) Us[i * LP + k] = g;   // unchanged rows: W_i = row i of G, coef = e_i
     }
-    for (int j = tid; j < L; j += nthr) lj_s[j] = (j < first_stale) ? o.Lj[(size_t)b * m + order[j]] : 0.0;
-    __syncthreads();
-    const double Kd = o.K, r = o.c1 / (1.0 - o.c1), am = o.M;
-    // 8 lanes per row (aligned groups inside a warp): the length-L dot products and updates are split 8 ways and folded
-    // with three shuffles, so that a step of the recurrence is ~L/8 dependent FP64 FMAs instead of L
-    const int sub = tid & 7, grp = tid >> 3, ngrp = nthr >> 3;
-    auto quad_sum = [&](double v) {
+    for (int j = tid; j < L; j += nthr) lj_s[j] = (j < first_stale) ? o.Lj[(size_t)b * m + order[j]] * invK : 0.0;
+    auto oct_sum = [&](double v) {
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         return v;
     };
-    auto finalize = [&](int j) {       // row j has had all its factors applied: W_j = G c_j, |v_j|^2, Lj_j (block-collective)
-        const double* cj = Cs + j * LP;
-        for (int k0 = 0; k0 < L; k0 += ngrp) {
-            const int k = k0 + grp;
-            double s0 = 0.0;
-            if (k < L) { const double* gk = Gs + k * LP; for (int l = sub; l <= j; l += 8) s0 = fma(gk[l], cj[l], s0); }
-            s0 = quad_sum(s0);
-            if (k < L && sub == 0) Ws[j * LP + k] = s0;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double s0 = 0.0;
-            for (int k = lane; k <= j; k += 32) s0 = fma(cj[k], Ws[j * LP + k], s0);
+    // a row that has had all its factors applied is scaled back (kp = K^i) and goes to shared memory; |v|^2 = c . U,
+    // Lj (cancellation-free form of lmcma.cpp:388-389).  Warp-collective (shuffles); `mine` is uniform over a row's 8 lanes
+    auto finish = [&](bool mine, double kp) {
+        double s0 = 0.0;
+        if (mine) {
 #pragma unroll
-            for (int ofs = 16; ofs > 0; ofs >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, ofs);
-            if (lane == 0) {
-                const double nv = s0 > 0.0 ? s0 : 0.0;
-                const double t = sqrt(1.0 + r * nv);
-                nv_s[j] = nv;
-                lj_s[j] = r / (am * t * (t + 1.0));               // cancellation-free form of lmcma.cpp:388-389
+            for (int t = 0; t < TMAX; ++t) {
+                const int k = sub + 8 * t;
+                const double cv = c[t] * kp, uv = u[t] * kp;
+                if (k < L) { Cs[i * LP + k] = cv; Us[i * LP + k] = uv; }
+                if (8 * t <= i) s0 = fma(cv, uv, s0);              // c is 0 beyond the row's support {0 .. i}
             }
         }
-        __syncthreads();
+        s0 = oct_sum(s0);
+        if (mine && sub == 0) {
+            const double nv = s0 > 0.0 ? s0 : 0.0;
+            const double t2 = sqrt(1.0 + r * nv);
+            nv_s[i] = nv;
+            lj_s[i] = r / (am * t2 * (t2 + 1.0)) * invK;
+        }
     };
-    for (int e = tid; e < first_stale * L; e += nthr) {             // final rows: coef(v_j) = e_j, W_j = row j of G
-        const int j = e / L, k = e - j * L;
-        Ws[j * LP + k] = Gs[j * LP + k];
-    }
+    if (first_stale == 0) finish(i == 0, 1.0);                    // v_0 = pc_0
     __syncthreads();
-    if (first_stale == 0) finalize(0);                              // v_0 = pc_0
+    double kp = 1.0;                                              // K^(j+1) inside step j
     for (int j = 0; j + 1 < L; ++j) {
-        // factor j on every pending row i > j: x <- K x - Lj_j (v_j . x) v_j (lmcma.cpp:455-461), 8 lanes per row
-        const double lj = lj_s[j];
-        const bool fresh = j >= first_stale;
-        const double* wj = Ws + j * LP;
+        kp *= Kd;
+        // factor j on every pending row i > j: x <- K x - Lj_j (v_j . x) v_j (lmcma.cpp:455-461), on y = x / K^j
+        const bool fresh = j >= first_stale;                      // v_j was recomputed in this sweep (else coef(v_j) = e_j)
+        const bool on = row_on && i > j && i >= first_stale;
         const double* cj = Cs + j * LP;
-        const int ibeg = max(j + 1, first_stale);
-        for (int i0 = ibeg; i0 < L; i0 += ngrp) {
-            const int i = i0 + grp;
-            const bool on = i < L;
-            double* ci = Cs + (on ? i : 0) * LP;
-            double d = 0.0;                                          // support of c_i: {0 .. j} and i
-            if (on) {
-                for (int k = sub; k <= j; k += 8) d = fma(ci[k], wj[k], d);
-                if (sub == 0) d = fma(ci[i], wj[i], d);
-            }
-            const double e = lj * quad_sum(d);
-            if (on) {
-                if (fresh) { for (int k = sub; k <= j; k += 8) ci[k] = Kd * ci[k] - e * cj[k]; }
-                else { for (int k = sub; k < j; k += 8) ci[k] *= Kd; if (sub == 0) ci[j] = Kd * ci[j] - e; }
-                if (sub == 1) ci[i] *= Kd;
+        const double* wj = Us + j * LP;
+        double cv[TMAX];
+        double d = 0.0;
+        if (on) {
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if (8 * t <= j) {                                  // block-uniform: the support of coef(v_j) is {0 .. j}
+                    const int k = sub + 8 * t;
+                    cv[t] = fresh ? ((k <= j) ? cj[k] : 0.0) : ((k == j) ? 1.0 : 0.0);
+                    d = fma(cv[t], u[t], d);
+                }
             }
         }
+        const double e = -lj_s[j] * oct_sum(d);
+        if (on) {
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                const int k = sub + 8 * t;
+                if (8 * t <= j) c[t] = fma(e, cv[t], c[t]);
+                if (k < L) u[t] = fma(e, wj[k], u[t]);             // the whole row: W_i[k], k > i, updates the rows behind i
+            }
+        }
+        finish(on && i == j + 1, kp);                             // row j + 1 is final now
         __syncthreads();
-        if (j + 1 >= first_stale) finalize(j + 1);                   // row j + 1 is final now
     }
     // ---- outputs: coefficients of the recomputed rows, Nj / Lj (lmcma.cpp:386-389) by slot and by position ----
     double* Cf = o.Cf + (size_t)b * m * m;
-    for (int e = tid; e < L * L; e += nthr) { const int i = e / L, k = e - i * L; if (i >= first_stale) Cf[(size_t)i * m + k] = (k <= i) ? Cs[i * LP + k] : 0.0; }
-    for (int i = first_stale + tid; i < L; i += nthr) {
-        const int slot = order[i];
-        const double nv = nv_s[i], t = sqrt(1.0 + r * nv);
-        const double nj = am * r / (t + 1.0);
-        o.Nj[(size_t)b * m + slot] = nj; o.Lj[(size_t)b * m + slot] = lj_s[i];
-        o.Njf[(size_t)b * m + slot] = (float)nj; o.Njs[(size_t)b * m + i] = (float)nj;
+    for (int e = tid; e < L * L; e += nthr) { const int i2 = e / L, k = e - i2 * L; if (i2 >= first_stale) Cf[(size_t)i2 * m + k] = (k <= i2) ? Cs[i2 * LP + k] : 0.0; }
+    for (int i2 = first_stale + tid; i2 < L; i2 += nthr) {
+        const int slot = order[i2];
+        const double nv = nv_s[i2], t2 = sqrt(1.0 + r * nv);
+        const double nj = am * r / (t2 + 1.0);
+        o.Nj[(size_t)b * m + slot] = nj; o.Lj[(size_t)b * m + slot] = lj_s[i2] * Kd;
+        o.Njf[(size_t)b * m + slot] = (float)nj; o.Njs[(size_t)b * m + i2] = (float)nj;
     }
 }
 
-// v_i = sum_{k <= i} C[i][k] b_k for the recomputed rows: grid = (ceil(nq / 128), ceil(m / 8), B), 128 threads,
-// each thread one float4 column of 8 rows; writes V (slot-indexed) and both halves of the mirror
+// v_i = sum_{k <= i} C[i][k] b_k for the recomputed rows: grid = (ceil(nq / 128), ceil(m / COMBINE_ROWS), B), 128 threads,
+// each thread one float4 column of COMBINE_ROWS rows; writes V (slot-indexed) and both halves of the mirror.  Bound by the
+// walk over the basis rows (one CTA reads rows 0 .. kmax of its column slab in turn), not by the FP64 accumulation: 2 rows
+// per CTA (117 CTAs for C4) measured 41 us against 28 us for 8 rows per CTA (30 CTAs).
+constexpr int COMBINE_ROWS = 8;
 __global__ void __launch_bounds__(128) k_combine(OptDev o) {
-    __shared__ double cs[8][128];                                   // coefficients of this CTA's 8 rows (m <= 128)
+    __shared__ double cs[COMBINE_ROWS][128];                        // coefficients of this CTA's rows (m <= 128)
     __shared__ const float* rowp[128];                              // basis row pointers (one dependent load chain, not L)
     const int b = blockIdx.z, nq = o.ns >> 2, q = blockIdx.x * 128 + threadIdx.x;
     const int2 hdr = o.gram_hdr[b];
     const int first_stale = hdr.x, L = hdr.y;
-    const int i0 = first_stale + blockIdx.y * 8;
+    const int i0 = first_stale + blockIdx.y * COMBINE_ROWS;
     if (i0 >= L) return;
-    const int rows = min(8, L - i0), kmax = i0 + rows - 1;
+    const int rows = min(COMBINE_ROWS, L - i0), kmax = i0 + rows - 1;
     const double* Cf = o.Cf + (size_t)b * o.m * o.m;
-    for (int e = threadIdx.x; e < 8 * 128; e += 128) { const int r2 = e >> 7, k = e & 127; cs[r2][k] = (r2 < rows && k <= i0 + r2) ? Cf[(size_t)(i0 + r2) * o.m + k] : 0.0; }
+    for (int e = threadIdx.x; e < COMBINE_ROWS * 128; e += 128) { const int r2 = e >> 7, k = e & 127; cs[r2][k] = (r2 < rows && k <= i0 + r2) ? Cf[(size_t)(i0 + r2) * o.m + k] : 0.0; }
     if (threadIdx.x <= kmax) rowp[threadIdx.x] = basis_row(o, b, threadIdx.x, first_stale);
     __syncthreads();
     if (q >= nq) return;
-    double acc[8][4];
+    double acc[COMBINE_ROWS][4];
 #pragma unroll
-    for (int r2 = 0; r2 < 8; ++r2) { acc[r2][0] = acc[r2][1] = acc[r2][2] = acc[r2][3] = 0.0; }
+    for (int r2 = 0; r2 < COMBINE_ROWS; ++r2) { acc[r2][0] = acc[r2][1] = acc[r2][2] = acc[r2][3] = 0.0; }
     for (int k0 = 0; k0 <= kmax; k0 += 4) {                         // 4 independent row loads in flight
         float4 bk[4];
 #pragma unroll
@@ -191,7 +217,7 @@ __global__ void __launch_bounds__(128) k_combine(OptDev o) {
             const double x = bk[u].x, y = bk[u].y, z = bk[u].z, w = bk[u].w;
             const int k = min(k0 + u, 127);
 #pragma unroll
-            for (int r2 = 0; r2 < 8; ++r2) {
+            for (int r2 = 0; r2 < COMBINE_ROWS; ++r2) {
                 const double c = cs[r2][k];                         // 0 beyond a row's support
                 acc[r2][0] = fma(c, x, acc[r2][0]); acc[r2][1] = fma(c, y, acc[r2][1]);
                 acc[r2][2] = fma(c, z, acc[r2][2]); acc[r2][3] = fma(c, w, acc[r2][3]);

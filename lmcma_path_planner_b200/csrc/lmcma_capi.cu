@@ -411,10 +411,12 @@ int launch_update(lmcma_b200_opt* o, const UpdateArgs& a_in, bool pdl, cudaStrea
         if (rc) return rc;
         const OptDev& d = o->d;
         const int tiles = (d.m + GRAM_TILE - 1) / GRAM_TILE;
-        k_gram<<<dim3(tiles, tiles, d.B), 256, 0, st>>>(d);
-        if (o->coef_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_coef, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->coef_smem));
-        k_coef<<<d.B, 1024, o->coef_smem, st>>>(d);
-        k_combine<<<dim3((d.ns / 4 + 127) / 128, (d.m + 7) / 8, d.B), 128, 0, st>>>(d);
+        k_gram<<<dim3(tiles, tiles, d.B * GRAM_KS), 256, 0, st>>>(d);
+        const int coef_threads = std::min(1024, (8 * d.m + 31) & ~31);    // 8 lanes per basis row (m <= 128)
+        auto coef = d.m <= 40 ? k_coef<5> : (d.m <= 80 ? k_coef<10> : (d.m <= 96 ? k_coef<12> : k_coef<16>));   // elements per lane: ceil(m / 8)
+        if (o->coef_smem > 48 * 1024) CU(cudaFuncSetAttribute(coef, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->coef_smem));
+        coef<<<d.B, coef_threads, o->coef_smem, st>>>(d);
+        k_combine<<<dim3((d.ns / 4 + 127) / 128, (d.m + COMBINE_ROWS - 1) / COMBINE_ROWS, d.B), 128, 0, st>>>(d);
         g_launches += 3;
         CU(cudaGetLastError());
         return 0;
@@ -454,7 +456,7 @@ int configure_update(lmcma_b200_opt* o) {
     o->upd_smem = fixed + (o->upd_rows_in_smem ? rows : 0);
     if (o->upd_smem > budget) return fail(LMCMA_B200_ERR_ARG, "k_update needs %zu B shared memory (m = %d too large)", o->upd_smem, o->d.m);
     // rows that fit neither the registers nor the shared memory of one SM: Gram-matrix recompute (k_gram.cuh)
-    o->coef_smem = (size_t)3 * o->d.m * (o->d.m | 1) * sizeof(double) + (size_t)2 * o->d.m * sizeof(double);
+    o->coef_smem = (size_t)2 * o->d.m * (o->d.m | 1) * sizeof(double) + (size_t)2 * o->d.m * sizeof(double);
     o->upd_gram = (!o->upd_rows_in_smem || env_int("LMCMA_B200_UPDATE_GRAM", 0)) && o->d.m <= 128 && o->coef_smem <= budget &&
                   !env_int("LMCMA_B200_UPDATE_STREAMING", 0);
     if (o->upd_gram) { o->upd_rows_in_smem = false; o->upd_smem = fixed; }
@@ -1132,7 +1134,7 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
         if (e2 != cudaSuccess) { cudaGetLastError(); o->overlap = false; }
     }
     if (!rc && o->upd_gram) {
-        rc = dmalloc(&d.G, B * m * m);
+        rc = dmalloc(&d.G, B * GRAM_KS * m * m);
         if (!rc) rc = dmalloc(&d.Cf, B * m * m);
         if (!rc) rc = dmalloc(&d.gram_hdr, B);
     }
