@@ -343,9 +343,12 @@ int configure_sample(lmcma_b200_opt* o) {
     const size_t budget = (size_t)env_int("LMCMA_B200_SAMPLE_SMEM_KB", 160) * 1024;
     int kc = (int)(budget / 2 / pair_bytes);
     kc = kc >= 8 ? 8 : (kc >= 4 ? 4 : (kc >= 2 ? 2 : 1));
+    // long rows (C4: 12 KB per pair): two stages of a FULL group of 8 still fit one SM (192 KB), and a 4-pair stage runs the
+    // 8-wide group code half empty
+    if (kc == 4 && 2 * 8 * pair_bytes + 24 * 1024 <= o->props->smem_optin && env_int("LMCMA_B200_SAMPLE_SMEM_KB", 0) == 0) kc = 8;
     o->smp_kc = kc;
     const int max_chunks = (o->d.m + kc - 1) / kc;
-    o->smp_stages = (int)std::max<size_t>(2, std::min<size_t>(std::min(max_chunks, SAMPLE_MAX_STAGES), budget / (kc * pair_bytes)));
+    o->smp_stages = (int)std::max<size_t>(2, std::min<size_t>(std::min(max_chunks, SAMPLE_MAX_STAGES), budget / (kc * pair_bytes)));   // >= 2 even beyond the budget
     o->smp_smem = (size_t)o->smp_stages * kc * pair_bytes + SAMPLE_MAX_STAGES * 8 + (size_t)(2 * o->d.m + 16) * sizeof(float);
     // one large population: split every row over CW column-warps (k_sample_wide) for occupancy
     o->smp_wide = false;
