@@ -32,8 +32,8 @@ W, LAM, M, SIGMA0 = 200, 1024, 40, 32.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cost launch of this workload, from the committed
 # `ncu --set full` capture (the map stays L2-resident between generations, so DRAM traffic is far BELOW the
 # algorithmic bytes: the kernel is bound by issue slots / L1 gather rate, not by HBM)
-NCU_DRAM_BYTES_PER_LAUNCH = 2.338e6
-NCU_SOURCE = "profiles/r1e_full.md (k_cost<2,0,0>: dram_read 2.338 MB, dram_write 0)"
+NCU_DRAM_BYTES_PER_LAUNCH = 2.378e6
+NCU_SOURCE = "profiles/r1f_full.md (k_cost<2,0,0>: dram_read 2.378 MB, dram_write 0)"
 
 
 def peaks():
