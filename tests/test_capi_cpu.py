@@ -151,3 +151,23 @@ def test_cholesky_matches_numpy_and_rejects_indefinite(golden):
     ours = np.zeros(400)
     assert K.lib().lmcma_b200_covariance(2, 10, K.dptr(ours)) == 0
     assert np.allclose(ours, golden["covariance_2_10_shim_pinned"], rtol=1e-9, atol=1e-12)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU implementation of the path: oracle/_ref when it was built here, else
+    the restatement) runs without a GPU and prints ONE JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 1 and j["steps"] == 2 and j["warmup"] == 1
+    assert j["unit"] == "evals/s" and j["higher_is_better"] is True and j["value"] > 0
+    assert j["config"]["lambda"] == 1024 and j["config"]["n"] == 400 and "C2" in j["config"]["workload"]
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["gpu_launches"] == 0
