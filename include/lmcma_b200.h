@@ -156,7 +156,9 @@ int lmcma_b200_ask_one(lmcma_b200_opt* opt, double* params, int32_t n);
 int lmcma_b200_tell_one(lmcma_b200_opt* opt, const double* feedbacks, int32_t num_feedbacks);
 
 /* Batched protocol: the whole population (batch x pop_count x n, FP32, dense) out, all fitnesses in.
- * tell_all runs LMCMA::update (lmcma.cpp:313-424) and LMCMA::sample (lmcma.cpp:301-311) on the device. */
+ * tell_all runs LMCMA::update (lmcma.cpp:313-424) and LMCMA::sample (lmcma.cpp:301-311) on the device; it returns when the
+ * next population is ready.  For one query with the device RNG the fitness-independent part of the update runs beside
+ * the fitness copy and the ranking (one forked CUDA graph per call; same bits as the serial order). */
 int lmcma_b200_ask_all(lmcma_b200_opt* opt, float* X_host);
 int lmcma_b200_tell_all(lmcma_b200_opt* opt, const float* f_host);
 
