@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(256) k_gram(OptDev o) {
 // one CTA per instance, 8 lanes per basis row.  Row i of C = coefficients of the current x_i; row i of U = G coef(x_i),
 // carried along with every update (x <- K x - e v_j  =>  U_i <- K U_i - e U_j), so that when a row becomes final its
 // W = G coef(v) is already there and v_j . x_i = coef(v_j) . U_i needs no pass over G: ONE phase and ONE barrier per factor.
-// Its time follows the FP64 instructions issued on its one SM (measured: ~6 G / s over three register layouts), so the
-// count is kept minimal:
+// What paces it is the dependent chain of a factor (loads, FMA chain, shuffle rounds, update, the finished row's |v|^2,
+// sqrt and divide, barrier: ~2500 cycles, ncu: half of the warp samples wait at the barrier), not the FP64 pipe (64 FMAs
+// per clock and SM, tools/micro/dfma.cu); the instructions per factor are kept minimal:
 //  * a pending row is held as y = x / K^j (every pending row has had the same j factors), which turns both updates into
 //    ONE fused multiply-add per element, y <- y - (Lj_j / K)(v_j . y) v_j, and drops the K c_i[i] term; a row is scaled back
 //    by K^i when it becomes final;

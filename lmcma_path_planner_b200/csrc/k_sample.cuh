@@ -73,7 +73,8 @@ __device__ __forceinline__ void sample_finish(const OptDev& o, const double* __r
 
 constexpr int SAMPLE_MAX_STAGES = 8;
 
-template <int NV, int RB, int MAXT>
+// SPEC: full groups of 8 pairs run a copy of the two group loops without the per-pair `g < gcnt` predicates
+template <int NV, int RB, int MAXT, bool SPEC = false>
 __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per stage, multiple of 8 */, int nstages) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.y;
@@ -161,25 +162,29 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
             for (int r = 0; r < RB; ++r)
 #pragma unroll
                 for (int g = 0; g < SAMPLE_G; ++g) d[r][g] = 0.f;
+            auto dots = [&](auto full_c) {
+                constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int q = lane + 32 * i;
-                if (q < nq) {
+                for (int i = 0; i < NV; ++i) {
+                    const int q = lane + 32 * i;
+                    if (q < nq) {
 #pragma unroll
-                    for (int g = 0; g < SAMPLE_G; ++g) {
-                        if (g < gcnt) {
-                            const float4 v = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g)) * ns)[q];
+                        for (int g = 0; g < SAMPLE_G; ++g) {
+                            if (FULL || g < gcnt) {
+                                const float4 v = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g)) * ns)[q];
 #pragma unroll
-                            for (int r = 0; r < RB; ++r) {
-                                d[r][g] = fmaf(v.x, z[r][i].x, d[r][g]);
-                                d[r][g] = fmaf(v.y, z[r][i].y, d[r][g]);
-                                d[r][g] = fmaf(v.z, z[r][i].z, d[r][g]);
-                                d[r][g] = fmaf(v.w, z[r][i].w, d[r][g]);
+                                for (int r = 0; r < RB; ++r) {
+                                    d[r][g] = fmaf(v.x, z[r][i].x, d[r][g]);
+                                    d[r][g] = fmaf(v.y, z[r][i].y, d[r][g]);
+                                    d[r][g] = fmaf(v.z, z[r][i].z, d[r][g]);
+                                    d[r][g] = fmaf(v.w, z[r][i].w, d[r][g]);
+                                }
                             }
                         }
                     }
                 }
-            }
+            };
+            if (SPEC && gcnt == SAMPLE_G) dots(std::true_type()); else dots(std::false_type());
             // ---- lane-sum, scale: c_g = Nj_g * (v_g . z) * M^-(g+1); broadcast to every lane ----
             const float scale_lane = (p_lane < gcnt) ? nj_s[k0 + k + p_lane] * minv_lane : 0.f;
             float w[RB][SAMPLE_G];
@@ -192,27 +197,31 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
             // ---- Az <- M^gcnt * (Az + sum_g c_g * pc_g) ----
             float mg = M8;
             if (gcnt < SAMPLE_G) { mg = 1.0f; for (int c2 = 0; c2 < gcnt; ++c2) mg *= Mf; }
+            auto recur = [&](auto full_c) {
+                constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int q = lane + 32 * i;
-                if (q < nq) {
+                for (int i = 0; i < NV; ++i) {
+                    const int q = lane + 32 * i;
+                    if (q < nq) {
 #pragma unroll
-                    for (int g = 0; g < SAMPLE_G; ++g) {
-                        if (g < gcnt) {
-                            const float4 p = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g) + 1) * ns)[q];
+                        for (int g = 0; g < SAMPLE_G; ++g) {
+                            if (FULL || g < gcnt) {
+                                const float4 p = reinterpret_cast<const float4*>(sb + (size_t)(2 * (k + g) + 1) * ns)[q];
 #pragma unroll
-                            for (int r = 0; r < RB; ++r) {
-                                az[r][i].x = fmaf(w[r][g], p.x, az[r][i].x);
-                                az[r][i].y = fmaf(w[r][g], p.y, az[r][i].y);
-                                az[r][i].z = fmaf(w[r][g], p.z, az[r][i].z);
-                                az[r][i].w = fmaf(w[r][g], p.w, az[r][i].w);
+                                for (int r = 0; r < RB; ++r) {
+                                    az[r][i].x = fmaf(w[r][g], p.x, az[r][i].x);
+                                    az[r][i].y = fmaf(w[r][g], p.y, az[r][i].y);
+                                    az[r][i].z = fmaf(w[r][g], p.z, az[r][i].z);
+                                    az[r][i].w = fmaf(w[r][g], p.w, az[r][i].w);
+                                }
                             }
                         }
-                    }
 #pragma unroll
-                    for (int r = 0; r < RB; ++r) { az[r][i].x *= mg; az[r][i].y *= mg; az[r][i].z *= mg; az[r][i].w *= mg; }
+                        for (int r = 0; r < RB; ++r) { az[r][i].x *= mg; az[r][i].y *= mg; az[r][i].z *= mg; az[r][i].w *= mg; }
+                    }
                 }
-            }
+            };
+            if (SPEC && gcnt == SAMPLE_G) recur(std::true_type()); else recur(std::false_type());
         }
         if (c + nstages < nchunks) {
             __syncthreads();                  // every warp is done with stage st

@@ -233,9 +233,9 @@ CostShape pick_cost_shape(int W, const float* start, const float* goal, int dims
     return sh;
 }
 
-template <int NV, int RB, int MAXT>
+template <int NV, int RB, int MAXT, bool SPEC = false>
 int launch_sample_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
-    auto kern = k_sample<NV, RB, MAXT>;
+    auto kern = k_sample<NV, RB, MAXT, SPEC>;
     if (o->smp_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_smem));
     const int rows_per_cta = (o->smp_threads / 32) * RB;
     const int ctas = (o->d.pop_count + rows_per_cta - 1) / rows_per_cta;
@@ -307,7 +307,7 @@ int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false, bool pro
     switch (o->smp_nv) {
         case 1: return launch_sample_t<1, 4, 512>(o, pdl, st);
         case 2: return launch_sample_t<2, 4, 512>(o, pdl, st);
-        case 4: return launch_sample_t<4, 2, 512>(o, pdl, st);
+        case 4: return env_int("LMCMA_B200_SAMPLE_SPEC", 1) ? launch_sample_t<4, 2, 512, true>(o, pdl, st) : launch_sample_t<4, 2, 512>(o, pdl, st);
         case 8: return launch_sample_t<8, 1, 512>(o, pdl, st);
         case 12: return launch_sample_t<12, 1, 256>(o, pdl, st);
         case 16: return launch_sample_t<16, 1, 256>(o, pdl, st);
