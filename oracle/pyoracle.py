@@ -98,6 +98,13 @@ def ref():
         R.ref_lmcma_get_array.argtypes = [C.c_void_p, C.c_int, _c_double_p]
         R.ref_lmcma_get_int_array.argtypes = [C.c_void_p, C.c_int, _c_int_p]
         R.ref_lmcma_generation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _c_double_p, _c_double_p]
+        R.ref_sibling_create.restype = C.c_void_p
+        R.ref_sibling_create.argtypes = [C.c_int, _c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p,
+                                         C.c_double, C.c_int]
+        R.ref_sibling_destroy.argtypes = [C.c_void_p]
+        R.ref_sibling_lambda.argtypes = [C.c_void_p]
+        R.ref_sibling_run.restype = C.c_double
+        R.ref_sibling_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_double_p]
         R.ref_rng_uniform.argtypes = [C.c_long, C.c_int, _c_double_p]
         R.ref_rng_gauss.argtypes = [C.c_long, C.c_long, C.c_long, _c_double_p]
         R.ref_myqsort.argtypes = [C.c_int, _c_double_p, _c_int_p]
@@ -221,6 +228,50 @@ class RefLMCMA(_Base):
         fn = C.cast(lib().orc_cost_batch_f64, C.c_void_p)
         self._L.ref_lmcma_generation(self._h, fn, C.addressof(problem.struct), _dp(X), _dp(f))
         return X, f
+
+
+_BATCH_COST = C.CFUNCTYPE(None, _c_double_p, C.c_int, C.c_int, _c_double_p, C.c_void_p)
+SIBLING_KINDS = {"LMCMA": 0, "SepCMA": 1, "CMAChol": 2}
+
+
+class RefSibling:
+    """The reference's sibling optimisers (SepCMA lmcma.hpp:152, CMAChol lmcma.hpp:211; LMCMA for a like-for-like
+    run) through the shared CMABase ask / tell protocol.  CPU cross-check of solution quality only."""
+
+    def __init__(self, kind, n, x0=None, lam=0, lo=None, hi=None, sigma=1.0, seed=1):
+        self._L = ref()
+        self.n = n
+        x0, lo, hi = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (x0, lo, hi)]
+        self._h = self._L.ref_sibling_create(SIBLING_KINDS[kind], _dp(x0), n, lam, _dp(lo), _dp(hi), float(sigma),
+                                             int(seed))
+        self.lam = self._L.ref_sibling_lambda(self._h)
+
+    def run(self, generations, problem=None, func=None):
+        """`generations` generations on a CostProblem (cost oracle) or on a python `func(X[k, n]) -> f[k]`.
+        Returns (BestF, best_x)."""
+        best_x = np.zeros(self.n, np.float64)
+        if problem is not None:
+            fn, ctx = C.cast(lib().orc_cost_batch_f64, C.c_void_p), C.addressof(problem.struct)
+        else:
+            def _cb(X, count, n, f, _ctx):
+                Xa = np.ctypeslib.as_array(X, shape=(count, n))
+                fa = np.ctypeslib.as_array(f, shape=(count,))
+                fa[:] = func(Xa)
+            keep = _BATCH_COST(_cb)
+            fn, ctx = C.cast(keep, C.c_void_p), None
+        best = self._L.ref_sibling_run(self._h, fn, ctx, int(generations), _dp(best_x))
+        return float(best), best_x
+
+    def close(self):
+        if self._h:
+            self._L.ref_sibling_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def rng_gauss(seed, count, skip=0, which="oracle"):

@@ -141,4 +141,54 @@ void ref_covariance(int dims, int waypoints, double* out) { covariance(dims, way
 void ref_cholesky(double* C, double* L, int n) { cholesky(C, L, n); }
 void ref_apply_cov_l(double* L, double* z, int n) { applyCovL(L, z, n); }
 
+// ---- sibling optimisers of the reference (SepCMA lmcma.hpp:152-205, CMAChol lmcma.hpp:211-254) ----
+// CPU cross-checks of solution quality only: never GPU targets.  kind: 0 LMCMA, 1 SepCMA, 2 CMAChol,
+// driven through the shared CMABase protocol (lmcma.cpp:172-205).
+struct RefSibling {
+    std::vector<double> x0, lo, hi;
+    CMABase* opt;
+    int n;
+};
+void* ref_sibling_create(int kind, const double* x0, int n, int lambda, const double* lo, const double* hi,
+                         double sigma, int seed) {
+    if (kind < 0 || kind > 2) return 0;
+    RefSibling* r = new RefSibling();
+    r->n = n;
+    if (x0) r->x0.assign(x0, x0 + n);
+    if (lo) r->lo.assign(lo, lo + n);
+    if (hi) r->hi.assign(hi, hi + n);
+    double* px = x0 ? r->x0.data() : 0;
+    double* pl = lo ? r->lo.data() : 0;
+    double* ph = hi ? r->hi.data() : 0;
+    if (kind == 0) r->opt = new LMCMA(px, lambda, pl, ph, sigma, 0, seed, false);
+    else if (kind == 1) r->opt = new SepCMA(px, lambda, pl, ph, sigma, 0, seed, false);
+    else r->opt = new CMAChol(px, lambda, pl, ph, sigma, 0, seed, false);
+    r->opt->init(n);
+    return r;
+}
+void ref_sibling_destroy(void* h) {
+    RefSibling* r = static_cast<RefSibling*>(h);
+    delete r->opt;
+    delete r;
+}
+int ref_sibling_lambda(void* h) { return static_cast<RefSibling*>(h)->opt->lambda; }
+// `generations` full generations of ask / tell with the caller's batch cost; best_x receives the best candidate
+// seen (strict <, first evaluation included - the BestF rule of lmcma.cpp:190-193).  Returns BestF.
+double ref_sibling_run(void* h, ref_batch_cost_fn cost, void* ctx, int generations, double* best_x) {
+    RefSibling* r = static_cast<RefSibling*>(h);
+    CMABase* o = r->opt;
+    const int lam = o->lambda, n = r->n;
+    std::vector<double> row(n);
+    double best = 0.0; bool have = false;
+    for (int g = 0; g < generations && !o->isBehaviorLearningDone(); ++g)
+        for (int i = 0; i < lam; ++i) {
+            o->getNextParameterVector(row.data(), n);
+            double f = 0.0;
+            cost(row.data(), 1, n, &f, ctx);
+            if (!have || f < best) { best = f; have = true; if (best_x) std::memcpy(best_x, row.data(), sizeof(double) * n); }
+            o->setEvaluationFeedback(&f, 1);
+        }
+    return o->BestF;
+}
+
 }  // extern "C"
