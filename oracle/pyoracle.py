@@ -98,13 +98,14 @@ def ref():
         R.ref_lmcma_get_array.argtypes = [C.c_void_p, C.c_int, _c_double_p]
         R.ref_lmcma_get_int_array.argtypes = [C.c_void_p, C.c_int, _c_int_p]
         R.ref_lmcma_generation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _c_double_p, _c_double_p]
-        R.ref_sibling_create.restype = C.c_void_p
-        R.ref_sibling_create.argtypes = [C.c_int, _c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p,
-                                         C.c_double, C.c_int]
-        R.ref_sibling_destroy.argtypes = [C.c_void_p]
-        R.ref_sibling_lambda.argtypes = [C.c_void_p]
-        R.ref_sibling_run.restype = C.c_double
-        R.ref_sibling_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_double_p]
+        if hasattr(R, "ref_sibling_create"):          # a prebuilt _ref from before the siblings were exposed lacks them
+            R.ref_sibling_create.restype = C.c_void_p
+            R.ref_sibling_create.argtypes = [C.c_int, _c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p,
+                                             C.c_double, C.c_int]
+            R.ref_sibling_destroy.argtypes = [C.c_void_p]
+            R.ref_sibling_lambda.argtypes = [C.c_void_p]
+            R.ref_sibling_run.restype = C.c_double
+            R.ref_sibling_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_double_p]
         R.ref_rng_uniform.argtypes = [C.c_long, C.c_int, _c_double_p]
         R.ref_rng_gauss.argtypes = [C.c_long, C.c_long, C.c_long, _c_double_p]
         R.ref_myqsort.argtypes = [C.c_int, _c_double_p, _c_int_p]
