@@ -164,3 +164,47 @@ def test_reference_bt_equals_its_binvox_source(name):
     want = np.zeros_like(occ)
     want[iz, iy, ix] = 1
     assert np.array_equal(occ, want) and occ.sum() == vox.sum()
+
+
+def test_corrupted_files_are_rejected_or_parsed_never_fatal(tmp_path):
+    """Seeded mutations (truncation, byte flips, extreme 32-bit header fields, trailing garbage) of one valid file per
+    format: every call returns an occupancy grid or raises LmcmaError - the parsers bound every size they read."""
+    rng = np.random.default_rng(7)
+    seeds = {}
+    p = str(tmp_path / "s.bmp")
+    _write_bmp24(p, rng.integers(0, 256, size=(9, 6, 3), dtype=np.uint8))
+    seeds["bmp"] = (p, maps.load_bmp)
+    p = str(tmp_path / "s.binvox")
+    open(p, "wb").write(b"#binvox 1\ndim 4 4 4\ntranslate 0 0 0\nscale 1\ndata\n" + bytes([0, 30, 1, 34]))
+    seeds["binvox"] = (p, maps.load_binvox)
+    p = str(tmp_path / "s.txt")
+    open(p, "w").write("1 2 3\n4 5 6\n")
+    seeds["txt"] = (p, maps.load_text_matrix)
+    p = str(tmp_path / "s.bt")
+    _write_bt(p, {(32768 + x, 32768 + y, 32768) for x in range(5) for y in range(3)}, {(32768, 32768, 32770)}, 0.1)
+    seeds["bt"] = (p, maps.load_bt)
+    for kind, (path, load) in seeds.items():
+        load(path)                                                       # the seed itself is valid
+        data = open(path, "rb").read()
+        outcomes = set()
+        for it in range(80):
+            b = bytearray(data)
+            mode = it % 4
+            if mode == 0:
+                b = b[:int(rng.integers(0, len(b)))]
+            elif mode == 1:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif mode == 2:
+                pos = int(rng.integers(0, max(1, min(len(b), 64) - 4)))
+                b[pos:pos + 4] = struct.pack("<i", int(rng.choice([-1, 0, 2 ** 31 - 1, -2 ** 31, 65536])))
+            else:
+                b += bytes(rng.integers(0, 256, 16, dtype=np.uint8))
+            q = str(tmp_path / ("m." + kind))
+            open(q, "wb").write(bytes(b))
+            try:
+                load(q)
+                outcomes.add("parsed")
+            except K.LmcmaError:
+                outcomes.add("rejected")
+        assert "rejected" in outcomes, kind
