@@ -42,9 +42,11 @@ constexpr int COST_MAX_WARPS = 8;
 template <int STORAGE> struct RawCell { typedef float type; };
 template <> struct RawCell<1> { typedef unsigned char type; };
 
-template <int DIMS, int STORAGE, bool TRACE>
-// 8 warps per CTA, 7 CTAs per SM: 32 registers per thread, every trajectory of a 1024-wide population resident at once
-__global__ void __launch_bounds__(COST_MAX_WARPS * 32, 7) k_cost(MapDev mp, CostArgs a) {
+template <int DIMS, int STORAGE, bool TRACE, int MINB = 7>
+// 8 warps per CTA, 7 CTAs per SM: 32 registers per thread, every trajectory of a 1024-wide population resident at once.
+// MINB = 6 (LMCMA_B200_COST_MINB=6, experiment: 40 registers, no local-memory spill, 1.17 waves at lambda = 1024) is
+// compiled beside it for timing; same arithmetic, same bits.
+__global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, CostArgs a) {
     typedef typename RawCell<STORAGE>::type raw_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = a.W, NSEG = W + 1;

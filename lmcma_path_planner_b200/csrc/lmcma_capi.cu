@@ -186,7 +186,7 @@ struct lmcma_b200_opt {
 // =================================================================================================
 namespace {
 
-template <int DIMS, int STORAGE, bool TRACE>
+template <int DIMS, int STORAGE, bool TRACE, int MINB = 7>
 int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostShape shape, cudaStream_t st) {
     CostArgs a = a0;
     a.cb = shape.cb;
@@ -194,7 +194,7 @@ int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostSha
     // + the candidate row (16-byte aligned)
     const size_t smem = (size_t)36 * (a.W + 1) + sizeof(int) * (a.W + 2) + 28 + (size_t)8 * shape.cb + (STORAGE == 1 ? 1024 : 0) +
                         sizeof(float) * DIMS * (size_t)a.W + 16;
-    auto kern = k_cost<DIMS, STORAGE, TRACE>;
+    auto kern = k_cost<DIMS, STORAGE, TRACE, MINB>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(rows, B), shape.tpt, smem, st>>>(mp, a);
     g_launches++;
@@ -207,6 +207,11 @@ int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, CostShape 
     if (trace) {
         if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, shape, st);
         return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, shape, st);
+    }
+    const int minb = env_int("LMCMA_B200_COST_MINB", 7);     // 6: the un-spilled 40-register build (experiment, k_cost.cuh)
+    if (minb == 6) {
+        if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false, 6>(mp, a, rows, B, shape, st);
+        return mp.storage == 0 ? launch_cost_t<3, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false, 6>(mp, a, rows, B, shape, st);
     }
     if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false>(mp, a, rows, B, shape, st);
     return mp.storage == 0 ? launch_cost_t<3, 0, false>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false>(mp, a, rows, B, shape, st);

@@ -648,3 +648,31 @@ def test_cost_long_trajectories_and_staged_rounds(po, monkeypatch):
             assert np.array_equal(got["ncoll"], ref["ncoll"]), (cb, storage)
             assert np.array_equal(got["nsamp"], ref["nsamp"]), (cb, storage)
             assert rel_err(got["f"], ref["f"]) < COST_RTOL, (cb, storage)
+
+
+@pytest.mark.gpu
+def test_cost_six_ctas_per_sm_build_meets_the_same_bar(po, monkeypatch):
+    """LMCMA_B200_COST_MINB=6 selects k_cost compiled for six CTAs per SM (40 registers, no local-memory spill; an
+    experiment to be timed): same source, so the same parity bar against the oracle - cell
+    indices bit-exact (collision and sample counts), cost within COST_RTOL - in 2-D and 3-D, f32 and u8 storage."""
+    monkeypatch.setenv("LMCMA_B200_COST_MINB", "6")
+    rng = np.random.default_rng(12)
+    dist, start, goal = maps.config2_map(size=512, n_rects=48, seed=3, clamp=64.0)
+    W = 60
+    lo, hi = maps.box_bounds((512, 512), W)
+    X = _candidates(rng, maps.straight_line(start, goal, W), 200, 6.0, lo - 3.0, hi + 3.0)
+    for storage in ("f32", "u8"):
+        cm = L.CostMap(dist, storage, u8_scale=0.25)
+        dd = dist if storage == "f32" else cm.dequantized()
+        ref = po.CostProblem(dd, start, goal, W).evaluate(X)
+        got = cm.evaluate(X, start, goal, W)
+        assert np.array_equal(got["ncoll"], ref["ncoll"]) and np.array_equal(got["nsamp"], ref["nsamp"]), storage
+        assert rel_err(got["f"], ref["f"]) < COST_RTOL, storage
+    d3, s3, g3 = maps.config4_map(size=64, n_boxes=4096, seed=9, clamp=16.0)
+    W3 = 40
+    lo3, hi3 = maps.box_bounds((64, 64, 64), W3)
+    X3 = _candidates(rng, maps.straight_line(s3, g3, W3), 100, 3.0, lo3, hi3)
+    ref = po.CostProblem(d3, s3, g3, W3).evaluate(X3)
+    got = L.CostMap(d3, "f32").evaluate(X3, s3, g3, W3)
+    assert np.array_equal(got["ncoll"], ref["ncoll"]) and np.array_equal(got["nsamp"], ref["nsamp"])
+    assert rel_err(got["f"], ref["f"]) < COST_RTOL
