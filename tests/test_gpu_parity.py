@@ -650,7 +650,6 @@ def test_cost_long_trajectories_and_staged_rounds(po, monkeypatch):
             assert rel_err(got["f"], ref["f"]) < COST_RTOL, (cb, storage)
 
 
-@pytest.mark.gpu
 def test_cost_six_ctas_per_sm_build_meets_the_same_bar(po, monkeypatch):
     """LMCMA_B200_COST_MINB=6 selects k_cost compiled for six CTAs per SM (40 registers, no local-memory spill; an
     experiment to be timed): same source, so the same parity bar against the oracle - cell
