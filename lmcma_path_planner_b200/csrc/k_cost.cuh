@@ -44,8 +44,9 @@ template <> struct RawCell<1> { typedef unsigned char type; };
 
 template <int DIMS, int STORAGE, bool TRACE, int MINB = 7>
 // 8 warps per CTA, 7 CTAs per SM: 32 registers per thread, every trajectory of a 1024-wide population resident at once.
-// MINB = 6 (LMCMA_B200_COST_MINB=6, experiment: 40 registers, no local-memory spill, 1.17 waves at lambda = 1024) is
-// compiled beside it for timing; same arithmetic, same bits.
+// MINB = 6 (LMCMA_B200_COST_MINB=6: 40 registers, no local-memory spill, 1.17 waves at lambda = 1024) is compiled
+// beside it; measured slower on the single C2 query (33.9 vs 31.0 us, profiles/r1g_minb_compare.txt), kept for the
+// many-wave batched shapes.
 __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, CostArgs a) {
     typedef typename RawCell<STORAGE>::type raw_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
