@@ -651,8 +651,8 @@ def test_cost_long_trajectories_and_staged_rounds(po, monkeypatch):
 
 
 def test_cost_six_ctas_per_sm_build_meets_the_same_bar(po, monkeypatch):
-    """LMCMA_B200_COST_MINB=6 selects k_cost compiled for six CTAs per SM (40 registers, no local-memory spill; an
-    experiment to be timed): same source, so the same parity bar against the oracle - cell
+    """LMCMA_B200_COST_MINB=6 selects k_cost compiled for six CTAs per SM (40 registers, no local-memory spill; kept
+    for many-wave batched shapes): same source, so the same parity bar against the oracle - cell
     indices bit-exact (collision and sample counts), cost within COST_RTOL - in 2-D and 3-D, f32 and u8 storage."""
     monkeypatch.setenv("LMCMA_B200_COST_MINB", "6")
     rng = np.random.default_rng(12)
