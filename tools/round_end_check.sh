@@ -13,3 +13,6 @@ LMCMA_B200_OVERLAP=0 ncu --metrics gpu__time_duration.sum --clock-control none -
     python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_ncu.log 2>&1; echo "ncu launch list rc=$?"
 LMCMA_B200_OVERLAP=0 ncu --set full --clock-control none --import-source on --launch-skip 180 -c 8 -f -o gpurun_out/prof_${tag} \
     python tools/profile_step.py > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -2 gpurun_out/${tag}_ncu_full.log
+# open measurement from round 1: k_cost at six CTAs per SM on the many-wave batched shape (C3); the single
+# query was measured and kept at seven (profiles/r1g_minb_compare.txt)
+for minb in 7 6; do LMCMA_B200_COST_MINB=$minb python tools/c3_batched.py 1024 30 > gpurun_out/${tag}_c3_minb${minb}.txt 2>&1; echo "c3 minb=$minb rc=$?"; tail -2 gpurun_out/${tag}_c3_minb${minb}.txt; done
