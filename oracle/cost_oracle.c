@@ -1,9 +1,15 @@
 /* TEST INFRASTRUCTURE ONLY (oracle/).  CPU restatement of the trajectory cost the LM-CMA planner
  * minimises.  The reference has no such function; it is ASSEMBLED from the
  * reference's cost-model pieces, each cited below, with the quadrature choices the reference
- * leaves to un-vendored OMPL fixed here (marked DECLARED).  PARITY UNPINNED for those choices:
- * no reference test or golden vector exists at that boundary; this file is the single source of
- * truth the CUDA cost kernel is checked against.
+ * leaves to un-vendored OMPL fixed here (marked DECLARED).
+ * PINNED to reference-executed code: the per-sample pieces (matrix cell incl. nearbyint ties, valid <=> E > 0,
+ * state cost 1 / clearance above the floor) and the objective weights — sample_state() below is checked against the
+ * reference's own ValidityChecker / ClearanceObjective / shortrisky / longsafe compiled from planner.cpp:587-690
+ * (oracle/_ref/libref_cost.so, OMPL stand-in) and against tests/golden/cost_pieces_reference.json generated from them
+ * (tests/test_cost_reference_pieces.py).
+ * PARITY UNPINNED for the DECLARED choices only (sub-step rule, trapezoid, c_min floor, out-of-map = collision): the
+ * path integral is OMPL's (un-vendored, unversioned), no reference test or golden vector exists at that boundary; for
+ * those this file is the single source of truth the CUDA cost kernel is checked against.
  *
  *   parameters  x[d*W + w], dimension-major (lmcma.cpp:786-791), D = 2 or 3, W interior waypoints
  *   poly-line   P_0 = start, P_1..P_W, P_{W+1} = goal      (start/goal fixed: planner.cpp:701-711)
@@ -63,6 +69,30 @@ static inline int64_t cell_of(const orc_problem* p, const float q[3]) {
     return idx;
 }
 
+/* One poly-line sample q: its cell (planner.cpp:595-600), whether it collides (the negation of
+ * ValidityChecker::isValid, planner.cpp:602: valid <=> E > 0) and its state cost 1 / clearance
+ * (ClearanceObjective::stateCost, planner.cpp:667) with the DECLARED floor / out-of-map rule.  This is the function
+ * eval_one runs per sample; orc_cost_sample exposes it so that tests/test_cost_reference_pieces.py can hold it against
+ * the reference's own ValidityChecker / ClearanceObjective (oracle/_ref/libref_cost.so). */
+static inline void sample_state(const orc_problem* p, const float q[3], int64_t* cell_out, int* hit_out, double* g_out) {
+    const double g_coll = 1.0 / (double)p->c_min;
+    const int64_t cell = cell_of(p, q);
+    int hit; double g;
+    if (cell < 0) { hit = 1; g = g_coll; }
+    else {
+        const float e = p->dist[cell];
+        hit = !(e > 0.0f);
+        g = hit ? g_coll : 1.0 / (double)(e > p->c_min ? e : p->c_min);
+    }
+    *cell_out = cell; *hit_out = hit; *g_out = g;
+}
+void orc_cost_sample(const orc_problem* p, const float* q, int count, int64_t* cell_out, int* hit_out, double* g_out) {
+    for (int i = 0; i < count; ++i) {
+        float qq[3] = {q[3 * i], q[3 * i + 1], q[3 * i + 2]};
+        sample_state(p, qq, &cell_out[i], &hit_out[i], &g_out[i]);
+    }
+}
+
 static inline void waypoint(const orc_problem* p, const float* x, int i, float out[3]) {
     const int W = p->waypoints;
     out[2] = 0.0f;
@@ -76,7 +106,6 @@ static inline void waypoint(const orc_problem* p, const float* x, int i, float o
 static void eval_one(const orc_problem* p, const float* x, double* f, int* ncoll, int* nsamp,
                      double* len_out, double* clr_out, int64_t* cells_out, int64_t max_cells) {
     const int W = p->waypoints;
-    const double g_coll = 1.0 / (double)p->c_min;
     double len_sum = 0.0, clr_sum = 0.0;
     int coll = 0; int64_t samples = 0;
     float A[3], B[3], d[3], q[3];
@@ -103,14 +132,8 @@ static void eval_one(const orc_problem* p, const float* x, double* f, int* ncoll
                 volatile float prod = t * d[c];      /* force the un-contracted FP32 product */
                 q[c] = A[c] + prod;
             }
-            const int64_t cell = cell_of(p, q);
-            int hit; double g;
-            if (cell < 0) { hit = 1; g = g_coll; }
-            else {
-                const float e = p->dist[cell];
-                hit = !(e > 0.0f);
-                g = hit ? g_coll : 1.0 / (double)(e > p->c_min ? e : p->c_min);
-            }
+            int64_t cell; int hit; double g;
+            sample_state(p, q, &cell, &hit, &g);
             acc += (k == 0 || k == K) ? 0.5 * g : g;
             if (k < K || s == W) coll += hit;
             if (cells_out && samples < max_cells) cells_out[samples] = cell;

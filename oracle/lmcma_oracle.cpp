@@ -308,7 +308,29 @@ int orc_lmcma_get_int_array(void* h, int which, int* out) {
     std::memcpy(out, src->data(), src->size() * sizeof(int));
     return static_cast<int>(src->size());
 }
-// teacher forcing in the other direction is not needed: tests load the oracle's state INTO the device.
+// Warm start (tests only): overwrite the distribution state, then sample() with Z (nullable -> Hansen stream).  Lets a
+// large-population oracle (C4: lambda = 8192) start from a state in which all m slots are live and being recycled — a
+// state produced by a cheap small-lambda run of this same restatement — instead of paying ~m full-size generations.
+// prev_fit: lambda values, ascending (what update() leaves behind, lmcma.cpp:99-103, 420-421).
+void orc_lmcma_set_state(void* h, const double* xmean, const double* pc, const double* V, const double* P, const double* Nj,
+                         const double* Lj, const double* prev_fit, const int* order, const int* stamp, int itr, int live,
+                         double sigma, double s, const double* Z) {
+    Opt* o = static_cast<Opt*>(h);
+    const size_t n = o->n, m = o->m;
+    std::memcpy(o->xmean.data(), xmean, n * sizeof(double));
+    std::memcpy(o->pc.data(), pc, n * sizeof(double));
+    std::memcpy(o->V.data(), V, n * m * sizeof(double));
+    std::memcpy(o->P.data(), P, n * m * sizeof(double));
+    std::memcpy(o->Nj.data(), Nj, m * sizeof(double));
+    std::memcpy(o->Lj.data(), Lj, m * sizeof(double));
+    std::memcpy(o->prev_fit.data(), prev_fit, o->lambda * sizeof(double));
+    std::memcpy(o->order.data(), order, m * sizeof(int));
+    std::memcpy(o->stamp.data(), stamp, m * sizeof(int));
+    o->itr = itr; o->live = live; o->sigma = sigma; o->s = s;
+    for (int i = 0; i < live; ++i) o->live_slots[i] = o->order[i];
+    o->sample_idx = 0;
+    o->sample(Z);
+}
 
 void orc_rng_uniform(long seed, int count, double* out) {
     HansenRng r; r.start(static_cast<unsigned long>(seed));

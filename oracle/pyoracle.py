@@ -24,7 +24,8 @@ _c_i64_p = C.POINTER(C.c_int64)
 def build(force=False):
     """Compile liboracle.so (always possible) and _ref/libref_lmcma.so (needs /root/reference)."""
     lib = os.path.join(HERE, "liboracle.so")
-    if force or not os.path.exists(lib) or not os.path.exists(os.path.join(HERE, "_ref", "libref_lmcma.so")):
+    if force or not os.path.exists(lib) or not os.path.exists(os.path.join(HERE, "_ref", "libref_lmcma.so")) or \
+            not os.path.exists(os.path.join(HERE, "_ref", "libref_cost.so")):
         subprocess.run(["make", "-C", HERE], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
     return lib
 
@@ -58,6 +59,8 @@ def lib():
         L.orc_lmcma_tell.argtypes = [C.c_void_p, C.c_double]
         L.orc_lmcma_tell_all.argtypes = [C.c_void_p, _c_double_p, _c_double_p]
         L.orc_lmcma_done.argtypes = [C.c_void_p]
+        L.orc_lmcma_set_state.argtypes = [C.c_void_p] + [_c_double_p] * 7 + [_c_int_p, _c_int_p, C.c_int, C.c_int,
+                                                                              C.c_double, C.c_double, _c_double_p]
         L.orc_lmcma_get_ints.argtypes = [C.c_void_p, _c_int_p]
         L.orc_lmcma_get_doubles.argtypes = [C.c_void_p, _c_double_p]
         L.orc_lmcma_get_array.argtypes = [C.c_void_p, C.c_int, _c_double_p]
@@ -67,6 +70,7 @@ def lib():
         L.orc_rank.argtypes = [C.c_int, _c_double_p, _c_int_p]
         L.orc_cost_batch.argtypes = [C.c_void_p, _c_float_p, C.c_int, _c_double_p, _c_int_p, _c_int_p,
                                      _c_double_p, _c_double_p]
+        L.orc_cost_sample.argtypes = [C.c_void_p, _c_float_p, C.c_int, _c_i64_p, _c_int_p, _c_double_p]
         L.orc_cost_trace.restype = C.c_int64
         L.orc_cost_trace.argtypes = [C.c_void_p, _c_float_p, _c_i64_p, C.c_int64]
         L.orc_edt_exact.argtypes = [C.c_void_p, C.c_int, _c_int_p, C.c_float, _c_float_p]
@@ -112,6 +116,57 @@ def ref():
         R.ref_covariance.argtypes = [C.c_int, C.c_int, _c_double_p]
         _ref = R
     return _ref
+
+
+_refcost = None
+
+
+def ref_cost_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_cost.so"))
+
+
+class RefCostPieces:
+    """The reference's own ValidityChecker / ClearanceObjective / shortrisky / longsafe (planner.cpp:587-690), compiled
+    against the OMPL stand-in by `make -C oracle ref_cost`.  One global map (the reference keeps EDT_Matrix global)."""
+
+    def __init__(self, dist):
+        global _refcost
+        if _refcost is None:
+            build()
+            R = C.CDLL(os.path.join(HERE, "_ref", "libref_cost.so"))
+            R.ref_cost_set_map.argtypes = [_c_double_p, C.c_int, C.c_int]
+            R.ref_cost_is_valid.argtypes = [C.c_double, C.c_double]
+            R.ref_cost_clearance.restype = C.c_double
+            R.ref_cost_clearance.argtypes = [C.c_double, C.c_double]
+            R.ref_cost_state_cost.restype = C.c_double
+            R.ref_cost_state_cost.argtypes = [C.c_double, C.c_double]
+            R.ref_cost_weights.argtypes = [C.c_int, _c_double_p]
+            R.ref_cost_threshold_path_length.restype = C.c_double
+            _refcost = R
+        self._R = _refcost
+        self.set_map(dist)
+
+    def set_map(self, dist):
+        d = np.ascontiguousarray(dist, np.float64)
+        self.shape = d.shape
+        self._R.ref_cost_set_map(_dp(d), d.shape[0], d.shape[1])
+
+    def is_valid(self, x, y):
+        return bool(self._R.ref_cost_is_valid(float(x), float(y)))
+
+    def clearance(self, x, y):
+        return float(self._R.ref_cost_clearance(float(x), float(y)))
+
+    def state_cost(self, x, y):
+        return float(self._R.ref_cost_state_cost(float(x), float(y)))
+
+    def weights(self, kind):
+        out = np.zeros(2, np.float64)
+        interp = self._R.ref_cost_weights({"shortrisky": 0, "longsafe": 1}[kind], _dp(out))
+        return float(out[0]), float(out[1]), interp
+
+    def threshold_path_length(self):
+        return float(self._R.ref_cost_threshold_path_length())
 
 
 ARRAYS = {"xmean": 0, "xold": 1, "pc": 2, "V": 3, "P": 4, "Nj": 5, "Lj": 6, "X": 7, "fit": 8,
@@ -202,6 +257,16 @@ class OracleLMCMA(_Base):
         self._keep = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (x0, lo, hi, Z0)]
         x0, lo, hi, Z0 = self._keep
         self._h = self._L.orc_lmcma_create(n, lam, m, _dp(x0), _dp(lo), _dp(hi), float(sigma), int(seed), _dp(Z0))
+
+    def load_state(self, st, prev_fit, Z=None):
+        """Warm start from a state dict of another OracleLMCMA of the same (n, m) — see orc_lmcma_set_state."""
+        a = {k: np.ascontiguousarray(st[k], np.float64) for k in ("xmean", "pc", "V", "P", "Nj", "Lj")}
+        pf = np.ascontiguousarray(prev_fit, np.float64)
+        t, vec = np.ascontiguousarray(st["t"], np.int32), np.ascontiguousarray(st["vec"], np.int32)
+        Zc = None if Z is None else np.ascontiguousarray(Z, np.float64)
+        self._L.orc_lmcma_set_state(self._h, _dp(a["xmean"]), _dp(a["pc"]), _dp(a["V"]), _dp(a["P"]), _dp(a["Nj"]), _dp(a["Lj"]),
+                                    _dp(pf), _ip(t), _ip(vec), int(st["itr"]), int(st["live"]), float(st["sigma"]),
+                                    float(st["s"]), _dp(Zc))
 
     def tell_all(self, f, Z_next=None):
         f = np.ascontiguousarray(f, np.float64)
@@ -338,6 +403,17 @@ class CostProblem:
         clr = np.zeros(cnt, np.float64)
         lib().orc_cost_batch(C.addressof(self.struct), _fp(X), cnt, _dp(f), _ip(ncoll), _ip(nsamp), _dp(ln), _dp(clr))
         return {"f": f, "ncoll": ncoll, "nsamp": nsamp, "length": ln, "clearance": clr}
+
+    def sample(self, Q):
+        """Per-sample pieces for points Q [k, dims] (FP32): (linear cell or -1, collides, state cost)."""
+        Q = np.ascontiguousarray(Q, np.float32).reshape(-1, self.dims)
+        q3 = np.zeros((len(Q), 3), np.float32)
+        q3[:, :self.dims] = Q
+        cell = np.zeros(len(Q), np.int64)
+        hit = np.zeros(len(Q), np.int32)
+        g = np.zeros(len(Q), np.float64)
+        lib().orc_cost_sample(C.addressof(self.struct), _fp(q3), len(Q), cell.ctypes.data_as(_c_i64_p), _ip(hit), _dp(g))
+        return cell, hit, g
 
     def trace(self, x, max_cells=1 << 22):
         x = np.ascontiguousarray(x, np.float32)
