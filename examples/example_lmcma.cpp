@@ -3,6 +3,7 @@
 //
 //   example_lmcma demo  [seed]                    two-Gaussian test function, reference ask/tell protocol,
 //                                                 writes path_to_min.csv like the reference demo
+//   example_lmcma democov [seed]                  the same with the covariance prior (test_lmcma_using_cov, :78-127)
 //   example_lmcma planfile <map.bmp|map.binvox> <start> <goal> <out.txt> [generations] [waypoints] [lambda]
 //                                                 start / goal as x,y or x,y,z (cells): load the map (g < 128 rule /
 //                                                 binvox voxels), distance transform + planning on the device
@@ -44,6 +45,29 @@ int demo(int seed) {
     }
     std::printf("the optimum point is: %.6f,%.6f f=%.6f BestF=%.6f counteval=%d done=%d\n", x[0], x[1], f, opt.BestF,
                 opt.counteval, (int)opt.isBehaviorLearningDone());
+    return 0;
+}
+
+// test_lmcma_using_cov of the reference (example_lmcma.cpp:78-127): the same search with the smoothness prior
+// covariance(numParams, 1, cov) passed to the constructor, through the reference's free-function names
+int demo_cov(int seed) {
+    const int N = 2;
+    double lo[N] = {-2, -2}, hi[N] = {15, 15}, x[N] = {0, 0};
+    double cov[N * N];
+    lmcma_b200::covariance(N, 1, cov);                 // lmcma.hpp:248: identity for one waypoint per dimension
+    lmcma_b200::LMCMA opt(x, -1, lo, hi, 1.0, cov, seed);
+    opt.init(N);
+    std::ofstream csv("path_to_max_using_cov.csv");
+    csv << "x,y,z,\n";
+    double f = 0;
+    for (int i = 0; i < 1000; ++i) {
+        opt.getNextParameterVector(x, N);
+        f = two_gaussians(x[0], x[1]);
+        opt.setEvaluationFeedback(&f, 1);
+        csv << x[0] << " , " << x[1] << " , " << f << "\n";
+    }
+    std::printf("the optimum point is: %.6f,%.6f f=%.6f BestF=%.6f counteval=%d cov=[%g %g; %g %g]\n", x[0], x[1], f, opt.BestF,
+                opt.counteval, cov[0], cov[1], cov[2], cov[3]);
     return 0;
 }
 
@@ -167,6 +191,7 @@ int planfile(int argc, char** argv) {
 
 int main(int argc, char** argv) {
     try {
+        if (argc >= 2 && !std::strcmp(argv[1], "democov")) return demo_cov(argc >= 3 ? std::atoi(argv[2]) : 1);
         if (argc >= 2 && !std::strcmp(argv[1], "planfile")) return planfile(argc, argv);
         if (argc >= 2 && !std::strcmp(argv[1], "plan"))
             return plan(argc >= 3 ? argv[2] : "path.txt", argc >= 4 ? std::atoi(argv[3]) : 300);

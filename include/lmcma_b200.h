@@ -13,6 +13,21 @@
  *
  * Host buffers may be pageable or pinned.  "_dev" variants take device pointers (resident in HBM)
  * and a cudaStream_t passed as void*.
+ *
+ * Thread / stream contract.  An optimiser handle (lmcma_b200_opt) is NOT re-entrant, like the reference object: one
+ * host thread at a time per handle; different handles are independent.  A map handle may be shared by any number of
+ * optimiser handles and host threads: lmcma_b200_cost_evaluate_dev may be called concurrently from several threads and
+ * on several streams for different queries (the end points travel by value with each launch; no per-map device state is
+ * written); lmcma_b200_cost_evaluate and lmcma_b200_cost_trace (host buffers) serialise on a per-map lock because they
+ * share the map's staging buffers and private stream.  lmcma_b200_map_set_l2_persist and lmcma_b200_map_destroy must not
+ * race with evaluations on the same map.
+ *
+ * Environment knobs (LMCMA_B200_*, experiments / debugging only) are read once when a handle is created, never on a
+ * launch path.  The overlapped single-query generation (a forked CUDA graph whose branches must run concurrently) is
+ * enabled only after a per-device probe has seen two graph branches co-scheduled (so profilers / sanitizers that
+ * serialise kernels get the linear graph automatically; LMCMA_B200_OVERLAP=0 forces it).  If co-scheduling is lost
+ * later, no kernel traps: the next synchronising call returns LMCMA_B200_ERR_CUDA once, the handle falls back to the
+ * linear graph, and the generation in flight is void (restore the state with set_* or recreate the handle).
  */
 #ifndef LMCMA_B200_H
 #define LMCMA_B200_H
@@ -259,6 +274,24 @@ int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out);
 /* cholesky() (lmcma.cpp:844-855): lower factor of a symmetric positive definite n x n matrix, row-major, zero above
  * the diagonal (the reference takes Eigen's LLT; this is plain Cholesky-Banachiewicz in FP64). */
 int lmcma_b200_cholesky(int32_t n, const double* C, double* L_out);
+
+/* The remaining free functions of the reference header (lmcma.hpp:32-38, 248-254), host-side FP64, so that code written
+ * against them keeps compiling through include/lmcma.hpp:
+ * differentiationMatrix (lmcma.cpp:812-834): centred 7-tap rule of `order` 0..3 into the top-left block of a row-major
+ * matrix with row stride row_len (< 0 -> num_time_steps). */
+int lmcma_b200_differentiation_matrix(int32_t num_time_steps, int32_t order, double dt, double* diff_matrix, int32_t row_len);
+/* invert (lmcma.cpp:836-842; Eigen's inverse there, Gauss-Jordan with partial pivoting here).  A != Ainv. */
+int lmcma_b200_invert(const double* A, double* Ainv, int32_t n);
+/* applyCovL (lmcma.cpp:857-864): z <- L z with L COLUMN-major n x n, the layout the reference's cholesky() writes. */
+int lmcma_b200_apply_cov_l(const double* L_colmajor, double* z, int32_t n);
+/* myqsort (lmcma.cpp:84-104): ascending stable order; the sorted values overwrite arfitness, ids go to arindex. */
+int lmcma_b200_myqsort(int32_t sz, double* arfitness_inout, int32_t* arindex_out);
+/* random_t + random_init / random_Uniform / random_Gauss / random_exit (lmcma.cpp:9-82) as an opaque stream object */
+typedef struct lmcma_b200_rng lmcma_b200_rng;
+int lmcma_b200_rng_create(int64_t seed, lmcma_b200_rng** rng_out);
+int lmcma_b200_rng_destroy(lmcma_b200_rng* rng);
+double lmcma_b200_rng_uniform(lmcma_b200_rng* rng);
+double lmcma_b200_rng_gauss(lmcma_b200_rng* rng);
 
 /* ---------------------------------------------------------------- map ingest (host-side file parsing) ---------- */
 /* All four: pass out == NULL to query the size first.

@@ -12,6 +12,9 @@
 //   setEvaluationFeedback        lmcma.cpp:184-205          LMCMA::setEvaluationFeedback  -> lmcma_b200_tell_one
 //   isBehaviorLearningDone       lmcma.cpp:426-429          LMCMA::isBehaviorLearningDone -> lmcma_b200_is_done
 //   counteval, BestF             lmcma.hpp:64-65            public members, maintained identically (lmcma.cpp:189-198)
+//   class CMABase                lmcma.hpp:41-81            lmcma_b200::CMABase (public surface; the hooks live on the device)
+//   covariance, differentiationMatrix, invert, cholesky, applyCovL, random_*, myqsort, compare
+//                                lmcma.hpp:26-38, 248-254   same names in namespace lmcma_b200 (global through include/lmcma.hpp)
 //   EDT_Matrix + ValidityChecker + ClearanceObjective       lmcma_b200::CostMap (batched evaluate)
 //                                planner.cpp:37, 587-690
 //   optimal_palnning_without_setting_path planner.cpp:694   lmcma_b200::plan(...) — the fused on-device planner
@@ -50,18 +53,58 @@ static const Weights kLongSafe = {1.0f, 1000.0f};
 //  * a `covariance` prior is factored on the host (plain Cholesky instead of Eigen's LLT) and applied on the device;
 //  * arithmetic on the device is FP32 for the bulk arrays (FP64 for sigma, s, xmean, Nj, Lj).
 // ---------------------------------------------------------------------------------------------------
-class LMCMA {
+// The reference's abstract base (lmcma.hpp:41-81): constructor arguments, the public ask / tell protocol and the public
+// counters.  The reference's protected members (arx, xmean, weights, ... and the update() / sample() hooks) live on the
+// device behind the C ABI here, so a subclass supplies the handle instead of the two hooks; code that only uses the
+// public surface (every caller in the reference tree) compiles unchanged.
+class CMABase {
 public:
     int counteval;
     double BestF;
 
+    CMABase(double* initialParams, int lambda, double* loBounds, double* hiBounds, double* covariance, int inseed,
+            bool verbose = false)
+        : counteval(0), BestF(DBL_MAX), x0_(initialParams), lo_(loBounds), hi_(hiBounds), cov_(covariance), lambda_(lambda),
+          seed_(inseed), verbose_(verbose), n_(0), h_(0) {}
+    virtual ~CMABase() { lmcma_b200_destroy(h_); }
+    CMABase(const CMABase&) = delete;
+    CMABase& operator=(const CMABase&) = delete;
+
+    virtual void init(int N) = 0;
+    void getNextParameterVector(double* params, int N) { check(lmcma_b200_ask_one(handle(), params, N)); }
+    // lmcma.cpp:184-205.  The fitness crosses the boundary as FP32 (the device ranks FP32 values): |f| beyond FLT_MAX is
+    // clamped by the library, costs closer than one FP32 ulp tie and then rank by index.  counteval / BestF are updated
+    // only after the library has accepted the value, so host and device protocol state cannot diverge on an error.
+    void setEvaluationFeedback(double* feedbacks, int numFeedbacks) {
+        check(lmcma_b200_tell_one(handle(), feedbacks, numFeedbacks));
+        double f = 0.0;
+        for (int i = 0; i < numFeedbacks; ++i) f += feedbacks[i];
+        ++counteval;
+        if (f < BestF || counteval == 1) {
+            BestF = f;
+            if (verbose_) std::cout << "Functions evaluation #" << counteval << ", value: " << f << std::endl;
+        }
+    }
+    virtual bool isBehaviorLearningDone() { return false; }      // lmcma.cpp:207-210
+    // the batched protocol and the state getters of the C ABI stay reachable
+    lmcma_b200_opt* handle() const {
+        if (!h_) throw Error(LMCMA_B200_ERR_STATE, "lmcma_b200: init(N) has not been called");
+        return h_;
+    }
+
+protected:
+    double *x0_, *lo_, *hi_, *cov_;
+    int lambda_, seed_;
+    bool verbose_;
+    int n_;
+    lmcma_b200_opt* h_;
+};
+
+class LMCMA : public CMABase {
+public:
     LMCMA(double* initialParams, int lambda = 0, double* loBounds = 0, double* hiBounds = 0, double sigma = 1.0,
           double* covariance = 0, int inseed = 0, bool verbose = false, int m = 0, int device = 0)
-        : counteval(0), BestF(DBL_MAX), x0_(initialParams), lo_(loBounds), hi_(hiBounds), cov_(covariance),
-          lambda_(lambda), m_(m), seed_(inseed), device_(device), sigma_(sigma), verbose_(verbose), n_(0), h_(0) {}
-    ~LMCMA() { lmcma_b200_destroy(h_); }
-    LMCMA(const LMCMA&) = delete;
-    LMCMA& operator=(const LMCMA&) = delete;
+        : CMABase(initialParams, lambda, loBounds, hiBounds, covariance, inseed, verbose), m_(m), device_(device), sigma_(sigma) {}
 
     void init(int N) {
         lmcma_b200_destroy(h_);
@@ -72,36 +115,62 @@ public:
         check(lmcma_b200_create_with_prior(&cfg, x0_, lo_, hi_, cov_, &h_));
         n_ = N; counteval = 0; BestF = DBL_MAX;
     }
-    void getNextParameterVector(double* params, int N) { check(lmcma_b200_ask_one(handle(), params, N)); }
-    void setEvaluationFeedback(double* feedbacks, int numFeedbacks) {
-        double f = 0.0;
-        for (int i = 0; i < numFeedbacks; ++i) f += feedbacks[i];
-        ++counteval;
-        if (f < BestF || counteval == 1) {
-            BestF = f;
-            if (verbose_) std::cout << "Functions evaluation #" << counteval << ", value: " << f << std::endl;
-        }
-        check(lmcma_b200_tell_one(handle(), feedbacks, numFeedbacks));
-    }
-    bool isBehaviorLearningDone() {
+    bool isBehaviorLearningDone() {                               // lmcma.cpp:426-429
         int32_t done = 0;
         check(lmcma_b200_is_done(handle(), &done));
         return done != 0;
     }
-    // the batched protocol and the state getters of the C ABI stay reachable
-    lmcma_b200_opt* handle() const {
-        if (!h_) throw Error(LMCMA_B200_ERR_STATE, "lmcma_b200: init(N) has not been called");
-        return h_;
-    }
 
 private:
-    double *x0_, *lo_, *hi_, *cov_;
-    int lambda_, m_, seed_, device_;
+    int m_, device_;
     double sigma_;
-    bool verbose_;
-    int n_;
-    lmcma_b200_opt* h_;
 };
+
+// ---------------------------------------------------------------------------------------------------
+// The free functions of the reference header (lmcma.hpp:4-38, 248-254), same names, argument meaning and array
+// layouts, forwarding to the host-side entry points of the C ABI.  include/lmcma.hpp brings them (and LMCMA / CMABase)
+// into the global namespace so that a translation unit written against the reference header compiles unchanged.
+// ---------------------------------------------------------------------------------------------------
+typedef struct { double value; int id; } sortedvals;              // lmcma.hpp:4-8
+struct random_t { lmcma_b200_rng* impl; long unsigned startseed; };   // lmcma.hpp:10-24 (the state lives behind the C ABI)
+
+inline long random_Start(random_t* t, long unsigned inseed) {     // lmcma.cpp:14-33
+    if (t->impl) lmcma_b200_rng_destroy(t->impl);
+    t->impl = 0;
+    if (inseed < 1) inseed = 1;
+    check(lmcma_b200_rng_create((int64_t)inseed, &t->impl));
+    t->startseed = inseed;
+    return (long)inseed;
+}
+inline long random_init(random_t* t, long unsigned inseed) {      // lmcma.cpp:35-47 (inseed < 1: seed 1 here, wall clock there)
+    t->impl = 0;
+    return random_Start(t, inseed);
+}
+inline void random_exit(random_t* t) { if (t->impl) lmcma_b200_rng_destroy(t->impl); t->impl = 0; }   // lmcma.cpp:9-12
+inline double random_Uniform(random_t* t) { return lmcma_b200_rng_uniform(t->impl); }                 // lmcma.cpp:49-61
+inline double random_Gauss(random_t* t) { return lmcma_b200_rng_gauss(t->impl); }                     // lmcma.cpp:63-82
+inline int compare(const void* a, const void* b) {                // lmcma.cpp:84-91
+    const double x = static_cast<const sortedvals*>(a)->value, y = static_cast<const sortedvals*>(b)->value;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+inline void myqsort(int sz, double* arfitness, int* arindex, sortedvals* arr) {   // lmcma.cpp:93-104
+    std::vector<int32_t> ids(sz > 0 ? sz : 0);
+    check(lmcma_b200_myqsort(sz, arfitness, ids.data()));
+    for (int i = 0; i < sz; ++i) { arindex[i] = ids[i]; if (arr) { arr[i].value = arfitness[i]; arr[i].id = ids[i]; } }
+}
+inline void covariance(int num_dims, int num_waypoints, double* cov) { check(lmcma_b200_covariance(num_dims, num_waypoints, cov)); }   // lmcma.cpp:769-810
+inline void differentiationMatrix(int num_time_steps, int order, double dt, double* diff_matrix, int rowLen = -1) {                      // lmcma.cpp:812-834
+    check(lmcma_b200_differentiation_matrix(num_time_steps, order, dt, diff_matrix, rowLen));
+}
+inline void invert(double* A, double* Ainv, int N) { check(lmcma_b200_invert(A, Ainv, N)); }                                            // lmcma.cpp:836-842
+// lmcma.cpp:844-855: the reference writes L[m * N + n] = L(n, m), i.e. the lower factor COLUMN-major
+inline void cholesky(double* C, double* L, int N) {
+    std::vector<double> rowmajor((size_t)N * N);
+    check(lmcma_b200_cholesky(N, C, rowmajor.data()));
+    for (int r = 0; r < N; ++r)
+        for (int c = 0; c < N; ++c) L[(size_t)c * N + r] = rowmajor[(size_t)r * N + c];
+}
+inline void applyCovL(double* L, double* z, int N) { check(lmcma_b200_apply_cov_l(L, z, N)); }                                          // lmcma.cpp:857-864
 
 // ---------------------------------------------------------------------------------------------------
 // Distance map + batched trajectory cost: what the global EDT_Matrix, ValidityChecker::isValid/clearance

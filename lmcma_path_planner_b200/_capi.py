@@ -94,6 +94,14 @@ SIGNATURES = {
     "lmcma_b200_hansen_uniform": (C.c_int, [_i64, _i64, _pd]),
     "lmcma_b200_covariance": (C.c_int, [_i32, _i32, _pd]),
     "lmcma_b200_cholesky": (C.c_int, [_i32, _pd, _pd]),
+    "lmcma_b200_differentiation_matrix": (C.c_int, [_i32, _i32, C.c_double, _pd, _i32]),
+    "lmcma_b200_invert": (C.c_int, [_pd, _pd, _i32]),
+    "lmcma_b200_apply_cov_l": (C.c_int, [_pd, _pd, _i32]),
+    "lmcma_b200_myqsort": (C.c_int, [_i32, _pd, _pi]),
+    "lmcma_b200_rng_create": (C.c_int, [_i64, C.POINTER(_vp)]),
+    "lmcma_b200_rng_destroy": (C.c_int, [_vp]),
+    "lmcma_b200_rng_uniform": (C.c_double, [_vp]),
+    "lmcma_b200_rng_gauss": (C.c_double, [_vp]),
 }
 
 _lib = None

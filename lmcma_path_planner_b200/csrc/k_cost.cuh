@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
     const int row = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const float* x = a.X + ((size_t)b * a.inst_rows + row) * a.ld;
-    const float* en = a.ends + (a.ends_per_instance ? (size_t)b * 6 : 0);
+    __shared__ float en[6];                                      // start[3], goal[3] of this instance's query
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) en[c] = a.ends_per_instance ? a.ends[(size_t)b * 6 + c] : a.ends0[c];   // constant indices: ends0 is read from the parameter bank
+    }
     if (STORAGE == 1) for (int i = tid; i < 256; i += nthr) lut[i] = mp.lut[i];
     for (int lb = tid; lb < a.cb; lb += nthr) blkrec[lb].x = 0u;    // first round of block records (phase 2a), zeroed ahead of the barrier below
     // the candidate row, read ONCE and coalesced (it may live in pinned host memory: lmcma_b200_cost_evaluate hands a

@@ -284,11 +284,20 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
     // progressive == 2 (overlapped generation): k_update is NOT a stream predecessor (it runs on a side branch of the graph,
     // concurrently with k_cost / k_rank), so there is no grid to fall back to: spin long, then fail loudly
     auto wait_flag = [&](const int* f) {
-        for (long long spin = 0; spin < (progressive == 2 ? (1ll << 26) : (1ll << 22)); ++spin) {
+        if (progressive == 2) {
+            const long long t0 = gtime();
+            for (long long spin = 0;; ++spin) {
+                if (ld_acquire_gpu(f) != 0) return;
+                __nanosleep(32);
+                if ((spin & 1023) == 1023 && (already_lost(o.err) || gtime() - t0 > LOST_TIMEOUT_NS)) break;
+            }
+            report_lost(o.err, LOST_SAMPLE_WAITING_FOR_UPDATE);   // the host sees it at its next sync; results of this generation are void
+            return;
+        }
+        for (long long spin = 0; spin < (1ll << 22); ++spin) {
             if (ld_acquire_gpu(f) != 0) return;
             __nanosleep(32);
         }
-        if (progressive == 2) __trap();
         griddep_wait();
     };
     if (!progressive) {
@@ -350,8 +359,22 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
     auto provide_chunk = [&](int c) {                           // warp 0: make sure chunk c is on its way, then run ahead
         while (next_issue <= c) {
             bool ok = false;
-            for (long long spin = 0; spin < (progressive == 2 ? (1ll << 26) : (1ll << 22)) && !ok; ++spin) { ok = chunk_ready(next_issue); if (!ok) __nanosleep(32); }
-            if (!ok) { if (progressive == 2) __trap(); griddep_wait(); }   // see wait_flag
+            if (progressive == 2) {
+                const long long t0 = gtime();
+                for (long long spin = 0; !ok; ++spin) {
+                    ok = chunk_ready(next_issue);
+                    if (ok) break;
+                    __nanosleep(32);
+                    if ((spin & 1023) == 1023) {                 // lane 0 decides for the warp
+                        const int giveup = (already_lost(o.err) || gtime() - t0 > LOST_TIMEOUT_NS) ? 1 : 0;
+                        if (__shfl_sync(0xffffffffu, giveup, 0)) break;
+                    }
+                }
+                if (!ok && lane == 0) report_lost(o.err, LOST_SAMPLE_WAITING_FOR_UPDATE);   // carry on (the chunk is requested as is)
+            } else {
+                for (long long spin = 0; spin < (1ll << 22) && !ok; ++spin) { ok = chunk_ready(next_issue); if (!ok) __nanosleep(32); }
+                if (!ok) griddep_wait();                        // see wait_flag
+            }
             request_chunk(next_issue++);
         }
         while (next_issue < nchunks && chunk_ready(next_issue)) request_chunk(next_issue++);

@@ -509,8 +509,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 const unsigned need = (unsigned)o.RS;
                 // plain polling by one thread (this wait is on the critical path); the fence is the acquire for the ranks /
                 // partial sums behind the tickets
+                const long long t0 = gtime();
                 for (long long spin = 0; *reinterpret_cast<const volatile int*>(o.rank_ticket + b) != (int)need; ++spin)
-                    if (spin > (1ll << 28)) __trap();                // a mis-built graph: fail loudly instead of hanging
+                    if ((spin & 255) == 255 && gtime() - t0 > LOST_TIMEOUT_NS) {   // k_rank never ran beside this kernel: tell the
+                        report_lost(o.err, LOST_UPDATE_WAITING_FOR_RANK);          // host and carry on (this generation is void)
+                        break;
+                    }
                 __threadfence();
             }
             __syncthreads();
@@ -664,11 +668,26 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 __global__ void k_gate(OptDev o) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= o.B) return;
+    // bounded: if k_update is not resident after 20 ms it is not going to run beside this branch (serialised launch); letting
+    // k_cost go is always correct - the gate only keeps one SM free for k_update
+    const long long t0 = gtime();
     for (long long spin = 0; ld_acquire_gpu(o.resident + b) == 0; ++spin) {
         __nanosleep(64);
-        if (spin > (1ll << 26)) __trap();
+        if ((spin & 63) == 63 && gtime() - t0 > 20000000ll) break;
     }
     o.resident[b] = 0;
+}
+
+// Co-scheduling probe (lmcma_capi.cu: probe_coschedule): two one-thread kernels on the two branches of a forked graph
+// shake hands through flags[side] / flags[1 - side] within `budget_ns`; ok[side] = 1 when the partner showed up.  Run once
+// per device before the overlapped generation is enabled: under a profiler or sanitizer that serialises kernels (or with
+// the SMs held by someone else) the branches do not run concurrently and the handle keeps the linear PDL graph.
+__global__ void k_probe(int* flags, int* ok, int side, long long budget_ns) {
+    st_release_gpu(flags + side, 1);
+    const long long t0 = gtime();
+    int seen = 0;
+    while (!(seen = ld_acquire_gpu(flags + 1 - side)) && gtime() - t0 < budget_ns) __nanosleep(100);
+    ok[side] = seen ? 1 : 0;
 }
 
 // rebuild the sequence-ordered mirror from the slot-indexed state (after create / a state setter): grid = (m, B)

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -82,11 +83,48 @@ int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+// Every LMCMA_B200_* environment knob, read ONCE when a handle (map or optimiser) is created and kept on the handle:
+// nothing on a launch path calls getenv.  All of them are experiment / debugging switches; the defaults are the product.
+struct Tuning {
+    int cost_minb = 7, cost_tpt = 0, cost_cb = 0, zerocopy = 1;
+    int sample_spec = 1, sample_threads = 0, sample_smem_kb = 160, sample_smem_kb_set = 0, sample_narrow = 0, sample_rbw = 0, sample_r = 0;
+    int update_blocked = 0, update_gram = 0, update_streaming = 0, update_sweep_warps = 0;
+    int progressive = 1, overlap = 1, tell_overlap = 1, rank_late = 1;
+    int graph_dbg = 0, dbg = 0, update_dbg = 0;
+    static Tuning from_env() {
+        Tuning t;
+        t.cost_minb = env_int("LMCMA_B200_COST_MINB", t.cost_minb);
+        t.cost_tpt = env_int("LMCMA_B200_COST_TPT", 0);
+        t.cost_cb = env_int("LMCMA_B200_COST_CB", 0);
+        t.zerocopy = env_int("LMCMA_B200_ZEROCOPY", 1);
+        t.sample_spec = env_int("LMCMA_B200_SAMPLE_SPEC", 1);
+        t.sample_threads = env_int("LMCMA_B200_SAMPLE_THREADS", 0);
+        t.sample_smem_kb_set = env_int("LMCMA_B200_SAMPLE_SMEM_KB", 0);
+        t.sample_smem_kb = t.sample_smem_kb_set ? t.sample_smem_kb_set : 160;
+        t.sample_narrow = env_int("LMCMA_B200_SAMPLE_NARROW", 0);
+        t.sample_rbw = env_int("LMCMA_B200_SAMPLE_RBW", 0);
+        t.sample_r = env_int("LMCMA_B200_SAMPLE_R", 0);
+        t.update_blocked = env_int("LMCMA_B200_UPDATE_BLOCKED", 0);
+        t.update_gram = env_int("LMCMA_B200_UPDATE_GRAM", 0);
+        t.update_streaming = env_int("LMCMA_B200_UPDATE_STREAMING", 0);
+        t.update_sweep_warps = env_int("LMCMA_B200_UPDATE_SWEEP_WARPS", 0);
+        t.progressive = env_int("LMCMA_B200_PROGRESSIVE", 1);
+        t.overlap = env_int("LMCMA_B200_OVERLAP", 1);
+        t.tell_overlap = env_int("LMCMA_B200_TELL_OVERLAP", 1);
+        t.rank_late = env_int("LMCMA_B200_RANK_LATE", 1);
+        t.graph_dbg = env_int("LMCMA_B200_GRAPH_DBG", 0);
+        t.dbg = getenv("LMCMA_B200_DBG") ? 1 : 0;
+        t.update_dbg = getenv("LMCMA_B200_UPDATE_DBG") ? 1 : 0;
+        return t;
+    }
+};
+
 struct DeviceProps {
     int sm_count = 0;
     size_t l2 = 0, smem_optin = 0, persist_max = 0;
     int cc = 0;
     bool ok = false;
+    int cosched = -1;     // probe_coschedule: -1 not probed yet, 0 branches of a forked graph are serialised here, 1 they run concurrently
 };
 DeviceProps g_props[64];
 int query_props(int device, DeviceProps** out) {
@@ -114,6 +152,7 @@ int query_props(int device, DeviceProps** out) {
 // =================================================================================================
 struct lmcma_b200_map {
     int device = 0;
+    Tuning tune;
     MapDev dev{};
     int storage = 0;
     float c_min = 0.5f, scale = 1.f;
@@ -126,14 +165,12 @@ struct lmcma_b200_map {
     // staging for the host-buffer evaluate path
     float* d_X = nullptr; size_t d_X_cap = 0;
     float* d_f = nullptr; int* d_nc = nullptr; int* d_ns = nullptr; size_t d_out_cap = 0;
-    float* d_ends = nullptr;
-    float ends_host[6] = {0, 0, 0, 0, 0, 0};   // what d_ends holds (cost_evaluate*: re-uploaded only when the query changes)
-    bool ends_valid = false;
-    cudaStream_t ends_stream = nullptr;
+    std::mutex host_path;            // lmcma_b200_cost_evaluate / cost_trace share the staging buffers and the private stream
 };
 
 struct lmcma_b200_opt {
     lmcma_b200_config cfg{};
+    Tuning tune;
     OptDev d{};
     DeviceProps* props = nullptr;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -173,6 +210,7 @@ struct lmcma_b200_opt {
     bool overlap = false;       // fused generation with k_update on a side branch, concurrent with k_cost / k_rank (k_update.cuh)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int* err_host = nullptr;          // page-locked, mapped: OptDev::err (a kernel of the overlapped generation gave up on its partner)
     long long* graph_dbg = nullptr;   // LMCMA_B200_GRAPH_DBG: k_update's timeline inside the fused generation, printed by lmcma_b200_sync
     int upd_nvb = 4, upd_rmax = 0, upd_sweep_warps = 16;
     bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
@@ -208,8 +246,7 @@ int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, CostShape 
         if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, shape, st);
         return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, shape, st);
     }
-    const int minb = env_int("LMCMA_B200_COST_MINB", 7);     // 6: the un-spilled 40-register build (experiment, k_cost.cuh)
-    if (minb == 6) {
+    if (shape.minb == 6) {                                    // the un-spilled 40-register build (experiment, k_cost.cuh)
         if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false, 6>(mp, a, rows, B, shape, st);
         return mp.storage == 0 ? launch_cost_t<3, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false, 6>(mp, a, rows, B, shape, st);
     }
@@ -218,7 +255,7 @@ int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, CostShape 
 }
 
 // CTA width and per-block record capacity of k_cost from the expected samples per trajectory
-CostShape pick_cost_shape(int W, const float* start, const float* goal, int dims) {
+CostShape pick_cost_shape(int W, const float* start, const float* goal, int dims, const Tuning& tune) {
     float linf = 0.f;
     if (start && goal)
         for (int c = 0; c < dims; ++c) linf = std::max(linf, std::fabs(goal[c] - start[c]));
@@ -228,12 +265,13 @@ CostShape pick_cost_shape(int W, const float* start, const float* goal, int dims
     // enough lanes for the samples, and a thread per segment (phase 1 is a chain of dependent loads per segment);
     // k_cost is built for at most 8 warps (COST_MAX_WARPS)
     while (sh.tpt < 256 && (est / sh.tpt > 24.0 || W + 1 > sh.tpt)) sh.tpt <<= 1;
-    const int forced = env_int("LMCMA_B200_COST_TPT", 0);
+    const int forced = tune.cost_tpt;
     if (forced >= 32 && forced <= 256 && forced % 32 == 0) sh.tpt = forced;
+    sh.minb = tune.cost_minb;
     // 32-sample blocks whose records are staged at once (longer trajectories take several rounds): ~3x the estimate
     sh.cb = 64;
     while (sh.cb < 2048 && sh.cb * 32.0 < 3.0 * est) sh.cb <<= 1;
-    const int forced_cb = env_int("LMCMA_B200_COST_CB", 0);
+    const int forced_cb = tune.cost_cb;
     if (forced_cb >= 8 && forced_cb <= 4096) sh.cb = forced_cb;
     return sh;
 }
@@ -312,7 +350,7 @@ int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false, bool pro
     switch (o->smp_nv) {
         case 1: return launch_sample_t<1, 4, 512>(o, pdl, st);
         case 2: return launch_sample_t<2, 4, 512>(o, pdl, st);
-        case 4: return env_int("LMCMA_B200_SAMPLE_SPEC", 1) ? launch_sample_t<4, 2, 512, true>(o, pdl, st) : launch_sample_t<4, 2, 512>(o, pdl, st);
+        case 4: return o->tune.sample_spec ? launch_sample_t<4, 2, 512, true>(o, pdl, st) : launch_sample_t<4, 2, 512>(o, pdl, st);
         case 8: return launch_sample_t<8, 1, 512>(o, pdl, st);
         case 12: return launch_sample_t<12, 1, 256>(o, pdl, st);
         case 16: return launch_sample_t<16, 1, 256>(o, pdl, st);
@@ -332,7 +370,7 @@ int configure_sample(lmcma_b200_opt* o) {
     const int maxt = o->smp_nv >= 12 ? 256 : 512;
     // as many warps per CTA as keeps >= ~1 CTA per SM
     int threads = maxt;
-    const int forced = env_int("LMCMA_B200_SAMPLE_THREADS", 0);
+    const int forced = o->tune.sample_threads;
     if (forced >= 32 && forced <= maxt && forced % 32 == 0) threads = forced;
     else
         while (threads > 64) {
@@ -345,27 +383,27 @@ int configure_sample(lmcma_b200_opt* o) {
     const size_t pair_bytes = (size_t)2 * o->d.ns * sizeof(float);
     // pairs per stage: one group of 8 when it fits (else 4 / 2 / 1); as many stages as the live pairs need, within
     // ~160 KB, so that for the common shapes every pair is requested up front and nothing is re-issued
-    const size_t budget = (size_t)env_int("LMCMA_B200_SAMPLE_SMEM_KB", 160) * 1024;
+    const size_t budget = (size_t)o->tune.sample_smem_kb * 1024;
     int kc = (int)(budget / 2 / pair_bytes);
     kc = kc >= 8 ? 8 : (kc >= 4 ? 4 : (kc >= 2 ? 2 : 1));
     // long rows (C4: 12 KB per pair): two stages of a FULL group of 8 still fit one SM (192 KB), and a 4-pair stage runs the
     // 8-wide group code half empty
-    if (kc == 4 && 2 * 8 * pair_bytes + 24 * 1024 <= o->props->smem_optin && env_int("LMCMA_B200_SAMPLE_SMEM_KB", 0) == 0) kc = 8;
+    if (kc == 4 && 2 * 8 * pair_bytes + 24 * 1024 <= o->props->smem_optin && o->tune.sample_smem_kb_set == 0) kc = 8;
     o->smp_kc = kc;
     const int max_chunks = (o->d.m + kc - 1) / kc;
     o->smp_stages = (int)std::max<size_t>(2, std::min<size_t>(std::min(max_chunks, SAMPLE_MAX_STAGES), budget / (kc * pair_bytes)));   // >= 2 even beyond the budget
     o->smp_smem = (size_t)o->smp_stages * kc * pair_bytes + SAMPLE_MAX_STAGES * 8 + (size_t)(2 * o->d.m + 16) * sizeof(float);
     // one large population: split every row over CW column-warps (k_sample_wide) for occupancy
     o->smp_wide = false;
-    if (o->d.pop_count >= 256 && nq > 32 && !env_int("LMCMA_B200_SAMPLE_NARROW", 0)) {
+    if (o->d.pop_count >= 256 && nq > 32 && !o->tune.sample_narrow) {
         o->smp_wide = true;
         o->smp_CW = (nq + 31) / 32;
         o->smp_qpw = (nq + o->smp_CW - 1) / o->smp_CW;
         // rows per warp: 2 (4 for very large populations); row-groups per CTA so that the grid still covers the SMs
-        o->smp_RBW = env_int("LMCMA_B200_SAMPLE_RBW", o->d.pop_count >= 1024 ? 4 : 2);
+        o->smp_RBW = o->tune.sample_rbw ? o->tune.sample_rbw : (o->d.pop_count >= 1024 ? 4 : 2);
         if (o->smp_RBW != 1 && o->smp_RBW != 2) o->smp_RBW = 4;
         int R = std::max(1, std::min(15, (o->smp_RBW == 4 ? 16 : 32) / o->smp_CW));
-        const int forced_R = env_int("LMCMA_B200_SAMPLE_R", 0);
+        const int forced_R = o->tune.sample_r;
         if (forced_R >= 1 && forced_R <= R) R = forced_R;
         else
             while (R > 1 && (long long)((o->d.pop_count + R * o->smp_RBW - 1) / (R * o->smp_RBW)) * o->d.B * 4 < (long long)o->props->sm_count * 3) R >>= 1;
@@ -447,7 +485,7 @@ UpdateArgs update_args_local(lmcma_b200_opt* o) {
     memset(&a, 0, sizeof(a));
     a.f_all = o->d.fit;
     a.slices = o->d.partial; a.n_slices = o->d.RS; a.slice_stride = o->d.ns; a.inst_stride = (long long)o->d.RS * o->d.ns;
-    a.blocked = env_int("LMCMA_B200_UPDATE_BLOCKED", 0);
+    a.blocked = o->tune.update_blocked;
     a.sweep_warps = o->upd_sweep_warps;
     return a;
 }
@@ -465,14 +503,13 @@ int configure_update(lmcma_b200_opt* o) {
     if (o->upd_smem > budget) return fail(LMCMA_B200_ERR_ARG, "k_update needs %zu B shared memory (m = %d too large)", o->upd_smem, o->d.m);
     // rows that fit neither the registers nor the shared memory of one SM: Gram-matrix recompute (k_gram.cuh)
     o->coef_smem = (size_t)2 * o->d.m * (o->d.m | 1) * sizeof(double) + (size_t)2 * o->d.m * sizeof(double);
-    o->upd_gram = (!o->upd_rows_in_smem || env_int("LMCMA_B200_UPDATE_GRAM", 0)) && o->d.m <= 128 && o->coef_smem <= budget &&
-                  !env_int("LMCMA_B200_UPDATE_STREAMING", 0);
+    o->upd_gram = (!o->upd_rows_in_smem || o->tune.update_gram) && o->d.m <= 128 && o->coef_smem <= budget && !o->tune.update_streaming;
     if (o->upd_gram) { o->upd_rows_in_smem = false; o->upd_smem = fixed; }
     // pending rows in registers when they fit: m <= 8 warps x RMAX rows of <= 128 float4 columns
     o->upd_rmax = 0;
-    if (o->upd_nvb == 4 && o->upd_rows_in_smem && !o->upd_gram && !env_int("LMCMA_B200_UPDATE_STREAMING", 0)) {
+    if (o->upd_nvb == 4 && o->upd_rows_in_smem && !o->upd_gram && !o->tune.update_streaming) {
         o->upd_sweep_warps = UPD_WARPS;
-        const int forced_sw = env_int("LMCMA_B200_UPDATE_SWEEP_WARPS", 0);
+        const int forced_sw = o->tune.update_sweep_warps;
         if (forced_sw >= 1 && forced_sw <= UPD_WARPS) o->upd_sweep_warps = forced_sw;
         if (o->d.m <= o->upd_sweep_warps * 3) o->upd_rmax = 3;
         else if (o->d.m <= o->upd_sweep_warps * 5) o->upd_rmax = 5;
@@ -521,6 +558,60 @@ int generation_tail(lmcma_b200_opt* o, cudaStream_t st) {
     return host_rng_and_sample(o, st, prog);
 }
 
+// Do the two branches of a forked CUDA graph really run concurrently on this device, in this process?  (Not under a
+// profiler / sanitizer that serialises kernels, not when someone else holds the SMs.)  Probed once per device with two
+// one-thread kernels that shake hands within 5 ms; the second of two launches counts (the first pays module loading).
+int probe_coschedule(lmcma_b200_opt* o) {
+    if (o->props->cosched >= 0) return o->props->cosched;
+    int result = 0;
+    int* d = nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    cudaStream_t st = o->own_stream;
+    if (cudaMalloc(&d, 4 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        ok = cudaEventRecord(o->ev_fork, st) == cudaSuccess && cudaStreamWaitEvent(o->side_stream, o->ev_fork, 0) == cudaSuccess;
+        if (ok) { k_probe<<<1, 1, 0, o->side_stream>>>(d, d + 2, 0, 5000000ll); ok = cudaEventRecord(o->ev_join, o->side_stream) == cudaSuccess; }
+        if (ok) { k_probe<<<1, 1, 0, st>>>(d, d + 2, 1, 5000000ll); ok = cudaStreamWaitEvent(st, o->ev_join, 0) == cudaSuccess; }
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        ok = ok && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    }
+    if (ok) {
+        for (int attempt = 0; attempt < 2 && ok; ++attempt) {
+            int h[4] = {0, 0, 0, 0};
+            ok = cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st) == cudaSuccess && cudaGraphLaunch(exec, st) == cudaSuccess &&
+                 cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+            result = ok && h[2] == 1 && h[3] == 1;
+        }
+        g_launches += 4;
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    cudaFree(d);
+    cudaGetLastError();
+    o->props->cosched = result;
+    return result;
+}
+
+// A kernel of the overlapped generation gave up waiting for its partner (OptDev::err): report it ONCE, and keep the
+// handle usable on the linear PDL graph from here on.  The generation in flight is void: the optimiser state must be
+// restored by the caller (set_* from a checkpoint) or the handle recreated.
+int check_lost(lmcma_b200_opt* o) {
+    if (!o->err_host || *reinterpret_cast<volatile int*>(o->err_host) == 0) return 0;
+    const int code = *reinterpret_cast<volatile int*>(o->err_host);
+    *reinterpret_cast<volatile int*>(o->err_host) = 0;
+    o->overlap = false;
+    o->props->cosched = 0;
+    if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
+    if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
+    o->tell_graph_failed = true;
+    o->mirror_dirty = true;
+    return fail(LMCMA_B200_ERR_CUDA, "overlapped generation lost co-scheduling (%s): the branches of the CUDA graph did not run "
+                "concurrently (profiler / sanitizer / SMs held elsewhere).  This handle now uses the linear graph; the generation in "
+                "flight is void - restore the state or recreate the handle (LMCMA_B200_OVERLAP=0 avoids the overlapped graph)",
+                code == LOST_UPDATE_WAITING_FOR_RANK ? "k_update timed out waiting for k_rank" : "k_sample timed out waiting for k_update");
+}
+
 int ensure_graph(lmcma_b200_opt* o) {
     if (o->graph_exec && o->graph_built_for == o->stream) return 0;
     if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
@@ -531,7 +622,7 @@ int ensure_graph(lmcma_b200_opt* o) {
     if ((rc = ensure_mirror(o, st))) return rc;
     cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
-    if (env_int("LMCMA_B200_GRAPH_DBG", 0) && !o->graph_dbg && cudaMalloc(&o->graph_dbg, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(o->graph_dbg, 0, 64 * sizeof(long long)); cudaDeviceSynchronize(); }
+    if (o->tune.graph_dbg && !o->graph_dbg && cudaMalloc(&o->graph_dbg, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(o->graph_dbg, 0, 64 * sizeof(long long)); cudaDeviceSynchronize(); }
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     UpdateArgs ua = update_args_local(o);
     ua.progressive = o->progressive ? 1 : 0;                 // ensure_mirror above: the mirror is clean
@@ -546,7 +637,7 @@ int ensure_graph(lmcma_b200_opt* o) {
         if (!rc && cudaEventRecord(o->ev_join, o->side_stream) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph join record failed");
         if (!rc) { k_gate<<<(o->d.B + 31) / 32, 32, 0, st>>>(o->d); g_launches++; }
         if (!rc) rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
-        if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN | RANK_KEEP_FLAGS | (env_int("LMCMA_B200_RANK_LATE", 1) ? 0 : 4), nullptr, st, true);
+        if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN | RANK_KEEP_FLAGS | (o->tune.rank_late ? 0 : 4), nullptr, st, true);
         if (!rc) rc = launch_sample(o, st, true, true, 2);
         if (!rc && cudaStreamWaitEvent(st, o->ev_join, 0) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph join failed");
     } else {
@@ -675,6 +766,7 @@ static int map_alloc(int device, int dims, const int32_t* shape, int storage, fl
     if (rc) return rc;
     CU(cudaSetDevice(device));
     lmcma_b200_map* m = new lmcma_b200_map();
+    m->tune = Tuning::from_env();
     m->device = device; m->storage = storage; m->c_min = c_min; m->scale = u8_scale;
     m->dev.dims = dims; m->dev.nx = shape[0]; m->dev.ny = shape[1]; m->dev.nz = dims == 3 ? shape[2] : 1;
     m->dev.storage = storage; m->dev.g_coll = 1.0f / c_min;
@@ -707,7 +799,6 @@ static int map_alloc(int device, int dims, const int32_t* shape, int storage, fl
         }
         m->dev.q8 = m->d_q8; m->dev.lut = m->d_lut;
     }
-    if (!rc) rc = dmalloc(&m->d_ends, 6);
     if (rc) { lmcma_b200_map_destroy(m); return rc; }
     *out = m;
     return 0;
@@ -825,7 +916,7 @@ int lmcma_b200_map_destroy(lmcma_b200_map* m) {
     if (!m) return 0;
     cudaSetDevice(m->device);
     cudaFree(m->d_g32); cudaFree(m->d_q8); cudaFree(m->d_lut); cudaFree(m->d_X); cudaFree(m->d_f);
-    cudaFree(m->d_nc); cudaFree(m->d_ns); cudaFree(m->d_ends);
+    cudaFree(m->d_nc); cudaFree(m->d_ns);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return 0;
@@ -906,19 +997,14 @@ int lmcma_b200_cost_evaluate_dev(lmcma_b200_map* m, const lmcma_b200_objective* 
     if (count == 0) return 0;
     CU(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    float e6[6] = {ends->start[0], ends->start[1], ends->start[2], ends->goal[0], ends->goal[1], ends->goal[2]};
-    if (!m->ends_valid || m->ends_stream != st || memcmp(m->ends_host, e6, sizeof(e6)) != 0) {   // a planner asks about one query many times
-        CU(cudaMemcpyAsync(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice, st));
-        memcpy(m->ends_host, e6, sizeof(e6));
-        m->ends_valid = true; m->ends_stream = st;
-    }
     CostArgs a;
     memset(&a, 0, sizeof(a));
     a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
-    a.X = X_dev; a.ld = ld; a.inst_rows = count; a.ends = m->d_ends; a.ends_per_instance = 0;
+    a.X = X_dev; a.ld = ld; a.inst_rows = count; a.ends = nullptr; a.ends_per_instance = 0;
+    for (int c = 0; c < 3; ++c) { a.ends0[c] = ends->start[c]; a.ends0[3 + c] = ends->goal[c]; }   // by value: nothing shared between callers
     a.f = f_dev; a.f_stride = count; a.f_offset = 0; a.ncoll = ncoll_dev; a.nsamp = nsamp_dev;
     if ((rc = apply_l2_window(m, st))) return rc;
-    return launch_cost(m->dev, a, count, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims), false, st);
+    return launch_cost(m->dev, a, count, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims, m->tune), false, st);
 }
 
 int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
@@ -927,13 +1013,14 @@ int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj,
     if (rc) return rc;
     ARG(ends && X_host && f_host && count >= 0, "null pointer / negative count");
     if (count == 0) return 0;
+    std::lock_guard<std::mutex> lock(m->host_path);   // staging buffers + private stream: one host-buffer call per map at a time
     CU(cudaSetDevice(m->device));
     const size_t n = (size_t)m->dev.dims * obj->waypoints;
     // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister) are handed to the kernel as they are: every CTA reads
     // its own candidate row across PCIe once, coalesced, while other CTAs compute (instead of a serial H2D copy in front
     // of the kernel), and the three results per trajectory are stored straight into the caller's arrays.  Pageable
     // buffers are staged through device memory.  LMCMA_B200_ZEROCOPY=0 forces staging.
-    const bool zc = env_int("LMCMA_B200_ZEROCOPY", 1) != 0;
+    const bool zc = m->tune.zerocopy != 0;
     const float* X_dev = zc ? static_cast<const float*>(mapped_device_pointer(X_host, m->device)) : nullptr;
     float* f_dev = zc ? static_cast<float*>(mapped_device_pointer(f_host, m->device)) : nullptr;
     int32_t* nc_dev = (zc && ncoll_host) ? static_cast<int32_t*>(mapped_device_pointer(ncoll_host, m->device)) : nullptr;
@@ -974,22 +1061,28 @@ int lmcma_b200_cost_trace(lmcma_b200_map* m, const lmcma_b200_objective* obj, co
     int rc = check_obj(m, obj);
     if (rc) return rc;
     ARG(ends && x_host && cells_host && n_cells_out && max_cells > 0, "null pointer");
+    std::lock_guard<std::mutex> lock(m->host_path);
     CU(cudaSetDevice(m->device));
     const size_t n = (size_t)m->dev.dims * obj->waypoints;
     float* dX = nullptr; float* df = nullptr; int* dns = nullptr; long long* dcells = nullptr;
-    DM(dX, n); DM(df, 1); DM(dns, 1); DM(dcells, (size_t)max_cells);
-    CU(cudaMemset(dcells, 0xff, (size_t)max_cells * sizeof(long long)));
-    CU(cudaMemcpy(dX, x_host, n * sizeof(float), cudaMemcpyHostToDevice));
-    float e6[6] = {ends->start[0], ends->start[1], ends->start[2], ends->goal[0], ends->goal[1], ends->goal[2]};
-    CU(cudaMemcpy(m->d_ends, e6, sizeof(e6), cudaMemcpyHostToDevice));
-    m->ends_valid = false;
-    CU(cudaStreamSynchronize(cudaStreamLegacy));   // the kernel runs on the map's non-blocking stream
+    rc = dmalloc(&dX, n);
+    if (!rc) rc = dmalloc(&df, 1);
+    if (!rc) rc = dmalloc(&dns, 1);
+    if (!rc) rc = dmalloc(&dcells, (size_t)max_cells);
+    if (!rc) {
+        cudaError_t e = cudaMemset(dcells, 0xff, (size_t)max_cells * sizeof(long long));
+        if (e == cudaSuccess) e = cudaMemcpy(dX, x_host, n * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);   // the kernel runs on the map's non-blocking stream
+        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "trace staging: %s", cudaGetErrorString(e));
+    }
+    if (rc) { cudaFree(dX); cudaFree(df); cudaFree(dns); cudaFree(dcells); return rc; }
     CostArgs a;
     memset(&a, 0, sizeof(a));
     a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
-    a.X = dX; a.ld = (long long)n; a.inst_rows = 1; a.ends = m->d_ends; a.ends_per_instance = 0;
+    a.X = dX; a.ld = (long long)n; a.inst_rows = 1; a.ends = nullptr; a.ends_per_instance = 0;
+    for (int c = 0; c < 3; ++c) { a.ends0[c] = ends->start[c]; a.ends0[3 + c] = ends->goal[c]; }
     a.f = df; a.f_stride = 1; a.nsamp = dns; a.cells = dcells; a.max_cells = max_cells;
-    rc = launch_cost(m->dev, a, 1, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims), true, m->stream);
+    rc = launch_cost(m->dev, a, 1, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims, m->tune), true, m->stream);
     if (!rc) {
         cudaError_t e = cudaStreamSynchronize(m->stream);
         if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "trace kernel: %s", cudaGetErrorString(e));
@@ -1012,6 +1105,9 @@ int lmcma_b200_create(const lmcma_b200_config* cfg, const double* x0, const doub
     return lmcma_b200_create_with_prior(cfg, x0, lo, hi, nullptr, out);
 }
 
+static int create_body(lmcma_b200_opt* o, DeviceProps* props, const lmcma_b200_config* cfg, const double* x0, const double* lo,
+                       const double* hi, const double* covariance);
+
 int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0, const double* lo, const double* hi,
                                  const double* covariance, lmcma_b200_opt** out) {
     ARG(cfg && out, "null pointer");
@@ -1027,6 +1123,16 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     CU(cudaSetDevice(cfg->device));
 
     lmcma_b200_opt* o = new lmcma_b200_opt();
+    rc = create_body(o, props, cfg, x0, lo, hi, covariance);   // any failure inside: everything allocated so far is released here
+    if (rc) { const std::string keep = g_err; lmcma_b200_destroy(o); g_err = keep; return rc; }
+    *out = o;
+    return 0;
+}
+
+static int create_body(lmcma_b200_opt* o, DeviceProps* props, const lmcma_b200_config* cfg, const double* x0, const double* lo,
+                       const double* hi, const double* covariance) {
+    int rc = 0;
+    o->tune = Tuning::from_env();
     o->cfg = *cfg;
     o->props = props;
     OptDev& d = o->d;
@@ -1036,11 +1142,11 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     d.mu = d.lambda / 2;                                                                  // lmcma.cpp:136
     d.m = cfg->m < 1 ? d.lambda : cfg->m;                                                 // lmcma.cpp:266
     d.B = cfg->batch;
-    if (d.lambda < 2 || d.mu < 1 || d.m < 2) { delete o; return fail(LMCMA_B200_ERR_ARG, "need lambda >= 2 and m >= 2"); }
+    if (d.lambda < 2 || d.mu < 1 || d.m < 2) { return fail(LMCMA_B200_ERR_ARG, "need lambda >= 2 and m >= 2"); }
     d.pop_offset = cfg->pop_count < 1 ? 0 : cfg->pop_offset;
     d.pop_count = cfg->pop_count < 1 ? d.lambda : cfg->pop_count;
-    if (d.pop_offset < 0 || d.pop_offset + d.pop_count > d.lambda) { delete o; return fail(LMCMA_B200_ERR_ARG, "population slice out of range"); }
-    if (cfg->rng == LMCMA_B200_RNG_HANSEN && d.pop_count != d.lambda) { delete o; return fail(LMCMA_B200_ERR_ARG, "HANSEN rng cannot be split"); }
+    if (d.pop_offset < 0 || d.pop_offset + d.pop_count > d.lambda) { return fail(LMCMA_B200_ERR_ARG, "population slice out of range"); }
+    if (cfg->rng == LMCMA_B200_RNG_HANSEN && d.pop_count != d.lambda) { return fail(LMCMA_B200_ERR_ARG, "HANSEN rng cannot be split"); }
     d.rng_mode = cfg->rng;
     d.record_z = cfg->record_z;
     d.seed = (unsigned long long)cfg->seed;
@@ -1071,7 +1177,7 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     if (cfg->rng != LMCMA_B200_RNG_PHILOX || cfg->record_z || covariance) DM(d.Z, B * pc * ns);
     if (covariance) {   // CMABase::init factors the prior once (cholesky, lmcma.cpp:165-169)
         std::vector<double> Ld((size_t)d.n * d.n);
-        if (!cholesky_lower(covariance, d.n, Ld.data())) { lmcma_b200_destroy(o); return fail(LMCMA_B200_ERR_ARG, "covariance prior is not symmetric positive definite"); }
+        if (!cholesky_lower(covariance, d.n, Ld.data())) { return fail(LMCMA_B200_ERR_ARG, "covariance prior is not symmetric positive definite"); }
         std::vector<float> Lf((size_t)d.n * ns, 0.f);
         for (int i = 0; i < d.n; ++i)
             for (int k = 0; k <= i; ++k) Lf[(size_t)i * ns + k] = (float)Ld[(size_t)i * d.n + k];
@@ -1091,10 +1197,10 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     DM(d.sc, B); DM(d.best_x, B * ns); DM(d.S_count, B); DM(d.done_count, B); DM(d.progress, B * (m + 2)); DM(d.rank_ticket, B); DM(d.resident, B);
     {   // row slices of k_tell's phase A: 32 rows per slice, at most 256 slices
         const int rows_per = std::max(32, (d.pop_count + 255) / 256);
-        if (rows_per > TELL_MAX_ROWS) { lmcma_b200_destroy(o); return fail(LMCMA_B200_ERR_ARG, "population too large (max %d rows per handle)", 256 * TELL_MAX_ROWS); }
+        if (rows_per > TELL_MAX_ROWS) { return fail(LMCMA_B200_ERR_ARG, "population too large (max %d rows per handle)", 256 * TELL_MAX_ROWS); }
         d.RS = (d.pop_count + rows_per - 1) / rows_per;
     }
-    if (getenv("LMCMA_B200_DBG")) DM(d.dbg, 64);
+    if (o->tune.dbg) DM(d.dbg, 64);
     DM(d.partial, B * d.RS * ns);
 
     std::vector<float> wf(o->weights.begin(), o->weights.end());
@@ -1133,29 +1239,33 @@ int lmcma_b200_create_with_prior(const lmcma_b200_config* cfg, const double* x0,
     // is still producing them (k_update.cuh / k_sample.cuh "progressive")
     o->progressive = !rc && B == 1 && o->smp_wide && o->upd_rmax > 0 && !o->upd_gram && !o->d_Lf && o->smp_kc == 8 &&
                      o->smp_stages >= (m + o->smp_kc - 1) / o->smp_kc && cfg->rng == LMCMA_B200_RNG_PHILOX &&
-                     env_int("LMCMA_B200_PROGRESSIVE", 1) != 0;
-    o->overlap = o->progressive && env_int("LMCMA_B200_OVERLAP", 1) != 0;
+                     o->tune.progressive != 0;
+    o->overlap = o->progressive && o->tune.overlap != 0;
     if (o->overlap) {
         cudaError_t e2 = cudaStreamCreateWithFlags(&o->side_stream, cudaStreamNonBlocking);
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming);
-        if (e2 != cudaSuccess) { cudaGetLastError(); o->overlap = false; }
+        if (e2 == cudaSuccess) e2 = cudaHostAlloc(&o->err_host, sizeof(int), cudaHostAllocMapped);
+        if (e2 == cudaSuccess) { *o->err_host = 0; e2 = cudaHostGetDevicePointer(&d.err, o->err_host, 0); }
+        if (e2 != cudaSuccess) { cudaGetLastError(); o->overlap = false; d.err = nullptr; }
+        // the overlapped generation needs the two branches of a forked graph to run CONCURRENTLY: enabled only where a probe
+        // has seen that happen (LMCMA_B200_OVERLAP=2 skips the probe)
+        if (o->overlap && o->tune.overlap != 2 && probe_coschedule(o) != 1) o->overlap = false;
     }
     if (!rc && o->upd_gram) {
         rc = dmalloc(&d.G, B * GRAM_KS * m * m);
         if (!rc) rc = dmalloc(&d.Cf, B * m * m);
         if (!rc) rc = dmalloc(&d.gram_hdr, B);
     }
-    if (rc) { lmcma_b200_destroy(o); return rc; }
+    if (rc) return rc;
     o->f_host.assign(B * lam, 0.f);
     // first population (LMCMA::init -> sample(), lmcma.cpp:298)
     if (cfg->rng == LMCMA_B200_RNG_INJECT) o->needs_sample = true;
     else {
         rc = host_rng_and_sample(o, o->stream);
         if (!rc) { cudaError_t e = cudaStreamSynchronize(o->stream); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "first sample: %s", cudaGetErrorString(e)); }
-        if (rc) { lmcma_b200_destroy(o); return rc; }
+        if (rc) return rc;
     }
-    *out = o;
     return 0;
 }
 
@@ -1170,6 +1280,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
     if (o->tell_graph) cudaGraphExecDestroy(o->tell_graph);
     if (o->f_pinned) cudaFreeHost(o->f_pinned);
+    if (o->err_host) cudaFreeHost(o->err_host);
     if (o->ev0) cudaEventDestroy(o->ev0);
     if (o->ev1) cudaEventDestroy(o->ev1);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
@@ -1231,7 +1342,8 @@ int lmcma_b200_ask_all(lmcma_b200_opt* o, float* X) {
     if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no population yet: inject_z first");
     CU(cudaSetDevice(o->cfg.device));
     const OptDev& d = o->d;
-    return d2h_rows(X, d.X, (size_t)d.B * d.pop_count, d.n * sizeof(float), d.ns * sizeof(float), o->stream);
+    int rc = d2h_rows(X, d.X, (size_t)d.B * d.pop_count, d.n * sizeof(float), d.ns * sizeof(float), o->stream);
+    return rc ? rc : check_lost(o);
 }
 
 int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
@@ -1241,7 +1353,7 @@ int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
     CU(cudaSetDevice(o->cfg.device));
     const OptDev& d = o->d;
     int rc;
-    if (o->overlap && !o->tell_graph_failed && env_int("LMCMA_B200_TELL_OVERLAP", 1) != 0) {
+    if (o->overlap && !o->tell_graph_failed && o->tune.tell_overlap != 0) {
         // One query (the conditions of the overlapped generation): everything in update() that does not
         // depend on this generation's fitness — slot bookkeeping, the sweep over every pending row but the newest — runs on
         // a side branch while the fitness crosses PCIe and k_rank runs; k_update then waits for k_rank's tickets and
@@ -1256,7 +1368,7 @@ int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
             o->sample_idx = 0;
             o->pending_z = false;
             CU(cudaStreamSynchronize(o->stream));
-            return 0;
+            return check_lost(o);
         }
         if (rc) return rc;
     }
@@ -1286,7 +1398,9 @@ int lmcma_b200_tell_one(lmcma_b200_opt* o, const double* feedbacks, int32_t num)
     if (o->d.B != 1 || o->d.pop_count != o->d.lambda) return fail(LMCMA_B200_ERR_STATE, "tell_one needs batch == 1 and an unsplit population");
     double f = 0.0;                                    // lmcma.cpp:186-188
     for (int i = 0; i < num; ++i) f += feedbacks[i];
-    o->f_host[o->sample_idx] = (float)f;
+    // the device ranks FP32 values: keep huge penalties finite and ordered instead of letting them round to +-inf
+    const double fmax = (double)std::numeric_limits<float>::max();
+    o->f_host[o->sample_idx] = (float)(f > fmax ? fmax : (f < -fmax ? -fmax : f));
     if (++o->sample_idx % o->d.lambda == 0) {          // lmcma.cpp:199-204
         o->sample_idx = 0;
         return lmcma_b200_tell_all(o, o->f_host.data());
@@ -1318,7 +1432,7 @@ int lmcma_b200_attach_cost(lmcma_b200_opt* o, lmcma_b200_map* map, const lmcma_b
         for (int c = 0; c < 3; ++c) { e6[b * 6 + c] = ends[b].start[c]; e6[b * 6 + 3 + c] = ends[b].goal[c]; }
     if (!o->d_ends) DM(o->d_ends, (size_t)o->d.B * 6);
     CU(cudaMemcpy(o->d_ends, e6.data(), e6.size() * sizeof(float), cudaMemcpyHostToDevice));
-    o->cost_shape = pick_cost_shape(obj->waypoints, ends[0].start, ends[0].goal, map->dev.dims);
+    o->cost_shape = pick_cost_shape(obj->waypoints, ends[0].start, ends[0].goal, map->dev.dims, o->tune);
     if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
     return 0;
 }
@@ -1359,6 +1473,7 @@ int lmcma_b200_sync(lmcma_b200_opt* o) {
     ARG(o, "null handle");
     CU(cudaSetDevice(o->cfg.device));
     CU(cudaStreamSynchronize(o->stream));
+    { int lost = check_lost(o); if (lost) return lost; }
     if (o->graph_dbg) {
         long long h[64];
         cudaMemcpy(h, o->graph_dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1411,7 +1526,7 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
     }
     cudaError_t se = cudaStreamSynchronize(st);
     if (!rc && se != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "profile run: %s", cudaGetErrorString(se));
-    if (!rc && getenv("LMCMA_B200_UPDATE_DBG")) {   // debug: timeline of k_update
+    if (!rc && o->tune.update_dbg) {   // debug: timeline of k_update
         long long* dbg = nullptr;
         if (cudaMalloc(&dbg, 64 * sizeof(long long)) == cudaSuccess) {
             cudaMemset(dbg, 0, 64 * sizeof(long long));
@@ -1707,6 +1822,7 @@ int lmcma_b200_mg_rank(lmcma_b200_opt* o, const float* f_all_dev, float* payload
 
 int lmcma_b200_mg_update(lmcma_b200_opt* o, const float* payload_all_dev, int32_t world, void* stream) {
     ARG(o && payload_all_dev && world >= 1, "bad argument");
+    if (o->cfg.rng != LMCMA_B200_RNG_PHILOX) return fail(LMCMA_B200_ERR_STATE, "split-population mode needs the PHILOX rng");   // before anything is launched
     CU(cudaSetDevice(o->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : o->stream;
     const long long pf = o->d.ns + 4;
@@ -1717,7 +1833,6 @@ int lmcma_b200_mg_update(lmcma_b200_opt* o, const float* payload_all_dev, int32_
     int rc = launch_update(o, a, false, st);
     if (rc) return rc;
     o->x_cache_valid = false;
-    if (o->cfg.rng != LMCMA_B200_RNG_PHILOX) return fail(LMCMA_B200_ERR_STATE, "split-population mode needs the PHILOX rng");
     return launch_sample(o, st, true);
 }
 
@@ -1740,6 +1855,43 @@ int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out) {
     if (!smoothness_covariance(dims, waypoints, out)) return fail(LMCMA_B200_ERR_ARG, "singular finite-difference block");
     return 0;
 }
+
+int lmcma_b200_differentiation_matrix(int32_t num_time_steps, int32_t order, double dt, double* diff_matrix, int32_t row_len) {
+    ARG(diff_matrix && num_time_steps >= 1 && order >= 0 && order <= 3 && dt != 0.0, "bad argument");
+    ARG(row_len < 0 || row_len >= num_time_steps, "row_len shorter than the block");
+    differentiation_matrix(num_time_steps, order, dt, diff_matrix, row_len);
+    return 0;
+}
+int lmcma_b200_invert(const double* A, double* Ainv, int32_t n) {
+    ARG(A && Ainv && n >= 1 && A != Ainv, "bad argument");
+    if (!invert_dense(A, n, Ainv)) return fail(LMCMA_B200_ERR_ARG, "matrix is singular");
+    return 0;
+}
+int lmcma_b200_apply_cov_l(const double* L_colmajor, double* z, int32_t n) {
+    ARG(L_colmajor && z && n >= 1, "bad argument");
+    std::vector<double> out(n, 0.0);
+    for (int j = 0; j < n; ++j) {                       // column by column: out += z_j * L(:, j)
+        const double zj = z[j];
+        const double* col = L_colmajor + (size_t)j * n;
+        for (int i = 0; i < n; ++i) out[i] += col[i] * zj;
+    }
+    std::copy(out.begin(), out.end(), z);
+    return 0;
+}
+int lmcma_b200_myqsort(int32_t sz, double* arfitness_inout, int32_t* arindex_out) {
+    ARG(sz >= 0 && (sz == 0 || (arfitness_inout && arindex_out)), "bad argument");
+    stable_rank(sz, arfitness_inout, arindex_out);
+    return 0;
+}
+struct lmcma_b200_rng { HansenStream s; explicit lmcma_b200_rng(int64_t seed) : s(seed) {} };
+int lmcma_b200_rng_create(int64_t seed, lmcma_b200_rng** out) {
+    ARG(out, "null pointer");
+    *out = new lmcma_b200_rng(seed);
+    return 0;
+}
+int lmcma_b200_rng_destroy(lmcma_b200_rng* r) { delete r; return 0; }
+double lmcma_b200_rng_uniform(lmcma_b200_rng* r) { return r ? r->s.uniform() : 0.0; }
+double lmcma_b200_rng_gauss(lmcma_b200_rng* r) { return r ? r->s.gauss() : 0.0; }
 
 int lmcma_b200_cholesky(int32_t n, const double* Cm, double* L_out) {
     ARG(Cm && L_out && n >= 1, "bad argument");

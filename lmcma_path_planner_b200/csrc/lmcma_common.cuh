@@ -85,7 +85,14 @@ struct OptDev {
     double c1, cc, cs, target, K, M, mueff;
     double pc_coef;    // sqrt(cc (2 - cc) mueff), lmcma.cpp:328
     long long* dbg;    // optional 64-slot debug timeline (LMCMA_B200_DBG); null in normal runs
+    int* err;          // host-visible (mapped, page-locked) error word of the handle: a kernel of the overlapped generation
+                       // that gives up waiting for its concurrently running partner writes a code here and carries on
+                       // (never __trap: that would poison the whole CUDA context); the host checks it at every sync
 };
+
+// codes written to OptDev::err
+enum { LOST_UPDATE_WAITING_FOR_RANK = 2, LOST_SAMPLE_WAITING_FOR_UPDATE = 3 };
+constexpr long long LOST_TIMEOUT_NS = 2000000000ll;      // 2 s: far beyond any scheduling jitter of a co-resident partner
 
 struct MapDev {
     int dims, nx, ny, nz;
@@ -104,8 +111,10 @@ struct CostArgs {
     const float* X;            // candidates
     long long ld;              // row stride (floats)
     long long inst_rows;       // rows per instance (gridDim.x)
-    const float* ends;         // per instance: start[3], goal[3]   (stride 6 floats)
-    int ends_per_instance;     // 1: ends[b], 0: ends[0] for every instance
+    const float* ends;         // per instance: start[3], goal[3]   (stride 6 floats); used when ends_per_instance != 0
+    int ends_per_instance;     // 1: ends[b] (device array of the attached optimiser), 0: ends0 for every instance
+    float ends0[6];            // start[3], goal[3] BY VALUE for the stand-alone evaluate calls: no device buffer shared
+                               // between callers / streams (two queries evaluated on one map from two streams cannot race)
     float* f;                  // outputs, indexed [b * f_stride + f_offset + row]
     long long f_stride;
     int f_offset;
@@ -116,7 +125,7 @@ struct CostArgs {
     int cb;                    // capacity of the per-block record stage (32-sample blocks), set by the launcher
 };
 
-struct CostShape { int tpt = 128, cb = 256; };   // launch shape of k_cost: threads per trajectory, block-record capacity
+struct CostShape { int tpt = 128, cb = 256, minb = 7; };   // launch shape of k_cost: threads per trajectory, block-record capacity, CTAs per SM it was compiled for
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -199,6 +208,13 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+
+// overlapped generation: the partner kernel did not show up in time (branches of the graph were serialised: profiler,
+// sanitizer, SMs held by another process).  Record it for the host and let the caller continue without waiting.
+__device__ __forceinline__ void report_lost(int* err, int code) {
+    if (err) { *reinterpret_cast<volatile int*>(err) = code; __threadfence_system(); }
+}
+__device__ __forceinline__ bool already_lost(const int* err) { return err && *reinterpret_cast<const volatile int*>(err) != 0; }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

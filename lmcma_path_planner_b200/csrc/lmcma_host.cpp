@@ -76,4 +76,62 @@ bool cholesky_lower(const double* C, int n, double* L) {
     return true;
 }
 
+bool differentiation_matrix(int steps, int order, double dt, double* out, int row_len) {
+    if (order < 0 || order > 3 || steps < 1) return false;
+    if (row_len < 0) row_len = steps;
+    // centred finite-difference rules, 7 taps (lmcma.cpp:759-764)
+    static const double rules[4][7] = {
+        {0, 0, 0, 1, 0, 0, 0},
+        {0, 0, -1, 1, 0, 0, 0},
+        {0, -1 / 12.0, 16 / 12.0, -30 / 12.0, 16 / 12.0, -1 / 12.0, 0},
+        {0, 1 / 12.0, -17 / 12.0, 46 / 12.0, -46 / 12.0, 17 / 12.0, -1 / 12.0}};
+    const double mult = 1.0 / std::pow(dt, order);
+    for (int i = 0; i < steps; ++i) {
+        double* row = out + static_cast<size_t>(i) * row_len;
+        std::fill(row, row + steps, 0.0);
+        for (int j = -3; j <= 3; ++j) {
+            const int c = i + j;
+            if (c >= 0 && c < steps) row[c] += mult * rules[order][j + 3];
+        }
+    }
+    return true;
+}
+
+bool invert_dense(const double* A, int n, double* Ainv) {
+    std::vector<double> a(A, A + static_cast<size_t>(n) * n);
+    std::fill(Ainv, Ainv + static_cast<size_t>(n) * n, 0.0);
+    for (int i = 0; i < n; ++i) Ainv[static_cast<size_t>(i) * n + i] = 1.0;
+    for (int col = 0; col < n; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < n; ++r)
+            if (std::fabs(a[static_cast<size_t>(r) * n + col]) > std::fabs(a[static_cast<size_t>(piv) * n + col])) piv = r;
+        const double p = a[static_cast<size_t>(piv) * n + col];
+        if (p == 0.0) return false;
+        if (piv != col)
+            for (int j = 0; j < n; ++j) {
+                std::swap(a[static_cast<size_t>(col) * n + j], a[static_cast<size_t>(piv) * n + j]);
+                std::swap(Ainv[static_cast<size_t>(col) * n + j], Ainv[static_cast<size_t>(piv) * n + j]);
+            }
+        for (int j = 0; j < n; ++j) { a[static_cast<size_t>(col) * n + j] /= p; Ainv[static_cast<size_t>(col) * n + j] /= p; }
+        for (int r = 0; r < n; ++r) {
+            const double f = a[static_cast<size_t>(r) * n + col];
+            if (r == col || f == 0.0) continue;
+            for (int j = 0; j < n; ++j) {
+                a[static_cast<size_t>(r) * n + j] -= f * a[static_cast<size_t>(col) * n + j];
+                Ainv[static_cast<size_t>(r) * n + j] -= f * Ainv[static_cast<size_t>(col) * n + j];
+            }
+        }
+    }
+    return true;
+}
+
+void stable_rank(int count, double* values_inout, int* ids_out) {
+    std::vector<int> ids(count);
+    for (int i = 0; i < count; ++i) ids[i] = i;
+    std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) { return values_inout[x] < values_inout[y]; });
+    std::vector<double> sorted(count);
+    for (int i = 0; i < count; ++i) sorted[i] = values_inout[ids[i]];
+    for (int i = 0; i < count; ++i) { values_inout[i] = sorted[i]; ids_out[i] = ids[i]; }
+}
+
 }  // namespace lmcma

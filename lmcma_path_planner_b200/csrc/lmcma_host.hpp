@@ -67,4 +67,17 @@ bool smoothness_covariance(int dims, int waypoints, double* out);
 // Eigen's LLT): L row-major, zero above the diagonal.  Returns false if C is not positive definite.
 bool cholesky_lower(const double* C, int n, double* L);
 
+// differentiationMatrix() of the reference (lmcma.cpp:812-834): centred 7-tap finite-difference operator of the given
+// order (0 position, 1 velocity, 2 acceleration, 3 jerk; rules lmcma.cpp:759-764) for `steps` time steps, truncated at
+// the ends, written into the top-left steps x steps block of a row-major matrix with row stride `row_len`.
+bool differentiation_matrix(int steps, int order, double dt, double* out, int row_len);
+
+// invert() of the reference (lmcma.cpp:836-842, Eigen's dense inverse there): Gauss-Jordan with partial pivoting, FP64.
+// Returns false for a singular matrix.  A and Ainv may not alias.
+bool invert_dense(const double* A, int n, double* Ainv);
+
+// myqsort() of the reference (lmcma.cpp:93-104): ascending, ties keep the lower id (glibc's qsort is a stable merge sort
+// for these sizes), the sorted values are written back over the input.
+void stable_rank(int count, double* values_inout, int* ids_out);
+
 }  // namespace lmcma

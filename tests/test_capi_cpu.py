@@ -171,3 +171,66 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == {"value": j["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["gpu_launches"] == 0
+
+
+def test_reference_free_functions_match_the_compiled_reference():
+    """differentiationMatrix / invert / cholesky / applyCovL / myqsort / random_* behind the reference's names
+    (include/lmcma.hpp -> lmcma_b200_* host entry points) against golden outputs of the compiled reference
+    (tests/golden/free_functions_reference.json; invert / cholesky / applyCovL there ran on the Eigen stand-in)."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "free_functions_reference.json")))
+    lib = K.lib()
+    for case in g["diff"]:
+        want = np.array(case["out"])
+        got = np.full(want.shape, 7.0)
+        assert lib.lmcma_b200_differentiation_matrix(case["steps"], case["order"], case["dt"], K.dptr(got), case["row_len"]) == 0
+        assert np.array_equal(got, want), case["order"]                                   # bit-exact, untouched cells included
+    A = np.array(g["invert"]["A"])
+    Ai = np.zeros_like(A)
+    assert lib.lmcma_b200_invert(K.dptr(A), K.dptr(Ai), 5) == 0
+    assert np.allclose(Ai, np.array(g["invert"]["Ainv_shim_pinned"]), rtol=1e-12, atol=1e-14)
+    assert np.allclose(Ai @ A, np.eye(5), atol=1e-12)
+    assert lib.lmcma_b200_invert(K.dptr(np.zeros((3, 3))), K.dptr(np.zeros((3, 3))), 3) == K.ERR_ARG      # singular
+    Cm = np.array(g["cholesky"]["C"])
+    Lr = np.zeros_like(Cm)
+    assert lib.lmcma_b200_cholesky(5, K.dptr(Cm), K.dptr(Lr)) == 0
+    Lcol = np.ascontiguousarray(Lr.T)                                                      # the reference's layout: L[m*N+n] = L(n,m)
+    assert np.allclose(Lcol, np.array(g["cholesky"]["L_shim_pinned"]), rtol=1e-12, atol=1e-14)
+    z = np.array(g["cholesky"]["z"])
+    assert lib.lmcma_b200_apply_cov_l(K.dptr(Lcol), K.dptr(z), 5) == 0
+    assert np.allclose(z, np.array(g["cholesky"]["Lz_shim_pinned"]), rtol=1e-12, atol=1e-14)
+
+
+def test_myqsort_and_rng_stream_objects(golden):
+    ties = np.array(golden["qsort_ties"]["in"], np.float64)
+    ids = np.zeros(len(ties), np.int32)
+    assert K.lib().lmcma_b200_myqsort(len(ties), K.dptr(ties), K.iptr(ids)) == 0
+    assert ids.tolist() == golden["qsort_ties"]["ids"] and ties.tolist() == golden["qsort_ties"]["sorted"]
+    h = C.c_void_p()
+    assert K.lib().lmcma_b200_rng_create(1, C.byref(h)) == 0
+    u = [K.lib().lmcma_b200_rng_uniform(h) for _ in range(4)]
+    assert u == golden["rng"]["1"]["uniform"][:4]
+    K.lib().lmcma_b200_rng_destroy(h)
+    assert K.lib().lmcma_b200_rng_create(1, C.byref(h)) == 0
+    gs = [K.lib().lmcma_b200_rng_gauss(h) for _ in range(6)]
+    assert gs == golden["rng"]["1"]["gauss"][:6]
+    K.lib().lmcma_b200_rng_destroy(h)
+
+
+def test_the_reference_s_own_demo_compiles_unchanged_against_the_drop_in_header(tmp_path):
+    """lmcma_path_planner/src/example_lmcma.cpp (test_lmcma + test_lmcma_using_cov: LMCMA,
+    covariance(), the ask/tell loop) builds UNCHANGED with include/ on the include path instead of the reference's src/
+    and links against liblmcma_b200.so.  The source is fed through stdin so that `#include "lmcma.hpp"` resolves to
+    include/lmcma.hpp; <eigen3/Eigen/Dense>, which the demo includes but never uses, comes from the test stand-in."""
+    import subprocess
+    src = "/root/reference/lmcma_path_planner/src/example_lmcma.cpp"
+    if not os.path.exists(src):
+        pytest.skip("reference tree not present on this box (the prebuilt oracle/_ref/ref_example_lmcma is run by the GPU tests)")
+    exe = tmp_path / "ref_example"
+    with open(src) as fh:
+        r = subprocess.run(["g++", "-std=c++11", "-O2", "-w", "-I" + os.path.join(ROOT, "include"),
+                            "-I" + os.path.join(ROOT, "oracle", "eigen_shim"), "-x", "c++", "-", "-o", str(exe),
+                            "-L" + os.path.join(ROOT, "lmcma_path_planner_b200"), "-llmcma_b200",
+                            "-Wl,-rpath," + os.path.join(ROOT, "lmcma_path_planner_b200")], stdin=fh, capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert exe.exists()

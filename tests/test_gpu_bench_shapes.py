@@ -113,10 +113,14 @@ def test_rank_beyond_one_fitness_tile(po, lam):
         assert np.array_equal(dev.get("rank")[0], inv), g
         so = ora.doubles()["sigma"]
         assert abs(dev.get("sigma")[0] - so) <= 1e-12 * so, g       # S = #{prev_j < cur_i} over 2*lambda values
-    f = fitness(); f[7] = np.nan; f[lam - 3] = np.nan                # NaN ranks last, lower id first
+    f = fitness(); f[7] = np.nan; f[lam - 3] = np.nan                # NaN ranks as +inf: last, ties by id
     dev.inject_z(z)
     dev.tell_all(f)
-    assert dev.get("arindex")[0][-2:].tolist() == [7, lam - 3]
+    _, want_ids = po.rank(np.where(np.isnan(f), np.inf, f).astype(np.float64))
+    got = dev.get("arindex")[0]
+    assert np.array_equal(got, want_ids)
+    tail = got[-int(np.sum(np.isinf(f) | np.isnan(f))):].tolist()      # the +inf and the two NaN candidates, in id order
+    assert 7 in tail and lam - 3 in tail and tail == sorted(tail)
 
 
 def test_split_population_at_the_c4_shape(po):

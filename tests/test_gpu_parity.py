@@ -623,8 +623,9 @@ def test_cost_evaluate_page_locked_buffers_match_staged(po, golden_maps, monkeyp
     obj, ends = _objective(W, L.LONGSAFE, 1e4), _endpoints(start, goal)
     for zc in ("1", "0"):
         monkeypatch.setenv("LMCMA_B200_ZEROCOPY", zc)
+        cm2 = L.CostMap(dist, "f32")                              # the knob is read when the map handle is created
         fp[:] = 0; ncp[:] = 0; nsp[:] = 0
-        K.check(K.lib().lmcma_b200_cost_evaluate(cm._h, C.byref(obj), C.byref(ends), K.fptr(Xp), 300, K.fptr(fp), K.iptr(ncp), K.iptr(nsp)))
+        K.check(K.lib().lmcma_b200_cost_evaluate(cm2._h, C.byref(obj), C.byref(ends), K.fptr(Xp), 300, K.fptr(fp), K.iptr(ncp), K.iptr(nsp)))
         assert np.array_equal(fp, ref["f"]) and np.array_equal(ncp, ref["ncoll"]) and np.array_equal(nsp, ref["nsamp"]), zc
     orc = po.CostProblem(dist, start, goal, W).evaluate(X)
     assert np.array_equal(ref["ncoll"], orc["ncoll"]) and rel_err(ref["f"], orc["f"]) < COST_RTOL
@@ -675,3 +676,34 @@ def test_cost_six_ctas_per_sm_build_meets_the_same_bar(po, monkeypatch):
     got = L.CostMap(d3, "f32").evaluate(X3, s3, g3, W3)
     assert np.array_equal(got["ncoll"], ref["ncoll"]) and np.array_equal(got["nsamp"], ref["nsamp"])
     assert rel_err(got["f"], ref["f"]) < COST_RTOL
+
+
+def test_cpp_facade_demo_with_the_covariance_prior(tmp_path):
+    """test_lmcma_using_cov (example_lmcma.cpp:78-127) against the facade: covariance(2, 1) through the reference's free
+    function name is the identity, so the run draws the same stream as the plain demo and converges to the same basin."""
+    r = _example(["democov", "1"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    tail = r.stdout.strip().split("is:")[1].split()
+    x, y = (float(v) for v in tail[0].split(","))
+    assert abs(x - 3.99966) < 2e-2 and abs(y - 3.99966) < 2e-2
+    assert "cov=[1 0; 0 1]" in r.stdout and "counteval=1000" in r.stdout
+    assert len(open(tmp_path / "path_to_max_using_cov.csv").read().strip().splitlines()) == 1001
+
+
+def test_the_reference_s_own_demo_binary_runs_on_the_b200_library(tmp_path):
+    """oracle/_ref/ref_example_lmcma is the reference's example_lmcma.cpp compiled UNCHANGED against include/lmcma.hpp
+    (oracle/Makefile ref_example; tests/test_capi_cpu.py repeats the compile where the reference tree exists): both of its
+    demos (plain and with the covariance prior) must run on the device library and end in the global basin (4, 4)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_example_lmcma")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_example_lmcma was not built (no reference tree in the authoring container)")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    pts = [ln.split("is:")[1] for ln in r.stdout.splitlines() if "optimum point is:" in ln]
+    assert len(pts) == 2, r.stdout
+    for p in pts:
+        x, y = (float(v) for v in p.split(","))
+        assert abs(x - 4.0) < 5e-2 and abs(y - 4.0) < 5e-2, r.stdout
+    assert (tmp_path / "path_to_min.csv").exists() and (tmp_path / "path_to_max_using_cov.csv").exists()
