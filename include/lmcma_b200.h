@@ -177,6 +177,14 @@ int lmcma_b200_tell_one(lmcma_b200_opt* opt, const double* feedbacks, int32_t nu
 int lmcma_b200_ask_all(lmcma_b200_opt* opt, float* X_host);
 int lmcma_b200_tell_all(lmcma_b200_opt* opt, const float* f_host);
 
+/* Zero-copy ask for the host-buffer protocol.  *X_host_view receives a READ-ONLY pointer to the handle's page-locked
+ * mirror of the current population (batch x pop_count rows, row stride *ld_out floats >= n; valid until the next
+ * tell / run / destroy).  Once this has been called, the sampler of every following tell_all writes the candidates into
+ * the mirror itself while it runs (posted PCIe writes overlapping the sampling), so this call only waits for the
+ * stream; lmcma_b200_cost_evaluate recognises a pointer into the mirror and evaluates the device copy it mirrors (no
+ * H2D of the candidates).  Same contents as lmcma_b200_ask_all. */
+int lmcma_b200_ask_all_view(lmcma_b200_opt* opt, const float** X_host_view, int64_t* ld_out);
+
 /* deviates for the NEXT sample(): batch x pop_count x n FP32 (rng == INJECT).  The first call after
  * create builds the first population immediately; later calls are consumed by the next tell. */
 int lmcma_b200_inject_z(lmcma_b200_opt* opt, const float* Z_host);

@@ -64,12 +64,18 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
 
     griddep_launch_dependents();          // k_rank may become resident as this grid drains; it waits for completion
     const int row = blockIdx.x, b = blockIdx.y;
+#define COST_STAMP(k) do { if (TRACE && a.dbg && (threadIdx.x & 31) == 0) { const long long t__ = gtime(); if ((k) == 0 || (k) == 1 || (k) == 2) { if (threadIdx.x == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = t__; } else atomicMax(reinterpret_cast<unsigned long long*>(a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)), (unsigned long long)t__); } } while (0)
+    COST_STAMP(0);
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const float* x = a.X + ((size_t)b * a.inst_rows + row) * a.ld;
-    __shared__ float en[6];                                      // start[3], goal[3] of this instance's query
+    // xs holds the whole poly-line per dimension: xs[c * (W + 2) + i], i = 0 start, 1..W the candidate's waypoints, W + 1 goal
+    const int WS = W + 2;
     if (tid == 0) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) en[c] = a.ends_per_instance ? a.ends[(size_t)b * 6 + c] : a.ends0[c];   // constant indices: ends0 is read from the parameter bank
+        for (int c = 0; c < DIMS; ++c) {                         // constant indices: ends0 is read from the parameter bank
+            xs[c * WS] = a.ends_per_instance ? a.ends[(size_t)b * 6 + c] : a.ends0[c];
+            xs[c * WS + W + 1] = a.ends_per_instance ? a.ends[(size_t)b * 6 + 3 + c] : a.ends0[3 + c];
+        }
     }
     if (STORAGE == 1) for (int i = tid; i < 256; i += nthr) lut[i] = mp.lut[i];
     for (int lb = tid; lb < a.cb; lb += nthr) blkrec[lb].x = 0u;    // first round of block records (phase 2a), zeroed ahead of the barrier below
@@ -77,13 +83,21 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
     // page-locked caller buffer to the kernel directly, and the row then crosses PCIe while other CTAs compute)
     {
         const int nflt = DIMS * W;
-        if ((reinterpret_cast<size_t>(x) & 15) == 0 && (nflt & 3) == 0) {
-            for (int i = tid; i < (nflt >> 2); i += nthr) reinterpret_cast<float4*>(xs)[i] = reinterpret_cast<const float4*>(x)[i];
+        if ((reinterpret_cast<size_t>(x) & 15) == 0 && (W & 3) == 0) {   // a float4 never straddles two dimensions
+            for (int i = tid; i < (nflt >> 2); i += nthr) {
+                const float4 v = reinterpret_cast<const float4*>(x)[i];
+                const int e = i << 2, c = (e >= W ? 1 : 0) + (DIMS == 3 && e >= 2 * W ? 1 : 0);
+                float* dst = xs + c * WS + 1 + (e - c * W);
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            }
         } else {
-            for (int i = tid; i < nflt; i += nthr) xs[i] = x[i];
+#pragma unroll
+            for (int c = 0; c < DIMS; ++c)
+                for (int i = tid; i < W; i += nthr) xs[c * WS + 1 + i] = x[c * W + i];
         }
     }
     __syncthreads();                                             // xs (and the lut)
+    COST_STAMP(1);
 
     const unsigned nxm1 = (unsigned)(mp.nx - 1), nym1 = (unsigned)(mp.ny - 1), nzm1 = (unsigned)(mp.nz - 1);
     const float fx1 = (float)(mp.nx - 1), fy1 = (float)(mp.ny - 1), fz1 = (float)(mp.nz - 1);
@@ -123,8 +137,8 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         A[2] = 0.f; D[2] = 0.f;
 #pragma unroll
         for (int c = 0; c < DIMS; ++c) {
-            A[c] = (s == 0) ? en[c] : xs[c * W + s - 1];
-            const float Bc = (s == W) ? en[3 + c] : xs[c * W + s];
+            A[c] = xs[c * WS + s];
+            const float Bc = xs[c * WS + s + 1];
             const float hi_c = c == 0 ? fx1 : (c == 1 ? fy1 : fz1);
             safe = safe && (A[c] >= 0.f) && (A[c] <= hi_c) && (Bc >= 0.f) && (Bc <= hi_c);
             D[c] = __fsub_rn(Bc, A[c]);
@@ -178,6 +192,7 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         if ((e >> 5) < nblk0) atomicOr(&blkrec[e >> 5].x, 1u << (e & 31));
     }
     __syncthreads();
+    COST_STAMP(2);
 
     // ---- phase 2 ----
     const int nblk = (int)((unsigned)(T + 31) >> 5);
@@ -266,6 +281,7 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
     if (all_safe) { accumulate(p0, w0, o0, false); accumulate(p1, w1, o1, false); accumulate(p2, w2, o2, false); }
     else { accumulate(p0, w0, o0, true); accumulate(p1, w1, o1, true); accumulate(p2, w2, o2, true); }
 
+    COST_STAMP(3);                                               // (max over warps) sample loop done
     // ---- 2c: the end samples (k = 0 and k = K) of my segments, by the same arithmetic as the sample loop ----
     float corr_clr = 0.f; int corr_coll = 0;
     for (int sg = s_begin; sg < s_end; ++sg) {
@@ -285,6 +301,7 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         corr_coll += (sg != last && gK < 0.f) ? 1 : 0;
     }
 
+    COST_STAMP(4);                                               // (max over warps) end samples done
     // ---- phase 3: block reduction ----
     len_acc = warp_sum(len_acc);
     clr_acc = warp_sum(clr_acc);
@@ -300,6 +317,8 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         if (a.ncoll) a.ncoll[(size_t)b * a.inst_rows + row] = NC;
         if (a.nsamp) a.nsamp[(size_t)b * a.inst_rows + row] = T;
     }
+    COST_STAMP(5);
+#undef COST_STAMP
 }
 
 }  // namespace lmcma

@@ -20,6 +20,61 @@ constexpr int TELL_FTILE = 4096;       // fitness values staged per shared-memor
 constexpr int TELL_MAX_ROWS = 256;     // rows per slice upper bound (rows_per = max(32, ceil(pop/256)))
 
 // ------------------------------------------------------------------------------------------------
+// Large unsplit populations (lambda > TELL_FTILE): counting costs lambda^2 compares (1.4 ms at lambda = 65536, half of
+// the generation).  k_rank_tiles sorts every TELL_FTILE-candidate tile of the fitness by (value, id) — the reference's
+// order: ascending, ties keep the lower id, -0 == +0, NaN as +inf — and k_rank then takes a candidate's rank as the sum
+// over the tiles of a binary search: tiles in front of its own count "<=", tiles behind it "<", its own tile contributes
+// its position in the sorted tile.  Exactly the rank the counting pass produces; the pair count of the step-size rule
+// becomes a binary search in the previous generation's sorted fitness.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long rank_key(float f, unsigned id) {
+    f = canon_fitness(f) + 0.0f;                                  // NaN -> +inf, -0 -> +0
+    unsigned u = __float_as_uint(f);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);              // order-preserving map of the float onto unsigned
+    return ((unsigned long long)u << 32) | id;
+}
+// grid = (tiles, B), 1024 threads: bitonic sort of one tile in shared memory (32 KB of 64-bit keys)
+__global__ void __launch_bounds__(1024) k_rank_tiles(OptDev o, const float* __restrict__ f_all) {
+    __shared__ unsigned long long key[TELL_FTILE];
+    griddep_wait();                                               // the fitness is the predecessor's output
+    griddep_launch_dependents();
+    const int b = blockIdx.y, base = blockIdx.x * TELL_FTILE, cnt = min(TELL_FTILE, o.lambda - base);
+    const float* cur = f_all + (size_t)b * o.lambda + base;
+    for (int j = threadIdx.x; j < TELL_FTILE; j += blockDim.x) key[j] = j < cnt ? rank_key(cur[j], (unsigned)j) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= TELL_FTILE; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < TELL_FTILE / 2; t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;    // pair (lo, hi = lo + j)
+                const bool up = (lo & k) == 0;
+                const unsigned long long a = key[lo], c = key[hi];
+                if ((a > c) == up) { key[lo] = c; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    float* ts = o.tile_sorted + (size_t)b * o.lambda + base;
+    int* tp = o.tile_pos + (size_t)b * o.lambda + base;
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        const unsigned long long kk = key[j];
+        unsigned u = (unsigned)(kk >> 32);
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        ts[j] = __uint_as_float(u);
+        tp[(unsigned)kk] = j;
+    }
+}
+// number of entries of the ascending array a[0, cnt) that are < v (STRICT) or <= v
+template <bool STRICT>
+__device__ __forceinline__ int count_below(const float* a, int cnt, float v) {
+    int lo = 0, hi = cnt;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float x = a[mid];
+        if (STRICT ? (x < v) : (x <= v)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
 // ranks + partial sums of one slice
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __restrict__ f_all, int b, int rs,
@@ -40,8 +95,10 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
 
 #define RNK_STAMP(k) do { if (o.dbg && threadIdx.x == 0 && blockIdx.x == 0 && b == 0) o.dbg[16 + (k)] = gtime(); } while (0)
     RNK_STAMP(0);
+    const bool sorted = o.tile_sorted != nullptr;                    // sorted-tile mode (k_rank_tiles ran just before this grid)
     const float* cur = f_all + (size_t)b * lambda;
-    const float* prev = o.prev_fit + (size_t)b * lambda;
+    const float* cur_stage = sorted ? o.tile_sorted + (size_t)b * lambda : cur;
+    const float* prev = (sorted ? o.prev_sorted : o.prev_fit) + (size_t)b * lambda;
     if (tid == 0) sh_S = 0ull;
 
     // threads per row: a power of two <= 32 so that a row's partial counts fold with warp shuffles
@@ -63,11 +120,20 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
             __syncthreads();                                         // previous tile fully consumed
             for (int j = tid; j < cnt4; j += nthr) {
                 const bool in = j < cnt;
-                cur_s[j] = in ? canon_fitness(cur[base + j]) : __int_as_float(0x7f800000);
+                cur_s[j] = in ? canon_fitness(cur_stage[base + j]) : __int_as_float(0x7f800000);
                 prev_s[j] = in ? prev[base + j] : __int_as_float(0x7f800000);
             }
             __syncthreads();
-            if (valid) {
+            if (valid && sorted) {
+                // both staged tiles are ascending: binary searches, the tiles shared out over the row's tpr threads
+                const int tile = base / TELL_FTILE;
+                if ((tile % tpr) == sub) {
+                    const int own = i / TELL_FTILE;
+                    c_lt += tile < own ? count_below<false>(cur_s, cnt, ki)
+                                       : (tile > own ? count_below<true>(cur_s, cnt, ki) : o.tile_pos[(size_t)b * lambda + i]);
+                    p_lt += (unsigned long long)count_below<true>(prev_s, cnt, ki);
+                }
+            } else if (valid) {
                 int pl = 0;
                 for (int j = sub * 4; j < cnt4; j += tpr * 4) {
                     const float4 kj = *reinterpret_cast<const float4*>(cur_s + j);

@@ -47,7 +47,7 @@ __device__ __forceinline__ float reduce_scatter8(const float (&v)[SAMPLE_G], int
 // -FLT_MAX / +FLT_MAX, the padding lanes are forced to 0.  Writes the candidate (FP32) and its offset from the mean
 // d = x - xmean, formed in FP64 and rounded once (see OptDev::D).
 __device__ __forceinline__ void sample_finish(const OptDev& o, const double* __restrict__ xm, double sigma, float4 az, int q,
-                                              float* __restrict__ xrow, float* __restrict__ drow) {
+                                              float* __restrict__ xrow, float* __restrict__ drow, float* __restrict__ hrow = nullptr) {
     const double2 m01 = reinterpret_cast<const double2*>(xm)[2 * q];
     const double2 m23 = reinterpret_cast<const double2*>(xm)[2 * q + 1];
     float4 lo4 = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f), hi4 = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f);
@@ -69,6 +69,7 @@ __device__ __forceinline__ void sample_finish(const OptDev& o, const double* __r
     }
     reinterpret_cast<float4*>(xrow)[q] = make_float4(xx[0], xx[1], xx[2], xx[3]);
     reinterpret_cast<float4*>(drow)[q] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+    if (hrow) __stcs(reinterpret_cast<float4*>(hrow) + q, make_float4(xx[0], xx[1], xx[2], xx[3]));   // host mirror (OptDev::Xh)
 }
 
 constexpr int SAMPLE_MAX_STAGES = 8;
@@ -237,10 +238,11 @@ __global__ void __launch_bounds__(MAXT) k_sample(OptDev o, int kc /* pairs per s
         if (row >= o.pop_count) continue;
         float* xrow = o.X + ((size_t)b * o.pop_count + row) * ns;
         float* drow = o.D + ((size_t)b * o.pop_count + row) * ns;
+        float* hrow = o.Xh ? o.Xh + ((size_t)b * o.pop_count + row) * ns : nullptr;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int q = lane + 32 * i;
-            if (q < nq) sample_finish(o, xm, sc.sigma, az[r][i], q, xrow, drow);
+            if (q < nq) sample_finish(o, xm, sc.sigma, az[r][i], q, xrow, drow, hrow);
         }
     }
 }
@@ -509,12 +511,210 @@ __global__ void __launch_bounds__(MAXT) k_sample_wide(OptDev o, int kc, int nsta
         const int row = row0 + r;
         if (qon && row < o.pop_count) {
             const size_t roff2 = ((size_t)b * o.pop_count + row) * ns;
-            sample_finish(o, o.xmean + (size_t)b * ns, sigma, az[r], q, o.X + roff2, o.D + roff2);
+            sample_finish(o, o.xmean + (size_t)b * ns, sigma, az[r], q, o.X + roff2, o.D + roff2, o.Xh ? o.Xh + roff2 : nullptr);
         }
     }
     if (progressive) griddep_wait();                            // stream order: this grid ends after k_update has
     SMP_STAMP(6);
 #undef SMP_STAMP
+}
+
+}  // namespace lmcma
+
+namespace lmcma {
+
+// ------------------------------------------------------------------------------------------------
+// k_sample_rows — the same computation laid out for MANY rows (batched queries: B x lambda in the hundreds of thousands;
+// one very large population), where the two kernels above spend more issue slots on cross-lane reductions than on
+// multiply-adds (one 32-lane reduction per dot product: ~2x the FMA work of the wide kernel).
+//
+//   * a LANE owns RL offspring rows, a WARP owns a slice of QW float4 columns: a dot product v_j . z is accumulated by
+//     the lane itself over its warp's slice — no shuffle at all — and the NW partial sums per (row, pair) are added once
+//     per chunk through shared memory;
+//   * every element of a direction pair is read by a warp as ONE broadcast shared-memory load (all lanes, same
+//     address) that feeds RL rows x 4 elements: 2 * RL packed multiply-adds (fma.rn.f32x2) per 16-byte load, so the
+//     inner loops are bound by the FP32 pipe, not by shared-memory bandwidth or issue slots;
+//   * two passes over the pairs instead of one interleaved pass: all dots are against the ORIGINAL z (lmcma.cpp:441-443),
+//     so pass 1 forms every coefficient c_j = Nj_j (v_j . z) M^(L-1-j) and pass 2 the closed form of the recurrence
+//     Az <- M Az + d_j pc_j (lmcma.cpp:444-445):  Az = M^L z + sum_j c_j pc_j  (same value in exact arithmetic; z is dead
+//     after pass 1, Az is born there: half the registers of the interleaved form);
+//   * the finished tile is transposed through shared memory so that x = xmean + sigma Az (FP64), the clamp and the two
+//     (three with the host mirror) row stores are coalesced.
+// grid = (ceil(pop_count / (32 RL)), B), block = 32 NW; all pairs resident in shared memory when they fit (C2 / C3 / C5
+// shapes: 128 KB), otherwise streamed twice through a ring of stages.
+// ------------------------------------------------------------------------------------------------
+template <int QW, int RL>
+__global__ void __launch_bounds__(512, 1) k_sample_rows(OptDev o, int kc, int nstages, int region_floats /* >= stages, >= transposition tile */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, nthr = blockDim.x;
+    const int ns = o.ns, nq = ns >> 2, m = o.m;
+    constexpr int ROWS = 32 * RL;
+    const size_t stage_floats = (size_t)kc * 2 * ns;
+    float* stage_base = reinterpret_cast<float*>(smem_raw);                        // nstages x kc x {v, pc} x ns
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_base + (size_t)region_floats);
+    float* scale_s = reinterpret_cast<float*>(bars + SAMPLE_MAX_STAGES);           // m (padded to kc): Nj_j M^(L-1-j)
+    float* coef_s = scale_s + ((m + kc + 3) & ~3);                                  // (m padded) x ROWS: c_j per row
+    float* part_s = coef_s + (size_t)((m + kc - 1) / kc) * kc * ROWS;              // nwarps x kc x ROWS partial dots
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < nstages; ++s2) mbar_init(&bars[s2], 1);
+        fence_barrier_init();
+    }
+    griddep_wait();                           // launched as a programmatic dependent of k_update: every input is its output
+    const Scalars sc = o.sc[b];
+    const int live = sc.live;
+    const int nchunks = (live + kc - 1) / kc;
+    const float* vps = o.VPs + (size_t)b * m * 2 * ns;
+    auto issue = [&](int chunk) {             // thread 0: ONE bulk async copy per chunk of consecutive pairs
+        const int st = chunk % nstages;
+        const int k0 = chunk * kc, cnt = min(kc, live - k0);
+        const unsigned bytes = (unsigned)(cnt * 2 * ns * sizeof(float));
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage_base + st * stage_floats, vps + (size_t)k0 * 2 * ns, bytes, &bars[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int c = 0; c < nchunks && c < nstages; ++c) issue(c);
+    // Nj_j M^(L-1-j): the powers by repeated multiplication from the newest pair down (one warp, fixed order)
+    const float Mf = (float)o.M;
+    if (warp == 0) {
+        const int lpad = nchunks * kc;
+        for (int j0 = 0; j0 < lpad; j0 += 32) {
+            const int j = j0 + lane;
+            float pw = 1.0f;
+            for (int e = 0; e < live - 1 - j; ++e) pw *= Mf;
+            if (j < lpad) scale_s[j] = j < live ? o.Njs[(size_t)b * m + j] * pw : 0.f;
+        }
+    }
+    float mL = 1.0f;
+    for (int e = 0; e < live; ++e) mL *= Mf;
+
+    // ---- z of my rows, my warp's column slice ----
+    const int qper = (nq + nwarps - 1) / nwarps;                    // <= QW
+    const int q0 = warp * qper;
+    const int row0 = blockIdx.x * ROWS;
+    float4 acc[RL][QW];                                             // z in pass 1, Az in pass 2
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+        const int row = row0 + r * 32 + lane;
+        const bool rv = row < o.pop_count;
+        const size_t roff = ((size_t)b * o.pop_count + (rv ? row : 0)) * ns;
+#pragma unroll
+        for (int i = 0; i < QW; ++i) {
+            const int q = q0 + i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rv && i < qper && q < nq) {
+                if (o.Zc) {
+                    v = reinterpret_cast<const float4*>(o.Zc + roff)[q];
+                } else if (o.rng_mode == 0) {
+                    v = philox_normal4((unsigned)q, (unsigned)(o.pop_offset + row), (unsigned)sc.itr, (unsigned)b, o.seed);
+                    const int e = q * 4;
+                    if (e + 1 >= o.n) v.y = 0.f;
+                    if (e + 2 >= o.n) v.z = 0.f;
+                    if (e + 3 >= o.n) v.w = 0.f;
+                    if (o.Z) reinterpret_cast<float4*>(o.Z + roff)[q] = v;
+                } else {
+                    v = reinterpret_cast<const float4*>(o.Z + roff)[q];
+                }
+            }
+            acc[r][i] = v;
+        }
+    }
+    __syncthreads();                                                // scale_s
+
+    // ---- pass 1: c_j for every live pair ----
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c % nstages;
+        mbar_wait(&bars[st], (unsigned)((c / nstages) & 1));
+        const float* sb = stage_base + st * stage_floats;
+        const int k0 = c * kc, cnt = min(kc, live - k0);
+        for (int g = 0; g < cnt; ++g) {
+            const float4* vrow = reinterpret_cast<const float4*>(sb + (size_t)(2 * g) * ns) + q0;
+            float2 d[RL];
+#pragma unroll
+            for (int r = 0; r < RL; ++r) d[r] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < QW; ++i) {
+                if (i < qper && q0 + i < nq) {
+                    const float4 v = vrow[i];                       // broadcast: every lane reads the same 16 bytes
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) {
+                        d[r] = ffma2(lo2(v), lo2(acc[r][i]), d[r]);
+                        d[r] = ffma2(hi2(v), hi2(acc[r][i]), d[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RL; ++r) part_s[((size_t)warp * kc + g) * ROWS + r * 32 + lane] = d[r].x + d[r].y;
+        }
+        __syncthreads();                                            // all partials of the chunk; every warp is done with its stage
+        for (int e = threadIdx.x; e < cnt * ROWS; e += nthr) {       // (pair, row): add the nwarps partials in warp order
+            const int g = e / ROWS, rr = e - g * ROWS;
+            float s = 0.f;
+            for (int w2 = 0; w2 < nwarps; ++w2) s += part_s[((size_t)w2 * kc + g) * ROWS + rr];
+            coef_s[(size_t)(k0 + g) * ROWS + rr] = s * scale_s[k0 + g];
+        }
+        if (threadIdx.x == 0 && c + nstages < nchunks) issue(c + nstages);     // ring: only when the pairs do not all fit
+        __syncthreads();                                            // part_s is free again; coef_s rows of this chunk are visible
+    }
+    // Az = M^L z + ...
+#pragma unroll
+    for (int r = 0; r < RL; ++r)
+#pragma unroll
+        for (int i = 0; i < QW; ++i) acc[r][i] = make_float4(acc[r][i].x * mL, acc[r][i].y * mL, acc[r][i].z * mL, acc[r][i].w * mL);
+
+    // ---- pass 2: Az += sum_j c_j pc_j ----
+    const bool resident = nchunks <= nstages;                       // the chunks of pass 1 are still in their stages
+    if (!resident) {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int c = 0; c < nchunks && c < nstages; ++c) issue(c);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c % nstages;
+        if (!resident) mbar_wait(&bars[st], (unsigned)((((nchunks - 1 - st) / nstages + 1) + c / nstages) & 1));
+        const float* sb = stage_base + st * stage_floats;
+        const int k0 = c * kc, cnt = min(kc, live - k0);
+        for (int g = 0; g < cnt; ++g) {
+            const float4* prow = reinterpret_cast<const float4*>(sb + (size_t)(2 * g + 1) * ns) + q0;
+            float2 w[RL];
+#pragma unroll
+            for (int r = 0; r < RL; ++r) { const float cw = coef_s[(size_t)(k0 + g) * ROWS + r * 32 + lane]; w[r] = make_float2(cw, cw); }
+#pragma unroll
+            for (int i = 0; i < QW; ++i) {
+                if (i < qper && q0 + i < nq) {
+                    const float4 p = prow[i];
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) {
+                        const float2 l = ffma2(w[r], lo2(p), lo2(acc[r][i])), h = ffma2(w[r], hi2(p), hi2(acc[r][i]));
+                        acc[r][i] = make_float4(l.x, l.y, h.x, h.y);
+                    }
+                }
+            }
+        }
+        if (!resident && c + nstages < nchunks) {
+            __syncthreads();
+            if (threadIdx.x == 0) issue(c + nstages);
+        }
+    }
+
+    // ---- transpose through shared memory (the stages are free), then the coalesced finish ----
+    __syncthreads();
+    const int tstride = ns + 4;                                     // rows 16 bytes apart modulo 128: conflict-free 16-byte stores
+    float* tile = stage_base;
+#pragma unroll
+    for (int r = 0; r < RL; ++r)
+#pragma unroll
+        for (int i = 0; i < QW; ++i)
+            if (i < qper && q0 + i < nq) reinterpret_cast<float4*>(tile + (size_t)(r * 32 + lane) * tstride)[q0 + i] = acc[r][i];
+    __syncthreads();
+    const double* xm = o.xmean + (size_t)b * ns;
+    for (int e = threadIdx.x; e < ROWS * nq; e += nthr) {
+        const int rr = e / nq, q = e - rr * nq, row = row0 + rr;
+        if (row >= o.pop_count) break;
+        const size_t roff = ((size_t)b * o.pop_count + row) * ns;
+        sample_finish(o, xm, sc.sigma, reinterpret_cast<const float4*>(tile + (size_t)rr * tstride)[q], q, o.X + roff, o.D + roff,
+                      o.Xh ? o.Xh + roff : nullptr);
+    }
 }
 
 }  // namespace lmcma

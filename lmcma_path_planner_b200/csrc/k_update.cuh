@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     }
     // prev_fit (lmcma.cpp:420-421): k_rank has finished reading the previous generation's values
     for (int j = tid; j < o.lambda; j += nthr) o.prev_fit[(size_t)b * o.lambda + j] = canon_fitness(__ldcg(fa + j));
+    if (o.prev_sorted)                                               // sorted-tile ranking (k_rank.cuh): the next generation searches it
+        for (int j = tid; j < o.lambda; j += nthr) o.prev_sorted[(size_t)b * o.lambda + j] = __ldcg(o.fit_sorted + (size_t)b * o.lambda + j);
 
     // ---- mean, evolution path, new pc_j (lmcma.cpp:316-329, 365-366): 128 float4 columns x 2 slice groups, up to
     //      8 slice loads in flight per thread; fixed summation order -> deterministic ----

@@ -87,10 +87,11 @@ int env_int(const char* name, int dflt) {
 // nothing on a launch path calls getenv.  All of them are experiment / debugging switches; the defaults are the product.
 struct Tuning {
     int cost_minb = 7, cost_tpt = 0, cost_cb = 0, zerocopy = 1;
+    int sample_rows = -1;   // k_sample_rows: -1 = where it pays (many rows), 0 = never, 1 = also for one large population
     int sample_spec = 1, sample_threads = 0, sample_smem_kb = 160, sample_smem_kb_set = 0, sample_narrow = 0, sample_rbw = 0, sample_r = 0;
     int update_blocked = 0, update_gram = 0, update_streaming = 0, update_sweep_warps = 0;
-    int progressive = 1, overlap = 1, tell_overlap = 1, rank_late = 1;
-    int graph_dbg = 0, dbg = 0, update_dbg = 0;
+    int progressive = 1, overlap = 1, tell_overlap = 1, rank_late = 1, rank_sorted = 1;
+    int graph_dbg = 0, dbg = 0, update_dbg = 0, cost_dbg = 0;
     static Tuning from_env() {
         Tuning t;
         t.cost_minb = env_int("LMCMA_B200_COST_MINB", t.cost_minb);
@@ -98,6 +99,7 @@ struct Tuning {
         t.cost_cb = env_int("LMCMA_B200_COST_CB", 0);
         t.zerocopy = env_int("LMCMA_B200_ZEROCOPY", 1);
         t.sample_spec = env_int("LMCMA_B200_SAMPLE_SPEC", 1);
+        t.sample_rows = env_int("LMCMA_B200_SAMPLE_ROWS", -1);
         t.sample_threads = env_int("LMCMA_B200_SAMPLE_THREADS", 0);
         t.sample_smem_kb_set = env_int("LMCMA_B200_SAMPLE_SMEM_KB", 0);
         t.sample_smem_kb = t.sample_smem_kb_set ? t.sample_smem_kb_set : 160;
@@ -112,9 +114,11 @@ struct Tuning {
         t.overlap = env_int("LMCMA_B200_OVERLAP", 1);
         t.tell_overlap = env_int("LMCMA_B200_TELL_OVERLAP", 1);
         t.rank_late = env_int("LMCMA_B200_RANK_LATE", 1);
+        t.rank_sorted = env_int("LMCMA_B200_RANK_SORTED", 1);
         t.graph_dbg = env_int("LMCMA_B200_GRAPH_DBG", 0);
         t.dbg = getenv("LMCMA_B200_DBG") ? 1 : 0;
         t.update_dbg = getenv("LMCMA_B200_UPDATE_DBG") ? 1 : 0;
+        t.cost_dbg = getenv("LMCMA_B200_COST_DBG") ? 1 : 0;
         return t;
     }
 };
@@ -202,6 +206,8 @@ struct lmcma_b200_opt {
     // sample launch config
     int smp_threads = 128, smp_kc = 1, smp_nv = 1, smp_rb = 1, smp_stages = 2;
     bool smp_wide = false; int smp_R = 1, smp_CW = 1, smp_qpw = 32, smp_RBW = 1;
+    bool smp_rows = false; int smp_rows_qw = 8, smp_rows_rl = 1, smp_rows_kc = 8, smp_rows_stages = 2, smp_rows_region = 0;   // k_sample_rows
+    size_t smp_rows_smem = 0;
     float* d_Lf = nullptr;             // lower Cholesky factor of the smoothness prior (n x ns FP32) or null
     bool mirror_dirty = true;          // the sequence-ordered pair mirror must be rebuilt (k_pack_pairs) before sampling
     size_t smp_smem = 0;
@@ -210,6 +216,8 @@ struct lmcma_b200_opt {
     bool overlap = false;       // fused generation with k_update on a side branch, concurrent with k_cost / k_rank (k_update.cuh)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    float* x_mirror = nullptr;        // page-locked, mapped host mirror of X (lmcma_b200_ask_all_view); OptDev::Xh is its device alias
+    bool mirror_on = false, mirror_suppressed = false, xh_fresh = false;
     int* err_host = nullptr;          // page-locked, mapped: OptDev::err (a kernel of the overlapped generation gave up on its partner)
     long long* graph_dbg = nullptr;   // LMCMA_B200_GRAPH_DBG: k_update's timeline inside the fused generation, printed by lmcma_b200_sync
     int upd_nvb = 4, upd_rmax = 0, upd_sweep_warps = 16;
@@ -231,7 +239,7 @@ int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostSha
     // segment records 36 B, sample offsets, per-block records 8 B (k_cost.cuh), 256-entry table (u8 storage)
     // + the candidate row (16-byte aligned)
     const size_t smem = (size_t)36 * (a.W + 1) + sizeof(int) * (a.W + 2) + 28 + (size_t)8 * shape.cb + (STORAGE == 1 ? 1024 : 0) +
-                        sizeof(float) * DIMS * (size_t)a.W + 16;
+                        sizeof(float) * DIMS * ((size_t)a.W + 2) + 16;
     auto kern = k_cost<DIMS, STORAGE, TRACE, MINB>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(rows, B), shape.tpt, smem, st>>>(mp, a);
@@ -277,7 +285,7 @@ CostShape pick_cost_shape(int W, const float* start, const float* goal, int dims
 }
 
 template <int NV, int RB, int MAXT, bool SPEC = false>
-int launch_sample_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
+int launch_sample_t(lmcma_b200_opt* o, const OptDev& d, bool pdl, cudaStream_t st) {
     auto kern = k_sample<NV, RB, MAXT, SPEC>;
     if (o->smp_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_smem));
     const int rows_per_cta = (o->smp_threads / 32) * RB;
@@ -289,13 +297,13 @@ int launch_sample_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    CU(cudaLaunchKernelEx(&cfg, kern, o->d, o->smp_kc, o->smp_stages));
+    CU(cudaLaunchKernelEx(&cfg, kern, d, o->smp_kc, o->smp_stages));
     g_launches++;
     return 0;
 }
 
 template <int RBW, int MAXT>
-int launch_sample_wide_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st, int progressive) {
+int launch_sample_wide_t(lmcma_b200_opt* o, const OptDev& d, bool pdl, cudaStream_t st, int progressive) {
     auto kern = k_sample_wide<RBW, MAXT>;
     if (o->smp_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_smem));
     cudaLaunchConfig_t cfg;
@@ -307,15 +315,40 @@ int launch_sample_wide_t(lmcma_b200_opt* o, bool pdl, cudaStream_t st, int progr
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    CU(cudaLaunchKernelEx(&cfg, kern, o->d, o->smp_kc, o->smp_stages, o->smp_R, o->smp_CW, o->smp_qpw, progressive));
+    CU(cudaLaunchKernelEx(&cfg, kern, d, o->smp_kc, o->smp_stages, o->smp_R, o->smp_CW, o->smp_qpw, progressive));
     g_launches++;
     return 0;
 }
-int launch_sample_wide(lmcma_b200_opt* o, bool pdl, cudaStream_t st, int progressive) {
+template <int QW, int RL>
+int launch_sample_rows_t(lmcma_b200_opt* o, const OptDev& d, bool pdl, cudaStream_t st) {
+    auto kern = k_sample_rows<QW, RL>;
+    if (o->smp_rows_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smp_rows_smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((d.pop_count + 32 * RL - 1) / (32 * RL), d.B); cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = o->smp_rows_smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, kern, d, o->smp_rows_kc, o->smp_rows_stages, o->smp_rows_region));
+    g_launches++;
+    return 0;
+}
+int launch_sample_rows(lmcma_b200_opt* o, const OptDev& d, bool pdl, cudaStream_t st) {
+    const bool two = o->smp_rows_rl == 2;
+    switch (o->smp_rows_qw) {
+        case 4: return two ? launch_sample_rows_t<4, 2>(o, d, pdl, st) : launch_sample_rows_t<4, 1>(o, d, pdl, st);
+        case 7: return two ? launch_sample_rows_t<7, 2>(o, d, pdl, st) : launch_sample_rows_t<7, 1>(o, d, pdl, st);
+        default: return two ? launch_sample_rows_t<8, 2>(o, d, pdl, st) : launch_sample_rows_t<8, 1>(o, d, pdl, st);
+    }
+}
+
+int launch_sample_wide(lmcma_b200_opt* o, const OptDev& d, bool pdl, cudaStream_t st, int progressive) {
     switch (o->smp_RBW) {
-        case 1: return launch_sample_wide_t<1, 1024>(o, pdl, st, progressive);
-        case 2: return launch_sample_wide_t<2, 1024>(o, pdl, st, progressive);
-        default: return launch_sample_wide_t<4, 512>(o, pdl, st, progressive);
+        case 1: return launch_sample_wide_t<1, 1024>(o, d, pdl, st, progressive);
+        case 2: return launch_sample_wide_t<2, 1024>(o, d, pdl, st, progressive);
+        default: return launch_sample_wide_t<4, 512>(o, d, pdl, st, progressive);
     }
 }
 
@@ -346,14 +379,20 @@ int launch_sample(lmcma_b200_opt* o, cudaStream_t st, bool pdl = false, bool pro
         CU(cudaGetLastError());
         pdl = false;
     }
-    if (o->smp_wide) return launch_sample_wide(o, pdl, st, (pdl && progressive && o->progressive) ? progressive_mode : 0);
+    // the host mirror of X (lmcma_b200_ask_all_view) is written by the samplers of the host-buffer protocol only: the fused
+    // on-device generations (lmcma_b200_run) and the split-population stages keep the candidates on the device
+    OptDev d = o->d;
+    if (!o->mirror_on || o->mirror_suppressed) d.Xh = nullptr;
+    o->xh_fresh = d.Xh != nullptr;
+    if (o->smp_rows) return launch_sample_rows(o, d, pdl, st);
+    if (o->smp_wide) return launch_sample_wide(o, d, pdl, st, (pdl && progressive && o->progressive) ? progressive_mode : 0);
     switch (o->smp_nv) {
-        case 1: return launch_sample_t<1, 4, 512>(o, pdl, st);
-        case 2: return launch_sample_t<2, 4, 512>(o, pdl, st);
-        case 4: return o->tune.sample_spec ? launch_sample_t<4, 2, 512, true>(o, pdl, st) : launch_sample_t<4, 2, 512>(o, pdl, st);
-        case 8: return launch_sample_t<8, 1, 512>(o, pdl, st);
-        case 12: return launch_sample_t<12, 1, 256>(o, pdl, st);
-        case 16: return launch_sample_t<16, 1, 256>(o, pdl, st);
+        case 1: return launch_sample_t<1, 4, 512>(o, d, pdl, st);
+        case 2: return launch_sample_t<2, 4, 512>(o, d, pdl, st);
+        case 4: return o->tune.sample_spec ? launch_sample_t<4, 2, 512, true>(o, d, pdl, st) : launch_sample_t<4, 2, 512>(o, d, pdl, st);
+        case 8: return launch_sample_t<8, 1, 512>(o, d, pdl, st);
+        case 12: return launch_sample_t<12, 1, 256>(o, d, pdl, st);
+        case 16: return launch_sample_t<16, 1, 256>(o, d, pdl, st);
     }
     return fail(LMCMA_B200_ERR_ARG, "unsupported n for k_sample (nv=%d)", o->smp_nv);
 }
@@ -411,12 +450,50 @@ int configure_sample(lmcma_b200_opt* o) {
         o->smp_smem += (size_t)o->smp_stages * ((kc + SAMPLE_G - 1) / SAMPLE_G) * o->smp_R * o->smp_CW * o->smp_RBW * SAMPLE_G * sizeof(float);
     }
     if (o->smp_smem > o->props->smem_optin) return fail(LMCMA_B200_ERR_ARG, "k_sample needs %zu B shared memory", o->smp_smem);
+    // many rows (batched queries, or one very large population): rows on lanes, column slices on warps (k_sample_rows)
+    o->smp_rows = false;
+    const long long total_rows = (long long)o->d.B * o->d.pop_count;
+    const bool many = total_rows >= 4096 && o->d.pop_count >= 32 && (o->d.B > 1 || o->tune.sample_rows == 1);
+    if (o->tune.sample_rows != 0 && many && nq <= 128 && o->d.m <= 256 && !o->d_Lf) {
+        const int NW = 16;
+        const int qper = (nq + NW - 1) / NW;
+        o->smp_rows_qw = qper <= 4 ? 4 : (qper <= 7 ? 7 : 8);
+        // two rows per lane when an instance has them and the grid still fills the SMs
+        o->smp_rows_rl = (o->d.pop_count >= 64 && total_rows / 64 >= 2LL * o->props->sm_count) ? 2 : 1;
+        const int rows = 32 * o->smp_rows_rl, kc2 = 8;
+        const int chunks = (o->d.m + kc2 - 1) / kc2;
+        const size_t stage_bytes = (size_t)kc2 * pair_bytes;
+        const size_t fixed2 = SAMPLE_MAX_STAGES * 8 + (size_t)((o->d.m + kc2 + 3) & ~3) * 4 + (size_t)chunks * kc2 * rows * 4 + (size_t)NW * kc2 * rows * 4;
+        const size_t tile_bytes = (size_t)rows * (o->d.ns + 4) * 4;
+        if (fixed2 + std::max(2 * stage_bytes, tile_bytes) + 1024 <= o->props->smem_optin) {
+            const size_t room = o->props->smem_optin - 1024 - fixed2;
+            int stages = (int)std::min<size_t>(std::min(chunks, SAMPLE_MAX_STAGES), room / stage_bytes);
+            stages = std::max(stages, 2);
+            const size_t region = std::max((size_t)stages * stage_bytes, tile_bytes);
+            o->smp_rows_kc = kc2; o->smp_rows_stages = stages; o->smp_rows_region = (int)(region / 4);
+            o->smp_rows_smem = region + fixed2;
+            o->smp_rows = true;
+            o->smp_wide = false;
+        }
+    }
     return 0;
 }
 
 // ranks + recombination partial sums (k_rank.cuh); RANK_PACK is the split-population stage
 // pdl: launched as a programmatic dependent of the kernel enqueued just before it on `st` (k_cost)
 int launch_rank(lmcma_b200_opt* o, const float* f_all, int mode, float* payload, cudaStream_t st, bool pdl = false) {
+    if (o->d.tile_sorted) {                                       // lambda > 4096, unsplit: sort the fitness tiles first (k_rank.cuh)
+        cudaLaunchConfig_t c0;
+        memset(&c0, 0, sizeof(c0));
+        c0.gridDim = dim3((o->d.lambda + TELL_FTILE - 1) / TELL_FTILE, o->d.B); c0.blockDim = dim3(1024); c0.stream = st;
+        cudaLaunchAttribute a0[1];
+        a0[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        a0[0].val.programmaticStreamSerializationAllowed = 1;
+        c0.attrs = a0; c0.numAttrs = pdl ? 1 : 0;
+        CU(cudaLaunchKernelEx(&c0, k_rank_tiles, o->d, f_all));
+        g_launches++;
+        pdl = false;                                              // k_rank itself follows in stream order
+    }
     auto kern = k_rank<1024>;
     if (o->rank_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->rank_smem));
     cudaLaunchConfig_t cfg;
@@ -624,6 +701,7 @@ int ensure_graph(lmcma_b200_opt* o) {
     const long long before = g_launches.load();
     if (o->tune.graph_dbg && !o->graph_dbg && cudaMalloc(&o->graph_dbg, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(o->graph_dbg, 0, 64 * sizeof(long long)); cudaDeviceSynchronize(); }
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    o->mirror_suppressed = true;                             // fused generations keep the candidates on the device
     UpdateArgs ua = update_args_local(o);
     ua.progressive = o->progressive ? 1 : 0;                 // ensure_mirror above: the mirror is clean
     ua.dbg = o->graph_dbg;
@@ -647,6 +725,7 @@ int ensure_graph(lmcma_b200_opt* o) {
         if (!rc) rc = launch_sample(o, st, true, o->progressive);
     }
     cudaError_t e = cudaStreamEndCapture(st, &graph);
+    o->mirror_suppressed = false;
     g_launches.store(before);   // capture enqueues nothing
     if (!rc && e == cudaSuccess) {
         e = cudaGraphInstantiate(&o->graph_exec, graph, 0);
@@ -707,6 +786,34 @@ void* mapped_device_pointer(const void* host, int device) {
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
     (void)device;
     return at.devicePointer;
+}
+
+// Page-locked host mirrors of candidate populations handed out by lmcma_b200_ask_all_view: lmcma_b200_cost_evaluate
+// recognises a pointer into one of them and evaluates the DEVICE copy it mirrors (no H2D of the candidates).
+struct MirrorEntry { const char* host; size_t bytes; const float* dev; long long ld; int device; };
+std::mutex g_mirror_mu;
+std::vector<MirrorEntry> g_mirrors;
+void register_mirror(const void* host, size_t bytes, const float* dev, long long ld, int device) {
+    std::lock_guard<std::mutex> lk(g_mirror_mu);
+    g_mirrors.push_back(MirrorEntry{static_cast<const char*>(host), bytes, dev, ld, device});
+}
+void unregister_mirror(const void* host) {
+    std::lock_guard<std::mutex> lk(g_mirror_mu);
+    for (size_t i = 0; i < g_mirrors.size(); ++i)
+        if (g_mirrors[i].host == host) { g_mirrors.erase(g_mirrors.begin() + i); break; }
+}
+// device row pointer + row stride behind a host pointer that lies inside a registered mirror (row-aligned), else null
+const float* mirrored_device_rows(const void* host, int device, size_t need_bytes, long long* ld) {
+    std::lock_guard<std::mutex> lk(g_mirror_mu);
+    const char* p = static_cast<const char*>(host);
+    for (const MirrorEntry& m : g_mirrors) {
+        if (m.device != device || p < m.host || p + need_bytes > m.host + m.bytes) continue;
+        const size_t off = (size_t)(p - m.host);
+        if (off % ((size_t)m.ld * sizeof(float)) != 0) continue;
+        *ld = m.ld;
+        return m.dev + off / sizeof(float);
+    }
+    return nullptr;
 }
 
 // dense <-> pitched copies
@@ -1021,7 +1128,15 @@ int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj,
     // of the kernel), and the three results per trajectory are stored straight into the caller's arrays.  Pageable
     // buffers are staged through device memory.  LMCMA_B200_ZEROCOPY=0 forces staging.
     const bool zc = m->tune.zerocopy != 0;
-    const float* X_dev = zc ? static_cast<const float*>(mapped_device_pointer(X_host, m->device)) : nullptr;
+    // a pointer into a population mirror handed out by lmcma_b200_ask_all_view: the device already holds these rows
+    long long ld_rows = (long long)n;
+    const float* X_dev = nullptr;
+    if (zc) {
+        long long ld_m = 0;
+        const float* mir = mirrored_device_rows(X_host, m->device, 1, &ld_m);
+        if (mir && ld_m >= (long long)n && mirrored_device_rows(X_host, m->device, ((size_t)(count - 1) * ld_m + n) * sizeof(float), &ld_m)) { X_dev = mir; ld_rows = ld_m; }
+    }
+    if (!X_dev && zc) X_dev = static_cast<const float*>(mapped_device_pointer(X_host, m->device));
     float* f_dev = zc ? static_cast<float*>(mapped_device_pointer(f_host, m->device)) : nullptr;
     int32_t* nc_dev = (zc && ncoll_host) ? static_cast<int32_t*>(mapped_device_pointer(ncoll_host, m->device)) : nullptr;
     int32_t* ns_dev = (zc && nsamp_host) ? static_cast<int32_t*>(mapped_device_pointer(nsamp_host, m->device)) : nullptr;
@@ -1044,7 +1159,7 @@ int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj,
         }
         f_dev = m->d_f; nc_dev = m->d_nc; ns_dev = m->d_ns;
     }
-    rc = lmcma_b200_cost_evaluate_dev(m, obj, ends, X_dev, (int64_t)n, count, f_dev, ncoll_host ? nc_dev : nullptr,
+    rc = lmcma_b200_cost_evaluate_dev(m, obj, ends, X_dev, (int64_t)ld_rows, count, f_dev, ncoll_host ? nc_dev : nullptr,
                                       nsamp_host ? ns_dev : nullptr, m->stream);
     if (rc) return rc;
     if (!out_direct) {
@@ -1188,6 +1303,9 @@ static int create_body(lmcma_b200_opt* o, DeviceProps* props, const lmcma_b200_c
     }
     DM(d.fit, B * lam); DM(d.fit_sorted, B * lam); DM(d.prev_fit, B * lam);
     DM(d.rank, B * lam); DM(d.arindex, B * lam);
+    if (d.lambda > TELL_FTILE && d.pop_count == d.lambda && o->tune.rank_sorted) {
+        DM(d.prev_sorted, B * lam); DM(d.tile_sorted, B * lam); DM(d.tile_pos, B * lam);
+    }
     DM(d.ncoll, B * pc); DM(d.nsamp, B * pc);
     DM(d.xmean, B * ns); DM(d.pc, B * ns);
     DM(d.V, B * m * ns); DM(d.P, B * m * ns);
@@ -1274,13 +1392,14 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     cudaSetDevice(o->cfg.device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     OptDev& d = o->d;
-    void* ptrs[] = {d.X, d.D, d.Z, d.Zc, o->d_Lf, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
+    void* ptrs[] = {d.prev_sorted, d.tile_sorted, d.tile_pos, d.X, d.D, d.Z, d.Zc, o->d_Lf, d.fit, d.fit_sorted, d.prev_fit, d.rank, d.arindex, d.ncoll, d.nsamp, d.xmean, d.pc, d.V, d.P,
                     d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.progress, d.rank_ticket, d.resident, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
     if (o->tell_graph) cudaGraphExecDestroy(o->tell_graph);
     if (o->f_pinned) cudaFreeHost(o->f_pinned);
     if (o->err_host) cudaFreeHost(o->err_host);
+    if (o->x_mirror) { unregister_mirror(o->x_mirror); cudaFreeHost(o->x_mirror); }
     if (o->ev0) cudaEventDestroy(o->ev0);
     if (o->ev1) cudaEventDestroy(o->ev1);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
@@ -1346,6 +1465,33 @@ int lmcma_b200_ask_all(lmcma_b200_opt* o, float* X) {
     return rc ? rc : check_lost(o);
 }
 
+int lmcma_b200_ask_all_view(lmcma_b200_opt* o, const float** X_view, int64_t* ld_out) {
+    ARG(o && X_view, "null pointer");
+    if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no population yet: inject_z first");
+    CU(cudaSetDevice(o->cfg.device));
+    OptDev& d = o->d;
+    const size_t floats = (size_t)d.B * d.pop_count * d.ns;
+    if (!o->x_mirror) {
+        CU(cudaStreamSynchronize(o->stream));
+        CU(cudaHostAlloc(&o->x_mirror, floats * sizeof(float), cudaHostAllocMapped));
+        cudaError_t e = cudaHostGetDevicePointer(&d.Xh, o->x_mirror, 0);
+        if (e != cudaSuccess) { cudaFreeHost(o->x_mirror); o->x_mirror = nullptr; d.Xh = nullptr; return fail(LMCMA_B200_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
+        o->mirror_on = true;
+        o->xh_fresh = false;
+        register_mirror(o->x_mirror, floats * sizeof(float), d.X, d.ns, o->cfg.device);
+        // the captured graphs carry the old kernel parameters (OptDev by value): rebuild them on next use
+        if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
+    }
+    if (!o->xh_fresh) {                                  // first use / after a fused run or a state setter: one ordinary copy
+        CU(cudaMemcpyAsync(o->x_mirror, d.X, floats * sizeof(float), cudaMemcpyDeviceToHost, o->stream));
+        o->xh_fresh = true;
+    }
+    CU(cudaStreamSynchronize(o->stream));
+    *X_view = o->x_mirror;
+    if (ld_out) *ld_out = d.ns;
+    return check_lost(o);
+}
+
 int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
     ARG(o && f, "null pointer");
     if (o->needs_sample) return fail(LMCMA_B200_ERR_STATE, "no population yet: inject_z first");
@@ -1363,7 +1509,8 @@ int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
         if ((rc = ensure_tell_graph(o)) == 0 && o->tell_graph) {
             memcpy(o->f_pinned, f, (size_t)d.B * d.lambda * sizeof(float));
             CU(cudaGraphLaunch(o->tell_graph, o->stream));
-            g_launches += 4;                                     // k_update, k_gate, k_rank, k_sample
+            g_launches += 4 + (o->d.tile_sorted ? 1 : 0);         // k_update, k_gate, (k_rank_tiles,) k_rank, k_sample
+            o->xh_fresh = o->mirror_on;                          // the captured sampler writes the host mirror when it is on
             o->x_cache_valid = false;
             o->sample_idx = 0;
             o->pending_z = false;
@@ -1445,19 +1592,20 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
     CU(cudaSetDevice(o->cfg.device));
     int rc = apply_l2_window(o->map, o->stream);
     if (rc) return rc;
-    CU(cudaEventRecord(o->ev0, o->stream));
     if (o->cfg.rng == LMCMA_B200_RNG_PHILOX) {
         if ((rc = ensure_graph(o))) return rc;
         if ((rc = ensure_mirror(o, o->stream))) return rc;       // a state setter since the last run: the graph's sampler reads the mirror
+        CU(cudaEventRecord(o->ev0, o->stream));                  // after the (host-side) graph build: last_run_ms is device time
         for (int g = 0; g < generations; ++g) {
             CU(cudaGraphLaunch(o->graph_exec, o->stream));
-            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0) + (o->overlap ? 1 : 0);
+            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0) + (o->overlap ? 1 : 0) + (o->d.tile_sorted ? 1 : 0);
         }
     } else {
         if (o->cfg.rng == LMCMA_B200_RNG_INJECT && generations > 1)
             return fail(LMCMA_B200_ERR_STATE, "INJECT rng: run one generation per injected Z");
         CostArgs ca;
         if ((rc = cost_args_for(o, &ca))) return rc;
+        CU(cudaEventRecord(o->ev0, o->stream));
         for (int g = 0; g < generations; ++g) {
             if ((rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, o->stream))) return rc;
             if ((rc = generation_tail(o, o->stream))) return rc;
@@ -1466,6 +1614,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
     CU(cudaEventRecord(o->ev1, o->stream));
     o->have_run_timing = true;
     o->x_cache_valid = false;
+    if (o->cfg.rng == LMCMA_B200_RNG_PHILOX) o->xh_fresh = false;    // the graph's sampler does not write the host mirror
     return 0;
 }
 
@@ -1526,6 +1675,40 @@ int lmcma_b200_profile_kernels(lmcma_b200_opt* o, int32_t generations, float* ms
     }
     cudaError_t se = cudaStreamSynchronize(st);
     if (!rc && se != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "profile run: %s", cudaGetErrorString(se));
+    if (!rc && o->tune.cost_dbg) {     // debug: per-CTA timeline of k_cost (phase stamps), one extra launch
+        const size_t ctas = (size_t)o->d.pop_count * o->d.B;
+        long long* dbg = nullptr;
+        if (cudaMalloc(&dbg, ctas * 8 * sizeof(long long)) == cudaSuccess) {
+            cudaMemset(dbg, 0, ctas * 8 * sizeof(long long));
+            cudaDeviceSynchronize();
+            CostArgs cd = ca; cd.dbg = dbg; cd.cells = nullptr; cd.max_cells = 0;
+            launch_cost(o->map->dev, cd, o->d.pop_count, o->d.B, o->cost_shape, true, st);   // the TRACE build carries the stamps (no cells requested)
+            cudaStreamSynchronize(st);
+            std::vector<long long> h(ctas * 8);
+            cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            long long t0 = h[0];
+            for (size_t c = 0; c < ctas; ++c) t0 = std::min(t0, h[c * 8]);
+            static const char* nm[] = {"start", "x loaded", "phase 1 done", "loop done", "end samples done", "end"};
+            fprintf(stderr, "k_cost timeline over %zu CTAs (ns since the first CTA start; min / median / max):", ctas);
+            for (int k = 0; k < 6; ++k) {
+                std::vector<long long> v(ctas);
+                for (size_t c = 0; c < ctas; ++c) v[c] = h[c * 8 + k] - t0;
+                std::sort(v.begin(), v.end());
+                fprintf(stderr, " %s=%lld/%lld/%lld", nm[k], v[0], v[ctas / 2], v[ctas - 1]);
+            }
+            // per-CTA durations of the phases
+            static const char* dn[] = {"x load", "phase 1", "loop", "end samples", "reduce"};
+            fprintf(stderr, " | per-CTA phase durations (median):");
+            for (int k = 0; k < 5; ++k) {
+                std::vector<long long> v(ctas);
+                for (size_t c = 0; c < ctas; ++c) v[c] = h[c * 8 + k + 1] - h[c * 8 + k];
+                std::sort(v.begin(), v.end());
+                fprintf(stderr, " %s=%lld", dn[k], v[ctas / 2]);
+            }
+            fprintf(stderr, "\n");
+            cudaFree(dbg);
+        }
+    }
     if (!rc && o->tune.update_dbg) {   // debug: timeline of k_update
         long long* dbg = nullptr;
         if (cudaMalloc(&dbg, 64 * sizeof(long long)) == cudaSuccess) {
@@ -1736,6 +1919,7 @@ int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_
         case LMCMA_B200_F32_X: {
             ARG(count == (int64_t)(B * d.pop_count * d.n), "count");
             o->x_cache_valid = false;
+            o->xh_fresh = false;
             // keep the offsets d = x - xmean consistent with the overwritten candidates
             std::vector<double> xm(B * d.n);
             int rc = d2h_rows(xm.data(), d.xmean, B, d.n * sizeof(double), d.ns * sizeof(double), o->stream);
@@ -1754,6 +1938,11 @@ int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_
             ARG(count == (int64_t)(B * d.lambda), "count");
             CU(cudaMemcpyAsync(d.prev_fit, in, B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, o->stream));
             CU(cudaStreamSynchronize(o->stream));
+            if (d.prev_sorted) {                                  // the sorted-tile ranking searches an ascending copy
+                std::vector<float> srt(in, in + B * d.lambda);
+                for (size_t b = 0; b < B; ++b) std::sort(srt.begin() + b * d.lambda, srt.begin() + (b + 1) * d.lambda);
+                CU(cudaMemcpy(d.prev_sorted, srt.data(), srt.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
             return 0;
     }
     return fail(LMCMA_B200_ERR_ARG, "f32 field %d is not settable", which);
@@ -1833,7 +2022,10 @@ int lmcma_b200_mg_update(lmcma_b200_opt* o, const float* payload_all_dev, int32_
     int rc = launch_update(o, a, false, st);
     if (rc) return rc;
     o->x_cache_valid = false;
-    return launch_sample(o, st, true);
+    o->mirror_suppressed = true;
+    rc = launch_sample(o, st, true);
+    o->mirror_suppressed = false;
+    return rc;
 }
 
 // ---- host-side reference pieces ------------------------------------------------------------------

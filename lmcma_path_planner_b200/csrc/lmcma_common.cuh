@@ -37,6 +37,9 @@ struct OptDev {
     unsigned long long seed;
     // population
     float* X;          // B x pop_count x ns
+    float* Xh;         // null, or the device alias of the handle's page-locked host mirror of X (same layout): the sampler
+                       // writes every candidate row there as well (posted PCIe writes that overlap the sampling), so the
+                       // host-buffer protocol needs no D2H copy of the population after the generation (lmcma_b200_ask_all_view)
     float* Z;          // B x pop_count x ns (INJECT / record_z) or null
     float* Zc;         // B x pop_count x ns  L z (smoothness prior, k_prior.cuh) or null: what computeAz sees
     const float* Lf;   // n x ns lower Cholesky factor of the prior (FP32) or null
@@ -45,6 +48,10 @@ struct OptDev {
     float* fit;        // B x lambda   fitness as evaluated / told (all rows, global order)
     float* fit_sorted; // B x lambda
     float* prev_fit;   // B x lambda   previous generation (any order)
+    // large unsplit populations (lambda > 4096, k_rank.cuh "sorted tiles"): ranks by binary search instead of counting
+    float* prev_sorted;   // B x lambda   previous generation, ascending (= its fit_sorted), or null
+    float* tile_sorted;   // B x lambda   this generation's fitness, each 4096-candidate tile sorted ascending, or null
+    int* tile_pos;        // B x lambda   position of candidate i inside its sorted tile
     int* rank;         // B x lambda   (only [pop_offset, +pop_count) written in split mode)
     int* arindex;      // B x lambda
     int* ncoll;        // B x pop_count
@@ -123,6 +130,7 @@ struct CostArgs {
     long long* cells;          // trace mode (nullable)
     long long max_cells;
     int cb;                    // capacity of the per-block record stage (32-sample blocks), set by the launcher
+    long long* dbg;            // optional (LMCMA_B200_COST_DBG): 8 globaltimer stamps per CTA, [cta * 8 + k]
 };
 
 struct CostShape { int tpt = 128, cb = 256, minb = 7; };   // launch shape of k_cost: threads per trajectory, block-record capacity, CTAs per SM it was compiled for

@@ -160,6 +160,14 @@ class Optimizer:
         K.check(K.lib().lmcma_b200_ask_all(self._h, K.fptr(X)))
         return X
 
+    def ask_all_view(self):
+        """Read-only numpy view [batch, pop_count, n] of the library's page-locked mirror of the population (no copy)."""
+        xp, ld = C.POINTER(C.c_float)(), C.c_int64(0)
+        K.check(K.lib().lmcma_b200_ask_all_view(self._h, C.byref(xp), C.byref(ld)))
+        a = np.ctypeslib.as_array(xp, shape=(self.batch, self.pop_count, int(ld.value)))
+        a.flags.writeable = False
+        return a[:, :, :self.n]
+
     def tell_all(self, f):
         f = K.f32c(f).reshape(self.batch, self.lam)
         K.check(K.lib().lmcma_b200_tell_all(self._h, K.fptr(f)))

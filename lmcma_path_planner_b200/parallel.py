@@ -49,9 +49,19 @@ class DeviceBackend:
     """Adapter from torch tensors to the C ABI's raw device pointers (lmcma_b200_mg_*)."""
 
     def __init__(self, opt, stream_ptr=None):
-        self.opt, self.stream = opt, stream_ptr
+        """stream_ptr: the cudaStream_t (int) the three stages are enqueued on.  None = torch's CURRENT stream at the time
+        of each call, i.e. the stream the exchanges of SplitPopulation are ordered with — never the optimiser's private
+        stream, which nothing would order against the all-gathers."""
+        self.opt, self._stream = opt, stream_ptr
         self.payload_floats = opt.mg_payload_floats()
         self.pop_count, self.lam = opt.pop_count, opt.lam
+
+    @property
+    def stream(self):
+        if self._stream is not None:
+            return self._stream
+        import torch
+        return torch.cuda.current_stream().cuda_stream
 
     def evaluate(self, f_local):
         self.opt.mg_evaluate(f_local.data_ptr(), self.stream)
@@ -96,6 +106,47 @@ class SplitPopulation:
         self._all_gather(self.payload_all, self.payload)    # exchange 2: G x (n+4) floats
         b.update(self.payload_all, self.world)
 
-    def run(self, generations):
+    def capture(self):
+        """Capture one generation (3 device stages + 2 exchanges) into ONE CUDA graph on the current stream; run() then
+        replays it: one launch per generation instead of five enqueue calls and two collective launches from Python.
+        Returns False (and keeps the eager path) where the capture is not possible (e.g. a gloo group)."""
+        t = self.torch
+        self._graph = None
+        if self.dist is not None and self.world > 1 and self.dist.get_backend(self.group) != "nccl":
+            return False
+        try:
+            g = t.cuda.CUDAGraph()
+            t.cuda.synchronize()
+            with t.cuda.graph(g, stream=t.cuda.current_stream()):
+                self.generation()
+            self._graph = g
+            return True
+        except Exception as e:                       # keep going eagerly; the caller reports which path ran
+            self.capture_error = str(e)
+            self._graph = None
+            return False
+
+    def profile_stages(self, generations):
+        """Mean device time (ms) of the five stages of the EAGER generation, CUDA events on the current stream."""
+        t = self.torch
+        b, acc = self.backend, [0.0] * 5
         for _ in range(generations):
-            self.generation()
+            e = [t.cuda.Event(enable_timing=True) for _ in range(6)]
+            e[0].record(); b.evaluate(self.f_local)
+            e[1].record(); self._all_gather(self.f_all, self.f_local)
+            e[2].record(); b.rank(self.f_all, self.payload)
+            e[3].record(); self._all_gather(self.payload_all, self.payload)
+            e[4].record(); b.update(self.payload_all, self.world)
+            e[5].record()
+            t.cuda.synchronize()
+            for k in range(5):
+                acc[k] += e[k].elapsed_time(e[k + 1]) / generations
+        return acc
+
+    def run(self, generations):
+        g = getattr(self, "_graph", None)
+        for _ in range(generations):
+            if g is not None:
+                g.replay()
+            else:
+                self.generation()

@@ -85,37 +85,49 @@ def ref_available():
         os.path.exists("/root/reference/lmcma_path_planner/src/lmcma.cpp")
 
 
-def ref():
-    global _ref
+_ref_o0 = None
+
+
+def ref(o0=False):
+    """The compiled reference: -O2 (default) or the -O0 -g build (the reference's CMakeLists set CMAKE_BUILD_TYPE Debug)."""
+    global _ref, _ref_o0
+    if o0:
+        if _ref_o0 is None:
+            build()
+            _ref_o0 = _bind_ref(C.CDLL(os.path.join(HERE, "_ref", "libref_lmcma_O0.so")))
+        return _ref_o0
     if _ref is None:
         build()
-        R = C.CDLL(os.path.join(HERE, "_ref", "libref_lmcma.so"))
-        R.ref_lmcma_create.restype = C.c_void_p
-        R.ref_lmcma_create.argtypes = [_c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_double,
-                                       _c_double_p, C.c_int]
-        R.ref_lmcma_destroy.argtypes = [C.c_void_p]
-        R.ref_lmcma_ask.argtypes = [C.c_void_p, _c_double_p]
-        R.ref_lmcma_tell.argtypes = [C.c_void_p, C.c_double]
-        R.ref_lmcma_done.argtypes = [C.c_void_p]
-        R.ref_lmcma_get_ints.argtypes = [C.c_void_p, _c_int_p]
-        R.ref_lmcma_get_doubles.argtypes = [C.c_void_p, _c_double_p]
-        R.ref_lmcma_get_array.argtypes = [C.c_void_p, C.c_int, _c_double_p]
-        R.ref_lmcma_get_int_array.argtypes = [C.c_void_p, C.c_int, _c_int_p]
-        R.ref_lmcma_generation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _c_double_p, _c_double_p]
-        if hasattr(R, "ref_sibling_create"):          # a prebuilt _ref from before the siblings were exposed lacks them
-            R.ref_sibling_create.restype = C.c_void_p
-            R.ref_sibling_create.argtypes = [C.c_int, _c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p,
-                                             C.c_double, C.c_int]
-            R.ref_sibling_destroy.argtypes = [C.c_void_p]
-            R.ref_sibling_lambda.argtypes = [C.c_void_p]
-            R.ref_sibling_run.restype = C.c_double
-            R.ref_sibling_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_double_p]
-        R.ref_rng_uniform.argtypes = [C.c_long, C.c_int, _c_double_p]
-        R.ref_rng_gauss.argtypes = [C.c_long, C.c_long, C.c_long, _c_double_p]
-        R.ref_myqsort.argtypes = [C.c_int, _c_double_p, _c_int_p]
-        R.ref_covariance.argtypes = [C.c_int, C.c_int, _c_double_p]
-        _ref = R
+        _ref = _bind_ref(C.CDLL(os.path.join(HERE, "_ref", "libref_lmcma.so")))
     return _ref
+
+
+def _bind_ref(R):
+    R.ref_lmcma_create.restype = C.c_void_p
+    R.ref_lmcma_create.argtypes = [_c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_double,
+                                   _c_double_p, C.c_int]
+    R.ref_lmcma_destroy.argtypes = [C.c_void_p]
+    R.ref_lmcma_ask.argtypes = [C.c_void_p, _c_double_p]
+    R.ref_lmcma_tell.argtypes = [C.c_void_p, C.c_double]
+    R.ref_lmcma_done.argtypes = [C.c_void_p]
+    R.ref_lmcma_get_ints.argtypes = [C.c_void_p, _c_int_p]
+    R.ref_lmcma_get_doubles.argtypes = [C.c_void_p, _c_double_p]
+    R.ref_lmcma_get_array.argtypes = [C.c_void_p, C.c_int, _c_double_p]
+    R.ref_lmcma_get_int_array.argtypes = [C.c_void_p, C.c_int, _c_int_p]
+    R.ref_lmcma_generation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _c_double_p, _c_double_p]
+    if hasattr(R, "ref_sibling_create"):          # a prebuilt _ref from before the siblings were exposed lacks them
+        R.ref_sibling_create.restype = C.c_void_p
+        R.ref_sibling_create.argtypes = [C.c_int, _c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p,
+                                         C.c_double, C.c_int]
+        R.ref_sibling_destroy.argtypes = [C.c_void_p]
+        R.ref_sibling_lambda.argtypes = [C.c_void_p]
+        R.ref_sibling_run.restype = C.c_double
+        R.ref_sibling_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_double_p]
+    R.ref_rng_uniform.argtypes = [C.c_long, C.c_int, _c_double_p]
+    R.ref_rng_gauss.argtypes = [C.c_long, C.c_long, C.c_long, _c_double_p]
+    R.ref_myqsort.argtypes = [C.c_int, _c_double_p, _c_int_p]
+    R.ref_covariance.argtypes = [C.c_int, C.c_int, _c_double_p]
+    return R
 
 
 _refcost = None
@@ -278,8 +290,8 @@ class RefLMCMA(_Base):
     """The compiled reference.  lambda < 1 -> reference default; seed must be >= 1 for determinism."""
     _prefix = "ref_lmcma_"
 
-    def __init__(self, n, x0=None, lam=0, lo=None, hi=None, sigma=1.0, seed=1, cov=None):
-        self._L = ref()
+    def __init__(self, n, x0=None, lam=0, lo=None, hi=None, sigma=1.0, seed=1, cov=None, o0=False):
+        self._L = ref(o0)
         self.n = n
         arrs = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (x0, lo, hi, cov)]
         x0, lo, hi, cov = arrs

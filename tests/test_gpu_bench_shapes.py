@@ -226,20 +226,108 @@ def test_is_done_and_constants(po, golden):
     assert not dev.is_done().any()
     dev.set("sigma", [1.0, 9.9e-21, 1e-20])                         # strict '<'
     assert dev.is_done().tolist() == [False, True, False]
-    # and through the optimiser itself: a constant fitness makes every generation a failure (success = -1/2 - ... < target),
-    # sigma shrinks geometrically and the run ends by the reference's own rule
+    # and through the optimiser itself: a fitness that gets worse every generation makes every generation a failure (all of
+    # the previous population ranks ahead: success = -1 < target), sigma shrinks geometrically and the run ends by the
+    # reference's own rule
     one = L.LMCMA(np.zeros(6), lambda_=8, sigma=1e-18, inseed=1)
     one.init(6)
     gens = 0
     while not one.isBehaviorLearningDone() and gens < 400:
         for i in range(8):
             one.getNextParameterVector()
-            one.setEvaluationFeedback([1.0], 1)
+            one.setEvaluationFeedback([float(gens)], 1)
         gens += 1
     assert one.isBehaviorLearningDone() and 1 < gens < 400
     ref = po.OracleLMCMA(6, x0=np.zeros(6), lam=8, sigma=1e-18, seed=1)
     rg = 0
     while not ref.done():
-        ref.tell_all(np.ones(8))
+        ref.tell_all(np.full(8, float(rg)))
         rg += 1
     assert rg == gens                                               # same stopping generation as the restated reference
+
+
+def _device_state(dev, b):
+    """The distribution state of instance b as the dict oracle.pyoracle.OracleLMCMA.load_state takes."""
+    st = {k: dev.get(k)[b].astype(np.float64) for k in ("xmean", "pc", "V", "P", "Nj", "Lj")}
+    st.update({k: dev.get(k)[b].copy() for k in ("t", "vec")})
+    st.update(itr=int(dev.get("itr")[b]), live=int(dev.get("live")[b]), sigma=float(dev.get("sigma")[b]), s=float(dev.get("s")[b]))
+    return st
+
+
+def _sampler_matches_oracle(po, dev, n, lam, m, lo, hi, instances):
+    """The population the device has just sampled == the oracle's sample() from the device's own state and deviates."""
+    worst = 0.0
+    Z, X = dev.get("Z"), dev.get("X")
+    for b in instances:
+        st = _device_state(dev, b)
+        ora = po.OracleLMCMA(n, x0=np.zeros(n), lam=lam, m=m, lo=lo, hi=hi, sigma=1.0)
+        ora.load_state(st, np.zeros(lam), Z[b].astype(np.float64))
+        Xo = ora.array("X")
+        scale = max(1.0, float(np.abs(Xo).max()))
+        worst = max(worst, float(np.abs(X[b] - Xo).max()) / scale)
+    return worst
+
+
+def test_rows_sampler_batched_queries_at_the_c3_shape(po, c2_problem):
+    """k_sample_rows (rows on lanes, column slices on warps, two passes; chosen for many rows) at the C3 per-query shape:
+    320 queries x lambda 64, n = 400, m = 40 on the 4096^2 map — two rows per lane (RL = 2, QW = 7).  After 12 and after 47
+    fused generations (pairs being filled / all 40 live and recycled) the sampled population of several instances is
+    held against the FP64 oracle's sample() from the same state and the same recorded deviates; fitness on a row sample
+    against the cost oracle."""
+    p = c2_problem
+    W, lam, m, B = p["W"], 64, 40, 320
+    n = 2 * W
+    starts, goals = maps.random_queries(p["dist"], B, seed=7, min_sep=1024)
+    x0 = np.stack([maps.straight_line(starts[q], goals[q], W) for q in range(B)])
+    dev = L.Optimizer(n, x0=x0, lam=lam, m=m, batch=B, lo=p["lo"], hi=p["hi"], sigma0=32.0, seed=7, record_z=True)
+    dev.attach_cost(p["cmap"], starts, goals, W, L.LONGSAFE, 1e4)
+    for gens in (12, 35):
+        dev.run(gens)
+        dev.sync()
+        assert _sampler_matches_oracle(po, dev, n, lam, m, p["lo"], p["hi"], (0, 7, B - 1)) < 2e-5
+    assert int(dev.get("live")[3]) == m
+    dev.run(1)
+    Xprev = None                                                   # fitness of the population evaluated by that generation: re-evaluate
+    b = 5
+    X = dev.get("X")[b]
+    ref = po.CostProblem(p["dist"], starts[b], goals[b], W, threads=8).evaluate(X[:16])
+    got = p["cmap"].evaluate(X[:16], starts[b], goals[b], W)
+    assert np.array_equal(got["ncoll"], ref["ncoll"]) and rel_err(got["f"], ref["f"]) < COST_RTOL
+
+
+@pytest.mark.parametrize("shape", [(400, 4096, 40, 46, 1), (100, 20480, 6, 14, 2), (48, 4096, 11, 30, 1)])
+def test_rows_sampler_teacher_forced_single_population(po, monkeypatch, shape):
+    """The same kernel forced on ONE large population (LMCMA_B200_SAMPLE_ROWS=1), teacher-forced against the oracle through
+    slot recycling: (n, lambda, m, generations, rows per lane) = C2 row length at lambda 4096; a short row (QW = 4) with two
+    rows per lane; an odd shape (n = 48: 12 float4 columns over 16 warps, four of them idle; m = 11: a partial chunk)."""
+    n, lam, m, gens, rl = shape
+    monkeypatch.setenv("LMCMA_B200_SAMPLE_ROWS", "1")
+    _teacher_forced(po, n, lam, m, gens, seed=31, sigma=0.5)
+
+
+def test_rows_sampler_streams_pairs_that_do_not_fit(po, monkeypatch):
+    """m = 120 pairs of n = 400 (192 KB) do not fit next to the partial-sum and coefficient buffers: both passes stream the
+    chunks through a ring of stages.  The state with all 120 slots live comes from a cheap small-population run of the
+    oracle; the device samples lambda = 4096 offspring from it with injected deviates."""
+    monkeypatch.setenv("LMCMA_B200_SAMPLE_ROWS", "1")
+    n, lam, m = 400, 4096, 120
+    small = po.OracleLMCMA(n, x0=np.full(n, 0.5), lam=16, m=m, sigma=0.4, seed=1)
+    for g in range(m + 9):
+        small.tell_all(weighted_sphere_np(small.array("X")))
+    st = small.state()
+    assert st["live"] == m
+    rng = np.random.default_rng(4)
+    Z = rng.standard_normal((lam, n)).astype(np.float32)
+    dev = L.Optimizer(n, x0=np.full(n, 0.5), lam=lam, m=m, sigma0=0.4, rng="inject")
+    dev.inject_z(Z)
+    dev.load_state(dict(st, prev_fit=np.zeros(lam)))
+    dev.resample()
+    ora = po.OracleLMCMA(n, x0=np.full(n, 0.5), lam=lam, m=m, sigma=0.4)
+    ora.load_state(st, np.zeros(lam), Z.astype(np.float64))
+    Xo, Xd = ora.array("X"), dev.get("X")[0]
+    assert float(np.abs(Xd - Xo).max()) / max(1.0, float(np.abs(Xo).max())) < 2e-5
+
+
+def weighted_sphere_np(X):
+    X = np.atleast_2d(X)
+    return np.sum((1.0 + np.arange(X.shape[1])) * X * X, axis=1)

@@ -707,3 +707,40 @@ def test_the_reference_s_own_demo_binary_runs_on_the_b200_library(tmp_path):
         x, y = (float(v) for v in p.split(","))
         assert abs(x - 4.0) < 5e-2 and abs(y - 4.0) < 5e-2, r.stdout
     assert (tmp_path / "path_to_min.csv").exists() and (tmp_path / "path_to_max_using_cov.csv").exists()
+
+
+def test_ask_all_view_mirror_tracks_the_population(po, golden_maps):
+    """lmcma_b200_ask_all_view: the page-locked mirror the sampler writes while it runs holds exactly what ask_all copies,
+    generation after generation through tell_all (graph path and stream-ordered path), after fused on-device generations
+    (which do not write it: one ordinary copy refreshes it) and after a state setter; lmcma_b200_cost_evaluate called with
+    the view pointer evaluates the device copy and returns the same bits as with the caller's own buffer."""
+    import ctypes as C
+    import torch
+    from lmcma_path_planner_b200 import _capi as K
+    from lmcma_path_planner_b200.optimizer import _endpoints, _objective
+    dist = po.edt_exact(golden_maps["problem2"])
+    cm = L.CostMap(dist, "f32")
+    W, start, goal = 100, (99.0, 0.0), (0.0, 99.0)
+    lo, hi = maps.box_bounds((100, 100), W)
+    x0 = maps.straight_line(start, goal, W)
+    obj, ends = _objective(W, L.LONGSAFE, 1e4), _endpoints(start, goal)
+    for lam, n_extra in ((512, 0), (24, 0)):                       # wide sampler + tell graph / narrow sampler, stream-ordered tell
+        dev = L.Optimizer(2 * W, x0=x0, lam=lam, m=12, lo=lo, hi=hi, sigma0=4.0, seed=3)
+        dev.attach_cost(cm, [start], [goal], W, L.LONGSAFE, 1e4)
+        fp = torch.zeros(lam, dtype=torch.float32).pin_memory().numpy()
+        for g in range(15):
+            V = dev.ask_all_view()
+            X = dev.ask_all()
+            assert np.array_equal(V, X), (lam, g)
+            ref = cm.evaluate(X[0], start, goal, W)
+            xp, ld = C.POINTER(C.c_float)(), C.c_int64(0)
+            K.check(K.lib().lmcma_b200_ask_all_view(dev._h, C.byref(xp), C.byref(ld)))
+            K.check(K.lib().lmcma_b200_cost_evaluate(cm._h, C.byref(obj), C.byref(ends), xp, lam, K.fptr(fp), None, None))
+            assert np.array_equal(fp, ref["f"]), (lam, g)
+            dev.tell_all(fp)
+            if g == 6:
+                dev.run(3)                                         # fused generations do not write the mirror
+                assert np.array_equal(dev.ask_all_view(), dev.ask_all())
+            if g == 9:
+                dev.set("X", dev.ask_all() + 1.0)                  # a setter invalidates it
+                assert np.array_equal(dev.ask_all_view(), dev.ask_all())
