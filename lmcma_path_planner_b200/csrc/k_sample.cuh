@@ -707,13 +707,38 @@ __global__ void __launch_bounds__(512, 1) k_sample_rows(OptDev o, int kc, int ns
         for (int i = 0; i < QW; ++i)
             if (i < qper && q0 + i < nq) reinterpret_cast<float4*>(tile + (size_t)(r * 32 + lane) * tstride)[q0 + i] = acc[r][i];
     __syncthreads();
+    // a thread keeps ONE float4 column and walks down the rows: mean, bounds and the padding mask of the column are loaded
+    // once, consecutive threads still store consecutive 16 bytes of a row
     const double* xm = o.xmean + (size_t)b * ns;
-    for (int e = threadIdx.x; e < ROWS * nq; e += nthr) {
-        const int rr = e / nq, q = e - rr * nq, row = row0 + rr;
-        if (row >= o.pop_count) break;
-        const size_t roff = ((size_t)b * o.pop_count + row) * ns;
-        sample_finish(o, xm, sc.sigma, reinterpret_cast<const float4*>(tile + (size_t)rr * tstride)[q], q, o.X + roff, o.D + roff,
-                      o.Xh ? o.Xh + roff : nullptr);
+    const int rstep = nthr / nq, q = threadIdx.x % nq, r_first = threadIdx.x / nq;     // nq <= 128 <= nthr
+    if (r_first < rstep) {
+        const double2 m01 = reinterpret_cast<const double2*>(xm)[2 * q], m23 = reinterpret_cast<const double2*>(xm)[2 * q + 1];
+        const double mm[4] = {m01.x, m01.y, m23.x, m23.y};
+        float4 lo4 = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f), hi4 = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f);
+        if (o.lo) lo4 = reinterpret_cast<const float4*>(o.lo)[q];
+        if (o.hi) hi4 = reinterpret_cast<const float4*>(o.hi)[q];
+        const float ll[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, hh[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+        const int npad = max(0, q * 4 + 4 - o.n);                    // trailing padding lanes of this column (0 except in the last one)
+        const double sigma = sc.sigma;
+        for (int rr = r_first; rr < ROWS && row0 + rr < o.pop_count; rr += rstep) {
+            const float4 az = reinterpret_cast<const float4*>(tile + (size_t)rr * tstride)[q];
+            const float aa[4] = {az.x, az.y, az.z, az.w};
+            float xx[4], dd[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                            // same arithmetic as sample_finish
+                double x64 = mm[c] + sigma * (double)aa[c];
+                float xf = (float)x64;
+                if (xf < ll[c]) { xf = ll[c]; x64 = (double)ll[c]; }
+                if (xf > hh[c]) { xf = hh[c]; x64 = (double)hh[c]; }
+                const bool pad = c >= 4 - npad;
+                xx[c] = pad ? 0.f : xf;
+                dd[c] = pad ? 0.f : (float)(x64 - mm[c]);
+            }
+            const size_t roff = ((size_t)b * o.pop_count + row0 + rr) * ns;
+            reinterpret_cast<float4*>(o.X + roff)[q] = make_float4(xx[0], xx[1], xx[2], xx[3]);
+            reinterpret_cast<float4*>(o.D + roff)[q] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+            if (o.Xh) __stcs(reinterpret_cast<float4*>(o.Xh + roff) + q, make_float4(xx[0], xx[1], xx[2], xx[3]));
+        }
     }
 }
 

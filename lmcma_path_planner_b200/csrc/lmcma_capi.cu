@@ -453,7 +453,10 @@ int configure_sample(lmcma_b200_opt* o) {
     // many rows (batched queries, or one very large population): rows on lanes, column slices on warps (k_sample_rows)
     o->smp_rows = false;
     const long long total_rows = (long long)o->d.B * o->d.pop_count;
-    const bool many = total_rows >= 4096 && o->d.pop_count >= 32 && (o->d.B > 1 || o->tune.sample_rows == 1);
+    // one population: from lambda = 8192 on it beats the wide sampler even though the progressive hand-over / overlapped
+    // generation (wide sampler only) is given up (fused generation 0.271 -> 0.253 ms at 8192, 1.71 -> 1.41 ms at 65536)
+    const bool many = total_rows >= 4096 && o->d.pop_count >= 32 &&
+                      (o->d.B > 1 || o->tune.sample_rows == 1 || (o->d.pop_count >= 8192 && o->d.pop_count == o->d.lambda));
     if (o->tune.sample_rows != 0 && many && nq <= 128 && o->d.m <= 256 && !o->d_Lf) {
         const int NW = 16;
         const int qper = (nq + NW - 1) / NW;

@@ -302,7 +302,10 @@ def test_rows_sampler_teacher_forced_single_population(po, monkeypatch, shape):
     rows per lane; an odd shape (n = 48: 12 float4 columns over 16 warps, four of them idle; m = 11: a partial chunk)."""
     n, lam, m, gens, rl = shape
     monkeypatch.setenv("LMCMA_B200_SAMPLE_ROWS", "1")
-    _teacher_forced(po, n, lam, m, gens, seed=31, sigma=0.5)
+    # V (k_update's FP32 sweep, not this kernel) carries 4e-5 of its scale at lambda = 4096: with mueff ~ 2300 the evolution
+    # paths are long and nearly collinear with the stored directions, so each factor removes most of a row (DESIGN.md 5);
+    # the sampled candidates X, the state the sampler produces, stay at 1e-6
+    _teacher_forced(po, n, lam, m, gens, seed=31, sigma=0.5, tol_v=1e-4)
 
 
 def test_rows_sampler_streams_pairs_that_do_not_fit(po, monkeypatch):

@@ -143,7 +143,7 @@ def test_cost_full_size_properties(po):
 # optimiser: teacher-forced generations against the FP64 oracle
 # ------------------------------------------------------------------------------------------------
 def _teacher_forced(po, n, lam, m, gens, seed, lo=None, hi=None, sigma=1.0, fobj=weighted_sphere, x0=None,
-                    tol=2e-5):
+                    tol=2e-5, tol_v=None):
     rng = np.random.default_rng(seed)
     x0 = np.full(n, 0.5) if x0 is None else x0
     dev = L.Optimizer(n, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=sigma, rng="inject")
@@ -188,7 +188,7 @@ def _teacher_forced(po, n, lam, m, gens, seed, lo=None, hi=None, sigma=1.0, fobj
         dev.resample()            # X of the next generation comes from the oracle's exact state + the same z
     assert worst["sigma"] < 1e-12, worst
     for k in ("X", "xmean", "pc", "V", "P"):
-        assert worst[k] < tol, (k, worst)
+        assert worst[k] < (tol_v if (k == "V" and tol_v) else tol), (k, worst)
     assert worst["Nj"] < 1e-4 and worst["Lj"] < 1e-4, worst
     return worst
 
@@ -744,3 +744,19 @@ def test_ask_all_view_mirror_tracks_the_population(po, golden_maps):
             if g == 9:
                 dev.set("X", dev.ask_all() + 1.0)                  # a setter invalidates it
                 assert np.array_equal(dev.ask_all_view(), dev.ask_all())
+
+
+def test_ipop_restarts_tool_runs_and_reports(tmp_path):
+    """C5 mechanics (tools/c5_ipop_restarts.py): doubling populations on the cluttered map, every restart a fresh optimiser
+    stopped by the reference's sigma rule or the generation cap, best path re-evaluated for its collision count.  Small
+    sizes here (512^2 map, lambda 64..256); the 8-GPU run at lambda 1024..65536 is under profiles/."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "c5_ipop_restarts.py"), "256", "40", "64", "512"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if "restart" in ln and "lambda" in ln]
+    assert len(lines) == 3 and "C5: 3 restarts (lambda 64..256)" in r.stdout, r.stdout
+    assert all("colliding samples" in ln for ln in lines)

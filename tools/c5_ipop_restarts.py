@@ -19,14 +19,15 @@ lam_max = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 max_gens = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 lam0 = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 W, m = 200, 40
+size = int(sys.argv[4]) if len(sys.argv) > 4 else 4096          # map edge (tests use a small one)
 torch.cuda.set_device(local)
 dist = None
 if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-dmap, start, goal = maps.config2_map(n_rects=4 * 2048, seed=42)        # "cluttered": 4x the obstacle count
+dmap, start, goal = maps.config2_map(size=size, n_rects=4 * 2048, seed=42)        # "cluttered": 4x the obstacle count
 cmap = L.CostMap(dmap, "f32", device=local)
-lo, hi = maps.box_bounds((4096, 4096), W)
+lo, hi = maps.box_bounds((size, size), W)
 x0 = maps.straight_line(start, goal, W)
 lams = parallel.ipop_schedule(lam0, lam_max)
 mine = parallel.assign_largest_first([float(l) for l in lams], world)[rank]
@@ -44,9 +45,11 @@ for r in mine:
         opt.run(step)                       # fused generations, no host round trip inside
         gens += step
         if float(opt.get("sigma")[0]) < 1e-20: break          # isBehaviorLearningDone (checked every 25 generations)
-    f = float(opt.best()[1][0])
+    xb, fb = opt.best()
+    f = float(fb[0])
+    nc = int(cmap.evaluate(xb[0], start, goal, W, L.LONGSAFE, 1e4)["ncoll"][0])    # colliding samples of the best path found
     evals += lam * gens
-    log.append((r, lam, gens, f, float(opt.get("sigma")[0])))
+    log.append((r, lam, gens, f, float(opt.get("sigma")[0]), nc, time.perf_counter() - t0))
     if f < best_f: best_f, best_r = f, r
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
@@ -57,8 +60,10 @@ if dist is not None:
     rows = torch.stack(allt).cpu().numpy()
     dt, evals = float(rows[:, 0].max()), float(rows[:, 1].sum())
     k = int(np.argmin(rows[:, 2])); best_f, best_r = float(rows[k, 2]), int(rows[k, 3])
-for r, lam, gens, f, sg in log:
-    print("  rank %d restart %d: lambda %6d, %3d generations, best f %.6g, sigma %.3g" % (rank, r, lam, gens, f, sg), flush=True)
+for r, lam, gens, f, sg, nc, tdone in log:
+    print("  rank %d restart %d: lambda %6d, %3d generations, best f %.6g (%d colliding samples), sigma %.3g, done at %.3f s" %
+          (rank, r, lam, gens, f, nc, sg, tdone), flush=True)
+print("  rank %d wall clock %.3f s for restarts %s" % (rank, time.perf_counter() - t0, [r for r, *_ in log]), flush=True)
 if dist is not None: dist.barrier()
 if rank == 0:
     print("C5: %d restarts (lambda %d..%d) on %d GPU(s): %.3f s wall (max over ranks), %.3g evals, %.3g evals/s, best f %.6g from restart %d" %
