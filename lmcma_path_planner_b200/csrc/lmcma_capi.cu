@@ -86,7 +86,7 @@ int env_int(const char* name, int dflt) {
 // Every LMCMA_B200_* environment knob, read ONCE when a handle (map or optimiser) is created and kept on the handle:
 // nothing on a launch path calls getenv.  All of them are experiment / debugging switches; the defaults are the product.
 struct Tuning {
-    int cost_minb = 7, cost_tpt = 0, cost_cb = 0, zerocopy = 1;
+    int cost_minb = 0 /* 0 = by launch size */, cost_tpt = 0, cost_cb = 0, zerocopy = 1;
     int sample_rows = -1;   // k_sample_rows: -1 = where it pays (many rows), 0 = never, 1 = also for one large population
     int sample_spec = 1, sample_threads = 0, sample_smem_kb = 160, sample_smem_kb_set = 0, sample_narrow = 0, sample_rbw = 0, sample_r = 0;
     int update_blocked = 0, update_gram = 0, update_streaming = 0, update_sweep_warps = 0;
@@ -254,7 +254,11 @@ int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, CostShape 
         if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, shape, st);
         return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, shape, st);
     }
-    if (shape.minb == 6) {                                    // the un-spilled 40-register build (experiment, k_cost.cuh)
+    // seven CTAs per SM (32 registers, some spills) keep a 1024-trajectory population resident in ONE wave; from four waves
+    // on the tail no longer matters and the un-spilled 40-register build at six per SM is 7 % faster (C3-shaped batch: 0.280 ->
+    // 0.261 ms for 16384 trajectories, profiles/r2_cost_timeline.txt; the single C2 query: 31.0 vs 33.9 us the other way round)
+    const int minb = shape.minb ? shape.minb : ((long long)rows * B >= 4LL * 7 * 148 ? 6 : 7);
+    if (minb == 6) {
         if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false, 6>(mp, a, rows, B, shape, st);
         return mp.storage == 0 ? launch_cost_t<3, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false, 6>(mp, a, rows, B, shape, st);
     }

@@ -133,7 +133,7 @@ struct CostArgs {
     long long* dbg;            // optional (LMCMA_B200_COST_DBG): 8 globaltimer stamps per CTA, [cta * 8 + k]
 };
 
-struct CostShape { int tpt = 128, cb = 256, minb = 7; };   // launch shape of k_cost: threads per trajectory, block-record capacity, CTAs per SM it was compiled for
+struct CostShape { int tpt = 128, cb = 256, minb = 0; };   // launch shape of k_cost: threads per trajectory, block-record capacity, CTAs per SM of the build to launch (0 = chosen by the launch size)
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers

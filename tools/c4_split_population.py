@@ -18,6 +18,7 @@ size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 500
 lam = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
 gens = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+strict = len(sys.argv) > 5 and sys.argv[5] == "strict"          # short run, tight bars (tests/test_gpu_parity.py, >= 2 GPUs)
 n = 3 * W
 m = int(2 * np.sqrt(n))
 torch.cuda.set_device(local)
@@ -55,6 +56,20 @@ if rank == 0:
     print("C4 split population: %d^3 u8 map, n=%d, lambda=%d over %d GPU(s), m=%d: %.3f ms/generation, %.3g evals/s" %
           (size, n, lam, world, m, ms / gens, lam * gens / (ms * 1e-3)))
     print("split vs unsplit after %d generations: sigma %.6g vs %.6g, max |xmean diff| %.3g cells" % (3 + gens, ss, sw, dx))
-    assert abs(ss - sw) <= 0.05 * sw and dx < 1.0, "split-population run does not track the unsplit optimiser"
+    if strict:
+        # same kernels, same Philox rows, same deterministic reductions: the split run differs from the unsplit one only by the
+        # association of the per-rank partial sums (FP32), which a short run cannot amplify
+        assert abs(ss - sw) <= 1e-9 * sw and dx < 1e-2, "split-population run differs from the unsplit optimiser"
+        print("strict check passed")
+    else:
+        # long free runs: FP32 rounding differences are amplified chaotically once a rank flips
+        assert abs(ss - sw) <= 0.05 * sw and dx < 1.0, "split-population run does not track the unsplit optimiser"
+# every rank holds the same replica, bit for bit
+chk = torch.tensor(np.concatenate([part.get("xmean")[0], [float(part.get("sigma")[0])]]), dtype=torch.float64, device="cuda")
+ref = chk.clone()
+dist.broadcast(ref, src=0)
+assert bool(torch.equal(chk, ref)), "replicas diverged on rank %d" % rank
+if rank == 0:
+    print("replicas bit-identical on all %d ranks" % world)
 dist.barrier()
 dist.destroy_process_group()
