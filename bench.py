@@ -43,8 +43,8 @@ FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cost launch of this workload, from the committed
 # `ncu --set full` capture (the map stays L2-resident between generations, so DRAM traffic is far BELOW the
 # algorithmic bytes: the kernel is bound by the L1 line rate of the gather, not by HBM)
-NCU_DRAM_BYTES_PER_LAUNCH = 2.378e6
-NCU_SOURCE = "profiles/r1f_full.md (k_cost<2,0,0>: dram_read 2.378 MB, dram_write 0)"
+NCU_DRAM_BYTES_PER_LAUNCH = 2.381e6
+NCU_SOURCE = "profiles/r2l_full.md (k_cost<2,0,0,7>: dram_read 2.381 MB, dram_write 0)"
 
 
 def peaks():
@@ -274,8 +274,14 @@ def run_b200(args):
             out["c3_sharded"] = c3
         if c4 is not None:
             out["c4_split"] = c4
+        out["cost_kernel"] = {"evals_per_s": LAM / (cost_ms * 1e-3), "note": "k_cost alone (CUDA events, L2 flushed): the numerator of the "
+                              "north star's '>= 100x the CPU trajectory-evaluation throughput' target"}
         if world == 1 and "cpu" not in skip:
             out["cpu_baseline"] = cpu_baseline_all(dist, start, goal, lo, hi, x0)
+            try:
+                out["cost_kernel"]["speedup_vs_cpu_cost_all_cores"] = out["cost_kernel"]["evals_per_s"] / out["cpu_baseline"]["parts"]["cost_only_all_cores"]["value"]
+            except Exception:
+                pass
         elif "cpu" not in skip:
             out["cpu_baseline"] = {"note": "timed at N = 1 only (rank 0); see the N = 1 line and --impl reference"}
         print(json.dumps(out))

@@ -144,8 +144,15 @@ __global__ void __launch_bounds__(64 * TMAX) k_coef(OptDev o) {
     if (first_stale == 0) finish(i == 0, 1.0);                    // v_0 = pc_0
     __syncthreads();
     double kp = 1.0;                                              // K^(j+1) inside step j
+    // a warp carries 4 consecutive rows: once its last row is final (or all of them are unchanged rows in front of the first
+    // stale position) it has nothing left but the barrier — without this every warp issued the shuffles and predicated
+    // bodies of every factor, and the one SM of this kernel is short of issue slots (ncu: 184 warp instructions per warp and
+    // factor, the samples waiting at the barrier)
+    const int warp_last_row = min(L - 1, (tid >> 5) * 4 + 3);
+    const bool warp_recomputes = (tid >> 5) * 4 < L && warp_last_row >= first_stale;
     for (int j = 0; j + 1 < L; ++j) {
         kp *= Kd;
+        if (!warp_recomputes || warp_last_row <= j) { __syncthreads(); continue; }   // warp-uniform
         // factor j on every pending row i > j: x <- K x - Lj_j (v_j . x) v_j (lmcma.cpp:455-461), on y = x / K^j
         const bool fresh = j >= first_stale;                      // v_j was recomputed in this sweep (else coef(v_j) = e_j)
         const bool on = row_on && i > j && i >= first_stale;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(64 * TMAX) k_coef(OptDev o) {
                 if (k < L) u[t] = fma(e, wj[k], u[t]);             // the whole row: W_i[k], k > i, updates the rows behind i
             }
         }
-        finish(on && i == j + 1, kp);                             // row j + 1 is final now
+        if (((j + 1) >> 2) == (tid >> 5)) finish(on && i == j + 1, kp);   // row j + 1 is final now (the warp that carries it)
         __syncthreads();
     }
     // ---- outputs: coefficients of the recomputed rows, Nj / Lj (lmcma.cpp:386-389) by slot and by position ----

@@ -1,69 +1,22 @@
-// lmcma_capi.cu — the C ABI declared in include/lmcma_b200.h: handles, HBM layout, kernel launches,
-// the per-generation CUDA graph.  No CPU fallback: every compute entry point needs a CUDA device.
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <atomic>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <limits>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "../../include/lmcma_b200.h"
-#include "lmcma_host.hpp"
-#include "lmcma_kernels.cuh"
+// lmcma_capi.cu — the C ABI declared in include/lmcma_b200.h: library / device queries, the optimiser entry points, launch
+// configuration of the sampler / rank / update kernels, the per-generation CUDA graphs, the split-population stages.
+// No CPU fallback: every compute entry point needs a CUDA device.  Cost map + evaluator: lmcma_capi_map.cu; state
+// access + host-side reference pieces: lmcma_capi_state.cu; shared declarations: lmcma_internal.cuh.
+#include "lmcma_internal.cuh"
+#include "k_rank.cuh"
+#include "k_sample.cuh"
+#include "k_update.cuh"
+#include "k_prior.cuh"
+#include "k_gram.cuh"
 
 using namespace lmcma;
+using namespace lmcma_capi;
 
-namespace {
-
+namespace lmcma_capi {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-
-int fail(int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
-}
-
-#define CU(call)                                                                                    \
-    do {                                                                                            \
-        cudaError_t e__ = (call);                                                                   \
-        if (e__ != cudaSuccess)                                                                     \
-            return fail(LMCMA_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-#define ARG(cond, msg)                                                   \
-    do {                                                                 \
-        if (!(cond)) return fail(LMCMA_B200_ERR_ARG, "%s (%s)", msg, #cond); \
-    } while (0)
-
-template <class T>
-int dmalloc(T** p, size_t count) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
-    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
-    e = cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T));
-    // the memset is asynchronous on the legacy stream, which the library's non-blocking streams do not wait for: without
-    // this wait it can land AFTER a copy / kernel that one of those streams issues into the new buffer
-    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
-    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
-    return 0;
-}
-#define DM(ptr, count)                              \
-    do {                                            \
-        int rc__ = dmalloc(&(ptr), (count));        \
-        if (rc__) return rc__;                      \
-    } while (0)
-
-}  // namespace
+DeviceProps g_props[64];
+}  // namespace lmcma_capi
 namespace lmcma {
 // error reporting for the other translation units of the library (lmcma_ingest.cpp)
 int set_error(int code, const char* fmt, ...) {
@@ -72,222 +25,12 @@ int set_error(int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    g_err = buf;
+    lmcma_capi::g_err = buf;
     return code;
 }
 }  // namespace lmcma
+
 namespace {
-
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
-// Every LMCMA_B200_* environment knob, read ONCE when a handle (map or optimiser) is created and kept on the handle:
-// nothing on a launch path calls getenv.  All of them are experiment / debugging switches; the defaults are the product.
-struct Tuning {
-    int cost_minb = 0 /* 0 = by launch size */, cost_tpt = 0, cost_cb = 0, zerocopy = 1;
-    int sample_rows = -1;   // k_sample_rows: -1 = where it pays (many rows), 0 = never, 1 = also for one large population
-    int sample_spec = 1, sample_threads = 0, sample_smem_kb = 160, sample_smem_kb_set = 0, sample_narrow = 0, sample_rbw = 0, sample_r = 0;
-    int update_blocked = 0, update_gram = 0, update_streaming = 0, update_sweep_warps = 0;
-    int progressive = 1, overlap = 1, tell_overlap = 1, rank_late = 1, rank_sorted = 1;
-    int graph_dbg = 0, dbg = 0, update_dbg = 0, cost_dbg = 0;
-    static Tuning from_env() {
-        Tuning t;
-        t.cost_minb = env_int("LMCMA_B200_COST_MINB", t.cost_minb);
-        t.cost_tpt = env_int("LMCMA_B200_COST_TPT", 0);
-        t.cost_cb = env_int("LMCMA_B200_COST_CB", 0);
-        t.zerocopy = env_int("LMCMA_B200_ZEROCOPY", 1);
-        t.sample_spec = env_int("LMCMA_B200_SAMPLE_SPEC", 1);
-        t.sample_rows = env_int("LMCMA_B200_SAMPLE_ROWS", -1);
-        t.sample_threads = env_int("LMCMA_B200_SAMPLE_THREADS", 0);
-        t.sample_smem_kb_set = env_int("LMCMA_B200_SAMPLE_SMEM_KB", 0);
-        t.sample_smem_kb = t.sample_smem_kb_set ? t.sample_smem_kb_set : 160;
-        t.sample_narrow = env_int("LMCMA_B200_SAMPLE_NARROW", 0);
-        t.sample_rbw = env_int("LMCMA_B200_SAMPLE_RBW", 0);
-        t.sample_r = env_int("LMCMA_B200_SAMPLE_R", 0);
-        t.update_blocked = env_int("LMCMA_B200_UPDATE_BLOCKED", 0);
-        t.update_gram = env_int("LMCMA_B200_UPDATE_GRAM", 0);
-        t.update_streaming = env_int("LMCMA_B200_UPDATE_STREAMING", 0);
-        t.update_sweep_warps = env_int("LMCMA_B200_UPDATE_SWEEP_WARPS", 0);
-        t.progressive = env_int("LMCMA_B200_PROGRESSIVE", 1);
-        t.overlap = env_int("LMCMA_B200_OVERLAP", 1);
-        t.tell_overlap = env_int("LMCMA_B200_TELL_OVERLAP", 1);
-        t.rank_late = env_int("LMCMA_B200_RANK_LATE", 1);
-        t.rank_sorted = env_int("LMCMA_B200_RANK_SORTED", 1);
-        t.graph_dbg = env_int("LMCMA_B200_GRAPH_DBG", 0);
-        t.dbg = getenv("LMCMA_B200_DBG") ? 1 : 0;
-        t.update_dbg = getenv("LMCMA_B200_UPDATE_DBG") ? 1 : 0;
-        t.cost_dbg = getenv("LMCMA_B200_COST_DBG") ? 1 : 0;
-        return t;
-    }
-};
-
-struct DeviceProps {
-    int sm_count = 0;
-    size_t l2 = 0, smem_optin = 0, persist_max = 0;
-    int cc = 0;
-    bool ok = false;
-    int cosched = -1;     // probe_coschedule: -1 not probed yet, 0 branches of a forked graph are serialised here, 1 they run concurrently
-};
-DeviceProps g_props[64];
-int query_props(int device, DeviceProps** out) {
-    ARG(device >= 0 && device < 64, "device ordinal out of range");
-    DeviceProps& p = g_props[device];
-    if (!p.ok) {
-        cudaDeviceProp dp;
-        CU(cudaGetDeviceProperties(&dp, device));
-        p.sm_count = dp.multiProcessorCount;
-        p.l2 = dp.l2CacheSize;
-        p.smem_optin = dp.sharedMemPerBlockOptin;
-        p.persist_max = dp.persistingL2CacheMaxSize;
-        p.cc = dp.major * 10 + dp.minor;
-        if (dp.major < 10) return fail(LMCMA_B200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, dp.major, dp.minor);
-        p.ok = true;
-    }
-    *out = &p;
-    return 0;
-}
-
-}  // namespace
-
-// =================================================================================================
-// handles
-// =================================================================================================
-struct lmcma_b200_map {
-    int device = 0;
-    Tuning tune;
-    MapDev dev{};
-    int storage = 0;
-    float c_min = 0.5f, scale = 1.f;
-    size_t cells = 0, stored = 0;   // logical cells / stored elements (bricked, padded)
-    float* d_g32 = nullptr;
-    unsigned char* d_q8 = nullptr;
-    float* d_lut = nullptr;
-    bool persist = false;
-    cudaStream_t stream = nullptr;   // private stream for the stand-alone evaluate calls
-    // staging for the host-buffer evaluate path
-    float* d_X = nullptr; size_t d_X_cap = 0;
-    float* d_f = nullptr; int* d_nc = nullptr; int* d_ns = nullptr; size_t d_out_cap = 0;
-    std::mutex host_path;            // lmcma_b200_cost_evaluate / cost_trace share the staging buffers and the private stream
-};
-
-struct lmcma_b200_opt {
-    lmcma_b200_config cfg{};
-    Tuning tune;
-    OptDev d{};
-    DeviceProps* props = nullptr;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    // host mirrors
-    std::vector<double> weights;       // mu
-    std::vector<float> lo_f, hi_f;
-    float* d_lo = nullptr; float* d_hi = nullptr; float* d_w = nullptr;
-    // rng
-    HansenStream hansen{1};
-    std::vector<float> z_host;         // staging for HANSEN
-    bool needs_sample = false, pending_z = false;
-    // reference one-at-a-time protocol
-    int sample_idx = 0;
-    std::vector<float> x_cache; bool x_cache_valid = false;
-    std::vector<float> f_host;
-    // attached cost
-    lmcma_b200_map* map = nullptr;
-    lmcma_b200_objective obj{};
-    float* d_ends = nullptr;
-    // graph
-    cudaGraphExec_t graph_exec = nullptr;
-    cudaStream_t graph_built_for = nullptr;
-    cudaGraphExec_t tell_graph = nullptr;     // tell_all of one query: H2D fitness -> k_rank -> k_sample, k_update on a side branch
-    cudaStream_t tell_graph_for = nullptr;
-    bool tell_graph_failed = false;
-    float* f_pinned = nullptr;                // the graph's copy source (the caller's fitness array is copied here first)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool have_run_timing = false;
-    // sample launch config
-    int smp_threads = 128, smp_kc = 1, smp_nv = 1, smp_rb = 1, smp_stages = 2;
-    bool smp_wide = false; int smp_R = 1, smp_CW = 1, smp_qpw = 32, smp_RBW = 1;
-    bool smp_rows = false; int smp_rows_qw = 8, smp_rows_rl = 1, smp_rows_kc = 8, smp_rows_stages = 2, smp_rows_region = 0;   // k_sample_rows
-    size_t smp_rows_smem = 0;
-    float* d_Lf = nullptr;             // lower Cholesky factor of the smoothness prior (n x ns FP32) or null
-    bool mirror_dirty = true;          // the sequence-ordered pair mirror must be rebuilt (k_pack_pairs) before sampling
-    size_t smp_smem = 0;
-    CostShape cost_shape;
-    bool progressive = false;   // k_update -> k_sample hand-over inside the fused generation (k_update.cuh)
-    bool overlap = false;       // fused generation with k_update on a side branch, concurrent with k_cost / k_rank (k_update.cuh)
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    float* x_mirror = nullptr;        // page-locked, mapped host mirror of X (lmcma_b200_ask_all_view); OptDev::Xh is its device alias
-    bool mirror_on = false, mirror_suppressed = false, xh_fresh = false;
-    int* err_host = nullptr;          // page-locked, mapped: OptDev::err (a kernel of the overlapped generation gave up on its partner)
-    long long* graph_dbg = nullptr;   // LMCMA_B200_GRAPH_DBG: k_update's timeline inside the fused generation, printed by lmcma_b200_sync
-    int upd_nvb = 4, upd_rmax = 0, upd_sweep_warps = 16;
-    bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
-    bool upd_rows_in_smem = true;
-    size_t upd_smem = 0, rank_smem = 0;
-    size_t cost_smem = 0;
-};
-
-// =================================================================================================
-// launch helpers
-// =================================================================================================
-namespace {
-
-template <int DIMS, int STORAGE, bool TRACE, int MINB = 7>
-int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostShape shape, cudaStream_t st) {
-    CostArgs a = a0;
-    a.cb = shape.cb;
-    // segment records 36 B, sample offsets, per-block records 8 B (k_cost.cuh), 256-entry table (u8 storage)
-    // + the candidate row (16-byte aligned)
-    const size_t smem = (size_t)36 * (a.W + 1) + sizeof(int) * (a.W + 2) + 28 + (size_t)8 * shape.cb + (STORAGE == 1 ? 1024 : 0) +
-                        sizeof(float) * DIMS * ((size_t)a.W + 2) + 16;
-    auto kern = k_cost<DIMS, STORAGE, TRACE, MINB>;
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(rows, B), shape.tpt, smem, st>>>(mp, a);
-    g_launches++;
-    CU(cudaGetLastError());
-    return 0;
-}
-
-int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, CostShape shape, bool trace, cudaStream_t st) {
-    if (rows <= 0 || B <= 0) return 0;
-    if (trace) {
-        if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, shape, st);
-        return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, shape, st);
-    }
-    // seven CTAs per SM (32 registers, some spills) keep a 1024-trajectory population resident in ONE wave; from four waves
-    // on the tail no longer matters and the un-spilled 40-register build at six per SM is 7 % faster (C3-shaped batch: 0.280 ->
-    // 0.261 ms for 16384 trajectories, profiles/r2_cost_timeline.txt; the single C2 query: 31.0 vs 33.9 us the other way round)
-    const int minb = shape.minb ? shape.minb : ((long long)rows * B >= 4LL * 7 * 148 ? 6 : 7);
-    if (minb == 6) {
-        if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false, 6>(mp, a, rows, B, shape, st);
-        return mp.storage == 0 ? launch_cost_t<3, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false, 6>(mp, a, rows, B, shape, st);
-    }
-    if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false>(mp, a, rows, B, shape, st);
-    return mp.storage == 0 ? launch_cost_t<3, 0, false>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false>(mp, a, rows, B, shape, st);
-}
-
-// CTA width and per-block record capacity of k_cost from the expected samples per trajectory
-CostShape pick_cost_shape(int W, const float* start, const float* goal, int dims, const Tuning& tune) {
-    float linf = 0.f;
-    if (start && goal)
-        for (int c = 0; c < dims; ++c) linf = std::max(linf, std::fabs(goal[c] - start[c]));
-    const double est = 2.0 * (W + 1) + linf;     // expected samples per trajectory
-    CostShape sh;
-    sh.tpt = 32;
-    // enough lanes for the samples, and a thread per segment (phase 1 is a chain of dependent loads per segment);
-    // k_cost is built for at most 8 warps (COST_MAX_WARPS)
-    while (sh.tpt < 256 && (est / sh.tpt > 24.0 || W + 1 > sh.tpt)) sh.tpt <<= 1;
-    const int forced = tune.cost_tpt;
-    if (forced >= 32 && forced <= 256 && forced % 32 == 0) sh.tpt = forced;
-    sh.minb = tune.cost_minb;
-    // 32-sample blocks whose records are staged at once (longer trajectories take several rounds): ~3x the estimate
-    sh.cb = 64;
-    while (sh.cb < 2048 && sh.cb * 32.0 < 3.0 * est) sh.cb <<= 1;
-    const int forced_cb = tune.cost_cb;
-    if (forced_cb >= 8 && forced_cb <= 4096) sh.cb = forced_cb;
-    return sh;
-}
-
 template <int NV, int RB, int MAXT, bool SPEC = false>
 int launch_sample_t(lmcma_b200_opt* o, const OptDev& d, bool pdl, cudaStream_t st) {
     auto kern = k_sample<NV, RB, MAXT, SPEC>;
@@ -680,7 +423,8 @@ int probe_coschedule(lmcma_b200_opt* o) {
 // A kernel of the overlapped generation gave up waiting for its partner (OptDev::err): report it ONCE, and keep the
 // handle usable on the linear PDL graph from here on.  The generation in flight is void: the optimiser state must be
 // restored by the caller (set_* from a checkpoint) or the handle recreated.
-int check_lost(lmcma_b200_opt* o) {
+}  // namespace
+int lmcma_capi::check_lost(lmcma_b200_opt* o) {
     if (!o->err_host || *reinterpret_cast<volatile int*>(o->err_host) == 0) return 0;
     const int code = *reinterpret_cast<volatile int*>(o->err_host);
     *reinterpret_cast<volatile int*>(o->err_host) = 0;
@@ -695,6 +439,7 @@ int check_lost(lmcma_b200_opt* o) {
                 "flight is void - restore the state or recreate the handle (LMCMA_B200_OVERLAP=0 avoids the overlapped graph)",
                 code == LOST_UPDATE_WAITING_FOR_RANK ? "k_update timed out waiting for k_rank" : "k_sample timed out waiting for k_update");
 }
+namespace {
 
 int ensure_graph(lmcma_b200_opt* o) {
     if (o->graph_exec && o->graph_built_for == o->stream) return 0;
@@ -785,63 +530,8 @@ int ensure_tell_graph(lmcma_b200_opt* o) {
     return 0;
 }
 
-// device-side alias of a page-locked host buffer (unified addressing), or null for pageable / foreign memory
-void* mapped_device_pointer(const void* host, int device) {
-    cudaPointerAttributes at;
-    memset(&at, 0, sizeof(at));
-    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
-    (void)device;
-    return at.devicePointer;
-}
-
-// Page-locked host mirrors of candidate populations handed out by lmcma_b200_ask_all_view: lmcma_b200_cost_evaluate
-// recognises a pointer into one of them and evaluates the DEVICE copy it mirrors (no H2D of the candidates).
-struct MirrorEntry { const char* host; size_t bytes; const float* dev; long long ld; int device; };
-std::mutex g_mirror_mu;
-std::vector<MirrorEntry> g_mirrors;
-void register_mirror(const void* host, size_t bytes, const float* dev, long long ld, int device) {
-    std::lock_guard<std::mutex> lk(g_mirror_mu);
-    g_mirrors.push_back(MirrorEntry{static_cast<const char*>(host), bytes, dev, ld, device});
-}
-void unregister_mirror(const void* host) {
-    std::lock_guard<std::mutex> lk(g_mirror_mu);
-    for (size_t i = 0; i < g_mirrors.size(); ++i)
-        if (g_mirrors[i].host == host) { g_mirrors.erase(g_mirrors.begin() + i); break; }
-}
-// device row pointer + row stride behind a host pointer that lies inside a registered mirror (row-aligned), else null
-const float* mirrored_device_rows(const void* host, int device, size_t need_bytes, long long* ld) {
-    std::lock_guard<std::mutex> lk(g_mirror_mu);
-    const char* p = static_cast<const char*>(host);
-    for (const MirrorEntry& m : g_mirrors) {
-        if (m.device != device || p < m.host || p + need_bytes > m.host + m.bytes) continue;
-        const size_t off = (size_t)(p - m.host);
-        if (off % ((size_t)m.ld * sizeof(float)) != 0) continue;
-        *ld = m.ld;
-        return m.dev + off / sizeof(float);
-    }
-    return nullptr;
-}
-
-// dense <-> pitched copies
-int d2h_rows(void* dst, const void* src, size_t rows, size_t width_bytes, size_t src_pitch_bytes, cudaStream_t st) {
-    if (width_bytes == src_pitch_bytes) CU(cudaMemcpyAsync(dst, src, rows * width_bytes, cudaMemcpyDeviceToHost, st));   // dense: one 1-D copy
-    else CU(cudaMemcpy2DAsync(dst, width_bytes, src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return 0;
-}
-int h2d_rows(void* dst, const void* src, size_t rows, size_t width_bytes, size_t dst_pitch_bytes, cudaStream_t st) {
-    if (width_bytes == dst_pitch_bytes) CU(cudaMemcpyAsync(dst, src, rows * width_bytes, cudaMemcpyHostToDevice, st));
-    else CU(cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, width_bytes, width_bytes, rows, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-    return 0;
-}
-
 }  // namespace
 
-// =================================================================================================
-// library / device
-// =================================================================================================
 extern "C" {
 
 int lmcma_b200_abi_version(void) { return LMCMA_B200_ABI_VERSION; }
@@ -861,362 +551,6 @@ int lmcma_b200_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t
     if (hbm_bytes) *hbm_bytes = (int64_t)dp.totalGlobalMem;
     if (cc) *cc = dp.major * 10 + dp.minor;
     return 0;
-}
-
-// =================================================================================================
-// cost map
-// =================================================================================================
-// handle + device buffers + LUT of a cost map (no contents yet)
-extern "C" int lmcma_b200_map_destroy(lmcma_b200_map* m);
-static int map_alloc(int device, int dims, const int32_t* shape, int storage, float u8_scale, float c_min, lmcma_b200_map** out) {
-    ARG(out && shape, "null pointer");
-    ARG(dims == 2 || dims == 3, "dims must be 2 or 3");
-    ARG(storage == LMCMA_B200_MAP_F32 || storage == LMCMA_B200_MAP_U8, "unknown storage");
-    ARG(c_min > 0.f, "c_min must be > 0");
-    ARG(storage == LMCMA_B200_MAP_F32 || u8_scale > 0.f, "u8_scale must be > 0");
-    for (int c = 0; c < dims; ++c) ARG(shape[c] >= 1, "bad shape");
-    DeviceProps* props;
-    int rc = query_props(device, &props);
-    if (rc) return rc;
-    CU(cudaSetDevice(device));
-    lmcma_b200_map* m = new lmcma_b200_map();
-    m->tune = Tuning::from_env();
-    m->device = device; m->storage = storage; m->c_min = c_min; m->scale = u8_scale;
-    m->dev.dims = dims; m->dev.nx = shape[0]; m->dev.ny = shape[1]; m->dev.nz = dims == 3 ? shape[2] : 1;
-    m->dev.storage = storage; m->dev.g_coll = 1.0f / c_min;
-    m->cells = (size_t)m->dev.nx * m->dev.ny * m->dev.nz;
-    const BrickShape bs = dims == 2 ? (storage == 0 ? brick_shape<2, 0>() : brick_shape<2, 1>())
-                                    : (storage == 0 ? brick_shape<3, 0>() : brick_shape<3, 1>());
-    const unsigned nbx = (m->dev.nx + bs.bx - 1) / bs.bx, nby = (m->dev.ny + bs.by - 1) / bs.by,
-                   nbz = (m->dev.nz + bs.bz - 1) / bs.bz;
-    m->dev.nbx = nbx; m->dev.nby = nby;
-    if (dims == 2) { m->dev.py = storage == 0 ? brick_pitch_y<2, 0>(nbx) : brick_pitch_y<2, 1>(nbx); m->dev.pz = 0; }
-    else {
-        m->dev.py = storage == 0 ? brick_pitch_y<3, 0>(nbx) : brick_pitch_y<3, 1>(nbx);
-        m->dev.pz = storage == 0 ? brick_pitch_z<3, 0>(nbx, nby) : brick_pitch_z<3, 1>(nbx, nby);
-    }
-    m->stored = (size_t)nbx * nby * nbz * bs.bx * bs.by * bs.bz;
-    if (m->stored >= ((size_t)1 << 32)) { delete m; return fail(LMCMA_B200_ERR_ARG, "map too large: %zu stored cells (limit 2^32)", m->stored); }
-    rc = 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
-    if (!rc && storage == LMCMA_B200_MAP_F32) { rc = dmalloc(&m->d_g32, m->stored); m->dev.g32 = m->d_g32; }   // padding cells are never addressed
-    if (!rc && storage == LMCMA_B200_MAP_U8) {
-        rc = dmalloc(&m->d_q8, m->stored);
-        if (!rc) rc = dmalloc(&m->d_lut, 256);
-        if (!rc) {
-            float lut[256];
-            lut[0] = -m->dev.g_coll;
-            for (int v = 1; v < 256; ++v) lut[v] = 1.0f / std::max((float)v * u8_scale, c_min);
-            e = cudaMemcpy(m->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
-        }
-        m->dev.q8 = m->d_q8; m->dev.lut = m->d_lut;
-    }
-    if (rc) { lmcma_b200_map_destroy(m); return rc; }
-    *out = m;
-    return 0;
-}
-
-// row-major distance field on the device -> the bricked storage (values + layout, lmcma_layout.hpp)
-static int map_fill_from_dist_dev(lmcma_b200_map* m, const float* d_dist, cudaStream_t st) {
-    const MapDev& d = m->dev;
-    const unsigned blocks = (unsigned)((m->cells + 255) / 256);
-    if (d.dims == 2) {
-        if (m->storage == 0) k_brick<2, 0><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
-        else k_brick<2, 1><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
-    } else {
-        if (m->storage == 0) k_brick<3, 0><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
-        else k_brick<3, 1><<<blocks, 256, 0, st>>>(d_dist, m->d_g32, m->d_q8, d.nx, d.ny, d.nz, d.nbx, d.nby, m->c_min, m->scale);
-    }
-    g_launches++;
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// exact Euclidean distance transform on the device (k_edt.cuh): d_occ (1 = obstacle) -> d_dist, both row-major [z][y][x]
-static int edt_device(int dims, const int32_t* shape, const unsigned char* d_occ, float clamp, float* d_dist, cudaStream_t st) {
-    const int nx = shape[0], ny = shape[1], nz = dims == 3 ? shape[2] : 1;
-    ARG(nx <= 32767 && ny <= 32767 && nz <= 32767, "axis longer than 32767 cells");
-    const size_t cells = (size_t)nx * ny * nz;
-    int *d2 = nullptr, *s = nullptr, *t = nullptr, *gh = nullptr;
-    int rc = dmalloc(&d2, cells);
-    if (!rc) rc = dmalloc(&s, cells);
-    if (!rc) rc = dmalloc(&t, cells);
-    if (!rc) rc = dmalloc(&gh, cells);
-    if (!rc) {
-        const long long nlines = (long long)ny * nz;
-        k_edt_x<<<(unsigned)((nlines + 7) / 8), 256, 0, st>>>(d_occ, d2, nx, nlines);
-        g_launches++;
-        if (ny > 1) {
-            const long long lines = (long long)nx * nz;
-            k_edt_axis<<<(unsigned)((lines + 127) / 128), 128, 0, st>>>(d2, ny, nx, nx, nz, (long long)nx * ny, s, t, gh);
-            g_launches++;
-        }
-        if (nz > 1) {
-            const long long lines = (long long)nx * ny;
-            k_edt_axis<<<(unsigned)((lines + 127) / 128), 128, 0, st>>>(d2, nz, (long long)nx * ny, nx * ny, 1, 0, s, t, gh);
-            g_launches++;
-        }
-        k_edt_finish<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(d2, d_dist, (long long)cells, clamp);
-        g_launches++;
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "distance transform: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d2); cudaFree(s); cudaFree(t); cudaFree(gh);
-    return rc;
-}
-
-int lmcma_b200_map_create(int device, int dims, const int32_t* shape, const float* dist, int storage, float u8_scale,
-                          float c_min, lmcma_b200_map** out) {
-    ARG(dist, "null pointer");
-    lmcma_b200_map* m = nullptr;
-    int rc = map_alloc(device, dims, shape, storage, u8_scale, c_min, &m);
-    if (rc) return rc;
-    float* d_dist = nullptr;
-    rc = dmalloc(&d_dist, m->cells);
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(d_dist, dist, m->cells * sizeof(float), cudaMemcpyHostToDevice, m->stream);
-        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
-    }
-    if (!rc) rc = map_fill_from_dist_dev(m, d_dist, m->stream);
-    if (!rc) { cudaError_t e = cudaStreamSynchronize(m->stream); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "map upload: %s", cudaGetErrorString(e)); }
-    cudaFree(d_dist);
-    if (rc) { lmcma_b200_map_destroy(m); return rc; }
-    *out = m;
-    return 0;
-}
-
-int lmcma_b200_edt(int device, int dims, const int32_t* shape, const uint8_t* occ_host, float clamp, float* dist_host_out) {
-    ARG(shape && occ_host && dist_host_out, "null pointer");
-    ARG(dims == 2 || dims == 3, "dims must be 2 or 3");
-    for (int c = 0; c < dims; ++c) ARG(shape[c] >= 1, "bad shape");
-    DeviceProps* props;
-    int rc = query_props(device, &props);
-    if (rc) return rc;
-    CU(cudaSetDevice(device));
-    const size_t cells = (size_t)shape[0] * shape[1] * (dims == 3 ? shape[2] : 1);
-    unsigned char* d_occ = nullptr; float* d_dist = nullptr;
-    rc = dmalloc(&d_occ, cells);
-    if (!rc) rc = dmalloc(&d_dist, cells);
-    if (!rc) { cudaError_t e = cudaMemcpy(d_occ, occ_host, cells, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
-    if (!rc) rc = edt_device(dims, shape, d_occ, clamp, d_dist, 0);
-    if (!rc) { cudaError_t e = cudaMemcpy(dist_host_out, d_dist, cells * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
-    cudaFree(d_occ); cudaFree(d_dist);
-    return rc;
-}
-
-int lmcma_b200_map_create_from_occupancy(int device, int dims, const int32_t* shape, const uint8_t* occ_host, float clamp, int storage,
-                                         float u8_scale, float c_min, lmcma_b200_map** out) {
-    ARG(occ_host, "null pointer");
-    lmcma_b200_map* m = nullptr;
-    int rc = map_alloc(device, dims, shape, storage, u8_scale, c_min, &m);
-    if (rc) return rc;
-    unsigned char* d_occ = nullptr; float* d_dist = nullptr;
-    rc = dmalloc(&d_occ, m->cells);
-    if (!rc) rc = dmalloc(&d_dist, m->cells);
-    if (!rc) { cudaError_t e = cudaMemcpy(d_occ, occ_host, m->cells, cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e)); }
-    if (!rc) rc = edt_device(dims, shape, d_occ, clamp, d_dist, m->stream);
-    if (!rc) rc = map_fill_from_dist_dev(m, d_dist, m->stream);
-    if (!rc) { cudaError_t e = cudaStreamSynchronize(m->stream); if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "map build: %s", cudaGetErrorString(e)); }
-    cudaFree(d_occ); cudaFree(d_dist);
-    if (rc) { lmcma_b200_map_destroy(m); return rc; }
-    *out = m;
-    return 0;
-}
-
-int lmcma_b200_map_destroy(lmcma_b200_map* m) {
-    if (!m) return 0;
-    cudaSetDevice(m->device);
-    cudaFree(m->d_g32); cudaFree(m->d_q8); cudaFree(m->d_lut); cudaFree(m->d_X); cudaFree(m->d_f);
-    cudaFree(m->d_nc); cudaFree(m->d_ns);
-    if (m->stream) cudaStreamDestroy(m->stream);
-    delete m;
-    return 0;
-}
-
-int lmcma_b200_map_dequantized(const lmcma_b200_map* m, float* out) {
-    ARG(m && out, "null pointer");
-    CU(cudaSetDevice(m->device));
-    const int dims = m->dev.dims, storage = m->storage;
-    const unsigned nbx = m->dev.nbx, nby = m->dev.nby;
-    auto offset_of = [&](unsigned x, unsigned y, unsigned z) -> size_t {
-        if (dims == 2) return storage == 0 ? brick_offset<2, 0>(x, y, z, nbx, nby) : brick_offset<2, 1>(x, y, z, nbx, nby);
-        return storage == 0 ? brick_offset<3, 0>(x, y, z, nbx, nby) : brick_offset<3, 1>(x, y, z, nbx, nby);
-    };
-    std::vector<float> g; std::vector<unsigned char> q;
-    if (storage == LMCMA_B200_MAP_F32) {
-        g.resize(m->stored);
-        CU(cudaMemcpy(g.data(), m->d_g32, m->stored * sizeof(float), cudaMemcpyDeviceToHost));
-    } else {
-        q.resize(m->stored);
-        CU(cudaMemcpy(q.data(), m->d_q8, m->stored, cudaMemcpyDeviceToHost));
-    }
-    for (int z = 0; z < m->dev.nz; ++z)
-        for (int y = 0; y < m->dev.ny; ++y)
-            for (int x = 0; x < m->dev.nx; ++x) {
-                const size_t o = offset_of(x, y, z), i = ((size_t)z * m->dev.ny + y) * m->dev.nx + x;
-                // F32 stores 1/max(E, c_min): not invertible below c_min, so report the effective clearance
-                if (storage == LMCMA_B200_MAP_F32) out[i] = g[o] < 0.f ? 0.f : 1.0f / g[o];
-                else out[i] = (float)q[o] * m->scale;
-            }
-    return 0;
-}
-
-int lmcma_b200_map_set_l2_persist(lmcma_b200_map* m, int enable) {
-    ARG(m, "null map");
-    CU(cudaSetDevice(m->device));
-    DeviceProps* props;
-    int rc = query_props(m->device, &props);
-    if (rc) return rc;
-    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->stored * 4 : m->stored;
-    if (enable) CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, props->persist_max)));
-    m->persist = enable != 0;
-    return 0;
-}
-
-static int apply_l2_window(lmcma_b200_map* m, cudaStream_t st) {
-    if (!m->persist) return 0;
-    DeviceProps* props;
-    int rc = query_props(m->device, &props);
-    if (rc) return rc;
-    int max_win = 0;
-    CU(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, m->device));
-    const size_t bytes = m->storage == LMCMA_B200_MAP_F32 ? m->stored * 4 : m->stored;
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof(v));
-    v.accessPolicyWindow.base_ptr = m->storage == LMCMA_B200_MAP_F32 ? (void*)m->d_g32 : (void*)m->d_q8;
-    v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_win);
-    v.accessPolicyWindow.hitRatio = std::min(1.0f, (float)props->persist_max / (float)std::max<size_t>(bytes, 1));
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
-    return 0;
-}
-
-static int check_obj(const lmcma_b200_map* m, const lmcma_b200_objective* obj) {
-    ARG(m && obj, "null pointer");
-    ARG(obj->waypoints >= 1 && obj->waypoints <= 8190, "waypoints out of range");
-    return 0;
-}
-
-int lmcma_b200_cost_evaluate_dev(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
-                                 const float* X_dev, int64_t ld, int32_t count, float* f_dev, int32_t* ncoll_dev,
-                                 int32_t* nsamp_dev, void* stream) {
-    int rc = check_obj(m, obj);
-    if (rc) return rc;
-    ARG(ends && X_dev && f_dev, "null pointer");
-    ARG(count >= 0 && ld >= (int64_t)m->dev.dims * obj->waypoints, "bad count / ld");
-    if (count == 0) return 0;
-    CU(cudaSetDevice(m->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    CostArgs a;
-    memset(&a, 0, sizeof(a));
-    a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
-    a.X = X_dev; a.ld = ld; a.inst_rows = count; a.ends = nullptr; a.ends_per_instance = 0;
-    for (int c = 0; c < 3; ++c) { a.ends0[c] = ends->start[c]; a.ends0[3 + c] = ends->goal[c]; }   // by value: nothing shared between callers
-    a.f = f_dev; a.f_stride = count; a.f_offset = 0; a.ncoll = ncoll_dev; a.nsamp = nsamp_dev;
-    if ((rc = apply_l2_window(m, st))) return rc;
-    return launch_cost(m->dev, a, count, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims, m->tune), false, st);
-}
-
-int lmcma_b200_cost_evaluate(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
-                             const float* X_host, int32_t count, float* f_host, int32_t* ncoll_host, int32_t* nsamp_host) {
-    int rc = check_obj(m, obj);
-    if (rc) return rc;
-    ARG(ends && X_host && f_host && count >= 0, "null pointer / negative count");
-    if (count == 0) return 0;
-    std::lock_guard<std::mutex> lock(m->host_path);   // staging buffers + private stream: one host-buffer call per map at a time
-    CU(cudaSetDevice(m->device));
-    const size_t n = (size_t)m->dev.dims * obj->waypoints;
-    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister) are handed to the kernel as they are: every CTA reads
-    // its own candidate row across PCIe once, coalesced, while other CTAs compute (instead of a serial H2D copy in front
-    // of the kernel), and the three results per trajectory are stored straight into the caller's arrays.  Pageable
-    // buffers are staged through device memory.  LMCMA_B200_ZEROCOPY=0 forces staging.
-    const bool zc = m->tune.zerocopy != 0;
-    // a pointer into a population mirror handed out by lmcma_b200_ask_all_view: the device already holds these rows
-    long long ld_rows = (long long)n;
-    const float* X_dev = nullptr;
-    if (zc) {
-        long long ld_m = 0;
-        const float* mir = mirrored_device_rows(X_host, m->device, 1, &ld_m);
-        if (mir && ld_m >= (long long)n && mirrored_device_rows(X_host, m->device, ((size_t)(count - 1) * ld_m + n) * sizeof(float), &ld_m)) { X_dev = mir; ld_rows = ld_m; }
-    }
-    if (!X_dev && zc) X_dev = static_cast<const float*>(mapped_device_pointer(X_host, m->device));
-    float* f_dev = zc ? static_cast<float*>(mapped_device_pointer(f_host, m->device)) : nullptr;
-    int32_t* nc_dev = (zc && ncoll_host) ? static_cast<int32_t*>(mapped_device_pointer(ncoll_host, m->device)) : nullptr;
-    int32_t* ns_dev = (zc && nsamp_host) ? static_cast<int32_t*>(mapped_device_pointer(nsamp_host, m->device)) : nullptr;
-    const bool out_direct = f_dev && (!ncoll_host || nc_dev) && (!nsamp_host || ns_dev);
-    if (!X_dev) {
-        if (m->d_X_cap < (size_t)count * n) {
-            cudaFree(m->d_X); m->d_X = nullptr; m->d_X_cap = 0;
-            DM(m->d_X, (size_t)count * n);
-            m->d_X_cap = (size_t)count * n;
-        }
-        CU(cudaMemcpyAsync(m->d_X, X_host, (size_t)count * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-        X_dev = m->d_X;
-    }
-    if (!out_direct) {
-        if (m->d_out_cap < (size_t)count) {
-            cudaFree(m->d_f); cudaFree(m->d_nc); cudaFree(m->d_ns);
-            m->d_f = nullptr; m->d_nc = nullptr; m->d_ns = nullptr; m->d_out_cap = 0;
-            DM(m->d_f, count); DM(m->d_nc, count); DM(m->d_ns, count);
-            m->d_out_cap = count;
-        }
-        f_dev = m->d_f; nc_dev = m->d_nc; ns_dev = m->d_ns;
-    }
-    rc = lmcma_b200_cost_evaluate_dev(m, obj, ends, X_dev, (int64_t)ld_rows, count, f_dev, ncoll_host ? nc_dev : nullptr,
-                                      nsamp_host ? ns_dev : nullptr, m->stream);
-    if (rc) return rc;
-    if (!out_direct) {
-        CU(cudaMemcpyAsync(f_host, m->d_f, count * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-        if (ncoll_host) CU(cudaMemcpyAsync(ncoll_host, m->d_nc, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-        if (nsamp_host) CU(cudaMemcpyAsync(nsamp_host, m->d_ns, count * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    }
-    CU(cudaStreamSynchronize(m->stream));
-    return 0;
-}
-
-int lmcma_b200_cost_trace(lmcma_b200_map* m, const lmcma_b200_objective* obj, const lmcma_b200_endpoints* ends,
-                          const float* x_host, int64_t* cells_host, int64_t max_cells, int64_t* n_cells_out) {
-    int rc = check_obj(m, obj);
-    if (rc) return rc;
-    ARG(ends && x_host && cells_host && n_cells_out && max_cells > 0, "null pointer");
-    std::lock_guard<std::mutex> lock(m->host_path);
-    CU(cudaSetDevice(m->device));
-    const size_t n = (size_t)m->dev.dims * obj->waypoints;
-    float* dX = nullptr; float* df = nullptr; int* dns = nullptr; long long* dcells = nullptr;
-    rc = dmalloc(&dX, n);
-    if (!rc) rc = dmalloc(&df, 1);
-    if (!rc) rc = dmalloc(&dns, 1);
-    if (!rc) rc = dmalloc(&dcells, (size_t)max_cells);
-    if (!rc) {
-        cudaError_t e = cudaMemset(dcells, 0xff, (size_t)max_cells * sizeof(long long));
-        if (e == cudaSuccess) e = cudaMemcpy(dX, x_host, n * sizeof(float), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);   // the kernel runs on the map's non-blocking stream
-        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "trace staging: %s", cudaGetErrorString(e));
-    }
-    if (rc) { cudaFree(dX); cudaFree(df); cudaFree(dns); cudaFree(dcells); return rc; }
-    CostArgs a;
-    memset(&a, 0, sizeof(a));
-    a.W = obj->waypoints; a.w_len = obj->w_len; a.w_clr = obj->w_clr; a.w_col = obj->w_col;
-    a.X = dX; a.ld = (long long)n; a.inst_rows = 1; a.ends = nullptr; a.ends_per_instance = 0;
-    for (int c = 0; c < 3; ++c) { a.ends0[c] = ends->start[c]; a.ends0[3 + c] = ends->goal[c]; }
-    a.f = df; a.f_stride = 1; a.nsamp = dns; a.cells = dcells; a.max_cells = max_cells;
-    rc = launch_cost(m->dev, a, 1, 1, pick_cost_shape(a.W, ends->start, ends->goal, m->dev.dims, m->tune), true, m->stream);
-    if (!rc) {
-        cudaError_t e = cudaStreamSynchronize(m->stream);
-        if (e != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "trace kernel: %s", cudaGetErrorString(e));
-    }
-    int ns = 0;
-    if (!rc) {
-        cudaMemcpy(&ns, dns, sizeof(int), cudaMemcpyDeviceToHost);
-        cudaMemcpy(cells_host, dcells, (size_t)std::min<int64_t>(ns, max_cells) * sizeof(long long), cudaMemcpyDeviceToHost);
-        *n_cells_out = ns;
-    }
-    cudaFree(dX); cudaFree(df); cudaFree(dns); cudaFree(dcells);
-    return rc;
 }
 
 // =================================================================================================
@@ -1777,214 +1111,6 @@ int lmcma_b200_best(lmcma_b200_opt* o, float* x_best, float* f_best) {
     return 0;
 }
 
-// ---- state access ------------------------------------------------------------------------------
-int lmcma_b200_get_f64(lmcma_b200_opt* o, int32_t which, double* out, int64_t cap) {
-    ARG(o && out, "null pointer");
-    CU(cudaSetDevice(o->cfg.device));
-    const OptDev& d = o->d;
-    const size_t B = d.B;
-    switch (which) {
-        case LMCMA_B200_F64_XMEAN:
-            ARG(cap >= (int64_t)(B * d.n), "capacity");
-            return d2h_rows(out, d.xmean, B, d.n * sizeof(double), d.ns * sizeof(double), o->stream);
-        case LMCMA_B200_F64_SIGMA: case LMCMA_B200_F64_S: case LMCMA_B200_F64_BESTF: {
-            ARG(cap >= (int64_t)B, "capacity");
-            std::vector<Scalars> sc(B);
-            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            for (size_t b = 0; b < B; ++b)
-                out[b] = which == LMCMA_B200_F64_SIGMA ? sc[b].sigma : (which == LMCMA_B200_F64_S ? sc[b].s : sc[b].best_f);
-            return 0;
-        }
-        case LMCMA_B200_F64_CONSTS:
-            ARG(cap >= 7, "capacity");
-            out[0] = d.c1; out[1] = d.cc; out[2] = d.cs; out[3] = d.target; out[4] = d.K; out[5] = d.M; out[6] = d.mueff;
-            return 0;
-        case LMCMA_B200_F64_WEIGHTS:
-            ARG(cap >= d.mu, "capacity");
-            std::copy(o->weights.begin(), o->weights.end(), out);
-            return 0;
-        case LMCMA_B200_F64_NJ: case LMCMA_B200_F64_LJ:
-            ARG(cap >= (int64_t)(B * d.m), "capacity");
-            CU(cudaMemcpyAsync(out, which == LMCMA_B200_F64_NJ ? d.Nj : d.Lj, B * d.m * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            return 0;
-    }
-    return fail(LMCMA_B200_ERR_ARG, "unknown f64 field %d", which);
-}
-
-int lmcma_b200_get_f32(lmcma_b200_opt* o, int32_t which, float* out, int64_t cap) {
-    ARG(o && out, "null pointer");
-    CU(cudaSetDevice(o->cfg.device));
-    const OptDev& d = o->d;
-    const size_t B = d.B, w = d.n * sizeof(float), p = d.ns * sizeof(float);
-    switch (which) {
-        case LMCMA_B200_F32_X:
-            ARG(cap >= (int64_t)(B * d.pop_count * d.n), "capacity");
-            return d2h_rows(out, d.X, B * d.pop_count, w, p, o->stream);
-        case LMCMA_B200_F32_Z:
-            if (!d.Z) return fail(LMCMA_B200_ERR_STATE, "deviates are not recorded (record_z = 0)");
-            ARG(cap >= (int64_t)(B * d.pop_count * d.n), "capacity");
-            return d2h_rows(out, d.Z, B * d.pop_count, w, p, o->stream);
-        case LMCMA_B200_F32_PC:
-            ARG(cap >= (int64_t)(B * d.n), "capacity");
-            return d2h_rows(out, d.pc, B, w, p, o->stream);
-        case LMCMA_B200_F32_V: case LMCMA_B200_F32_P:
-            ARG(cap >= (int64_t)(B * d.m * d.n), "capacity");
-            return d2h_rows(out, which == LMCMA_B200_F32_V ? d.V : d.P, B * d.m, w, p, o->stream);
-        case LMCMA_B200_F32_FIT: case LMCMA_B200_F32_FIT_SORTED: case LMCMA_B200_F32_PREV_FIT: {
-            ARG(cap >= (int64_t)(B * d.lambda), "capacity");
-            const float* src = which == LMCMA_B200_F32_FIT ? d.fit : (which == LMCMA_B200_F32_FIT_SORTED ? d.fit_sorted : d.prev_fit);
-            CU(cudaMemcpyAsync(out, src, B * d.lambda * sizeof(float), cudaMemcpyDeviceToHost, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            if (which == LMCMA_B200_F32_PREV_FIT)   // the device keeps it in evaluation order; the reference keeps it sorted
-                for (size_t b = 0; b < B; ++b) std::sort(out + b * d.lambda, out + (b + 1) * d.lambda);
-            return 0;
-        }
-    }
-    return fail(LMCMA_B200_ERR_ARG, "unknown f32 field %d", which);
-}
-
-int lmcma_b200_get_i32(lmcma_b200_opt* o, int32_t which, int32_t* out, int64_t cap) {
-    ARG(o && out, "null pointer");
-    CU(cudaSetDevice(o->cfg.device));
-    const OptDev& d = o->d;
-    const size_t B = d.B;
-    const int* src = nullptr; size_t cnt = 0;
-    switch (which) {
-        case LMCMA_B200_I32_T: src = d.t; cnt = B * d.m; break;
-        case LMCMA_B200_I32_VEC: src = d.vec; cnt = B * d.m; break;
-        case LMCMA_B200_I32_ARINDEX: src = d.arindex; cnt = B * d.lambda; break;
-        case LMCMA_B200_I32_RANK: src = d.rank; cnt = B * d.lambda; break;
-        case LMCMA_B200_I32_NCOLL: src = d.ncoll; cnt = B * d.pop_count; break;
-        case LMCMA_B200_I32_NSAMP: src = d.nsamp; cnt = B * d.pop_count; break;
-        case LMCMA_B200_I32_ITR: case LMCMA_B200_I32_LIVE: case LMCMA_B200_I32_COUNTEVAL: {
-            ARG(cap >= (int64_t)B, "capacity");
-            std::vector<Scalars> sc(B);
-            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            for (size_t b = 0; b < B; ++b)
-                out[b] = which == LMCMA_B200_I32_ITR ? sc[b].itr : (which == LMCMA_B200_I32_LIVE ? sc[b].live : (int)sc[b].counteval);
-            return 0;
-        }
-        default: return fail(LMCMA_B200_ERR_ARG, "unknown i32 field %d", which);
-    }
-    ARG(cap >= (int64_t)cnt, "capacity");
-    CU(cudaMemcpyAsync(out, src, cnt * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
-    CU(cudaStreamSynchronize(o->stream));
-    return 0;
-}
-
-int lmcma_b200_set_f64(lmcma_b200_opt* o, int32_t which, const double* in, int64_t count) {
-    ARG(o && in, "null pointer");
-    CU(cudaSetDevice(o->cfg.device));
-    const OptDev& d = o->d;
-    const size_t B = d.B;
-    switch (which) {
-        case LMCMA_B200_F64_XMEAN:
-            ARG(count == (int64_t)(B * d.n), "count");
-            return h2d_rows(d.xmean, in, B, d.n * sizeof(double), d.ns * sizeof(double), o->stream);
-        case LMCMA_B200_F64_SIGMA: case LMCMA_B200_F64_S: {
-            ARG(count == (int64_t)B, "count");
-            std::vector<Scalars> sc(B);
-            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            for (size_t b = 0; b < B; ++b) (which == LMCMA_B200_F64_SIGMA ? sc[b].sigma : sc[b].s) = in[b];
-            CU(cudaMemcpyAsync(d.sc, sc.data(), B * sizeof(Scalars), cudaMemcpyHostToDevice, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            return 0;
-        }
-        case LMCMA_B200_F64_NJ: case LMCMA_B200_F64_LJ: {
-            ARG(count == (int64_t)(B * d.m), "count");
-            o->mirror_dirty = true;
-            CU(cudaMemcpyAsync(which == LMCMA_B200_F64_NJ ? d.Nj : d.Lj, in, B * d.m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
-            if (which == LMCMA_B200_F64_NJ) {
-                std::vector<float> f(in, in + B * d.m);
-                CU(cudaMemcpyAsync(d.Njf, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, o->stream));
-                CU(cudaStreamSynchronize(o->stream));
-            }
-            CU(cudaStreamSynchronize(o->stream));
-            return 0;
-        }
-    }
-    return fail(LMCMA_B200_ERR_ARG, "f64 field %d is not settable", which);
-}
-
-int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_t count) {
-    ARG(o && in, "null pointer");
-    CU(cudaSetDevice(o->cfg.device));
-    const OptDev& d = o->d;
-    const size_t B = d.B, w = d.n * sizeof(float), p = d.ns * sizeof(float);
-    switch (which) {
-        case LMCMA_B200_F32_PC:
-            ARG(count == (int64_t)(B * d.n), "count");
-            return h2d_rows(d.pc, in, B, w, p, o->stream);
-        case LMCMA_B200_F32_V: case LMCMA_B200_F32_P:
-            ARG(count == (int64_t)(B * d.m * d.n), "count");
-            o->mirror_dirty = true;
-            return h2d_rows(which == LMCMA_B200_F32_V ? d.V : d.P, in, B * d.m, w, p, o->stream);
-        case LMCMA_B200_F32_X: {
-            ARG(count == (int64_t)(B * d.pop_count * d.n), "count");
-            o->x_cache_valid = false;
-            o->xh_fresh = false;
-            // keep the offsets d = x - xmean consistent with the overwritten candidates
-            std::vector<double> xm(B * d.n);
-            int rc = d2h_rows(xm.data(), d.xmean, B, d.n * sizeof(double), d.ns * sizeof(double), o->stream);
-            if (rc) return rc;
-            std::vector<float> dd((size_t)count);
-            for (size_t b = 0; b < B; ++b)
-                for (size_t r = 0; r < (size_t)d.pop_count; ++r)
-                    for (int k = 0; k < d.n; ++k) {
-                        const size_t idx = (b * d.pop_count + r) * d.n + k;
-                        dd[idx] = (float)((double)in[idx] - xm[b * d.n + k]);
-                    }
-            if ((rc = h2d_rows(d.D, dd.data(), B * d.pop_count, w, p, o->stream))) return rc;
-            return h2d_rows(d.X, in, B * d.pop_count, w, p, o->stream);
-        }
-        case LMCMA_B200_F32_PREV_FIT:
-            ARG(count == (int64_t)(B * d.lambda), "count");
-            CU(cudaMemcpyAsync(d.prev_fit, in, B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            if (d.prev_sorted) {                                  // the sorted-tile ranking searches an ascending copy
-                std::vector<float> srt(in, in + B * d.lambda);
-                for (size_t b = 0; b < B; ++b) std::sort(srt.begin() + b * d.lambda, srt.begin() + (b + 1) * d.lambda);
-                CU(cudaMemcpy(d.prev_sorted, srt.data(), srt.size() * sizeof(float), cudaMemcpyHostToDevice));
-            }
-            return 0;
-    }
-    return fail(LMCMA_B200_ERR_ARG, "f32 field %d is not settable", which);
-}
-
-int lmcma_b200_set_i32(lmcma_b200_opt* o, int32_t which, const int32_t* in, int64_t count) {
-    ARG(o && in, "null pointer");
-    CU(cudaSetDevice(o->cfg.device));
-    const OptDev& d = o->d;
-    const size_t B = d.B;
-    switch (which) {
-        case LMCMA_B200_I32_T: case LMCMA_B200_I32_VEC:
-            ARG(count == (int64_t)(B * d.m), "count");
-            o->mirror_dirty = true;
-            CU(cudaMemcpyAsync(which == LMCMA_B200_I32_T ? d.t : d.vec, in, B * d.m * sizeof(int), cudaMemcpyHostToDevice, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            return 0;
-        case LMCMA_B200_I32_ITR: case LMCMA_B200_I32_LIVE: case LMCMA_B200_I32_COUNTEVAL: {
-            ARG(count == (int64_t)B, "count");
-            std::vector<Scalars> sc(B);
-            CU(cudaMemcpyAsync(sc.data(), d.sc, B * sizeof(Scalars), cudaMemcpyDeviceToHost, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            for (size_t b = 0; b < B; ++b) {
-                if (which == LMCMA_B200_I32_ITR) sc[b].itr = in[b];
-                else if (which == LMCMA_B200_I32_LIVE) sc[b].live = in[b];
-                else sc[b].counteval = in[b];
-            }
-            CU(cudaMemcpyAsync(d.sc, sc.data(), B * sizeof(Scalars), cudaMemcpyHostToDevice, o->stream));
-            CU(cudaStreamSynchronize(o->stream));
-            return 0;
-        }
-    }
-    return fail(LMCMA_B200_ERR_ARG, "i32 field %d is not settable", which);
-}
-
 // ---- split-population mode ---------------------------------------------------------------------
 int lmcma_b200_mg_payload_floats(lmcma_b200_opt* o, int32_t* floats_out) {
     ARG(o && floats_out, "null pointer");
@@ -2033,69 +1159,6 @@ int lmcma_b200_mg_update(lmcma_b200_opt* o, const float* payload_all_dev, int32_
     rc = launch_sample(o, st, true);
     o->mirror_suppressed = false;
     return rc;
-}
-
-// ---- host-side reference pieces ------------------------------------------------------------------
-int lmcma_b200_hansen_gauss(int64_t seed, int64_t skip, int64_t count, double* out) {
-    ARG(out && count >= 0 && skip >= 0, "bad argument");
-    HansenStream r(seed);
-    for (int64_t i = 0; i < skip; ++i) (void)r.gauss();
-    for (int64_t i = 0; i < count; ++i) out[i] = r.gauss();
-    return 0;
-}
-int lmcma_b200_hansen_uniform(int64_t seed, int64_t count, double* out) {
-    ARG(out && count >= 0, "bad argument");
-    HansenStream r(seed);
-    for (int64_t i = 0; i < count; ++i) out[i] = r.uniform();
-    return 0;
-}
-int lmcma_b200_covariance(int32_t dims, int32_t waypoints, double* out) {
-    ARG(out && dims >= 1 && waypoints >= 1, "bad argument");
-    if (!smoothness_covariance(dims, waypoints, out)) return fail(LMCMA_B200_ERR_ARG, "singular finite-difference block");
-    return 0;
-}
-
-int lmcma_b200_differentiation_matrix(int32_t num_time_steps, int32_t order, double dt, double* diff_matrix, int32_t row_len) {
-    ARG(diff_matrix && num_time_steps >= 1 && order >= 0 && order <= 3 && dt != 0.0, "bad argument");
-    ARG(row_len < 0 || row_len >= num_time_steps, "row_len shorter than the block");
-    differentiation_matrix(num_time_steps, order, dt, diff_matrix, row_len);
-    return 0;
-}
-int lmcma_b200_invert(const double* A, double* Ainv, int32_t n) {
-    ARG(A && Ainv && n >= 1 && A != Ainv, "bad argument");
-    if (!invert_dense(A, n, Ainv)) return fail(LMCMA_B200_ERR_ARG, "matrix is singular");
-    return 0;
-}
-int lmcma_b200_apply_cov_l(const double* L_colmajor, double* z, int32_t n) {
-    ARG(L_colmajor && z && n >= 1, "bad argument");
-    std::vector<double> out(n, 0.0);
-    for (int j = 0; j < n; ++j) {                       // column by column: out += z_j * L(:, j)
-        const double zj = z[j];
-        const double* col = L_colmajor + (size_t)j * n;
-        for (int i = 0; i < n; ++i) out[i] += col[i] * zj;
-    }
-    std::copy(out.begin(), out.end(), z);
-    return 0;
-}
-int lmcma_b200_myqsort(int32_t sz, double* arfitness_inout, int32_t* arindex_out) {
-    ARG(sz >= 0 && (sz == 0 || (arfitness_inout && arindex_out)), "bad argument");
-    stable_rank(sz, arfitness_inout, arindex_out);
-    return 0;
-}
-struct lmcma_b200_rng { HansenStream s; explicit lmcma_b200_rng(int64_t seed) : s(seed) {} };
-int lmcma_b200_rng_create(int64_t seed, lmcma_b200_rng** out) {
-    ARG(out, "null pointer");
-    *out = new lmcma_b200_rng(seed);
-    return 0;
-}
-int lmcma_b200_rng_destroy(lmcma_b200_rng* r) { delete r; return 0; }
-double lmcma_b200_rng_uniform(lmcma_b200_rng* r) { return r ? r->s.uniform() : 0.0; }
-double lmcma_b200_rng_gauss(lmcma_b200_rng* r) { return r ? r->s.gauss() : 0.0; }
-
-int lmcma_b200_cholesky(int32_t n, const double* Cm, double* L_out) {
-    ARG(Cm && L_out && n >= 1, "bad argument");
-    if (!cholesky_lower(Cm, n, L_out)) return fail(LMCMA_B200_ERR_ARG, "matrix is not symmetric positive definite");
-    return 0;
 }
 
 }  // extern "C"

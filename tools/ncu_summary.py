@@ -60,6 +60,15 @@ def launches(src, dst):
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             fh.write("| `%s` | %d | %.1f | %.2f | %.1f %% |\n" % (k, n, t / 1e3, t / n / 1e3, 100 * t / total))
         fh.write("\ncaptured launches: %d, total %.1f us\n" % (sum(a[0] for a in agg.values()), total / 1e3))
+        # the kernels of the generation only (k_probe is the one-off co-scheduling probe, which times out under the profiler
+        # by design; the fill kernel is bench.py's L2 flush; k_brick / k_pack_pairs are set-up)
+        gen = OrderedDict((k, v) for k, v in agg.items() if k.startswith(("k_cost", "k_rank", "k_update", "k_sample", "k_gate", "k_gram", "k_coef", "k_combine")))
+        gtot = sum(a[1] for a in gen.values())
+        if gtot > 0:
+            fh.write("\nShare among the kernels of the generation (what bench.py's `kernel_ms` shares are compared with):\n\n")
+            fh.write("| kernel | mean us | share of the generation |\n|---|---|---|\n")
+            for k, (n, t) in sorted(gen.items(), key=lambda kv: -kv[1][1]):
+                fh.write("| `%s` | %.2f | %.1f %% |\n" % (k, t / n / 1e3, 100 * t / gtot))
     print(open(dst).read())
 
 
