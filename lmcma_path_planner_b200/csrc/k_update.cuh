@@ -27,6 +27,7 @@ namespace lmcma {
 constexpr int UPD_WARPS = 16;
 constexpr int UPD_GROUPS = UPD_WARPS / 4;   // 128-thread groups of the mean phase
 constexpr int UPD_THREADS = 32 * UPD_WARPS;
+constexpr int UPD_BLK = 8;            // factors per block of the newest row's chain (k_update: newest_row)
 
 struct UpdateArgs {
     const float* f_all;        // B x lambda fitness of this generation (global candidate order)
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     unsigned long long* scalbar = rowbar + m;                      // m mbarriers: |v_i|^2 and Lj_i / K are published
     float4* red4 = reinterpret_cast<float4*>(smem_raw + (((size_t)m * 36 + 8 + 127) & ~(size_t)127));                      // 128 float4 scratch
     float* rows_s = reinterpret_cast<float*>(red4 + 128 * (UPD_GROUPS - 1));                                                                  // m x ns (SMEM)
+    float* Gs = rows_s + (size_t)m * ns;                           // register sweep: m x UPD_BLK, Gs[k][r] = v_k . v_(j0 + r), j0 = k rounded down to its block, r < k - j0
     __shared__ unsigned long long sh_key;
     __shared__ __align__(8) unsigned long long sh_bar;
     __shared__ float am_v[UPD_WARPS];
@@ -176,9 +178,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 
     // ---- best-so-far: first occurrence of the minimum in evaluation order; strict improvement, or the very first
     //      evaluation (lmcma.cpp:192-198).  The fitness is k_cost's output (block-collective) ----
-    // w0 = first participating warp (0: the whole CTA, barrier 0; 1: warps 1.. while warp 0 is busy elsewhere, named barrier 1)
-    auto best_so_far = [&](const int w0) {
-    const int nt = nthr - 32 * w0, t = tid - 32 * w0;
+    // warps w0 .. w0 + nw - 1 take part (the whole CTA: barrier 0; otherwise named barrier 2 while the others are busy elsewhere)
+    auto best_so_far = [&](const int w0, const int nw) {
+    const int nt = 32 * nw, t = tid - 32 * w0;
     {
         float bf = __int_as_float(0x7f800000); int bi = 0x7fffffff;
         for (int j0 = 0; j0 < o.lambda; j0 += 4 * nt) {              // 4 loads in flight per thread
@@ -195,14 +197,14 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         }
         if (lane == 0) { am_v[warp] = bf; am_i[warp] = bi; }
     }
-    if (w0 == 0) __syncthreads(); else named_bar_sync(1, nt);
+    if (nw == nwarps) __syncthreads(); else named_bar_sync(2, nt);
     {
         float bf = am_v[w0]; int bi = am_i[w0];
-        for (int w2 = w0 + 1; w2 < nwarps; ++w2) if (am_v[w2] < bf || (am_v[w2] == bf && am_i[w2] < bi)) { bf = am_v[w2]; bi = am_i[w2]; }
+        for (int w2 = w0 + 1; w2 < w0 + nw; ++w2) if (am_v[w2] < bf || (am_v[w2] == bf && am_i[w2] < bi)) { bf = am_v[w2]; bi = am_i[w2]; }
         if (bi == 0x7fffffff) bi = 0;
         const bool take = ((double)bf < sc0.best_f) || (sc0.counteval == 0);
         const bool local = bi >= o.pop_offset && bi < o.pop_offset + o.pop_count;
-        if (take && local && warp == nwarps - 1) {
+        if (take && local && warp == w0 + nw - 1) {
             const float4* src = reinterpret_cast<const float4*>(o.X + ((size_t)b * o.pop_count + (bi - o.pop_offset)) * ns);
             float4* dst = reinterpret_cast<float4*>(o.best_x + (size_t)b * ns);
             for (int q = lane; q < nq; q += 32) dst[q] = src[q];
@@ -222,16 +224,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     } else if (live > 1) {
         mbar_wait(&sh_bar, 0);
     }
-    if (OVERLAP) __syncthreads(); else best_so_far(0);             // overlap: k_cost is still running
+    if (OVERLAP) __syncthreads(); else best_so_far(0, nwarps);             // overlap: k_cost is still running
     UPD_STAMP(2);
 
     // =============================== needs k_rank's partial sums ===============================
-    auto post_rank = [&]() {                                         // block-collective
-    UPD_STAMP(3);
-    if (tid == 0) o.rank_ticket[b] = 0u;                             // k_rank's CTAs of this generation have all drawn one
     // ---- population-success step size (lmcma.cpp:393-419), counters (lmcma.cpp:189, 423): needs only k_rank's pair
-    //      count, so it goes first (the progressive hand-over publishes the scalars before the sweep) ----
-    if (tid == nthr - 1) {
+    //      count (one thread) ----
+    auto step_size_and_counters = [&]() {
         unsigned long long S = 0;
         if (a.payload_mode) {
             for (int k = 0; k < a.n_slices; ++k) {
@@ -255,7 +254,36 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         scp->itr = itr + 1;
         scp->live = live;
         scp->counteval = sc0.counteval + o.lambda;
-    }
+    };
+    // ---- one float4 column of the mean / evolution path / new pc_j (lmcma.cpp:316-329, 365-366); d = sum_i w_i (x_i - xmean) ----
+    auto finish_column = [&](const int q, const float (&d)[4], const double2 xm01, const double2 xm23, const float4 pc4) {
+        const double coef = o.pc_coef / sigma_old;                   // sqrt(cc (2 - cc) mueff) / sigma
+        double* xm = o.xmean + (size_t)b * ns;
+        float* pc = o.pc + (size_t)b * ns;
+        float* pnew = Pb + (size_t)slot_new * ns;
+        float* rnew = row_ptr(live - 1);
+        const double xo[4] = {xm01.x, xm01.y, xm23.x, xm23.y};
+        const float po[4] = {pc4.x, pc4.y, pc4.z, pc4.w};
+        double xn[4]; float pn[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const double shift = (double)d[c];                       // new mean - old mean = sum_i w_i (x_i - xmean)
+            xn[c] = xo[c] + shift;
+            pn[c] = (float)__fma_rn(1.0 - o.cc, (double)po[c], __dmul_rn(coef, shift));   // explicit: the same bits wherever this is inlined
+        }
+        reinterpret_cast<double2*>(xm)[2 * q] = make_double2(xn[0], xn[1]);
+        reinterpret_cast<double2*>(xm)[2 * q + 1] = make_double2(xn[2], xn[3]);
+        const float4 p4 = make_float4(pn[0], pn[1], pn[2], pn[3]);
+        reinterpret_cast<float4*>(pc)[q] = p4;
+        reinterpret_cast<float4*>(pnew)[q] = p4;
+        reinterpret_cast<float4*>(rnew)[q] = p4;
+    };
+    auto post_rank = [&]() {                                         // block-collective
+    UPD_STAMP(3);
+    if (tid == 0) o.rank_ticket[b] = 0u;                             // k_rank's CTAs of this generation have all drawn one
+    // ---- population-success step size (lmcma.cpp:393-419), counters (lmcma.cpp:189, 423): needs only k_rank's pair
+    //      count, so it goes first (the progressive hand-over publishes the scalars before the sweep) ----
+    if (tid == nthr - 1) step_size_and_counters();
     // prev_fit (lmcma.cpp:420-421): k_rank has finished reading the previous generation's values
     for (int j = tid; j < o.lambda; j += nthr) o.prev_fit[(size_t)b * o.lambda + j] = canon_fitness(__ldcg(fa + j));
     if (o.prev_sorted)                                               // sorted-tile ranking (k_rank.cuh): the next generation searches it
@@ -264,11 +292,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     // ---- mean, evolution path, new pc_j (lmcma.cpp:316-329, 365-366): 128 float4 columns x 2 slice groups, up to
     //      8 slice loads in flight per thread; fixed summation order -> deterministic ----
     {
-        const double coef = o.pc_coef / sigma_old;                   // sqrt(cc (2 - cc) mueff) / sigma
-        double* xm = o.xmean + (size_t)b * ns;
-        float* pc = o.pc + (size_t)b * ns;
-        float* pnew = Pb + (size_t)slot_new * ns;
-        float* rnew = row_ptr(live - 1);
+        const double* xm = o.xmean + (size_t)b * ns;
+        const float* pc = o.pc + (size_t)b * ns;
         const int tq = tid & 127, g = tid >> 7;                      // UPD_GROUPS x 128 threads
         for (int q0 = 0; q0 < nq; q0 += 128) {
             const int q = q0 + tq;
@@ -299,21 +324,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 #pragma unroll
                 for (int g2 = 0; g2 + 1 < UPD_GROUPS; ++g2) { const float4 u4 = red4[g2 * 128 + tq]; t.x += u4.x; t.y += u4.y; t.z += u4.z; t.w += u4.w; }
                 const float d[4] = {acc.x + t.x, acc.y + t.y, acc.z + t.z, acc.w + t.w};
-                const double xo[4] = {xm01.x, xm01.y, xm23.x, xm23.y};
-                const float po[4] = {pc4.x, pc4.y, pc4.z, pc4.w};
-                double xn[4]; float pn[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double shift = (double)d[c];               // new mean - old mean = sum_i w_i (x_i - xmean)
-                    xn[c] = xo[c] + shift;
-                    pn[c] = (float)((1.0 - o.cc) * (double)po[c] + coef * shift);
-                }
-                reinterpret_cast<double2*>(xm)[2 * q] = make_double2(xn[0], xn[1]);
-                reinterpret_cast<double2*>(xm)[2 * q + 1] = make_double2(xn[2], xn[3]);
-                const float4 p4 = make_float4(pn[0], pn[1], pn[2], pn[3]);
-                reinterpret_cast<float4*>(pc)[q] = p4;
-                reinterpret_cast<float4*>(pnew)[q] = p4;
-                reinterpret_cast<float4*>(rnew)[q] = p4;
+                finish_column(q, d, xm01, xm23, pc4);
             }
             __syncthreads();
         }
@@ -369,8 +380,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         constexpr int R = RMAX > 0 ? RMAX : 1;
         const int sw = a.sweep_warps;
         const int rstride = a.blocked ? 1 : sw;
-        // overlap: the newest row (this generation's evolution path) does not exist yet; it is finished after the sweep
-        const int hi = OVERLAP ? live - 1 : live;
+        // The newest row (this generation's evolution path) is not part of the sweep: it takes its factors a BLOCK at a time
+        // (newest_row below).  In the overlapped generation it does not even exist yet when the sweep starts.
+        const int hi = live - 1;
         const int base = warp < sw ? first_stale + (a.blocked ? warp * R : warp) : hi;     // warps >= sw own nothing
         float4 y[R][NVB];
 #pragma unroll
@@ -384,9 +396,60 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 if (on && q < nq) reinterpret_cast<float4*>(VPb + ((size_t)i * 2 + 1) * ns)[q] = y[r][it];   // pc_i at its (new) position
             }
         }
-        int my_last = -1;                                            // my largest row
+        // y[0 .. n-1] are my pending rows in index order, y[0] the next one to become final (row `next`): when it does, the
+        // others move down one place, so that a step costs what the rows still pending cost (the SM is issue-bound here)
+        int n = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) if (base + r * rstride < hi) my_last = base + r * rstride;
+        for (int r = 0; r < R; ++r) n += (base + r * rstride < hi) ? 1 : 0;
+        int next = base;
+        auto retire_first = [&]() {
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r) {
+#pragma unroll
+                for (int it = 0; it < NVB; ++it) y[r][it] = y[r + 1][it];
+            }
+            --n; next += rstride;
+        };
+        // Block Gram entries of a final row k (in registers, x) against the earlier rows of its block of UPD_BLK: what lets the
+        // newest row take a whole block of factors at once.  Warp-collective; rows j0 .. k-1 are final in shared memory.
+        auto gram_entries = [&](const float4 (&x)[NVB], const int k) {
+            const int j0 = k & ~(UPD_BLK - 1), nbk = k - j0;
+            if (nbk == 0) return;
+            float gd[UPD_BLK - 1];
+#pragma unroll
+            for (int r = 0; r < UPD_BLK - 1; ++r) {
+                gd[r] = 0.f;
+                if (r < nbk) {
+                    const float4* vr = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + r) * ns);
+                    float2 d0 = make_float2(0.f, 0.f), d1 = d0;
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        const int q = lane + 32 * it;
+                        const float4 v = (q < nq) ? vr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        d0 = ffma2(lo2(v), lo2(x[it]), d0); d1 = ffma2(hi2(v), hi2(x[it]), d1);
+                    }
+                    gd[r] = (d0.x + d0.y) + (d1.x + d1.y);
+                }
+            }
+#pragma unroll
+            for (int ofs = 16; ofs > 0; ofs >>= 1) {
+#pragma unroll
+                for (int r = 0; r < UPD_BLK - 1; ++r) gd[r] += __shfl_xor_sync(0xffffffffu, gd[r], ofs);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < UPD_BLK - 1; ++r) if (r < nbk) Gs[k * UPD_BLK + r] = gd[r];
+            }
+        };
+        auto gram_row = [&](const int k) {                           // row k is final in shared memory
+            float4 x[NVB];
+#pragma unroll
+            for (int it = 0; it < NVB; ++it) {
+                const int q = lane + 32 * it;
+                x[it] = (q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)k * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            gram_entries(x, k);
+        };
         auto publish = [&](const float4 (&row)[NVB], int i, double kp) {   // warp-collective: y_i K^i is the final v_i
             const float kf = (float)kp;
             float4* srow = reinterpret_cast<float4*>(rows_s + (size_t)i * ns);
@@ -402,6 +465,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             }
             __syncwarp();                                            // orders the lanes' stores before lane 0's release
             if (lane == 0) mbar_arrive(&rowbar[i]);                  // ONE arrive: 32 arrives on one mbarrier serialise (~27 cycles each)
+            if (a.dbg && lane == 0 && i < 40) a.dbg[24 + i] = gtime();
             float2 nn = make_float2(0.f, 0.f);                       // |v_i|^2: after the hand-over, off the chain
 #pragma unroll
             for (int it = 0; it < NVB; ++it) { nn = ffma2(lo2(x[it]), lo2(x[it]), nn); nn = ffma2(hi2(x[it]), hi2(x[it]), nn); }
@@ -426,11 +490,103 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 }
             }
         };
-        if (first_stale == 0 && warp == 0 && hi > 0) publish(y[0], 0, 1.0);   // row 0 has no factors (v_0 = pc_0)
+        // ---- the newest row: this generation's evolution path through the factors 0 .. live-2 (lmcma.cpp:375-382), a block of
+        //      UPD_BLK factors at a time.  With y the row at the start of a block j0 .. j0+nb-1 (held as x / K^j like the sweep's
+        //      rows) and g_k = v_k . y, the dot products the factors would see one after the other are
+        //          d_k = g_k - sum_{i < k} e_i (v_k . v_i),   e_k = (Lj_k / K) d_k,
+        //      a recurrence on scalars over the block's Gram entries (gram_entries above: they do not depend on this generation's
+        //      fitness), and the block leaves y - sum_k e_k v_k: nb independent dot products, ONE batched warp reduction and nb
+        //      multiply-adds per element instead of nb dependent dot-reduce-update steps (39 of those were 10 us on the critical
+        //      path of the single-query generation).  Warp-collective. ----
+        auto newest_row = [&]() {
+            float4 yn[NVB];
+#pragma unroll
+            for (int it = 0; it < NVB; ++it) {
+                const int q = lane + 32 * it;
+                yn[it] = (q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            double kn = 1.0;
+            for (int j = 0; j + 1 < live; ++j) kn *= Kd;             // the same product the sweep forms step by step
+            float* part = reinterpret_cast<float*>(red4);            // UPD_BLK x 32 lane-partial dot products (the mean phase is over)
+            const int rr = lane >> 2, qq = lane & 3;                 // lanes 4 rr .. 4 rr + 3 look after row j0 + rr of the block
+            // The loops over the rows of a block are NOT unrolled: this code runs once per generation, on the critical path, and
+            // after an L2 flush every instruction line of it comes from HBM (the straight-line version spent 5.5 us in its first
+            // block and 0.6 us in each of the following ones).
+#pragma unroll 1
+            for (int j0 = 0; j0 + 1 < live; j0 += UPD_BLK) {
+                const int nb = min(UPD_BLK, live - 1 - j0);
+#pragma unroll 1
+                for (int r = 0; r < nb; r += 2) {                    // g_r, lane by lane; two rows per trip (the second may be absent)
+                    const float4* vr = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + r) * ns);
+                    const float4* vs = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + min(r + 1, nb - 1)) * ns);
+                    float2 d0 = make_float2(0.f, 0.f), d1 = d0, f0 = d0, f1 = d0;
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        const int q = lane + 32 * it;
+                        const float4 v = (q < nq) ? vr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 w = (q < nq) ? vs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        d0 = ffma2(lo2(v), lo2(yn[it]), d0); d1 = ffma2(hi2(v), hi2(yn[it]), d1);
+                        f0 = ffma2(lo2(w), lo2(yn[it]), f0); f1 = ffma2(hi2(w), hi2(yn[it]), f1);
+                    }
+                    part[r * 32 + lane] = (d0.x + d0.y) + (d1.x + d1.y);
+                    if (r + 1 < nb) part[(r + 1) * 32 + lane] = (f0.x + f0.y) + (f1.x + f1.y);
+                }
+                __syncwarp();
+                float gs = 0.f;                                      // g of my row: 8 lanes' partials per quarter, then the 4 quarters
+                if (rr < nb) {
+                    const float4 p0 = *reinterpret_cast<const float4*>(part + rr * 32 + qq * 8), p1 = *reinterpret_cast<const float4*>(part + rr * 32 + qq * 8 + 4);
+                    gs = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
+                }
+                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+                __syncwarp();                                        // part is rewritten by the next block
+                // the scalar recurrence: e_i is final on the lanes of row i once e_0 .. e_(i-1) have been taken off
+                const float ljm = (rr < nb) ? lj_s[j0 + rr] : 0.f;
+                float acc = 0.f, em = 0.f;
+#pragma unroll 1
+                for (int i = 0; i < nb; ++i) {
+                    const float gi = (rr > i && rr < nb) ? Gs[(j0 + rr) * UPD_BLK + i] : 0.f;
+                    const float ei = __shfl_sync(0xffffffffu, ljm * (gs - acc), 4 * i);
+                    if (rr == i) em = ei;
+                    acc = fmaf(ei, gi, acc);
+                }
+#pragma unroll 1
+                for (int r = 0; r < nb; r += 2) {                    // y <- y - e_r v_r - e_(r+1) v_(r+1), in that order
+                    const float4* vr = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + r) * ns);
+                    const float4* vs = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + min(r + 1, nb - 1)) * ns);
+                    const float er = __shfl_sync(0xffffffffu, em, 4 * r);
+                    const float es = __shfl_sync(0xffffffffu, em, 4 * min(r + 1, UPD_BLK - 1));
+                    const float2 me = make_float2(-er, -er);
+                    const float ms1 = (r + 1 < nb) ? -es : 0.f;      // an absent row takes nothing off: y - 0 v = y
+                    const float2 ms = make_float2(ms1, ms1);
+#pragma unroll
+                    for (int it = 0; it < NVB; ++it) {
+                        const int q = lane + 32 * it;
+                        const float4 v = (q < nq) ? vr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 w = (q < nq) ? vs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float2 l = ffma2(me, lo2(v), lo2(yn[it])), h = ffma2(me, hi2(v), hi2(yn[it]));
+                        l = ffma2(ms, lo2(w), l); h = ffma2(ms, hi2(w), h);
+                        yn[it] = make_float4(l.x, l.y, h.x, h.y);
+                    }
+                }
+                if (a.dbg && lane == 0 && OVERLAP) a.dbg[12 + (j0 >> 3)] = gtime();
+            }
+            {   // pc at its position in the mirror (after the chain: nothing in it should queue behind these stores)
+                const float4* pcs = reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns);
+#pragma unroll
+                for (int it = 0; it < NVB; ++it) {
+                    const int q = lane + 32 * it;
+                    if (q < nq) reinterpret_cast<float4*>(VPb + ((size_t)(live - 1) * 2 + 1) * ns)[q] = pcs[q];
+                }
+            }
+            if (OVERLAP) { if (a.dbg && lane == 0) a.dbg[18] = gtime(); __syncthreads(); }   // the other warps have copied the best-so-far candidate out of X
+            publish(yn, live - 1, kn);
+        };
+        if (first_stale == 0 && warp == 0 && hi > 0) { publish(y[0], 0, 1.0); retire_first(); }   // row 0 has no factors (v_0 = pc_0)
         double kp = 1.0;                                             // K^(j+1) inside step j
         for (int j = 0; j + 1 < hi; ++j) {
             kp *= Kd;
-            if (j >= my_last) break;                                 // all my rows are final
+            if (n == 0) break;                                       // all my rows are final
             if (j >= first_stale) mbar_wait(&rowbar[j], 0);
             const float4* vj = reinterpret_cast<const float4*>(rows_s + (size_t)j * ns);
             float4 a4[NVB];
@@ -440,36 +596,29 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 a4[it] = (q < nq) ? vj[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             // the row that becomes final in this step goes first and alone: the next step waits for it
+            if (next == j + 1) {
+                float2 dd = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (base + r * rstride == j + 1) {
-                    float2 dd = make_float2(0.f, 0.f);
+                for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(y[0][it]), dd); dd = ffma2(hi2(a4[it]), hi2(y[0][it]), dd); }
+                const float d = warp_sum(dd.x + dd.y);
+                if (j >= first_stale) mbar_wait(&scalbar[j], 0);   // Lj_j / K, |v_j|^2: published right after the row (long done)
+                const float e = lj_s[j] * d;
+                const float2 me = make_float2(-e, -e);
 #pragma unroll
-                    for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(y[r][it]), dd); dd = ffma2(hi2(a4[it]), hi2(y[r][it]), dd); }
-                    const float d = warp_sum(dd.x + dd.y);
-                    if (j >= first_stale) mbar_wait(&scalbar[j], 0);   // Lj_j / K, |v_j|^2: published right after the row (long done)
-                    const float e = lj_s[j] * d;
-                    const float2 me = make_float2(-e, -e);
-#pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        const float2 l = ffma2(me, lo2(a4[it]), lo2(y[r][it])), h = ffma2(me, hi2(a4[it]), hi2(y[r][it]));
-                        y[r][it] = make_float4(l.x, l.y, h.x, h.y);
-                    }
-                    publish(y[r], j + 1, kp);
+                for (int it = 0; it < NVB; ++it) {
+                    const float2 l = ffma2(me, lo2(a4[it]), lo2(y[0][it])), h = ffma2(me, hi2(a4[it]), hi2(y[0][it]));
+                    y[0][it] = make_float4(l.x, l.y, h.x, h.y);
                 }
+                publish(y[0], j + 1, kp);
+                retire_first();
             }
-            // the other pending rows of this warp: always a suffix r >= r0 of its rows (they finish in index order).
-            // One straight-line block per r0, so that the dot-product chains and the 5 shuffle rounds of the rows
-            // interleave (a branch per row would serialise their latencies) and finished rows cost no issue slots —
-            // the single SM of this CTA is issue-bound in this loop (ncu: ~200 warp instructions per warp and step)
-            int r0 = 0;
+            // my other pending rows: one straight-line block per count, so that the dot-product chains and the 5 shuffle
+            // rounds of the rows interleave (a branch per row would serialise their latencies)
+            auto others = [&](auto nc) {
+                constexpr int N = decltype(nc)::value;
+                float d[N];
 #pragma unroll
-            for (int r = 0; r < R; ++r) r0 += (base + r * rstride <= j + 1) ? 1 : 0;
-            auto others = [&](auto r0c) {
-                constexpr int R0 = decltype(r0c)::value;
-                float d[R];
-#pragma unroll
-                for (int r = R0; r < R; ++r) {
+                for (int r = 0; r < N; ++r) {
                     float2 d0 = make_float2(0.f, 0.f), d1 = d0;
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) { d0 = ffma2(lo2(a4[it]), lo2(y[r][it]), d0); d1 = ffma2(hi2(a4[it]), hi2(y[r][it]), d1); }
@@ -478,13 +627,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 #pragma unroll
                 for (int ofs = 16; ofs > 0; ofs >>= 1) {
 #pragma unroll
-                    for (int r = R0; r < R; ++r) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
+                    for (int r = 0; r < N; ++r) d[r] += __shfl_xor_sync(0xffffffffu, d[r], ofs);
                 }
                 if (j >= first_stale) mbar_wait(&scalbar[j], 0);
                 const float ljk = lj_s[j];
 #pragma unroll
-                for (int r = R0; r < R; ++r) {
-                    const float e = (base + r * rstride < hi) ? ljk * d[r] : 0.f;   // an absent row rides along: y - 0 * a = y
+                for (int r = 0; r < N; ++r) {
+                    const float e = ljk * d[r];
                     const float2 me = make_float2(-e, -e);
 #pragma unroll
                     for (int it = 0; it < NVB; ++it) {
@@ -493,21 +642,22 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     }
                 }
             };
-            if (r0 < R && base + r0 * rstride < hi) {
-                switch (r0) {
-                    case 0: others(std::integral_constant<int, 0>()); break;
-                    case 1: others(std::integral_constant<int, (R > 1 ? 1 : 0)>()); break;
-                    case 2: others(std::integral_constant<int, (R > 2 ? 2 : 0)>()); break;
-                    case 3: others(std::integral_constant<int, (R > 3 ? 3 : 0)>()); break;
-                    default: others(std::integral_constant<int, (R > 4 ? 4 : 0)>()); break;
-                }
+            switch (n) {
+                case 0: break;
+                case 1: others(std::integral_constant<int, 1>()); break;
+                case 2: others(std::integral_constant<int, (R >= 2 ? 2 : 1)>()); break;
+                case 3: others(std::integral_constant<int, (R >= 3 ? 3 : 1)>()); break;
+                case 4: others(std::integral_constant<int, (R >= 4 ? 4 : 1)>()); break;
+                default: others(std::integral_constant<int, (R >= 5 ? 5 : 1)>()); break;
             }
         }
+        // every older row is final
+        __syncthreads();
+        UPD_STAMP(7);
+        for (int k = 1 + warp; k < hi; k += UPD_WARPS) gram_row(k);  // block Gram entries for the newest row's chain
         if (OVERLAP) {
-            // ---------------- overlap: every older row is final; now the part that needs this generation's ranks ----------------
-            __syncthreads();
-            UPD_STAMP(7);
-            if (tid == 0) {                                          // k_rank: one ticket per CTA after its last store (k_rank.cuh)
+            // ---------------- overlap: the part that needs this generation's ranks ----------------
+            if (tid == 32) {                                         // k_rank: one ticket per CTA after its last store (k_rank.cuh)
                 const unsigned need = (unsigned)o.RS;
                 // plain polling by one thread (this wait is on the critical path); the fence is the acquire for the ranks /
                 // partial sums behind the tickets
@@ -523,69 +673,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             UPD_STAMP(8);
             post_rank();                                             // mean, step size, the new evolution path -> rows_s[live - 1]
             // warps 1.. track the best-so-far candidate (it reads X, which the sampler overwrites only after the newest pair
-            // below has been published) while warp 0 runs the newest row's chain
-            if (warp > 0) best_so_far(1);
-            float4 yn[NVB];
-            double kn = 1.0;
-            if (warp == 0) {
-                // the newest row: factors 0 .. live-2 in order, with the same arithmetic as the sweep (every factor but the
-                // last by the pending-row form, the last by the final-step form), then published like any other row
-#pragma unroll
-                for (int it = 0; it < NVB; ++it) {
-                    const int q = lane + 32 * it;
-                    yn[it] = (q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q < nq) reinterpret_cast<float4*>(VPb + ((size_t)(live - 1) * 2 + 1) * ns)[q] = yn[it];   // pc at its position
-                }
-                // every factor row is final and in shared memory by now: the next factor is fetched while this one's
-                // dot product is in the shuffle rounds (the loads would otherwise sit on the 39-step chain)
-                float4 a4[NVB];
-                float ljn = lj_s[0];
-#pragma unroll
-                for (int it = 0; it < NVB; ++it) {
-                    const int q = lane + 32 * it;
-                    a4[it] = (q < nq && live > 1) ? reinterpret_cast<const float4*>(rows_s)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll 2
-                for (int j = 0; j + 1 < live; ++j) {
-                    kn *= Kd;
-                    const float ljj = ljn;
-                    float4 an[NVB];
-                    const float4* vn = reinterpret_cast<const float4*>(rows_s + (size_t)(j + 1) * ns);   // row live-1 (the path itself) is read but unused
-#pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        const int q = lane + 32 * it;
-                        an[it] = (q < nq) ? vn[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    ljn = lj_s[j + 1];
-                    float d;
-                    if (j + 2 < live) {
-                        float2 d0 = make_float2(0.f, 0.f), d1 = d0;
-#pragma unroll
-                        for (int it = 0; it < NVB; ++it) { d0 = ffma2(lo2(a4[it]), lo2(yn[it]), d0); d1 = ffma2(hi2(a4[it]), hi2(yn[it]), d1); }
-                        d = (d0.x + d0.y) + (d1.x + d1.y);
-                    } else {
-                        float2 dd = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int it = 0; it < NVB; ++it) { dd = ffma2(lo2(a4[it]), lo2(yn[it]), dd); dd = ffma2(hi2(a4[it]), hi2(yn[it]), dd); }
-                        d = dd.x + dd.y;
-                    }
-#pragma unroll
-                    for (int ofs = 16; ofs > 0; ofs >>= 1) d += __shfl_xor_sync(0xffffffffu, d, ofs);
-                    const float e = ljj * d;
-                    const float2 me = make_float2(-e, -e);
-#pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        const float2 l = ffma2(me, lo2(a4[it]), lo2(yn[it])), h = ffma2(me, hi2(a4[it]), hi2(yn[it]));
-                        yn[it] = make_float4(l.x, l.y, h.x, h.y);
-                        a4[it] = an[it];
-                    }
-                }
-            }
-            __syncthreads();                                         // best-so-far has copied its row out of X
-            if (warp == 0) {
-                publish(yn, live - 1, kn);
-                UPD_STAMP(9);
-            }
+            // has been published) while warp 0 runs the newest row's chain
+            if (warp > 0) { best_so_far(1, nwarps - 1); __syncthreads(); }
+            else { newest_row(); UPD_STAMP(9); }
+        } else {
+            __syncthreads();
+            if (warp == 0) newest_row();
         }
     } else {
         // ---------------- streaming sweep: pending rows stay in shared memory (or HBM/L2) ----------------

@@ -323,7 +323,7 @@ int configure_update(lmcma_b200_opt* o) {
     o->upd_nvb = nq <= 128 ? 4 : 16;
     o->rank_smem = (size_t)2 * TELL_FTILE * 4 + (size_t)3 * TELL_MAX_ROWS * 4 + (size_t)7 * 128 * 16;
     const size_t fixed = (((size_t)o->d.m * 36 + 8 + 127) & ~(size_t)127) + (size_t)2048 * (UPD_GROUPS - 1);
-    const size_t rows = (size_t)o->d.m * o->d.ns * sizeof(float);
+    const size_t rows = (size_t)o->d.m * o->d.ns * sizeof(float) + (size_t)o->d.m * (UPD_BLK + 1) * sizeof(float);   // + the block Gram entries and their flags (k_update.cuh)
     const size_t budget = o->props->smem_optin - 2048;            // static shared + slack
     o->upd_rows_in_smem = fixed + rows <= budget;
     o->upd_smem = fixed + (o->upd_rows_in_smem ? rows : 0);
@@ -969,6 +969,10 @@ int lmcma_b200_sync(lmcma_b200_opt* o) {
         cudaMemcpy(h, o->graph_dbg, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "fused generation, k_update (ns since its start): bookkeeping=%lld prologue=%lld sweep: warp 0 done=%lld, all done + ranks seen=%lld post start=%lld mean=%lld newest row=%lld tail=%lld end=%lld",
                 h[1] - h[0], h[2] - h[0], h[7] - h[0], h[8] - h[0], h[3] - h[0], h[4] - h[0], h[9] - h[0], h[5] - h[0], h[6] - h[0]);
+        fprintf(stderr, " chain blocks:");
+        for (int i = 12; i < 21; ++i) fprintf(stderr, " %lld", (h[i] - h[0]) / 100);
+        fprintf(stderr, " rows:");
+        for (int i = 0; i < 40; ++i) fprintf(stderr, " %lld", (h[24 + i] - h[0]) / 100);
         if (o->d.dbg) {
             long long g[64];
             cudaMemcpy(g, o->d.dbg, sizeof(g), cudaMemcpyDeviceToHost);

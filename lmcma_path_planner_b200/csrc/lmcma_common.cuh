@@ -209,6 +209,13 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// cta-scope release / acquire on a flag in shared memory (no membar: a fence would wait for the thread's global stores)
+__device__ __forceinline__ void st_release_cta_shared(int* p, int v) { asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_cta_shared(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ long long gtime() {
