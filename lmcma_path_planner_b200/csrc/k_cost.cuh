@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         }
     }
     if (STORAGE == 1) for (int i = tid; i < 256; i += nthr) lut[i] = mp.lut[i];
-    for (int lb = tid; lb < a.cb; lb += nthr) blkrec[lb].x = 0u;    // first round of block records (phase 2a), zeroed ahead of the barrier below
+    // first round of block records (phase 2a), zeroed ahead of the barrier below: two records per 16-byte store (a.cb is even;
+    // the .y halves are written after the next barrier)
+    for (int lb = tid; lb < (a.cb >> 1); lb += nthr) reinterpret_cast<uint4*>(blkrec)[lb] = make_uint4(0u, 0u, 0u, 0u);
     // the candidate row, read ONCE and coalesced (it may live in pinned host memory: lmcma_b200_cost_evaluate hands a
     // page-locked caller buffer to the kernel directly, and the row then crosses PCIe while other CTAs compute)
     {
@@ -176,8 +178,10 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
     }
     if (lane == 31) warp_tot[warp] = incl;
     const bool all_safe = __syncthreads_and(safe ? 1 : 0) != 0;
-    int base = incl - my_cnt, T = 0;
-    for (int w2 = 0; w2 < nwarps; ++w2) { const int v = warp_tot[w2]; if (w2 < warp) base += v; T += v; }
+    // the warps' totals: one load and two integer warp reductions (REDUX.SUM) instead of a dependent loop over shared memory
+    const int wt = lane < nwarps ? warp_tot[lane] : 0;
+    const int T = __reduce_add_sync(0xffffffffu, wt);
+    int base = incl - my_cnt + __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0);
     if (tid == 0) off[0] = 0;
     const int nblk0 = min(a.cb, (int)((unsigned)(T + 31) >> 5));    // blocks of the first round
     for (int s = s_begin; s < s_end; ++s) {

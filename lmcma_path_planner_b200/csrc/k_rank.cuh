@@ -259,8 +259,10 @@ __global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict
     // this kernel's own wait: k_update's prologue reads the fitness, so it may only start once k_cost has completed
     // (its prologue does not depend on THIS kernel, see k_update.cuh).
     griddep_wait();
-    // overlapped generation (RANK_KEEP_FLAGS): the dependent is k_sample, whose 128 CTAs would share SMs with this grid and
-    // slow the ranks k_update is waiting for; it is released when this CTA is done instead (env LMCMA_B200_RANK_LATE=0: early)
+    // overlapped generation (RANK_KEEP_FLAGS): the dependent is k_sample.  mode & 4 (the fused generation's default): released
+    // here, so that it works through the pairs k_update has already finished while this grid ranks (its 128 CTAs share SMs
+    // with this grid: the ranks arrive ~1 us later, the sampler is done 8 us earlier).  Otherwise (tell_all, where the sweep is
+    // the longer branch; LMCMA_B200_RANK_LATE=1) it is released when this CTA is done
     const bool late_release = (mode & RANK_KEEP_FLAGS) && !(mode & 4);
     if (!late_release) griddep_launch_dependents();
     const int b = blockIdx.y;

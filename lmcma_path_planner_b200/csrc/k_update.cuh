@@ -43,6 +43,7 @@ struct UpdateArgs {
                                // bookkeeping, and the sweep over every pending row but the newest — comes first; then it
                                // waits for k_rank's tickets, forms the mean / new evolution path and finishes the newest
                                // row.  Implies `progressive` (k_sample is released by k_rank and follows the flags)
+    int no_dry;                // overlapped generation: skip the pre-execution pass of the post-rank code (LMCMA_B200_UPDATE_DRY=0)
     int progressive;           // publish OptDev::progress flags as the outputs become final: k_sample (launched as a
                                // programmatic dependent) consumes the pairs while the sweep is still producing them
 };
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     float4* red4 = reinterpret_cast<float4*>(smem_raw + (((size_t)m * 36 + 8 + 127) & ~(size_t)127));                      // 128 float4 scratch
     float* rows_s = reinterpret_cast<float*>(red4 + 128 * (UPD_GROUPS - 1));                                                                  // m x ns (SMEM)
     float* Gs = rows_s + (size_t)m * ns;                           // register sweep: m x UPD_BLK, Gs[k][r] = v_k . v_(j0 + r), j0 = k rounded down to its block, r < k - j0
+    // register sweep: lane-partial dot products of the newest row's chain, 2 stages x NVB warps x UPD_BLK rows x 32 lanes, + NVB norms
+    float* chain_part = reinterpret_cast<float*>((reinterpret_cast<size_t>(Gs + (size_t)m * (UPD_BLK + 1)) + 15) & ~(size_t)15);
     __shared__ unsigned long long sh_key;
+    __shared__ int sh_dry;
     __shared__ __align__(8) unsigned long long sh_bar;
     __shared__ float am_v[UPD_WARPS];
     __shared__ int am_i[UPD_WARPS];
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         scp->counteval = sc0.counteval + o.lambda;
     };
     // ---- one float4 column of the mean / evolution path / new pc_j (lmcma.cpp:316-329, 365-366); d = sum_i w_i (x_i - xmean) ----
-    auto finish_column = [&](const int q, const float (&d)[4], const double2 xm01, const double2 xm23, const float4 pc4) {
+    auto finish_column = [&](const int q, const float (&d)[4], const double2 xm01, const double2 xm23, const float4 pc4, const bool dry) {
         const double coef = o.pc_coef / sigma_old;                   // sqrt(cc (2 - cc) mueff) / sigma
         double* xm = o.xmean + (size_t)b * ns;
         float* pc = o.pc + (size_t)b * ns;
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             xn[c] = xo[c] + shift;
             pn[c] = (float)__fma_rn(1.0 - o.cc, (double)po[c], __dmul_rn(coef, shift));   // explicit: the same bits wherever this is inlined
         }
+        if (dry) return;                                             // pre-execution pass (see the overlapped tail): no side effects
         reinterpret_cast<double2*>(xm)[2 * q] = make_double2(xn[0], xn[1]);
         reinterpret_cast<double2*>(xm)[2 * q + 1] = make_double2(xn[2], xn[3]);
         const float4 p4 = make_float4(pn[0], pn[1], pn[2], pn[3]);
@@ -278,15 +283,15 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         reinterpret_cast<float4*>(pnew)[q] = p4;
         reinterpret_cast<float4*>(rnew)[q] = p4;
     };
-    auto post_rank = [&]() {                                         // block-collective
-    UPD_STAMP(3);
-    if (tid == 0) o.rank_ticket[b] = 0u;                             // k_rank's CTAs of this generation have all drawn one
+    auto post_rank = [&](const bool dry) {                           // block-collective; dry: same instructions, no side effects
+    if (!dry) UPD_STAMP(3);
+    if (tid == 0 && !dry) o.rank_ticket[b] = 0u;                             // k_rank's CTAs of this generation have all drawn one
     // ---- population-success step size (lmcma.cpp:393-419), counters (lmcma.cpp:189, 423): needs only k_rank's pair
     //      count, so it goes first (the progressive hand-over publishes the scalars before the sweep) ----
-    if (tid == nthr - 1) step_size_and_counters();
+    if (tid == nthr - 1 && !dry) step_size_and_counters();
     // prev_fit (lmcma.cpp:420-421): k_rank has finished reading the previous generation's values
-    for (int j = tid; j < o.lambda; j += nthr) o.prev_fit[(size_t)b * o.lambda + j] = canon_fitness(__ldcg(fa + j));
-    if (o.prev_sorted)                                               // sorted-tile ranking (k_rank.cuh): the next generation searches it
+    for (int j = tid; j < o.lambda && !dry; j += nthr) o.prev_fit[(size_t)b * o.lambda + j] = canon_fitness(__ldcg(fa + j));
+    if (o.prev_sorted && !dry)                                               // sorted-tile ranking (k_rank.cuh): the next generation searches it
         for (int j = tid; j < o.lambda; j += nthr) o.prev_sorted[(size_t)b * o.lambda + j] = __ldcg(o.fit_sorted + (size_t)b * o.lambda + j);
 
     // ---- mean, evolution path, new pc_j (lmcma.cpp:316-329, 365-366): 128 float4 columns x 2 slice groups, up to
@@ -324,15 +329,15 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 #pragma unroll
                 for (int g2 = 0; g2 + 1 < UPD_GROUPS; ++g2) { const float4 u4 = red4[g2 * 128 + tq]; t.x += u4.x; t.y += u4.y; t.z += u4.z; t.w += u4.w; }
                 const float d[4] = {acc.x + t.x, acc.y + t.y, acc.z + t.z, acc.w + t.w};
-                finish_column(q, d, xm01, xm23, pc4);
+                finish_column(q, d, xm01, xm23, pc4, dry);
             }
             __syncthreads();
         }
     }
     if (!SMEM) __threadfence();
     __syncthreads();
-    UPD_STAMP(4);
-    if (a.progressive) {
+    if (!dry) UPD_STAMP(4);
+    if (a.progressive && !dry) {
         // scalars and mean are final; so are the pairs in front of the first stale position (untouched this generation;
         // overlap mode has published those before its sweep)
         if (!OVERLAP) for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     if (!OVERLAP) {
         griddep_wait();
         if (a.progressive) griddep_launch_dependents();
-        post_rank();
+        post_rank(false);
     } else {
         for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);   // untouched pairs: final already
     }
@@ -495,92 +500,113 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         //      rows) and g_k = v_k . y, the dot products the factors would see one after the other are
         //          d_k = g_k - sum_{i < k} e_i (v_k . v_i),   e_k = (Lj_k / K) d_k,
         //      a recurrence on scalars over the block's Gram entries (gram_entries above: they do not depend on this generation's
-        //      fitness), and the block leaves y - sum_k e_k v_k: nb independent dot products, ONE batched warp reduction and nb
-        //      multiply-adds per element instead of nb dependent dot-reduce-update steps (39 of those were 10 us on the critical
-        //      path of the single-query generation).  Warp-collective. ----
-        auto newest_row = [&]() {
-            float4 yn[NVB];
-#pragma unroll
-            for (int it = 0; it < NVB; ++it) {
-                const int q = lane + 32 * it;
-                yn[it] = (q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        //      fitness), and the block leaves y - sum_k e_k v_k: nb independent dot products, ONE batched reduction and nb
+        //      multiply-adds per element instead of nb dependent dot-reduce-update steps.
+        //      The chain is on the critical path of the single-query generation (nothing else runs on this SM by then), so it is
+        //      spread over NVB warps: warp w owns float4 column lane + 32 w of the row, the lane-partial dot products of the NVB
+        //      warps meet in shared memory (one named barrier per block, double-buffered), and every warp runs the same
+        //      reduction and scalar recurrence on the same numbers in the same order, so all of them hold the same e_k.  One
+        //      warp walking 4 columns per lane took 1.2 us per block (2.4 K cycles of dependent loads and multiply-adds).
+        //      Collective over warps 0 .. NVB-1. ----
+        auto newest_row = [&](const bool dry) {
+            const int q = lane + 32 * warp;
+            const bool has = q < nq;
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 pc4 = has ? reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns)[q] : zero4;
+            float4 yn = pc4;
             double kn = 1.0;
             for (int j = 0; j + 1 < live; ++j) kn *= Kd;             // the same product the sweep forms step by step
-            float* part = reinterpret_cast<float*>(red4);            // UPD_BLK x 32 lane-partial dot products (the mean phase is over)
             const int rr = lane >> 2, qq = lane & 3;                 // lanes 4 rr .. 4 rr + 3 look after row j0 + rr of the block
-            // The loops over the rows of a block are NOT unrolled: this code runs once per generation, on the critical path, and
-            // after an L2 flush every instruction line of it comes from HBM (the straight-line version spent 5.5 us in its first
-            // block and 0.6 us in each of the following ones).
+            int buf = 0;
 #pragma unroll 1
-            for (int j0 = 0; j0 + 1 < live; j0 += UPD_BLK) {
+            for (int j0 = 0; j0 + 1 < live; j0 += UPD_BLK, buf ^= 1) {
                 const int nb = min(UPD_BLK, live - 1 - j0);
-#pragma unroll 1
-                for (int r = 0; r < nb; r += 2) {                    // g_r, lane by lane; two rows per trip (the second may be absent)
-                    const float4* vr = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + r) * ns);
-                    const float4* vs = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + min(r + 1, nb - 1)) * ns);
-                    float2 d0 = make_float2(0.f, 0.f), d1 = d0, f0 = d0, f1 = d0;
+                float* pw = chain_part + (size_t)((buf * NVB + warp) * UPD_BLK) * 32;
+                float4 v[UPD_BLK];
 #pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        const int q = lane + 32 * it;
-                        const float4 v = (q < nq) ? vr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 w = (q < nq) ? vs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        d0 = ffma2(lo2(v), lo2(yn[it]), d0); d1 = ffma2(hi2(v), hi2(yn[it]), d1);
-                        f0 = ffma2(lo2(w), lo2(yn[it]), f0); f1 = ffma2(hi2(w), hi2(yn[it]), f1);
-                    }
-                    part[r * 32 + lane] = (d0.x + d0.y) + (d1.x + d1.y);
-                    if (r + 1 < nb) part[(r + 1) * 32 + lane] = (f0.x + f0.y) + (f1.x + f1.y);
+                for (int r = 0; r < UPD_BLK; ++r) {                  // my column's share of g_r (an absent row gives 0)
+                    v[r] = (has && r < nb) ? reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + r) * ns)[q] : zero4;
+                    float2 d = fmul2(lo2(v[r]), lo2(yn));
+                    d = ffma2(hi2(v[r]), hi2(yn), d);
+                    pw[r * 32 + lane] = d.x + d.y;
                 }
-                __syncwarp();
-                float gs = 0.f;                                      // g of my row: 8 lanes' partials per quarter, then the 4 quarters
-                if (rr < nb) {
-                    const float4 p0 = *reinterpret_cast<const float4*>(part + rr * 32 + qq * 8), p1 = *reinterpret_cast<const float4*>(part + rr * 32 + qq * 8 + 4);
-                    gs = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
+                // what the recurrence needs besides g: my row's Gram entries against the earlier rows of the block and its Lj / K
+                float gi[UPD_BLK];
+                {
+                    const float4* gp = reinterpret_cast<const float4*>(Gs + (size_t)(j0 + min(rr, nb - 1)) * UPD_BLK);
+                    const float4 g0 = gp[0], g1 = gp[1];
+                    const float gg[UPD_BLK] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int i = 0; i < UPD_BLK; ++i) gi[i] = (rr > i && rr < nb) ? gg[i] : 0.f;
+                }
+                const float ljm = (rr < nb) ? lj_s[j0 + rr] : 0.f;
+                named_bar_sync(3, 32 * NVB);
+                float gs;                                            // g of my row: 8 lanes' partials per quarter and warp, then the 4 quarters
+                {
+                    float sw[NVB];
+#pragma unroll
+                    for (int w = 0; w < NVB; ++w) {
+                        const float4* pp = reinterpret_cast<const float4*>(chain_part + (size_t)((buf * NVB + w) * UPD_BLK + rr) * 32 + qq * 8);
+                        const float4 p0 = pp[0], p1 = pp[1];
+                        sw[w] = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
+                    }
+                    gs = sw[0];
+#pragma unroll
+                    for (int w = 1; w < NVB; ++w) gs += sw[w];
                 }
                 gs += __shfl_xor_sync(0xffffffffu, gs, 1);
                 gs += __shfl_xor_sync(0xffffffffu, gs, 2);
-                __syncwarp();                                        // part is rewritten by the next block
-                // the scalar recurrence: e_i is final on the lanes of row i once e_0 .. e_(i-1) have been taken off
-                const float ljm = (rr < nb) ? lj_s[j0 + rr] : 0.f;
+                // the scalar recurrence: e_i is final on the lanes of row i once e_0 .. e_(i-1) have been taken off (rows past the
+                // block's end have Lj = 0: their e is 0)
                 float acc = 0.f, em = 0.f;
-#pragma unroll 1
-                for (int i = 0; i < nb; ++i) {
-                    const float gi = (rr > i && rr < nb) ? Gs[(j0 + rr) * UPD_BLK + i] : 0.f;
+#pragma unroll
+                for (int i = 0; i < UPD_BLK; ++i) {
                     const float ei = __shfl_sync(0xffffffffu, ljm * (gs - acc), 4 * i);
                     if (rr == i) em = ei;
-                    acc = fmaf(ei, gi, acc);
+                    acc = fmaf(ei, gi[i], acc);
                 }
-#pragma unroll 1
-                for (int r = 0; r < nb; r += 2) {                    // y <- y - e_r v_r - e_(r+1) v_(r+1), in that order
-                    const float4* vr = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + r) * ns);
-                    const float4* vs = reinterpret_cast<const float4*>(rows_s + (size_t)(j0 + min(r + 1, nb - 1)) * ns);
+#pragma unroll
+                for (int r = 0; r < UPD_BLK; ++r) {                  // y <- y - e_r v_r, in the order of the factors
                     const float er = __shfl_sync(0xffffffffu, em, 4 * r);
-                    const float es = __shfl_sync(0xffffffffu, em, 4 * min(r + 1, UPD_BLK - 1));
                     const float2 me = make_float2(-er, -er);
-                    const float ms1 = (r + 1 < nb) ? -es : 0.f;      // an absent row takes nothing off: y - 0 v = y
-                    const float2 ms = make_float2(ms1, ms1);
-#pragma unroll
-                    for (int it = 0; it < NVB; ++it) {
-                        const int q = lane + 32 * it;
-                        const float4 v = (q < nq) ? vr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 w = (q < nq) ? vs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        float2 l = ffma2(me, lo2(v), lo2(yn[it])), h = ffma2(me, hi2(v), hi2(yn[it]));
-                        l = ffma2(ms, lo2(w), l); h = ffma2(ms, hi2(w), h);
-                        yn[it] = make_float4(l.x, l.y, h.x, h.y);
-                    }
+                    const float2 l = ffma2(me, lo2(v[r]), lo2(yn)), h = ffma2(me, hi2(v[r]), hi2(yn));
+                    yn = make_float4(l.x, l.y, h.x, h.y);
                 }
-                if (a.dbg && lane == 0 && OVERLAP) a.dbg[12 + (j0 >> 3)] = gtime();
+                if (a.dbg && tid == 0 && OVERLAP && !dry) a.dbg[12 + (j0 >> 3)] = gtime();
             }
-            {   // pc at its position in the mirror (after the chain: nothing in it should queue behind these stores)
-                const float4* pcs = reinterpret_cast<const float4*>(rows_s + (size_t)(live - 1) * ns);
+            // pc at its position in the mirror (after the chain: nothing in it should queue behind these stores)
+            if (has && !dry) reinterpret_cast<float4*>(VPb + ((size_t)(live - 1) * 2 + 1) * ns)[q] = pc4;
+            if (OVERLAP) { if (a.dbg && tid == 0 && !dry) a.dbg[18] = gtime(); __syncthreads(); }   // the other warps have copied the best-so-far candidate out of X
+            // ---- publish: y K^(live-1) is the final v of the newest pair (what publish() does for a row held by one warp) ----
+            const int i = live - 1;
+            const float kf = (float)kn;
+            const float2 k2 = make_float2(kf, kf), xl = fmul2(lo2(yn), k2), xh = fmul2(hi2(yn), k2);
+            const float4 x = make_float4(xl.x, xl.y, xh.x, xh.y);
+            if (has && !dry) reinterpret_cast<float4*>(rows_s + (size_t)i * ns)[q] = x;
+            float2 nn = fmul2(lo2(x), lo2(x));
+            nn = ffma2(hi2(x), hi2(x), nn);
+            const float nw = warp_sum(nn.x + nn.y);
+            float* norm_part = chain_part + 2 * NVB * UPD_BLK * 32;  // behind the two dot-product stages
+            if (lane == 0) norm_part[warp] = nw;
+            if (has && !dry) {
+                reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns)[q] = x;
+                reinterpret_cast<float4*>(VPb + (size_t)i * 2 * ns)[q] = x;
+            }
+            named_bar_sync(3, 32 * NVB);                              // every chain warp's stores come before thread 0's release
+            if (tid == 0 && !dry) {
+                float nv = norm_part[0];
 #pragma unroll
-                for (int it = 0; it < NVB; ++it) {
-                    const int q = lane + 32 * it;
-                    if (q < nq) reinterpret_cast<float4*>(VPb + ((size_t)(live - 1) * 2 + 1) * ns)[q] = pcs[q];
+                for (int w = 1; w < NVB; ++w) nv += norm_part[w];
+                mbar_arrive(&rowbar[i]);
+                if (a.dbg && i < 40) a.dbg[24 + i] = gtime();
+                publish_scalars(i, nv);
+                mbar_arrive(&scalbar[i]);
+                if (a.progressive) {                                 // pair i of the mirror and Njs[i] are final
+                    const double r = o.c1 / (1.0 - o.c1), t = sqrt(1.0 + r * (double)nv);
+                    Njsb[i] = (float)(o.M * r / (t + 1.0));          // the value the epilogue stores, too
+                    st_release_gpu(flags + 1 + i, 1);
                 }
             }
-            if (OVERLAP) { if (a.dbg && lane == 0) a.dbg[18] = gtime(); __syncthreads(); }   // the other warps have copied the best-so-far candidate out of X
-            publish(yn, live - 1, kn);
         };
         if (first_stale == 0 && warp == 0 && hi > 0) { publish(y[0], 0, 1.0); retire_first(); }   // row 0 has no factors (v_0 = pc_0)
         double kp = 1.0;                                             // K^(j+1) inside step j
@@ -657,28 +683,46 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         for (int k = 1 + warp; k < hi; k += UPD_WARPS) gram_row(k);  // block Gram entries for the newest row's chain
         if (OVERLAP) {
             // ---------------- overlap: the part that needs this generation's ranks ----------------
-            if (tid == 32) {                                         // k_rank: one ticket per CTA after its last store (k_rank.cuh)
-                const unsigned need = (unsigned)o.RS;
-                // plain polling by one thread (this wait is on the critical path); the fence is the acquire for the ranks /
-                // partial sums behind the tickets
-                const long long t0 = gtime();
-                for (long long spin = 0; *reinterpret_cast<const volatile int*>(o.rank_ticket + b) != (int)need; ++spin)
-                    if ((spin & 255) == 255 && gtime() - t0 > LOST_TIMEOUT_NS) {   // k_rank never ran beside this kernel: tell the
-                        report_lost(o.err, LOST_UPDATE_WAITING_FOR_RANK);          // host and carry on (this generation is void)
-                        break;
+            // Everything from here to the sampler's last chunk is the critical path of the single-query generation, and it is
+            // code this SM has not executed yet: its instruction lines come from L2 (from HBM after an L2 flush) one miss after
+            // the other - the first block of the newest row's chain took 4.7 us against 0.65 us for each of the following ones.
+            // The sweep, however, is normally done well before k_rank is (the fused generation: ~10 us), so while the ranks
+            // are not there yet the SAME instructions are run once with their side effects switched off (`dry`: loads, arithmetic,
+            // barriers, no global store, no flag): the real pass then finds them in the instruction cache.  One code path for
+            // both passes (a loop, not two inlined copies).  No dry pass when the ranks are already there (tell_all, where the
+            // sweep is the longer branch).
+            const unsigned need = (unsigned)o.RS;                    // k_rank: one ticket per CTA after its last store (k_rank.cuh)
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const bool dry = pass == 0;
+                if (dry) {
+                    if (tid == 32) sh_dry = (*reinterpret_cast<const volatile int*>(o.rank_ticket + b) != (int)need && !a.no_dry) ? 1 : 0;
+                    __syncthreads();
+                    if (!sh_dry) continue;
+                } else {
+                    if (tid == 32) {
+                        // plain polling by one thread (this wait is on the critical path); the fence is the acquire for the ranks /
+                        // partial sums behind the tickets
+                        const long long t0 = gtime();
+                        for (long long spin = 0; *reinterpret_cast<const volatile int*>(o.rank_ticket + b) != (int)need; ++spin)
+                            if ((spin & 255) == 255 && gtime() - t0 > LOST_TIMEOUT_NS) {   // k_rank never ran beside this kernel: tell the
+                                report_lost(o.err, LOST_UPDATE_WAITING_FOR_RANK);          // host and carry on (this generation is void)
+                                break;
+                            }
+                        __threadfence();
                     }
-                __threadfence();
+                    __syncthreads();
+                    UPD_STAMP(8);
+                }
+                post_rank(dry);                                      // mean, step size, the new evolution path -> rows_s[live - 1]
+                // warps NVB.. track the best-so-far candidate (it reads X, which the sampler overwrites only after the newest pair
+                // has been published) while warps 0 .. NVB-1 run the newest row's chain
+                if (warp >= NVB) { if (!dry) best_so_far(NVB, nwarps - NVB); __syncthreads(); }
+                else { newest_row(dry); if (!dry) UPD_STAMP(9); }
             }
-            __syncthreads();
-            UPD_STAMP(8);
-            post_rank();                                             // mean, step size, the new evolution path -> rows_s[live - 1]
-            // warps 1.. track the best-so-far candidate (it reads X, which the sampler overwrites only after the newest pair
-            // has been published) while warp 0 runs the newest row's chain
-            if (warp > 0) { best_so_far(1, nwarps - 1); __syncthreads(); }
-            else { newest_row(); UPD_STAMP(9); }
         } else {
             __syncthreads();
-            if (warp == 0) newest_row();
+            if (warp < NVB) newest_row(false);
         }
     } else {
         // ---------------- streaming sweep: pending rows stay in shared memory (or HBM/L2) ----------------

@@ -314,6 +314,7 @@ UpdateArgs update_args_local(lmcma_b200_opt* o) {
     a.slices = o->d.partial; a.n_slices = o->d.RS; a.slice_stride = o->d.ns; a.inst_stride = (long long)o->d.RS * o->d.ns;
     a.blocked = o->tune.update_blocked;
     a.sweep_warps = o->upd_sweep_warps;
+    a.no_dry = o->tune.update_dry ? 0 : 1;
     return a;
 }
 
@@ -323,7 +324,9 @@ int configure_update(lmcma_b200_opt* o) {
     o->upd_nvb = nq <= 128 ? 4 : 16;
     o->rank_smem = (size_t)2 * TELL_FTILE * 4 + (size_t)3 * TELL_MAX_ROWS * 4 + (size_t)7 * 128 * 16;
     const size_t fixed = (((size_t)o->d.m * 36 + 8 + 127) & ~(size_t)127) + (size_t)2048 * (UPD_GROUPS - 1);
-    const size_t rows = (size_t)o->d.m * o->d.ns * sizeof(float) + (size_t)o->d.m * (UPD_BLK + 1) * sizeof(float);   // + the block Gram entries and their flags (k_update.cuh)
+    // + the block Gram entries, and the stages of the newest row's multi-warp chain (k_update.cuh: chain_part)
+    const size_t rows = (size_t)o->d.m * o->d.ns * sizeof(float) + (size_t)o->d.m * (UPD_BLK + 1) * sizeof(float) +
+                        (o->upd_nvb == 4 ? (size_t)(2 * 4 * UPD_BLK * 32 + 16) * sizeof(float) + 16 : 0);
     const size_t budget = o->props->smem_optin - 2048;            // static shared + slack
     o->upd_rows_in_smem = fixed + rows <= budget;
     o->upd_smem = fixed + (o->upd_rows_in_smem ? rows : 0);

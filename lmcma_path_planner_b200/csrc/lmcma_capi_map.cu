@@ -11,7 +11,7 @@ namespace {
 template <int DIMS, int STORAGE, bool TRACE, int MINB = 7>
 int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostShape shape, cudaStream_t st) {
     CostArgs a = a0;
-    a.cb = shape.cb;
+    a.cb = shape.cb & ~1;                                       // even: k_cost zeroes two block records per store
     // segment records 36 B, sample offsets, per-block records 8 B (k_cost.cuh), 256-entry table (u8 storage)
     // + the candidate row (16-byte aligned)
     const size_t smem = (size_t)36 * (a.W + 1) + sizeof(int) * (a.W + 2) + 28 + (size_t)8 * shape.cb + (STORAGE == 1 ? 1024 : 0) +

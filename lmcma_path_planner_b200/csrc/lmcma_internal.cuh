@@ -77,7 +77,11 @@ struct Tuning {
     int sample_rows = -1;   // k_sample_rows: -1 = where it pays (many rows), 0 = never, 1 = also for one large population
     int sample_spec = 1, sample_threads = 0, sample_smem_kb = 160, sample_smem_kb_set = 0, sample_narrow = 0, sample_rbw = 0, sample_r = 0;
     int update_blocked = 0, update_gram = 0, update_streaming = 0, update_sweep_warps = 0;
-    int progressive = 1, overlap = 1, tell_overlap = 1, rank_late = 1, rank_sorted = 1;
+    int progressive = 1, overlap = 1, tell_overlap = 1, rank_sorted = 1;
+    int rank_late = 0;      // fused generation: 1 = k_sample is released when k_rank's CTAs are done, 0 = when k_rank starts (it then works
+                            // through the finished pairs beside the ranking: 66.5 -> 63.2 us per C2 generation once the newest row's
+                            // chain stopped being the longer branch)
+    int update_dry = 1;     // overlapped generation: pre-execute the post-rank code while k_rank is busy (k_update.cuh)
     int graph_dbg = 0, dbg = 0, update_dbg = 0, cost_dbg = 0;
     static Tuning from_env() {
         Tuning t;
@@ -100,7 +104,8 @@ struct Tuning {
         t.progressive = env_int("LMCMA_B200_PROGRESSIVE", 1);
         t.overlap = env_int("LMCMA_B200_OVERLAP", 1);
         t.tell_overlap = env_int("LMCMA_B200_TELL_OVERLAP", 1);
-        t.rank_late = env_int("LMCMA_B200_RANK_LATE", 1);
+        t.rank_late = env_int("LMCMA_B200_RANK_LATE", 0);
+        t.update_dry = env_int("LMCMA_B200_UPDATE_DRY", 1);
         t.rank_sorted = env_int("LMCMA_B200_RANK_SORTED", 1);
         t.graph_dbg = env_int("LMCMA_B200_GRAPH_DBG", 0);
         t.dbg = getenv("LMCMA_B200_DBG") ? 1 : 0;
