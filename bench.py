@@ -219,6 +219,28 @@ def run_b200(args):
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist_pg.all_reduce(lt)
         launches = int(lt.item())
+    # the same C2 population through k_cost on the two map storages (stand-alone launches, CUDA events, L2 flushed): what the
+    # bytes per cell do to a kernel whose gather is paced by the 128-byte lines a warp request touches
+    storage_ms = {}
+    if "cpu" not in skip or "c3" not in skip:
+        Xd = torch.from_numpy(np.ascontiguousarray(opt.get("X")[0])).cuda()
+        fd = torch.empty(LAM, dtype=torch.float32, device="cuda")
+        for storage in ("f32", "u8"):
+            cm2 = cmap if storage == "f32" else L.CostMap(np.minimum(dist, 63.0), "u8", device=local)
+            tot = 0.0
+            for it in range(3 + min(args.steps, 20)):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record(stream)
+                cm2.evaluate_dev(Xd.data_ptr(), Xd.shape[1], LAM, fd.data_ptr(), start, goal, W, L.LONGSAFE, 1e4, stream=stream.cuda_stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if it >= 3:
+                    tot += e0.elapsed_time(e1)
+            storage_ms[storage] = tot / min(args.steps, 20)
+            if storage == "u8":
+                cm2.close()
+        del Xd, fd
     opt.close()
 
     peak, peak_src = peaks()
@@ -276,6 +298,10 @@ def run_b200(args):
             out["c4_split"] = c4
         out["cost_kernel"] = {"evals_per_s": LAM / (cost_ms * 1e-3), "note": "k_cost alone (CUDA events, L2 flushed): the numerator of the "
                               "north star's '>= 100x the CPU trajectory-evaluation throughput' target"}
+        if storage_ms:
+            out["cost_kernel"]["launch_ms_by_map_storage"] = dict(storage_ms, note="stand-alone k_cost launches on the last C2 population, "
+                                                                  "f32 bricks (8x4 cells per 128-byte line) vs u8 bricks (16x8, distance "
+                                                                  "quantised to 1/4 cell and clamped at 63 cells: a different map, not the C2 workload)")
         if world == 1 and "cpu" not in skip:
             out["cpu_baseline"] = cpu_baseline_all(dist, start, goal, lo, hi, x0)
             try:

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
     auto value_of = [&](raw_t r) -> float { return STORAGE == 0 ? (float)r : lut[(int)r]; };   // lut is read after a barrier
 
     // ---- phase 1: per-segment records, sub-step counts, lengths, end samples; block scan of the sample counts ----
-    const int spt = (NSEG + nthr - 1) / nthr;                    // consecutive segments per thread
+    const int spt = a.spt;                                       // consecutive segments per thread, ceil(NSEG / nthr): formed by the launcher
     const int s_begin = min(NSEG, tid * spt), s_end = min(NSEG, s_begin + spt);
     float len_acc = 0.f; int my_cnt = 0;
     bool safe = true;                                            // every waypoint of my segments inside the map

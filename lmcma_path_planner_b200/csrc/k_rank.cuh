@@ -77,8 +77,28 @@ __device__ __forceinline__ int count_below(const float* a, int cnt, float v) {
 // ------------------------------------------------------------------------------------------------
 // ranks + partial sums of one slice
 // ------------------------------------------------------------------------------------------------
+// What a CTA can do BEFORE the fitness exists (k_rank is resident while k_cost drains): stage the previous generation's
+// fitness (written by the last generation's k_update) when one tile holds it, and pull the slice's rows of d = x - xmean
+// towards L2 — after an L2 flush both would otherwise be HBM round trips between the ranks and the partial sums.
+__device__ __forceinline__ void tell_prologue(const OptDev& o, int b, int rs, unsigned char* smem_raw) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lambda = o.lambda;
+    if (lambda <= TELL_FTILE) {
+        float* prev_s = reinterpret_cast<float*>(smem_raw) + TELL_FTILE;
+        const float* prev = (o.tile_sorted ? o.prev_sorted : o.prev_fit) + (size_t)b * lambda;
+        const int cnt4 = (lambda + 3) & ~3;
+        for (int j = tid; j < cnt4; j += nthr) prev_s[j] = j < lambda ? prev[j] : __int_as_float(0x7f800000);
+    }
+    const int rows_per = (o.pop_count + o.RS - 1) / o.RS;
+    const int r0 = rs * rows_per, r1 = min(o.pop_count, r0 + rows_per);
+    if (r1 > r0 && o.B == 1) {                                      // one query: latency; a batch is throughput-bound and only mu of the rows are read
+        const char* d0 = reinterpret_cast<const char*>(o.D + ((size_t)b * o.pop_count + r0) * o.ns);
+        const size_t bytes = (size_t)(r1 - r0) * o.ns * sizeof(float);
+        for (size_t ofs = (size_t)tid * 128; ofs < bytes; ofs += (size_t)nthr * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(d0 + ofs));
+    }
+}
+
 __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __restrict__ f_all, int b, int rs,
-                                             unsigned char* smem_raw) {
+                                             unsigned char* smem_raw, const bool prev_staged) {
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const int lambda = o.lambda;
     const int rows_per = (o.pop_count + o.RS - 1) / o.RS;
@@ -121,7 +141,7 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
             for (int j = tid; j < cnt4; j += nthr) {
                 const bool in = j < cnt;
                 cur_s[j] = in ? canon_fitness(cur_stage[base + j]) : __int_as_float(0x7f800000);
-                prev_s[j] = in ? prev[base + j] : __int_as_float(0x7f800000);
+                if (!prev_staged) prev_s[j] = in ? prev[base + j] : __int_as_float(0x7f800000);   // else: tell_prologue
             }
             __syncthreads();
             if (valid && sorted) {
@@ -258,6 +278,8 @@ __global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict
     // Launched as a programmatic dependent of k_cost inside the fused generation.  The trigger for k_update comes AFTER
     // this kernel's own wait: k_update's prologue reads the fitness, so it may only start once k_cost has completed
     // (its prologue does not depend on THIS kernel, see k_update.cuh).
+    const bool prev_staged = o.lambda <= TELL_FTILE;              // one tile, one pass: staged once, ahead of the wait
+    tell_prologue(o, blockIdx.y, blockIdx.x, smem_raw);
     griddep_wait();
     // overlapped generation (RANK_KEEP_FLAGS): the dependent is k_sample.  mode & 4 (the fused generation's default): released
     // here, so that it works through the pairs k_update has already finished while this grid ranks (its 128 CTAs share SMs
@@ -268,7 +290,7 @@ __global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict
     const int b = blockIdx.y;
     // the hand-over flags of this generation's k_update -> k_sample (both start after this grid has completed)
     if (blockIdx.x == 0 && !(mode & RANK_KEEP_FLAGS)) for (int i = threadIdx.x; i < o.m + 2; i += blockDim.x) o.progress[(size_t)b * (o.m + 2) + i] = 0;
-    tell_phase_a(o, f_all, b, blockIdx.x, smem_raw);
+    tell_phase_a(o, f_all, b, blockIdx.x, smem_raw, prev_staged);
     // one ticket per CTA once its ranks / partial sums are stored: the overlapped generation's k_update (not a stream
     // successor of this grid) waits for RS of them; every k_update resets the counter
     __syncthreads();

@@ -43,10 +43,27 @@ struct UpdateArgs {
                                // bookkeeping, and the sweep over every pending row but the newest — comes first; then it
                                // waits for k_rank's tickets, forms the mean / new evolution path and finishes the newest
                                // row.  Implies `progressive` (k_sample is released by k_rank and follows the flags)
+    int phase;                 // overlapped tell_all only (lmcma_b200_tell_all): 0 = the whole update; 1 = SPECULATIVE part of the NEXT
+                               // generation's update, run right after this generation's (beside the sampler's last chunk and the
+                               // candidates' trip across PCIe): bookkeeping, the sweep over every pending row but the newest and the
+                               // block Gram entries — none of which depends on a fitness — with every global store switched off;
+                               // the final rows, their |v|^2 and Lj / K and the Gram entries go to `spec`.  2 = the next tell_all
+                               // resumes from `spec`: no sweep, the rows are committed to V / the mirror and published at once.
+                               // Same arithmetic on the same inputs: bit-identical to phase 0
+    float* spec;               // phase 1 / 2 scratch of one instance x spec_stride floats (layout: spec_* below)
+    long long spec_stride;
     int no_dry;                // overlapped generation: skip the pre-execution pass of the post-rank code (LMCMA_B200_UPDATE_DRY=0)
     int progressive;           // publish OptDev::progress flags as the outputs become final: k_sample (launched as a
                                // programmatic dependent) consumes the pairs while the sweep is still producing them
 };
+
+// layout of UpdateArgs::spec (floats): [0] the generation (itr) the rows were computed for, [4 ..) Lj / K per position,
+// |v|^2 per position, block Gram entries (m x UPD_BLK), rows (m x ns, 16-byte aligned)
+__host__ __device__ __forceinline__ size_t spec_lj_off() { return 4; }
+__host__ __device__ __forceinline__ size_t spec_nv_off(int m) { return 4 + (size_t)((m + 3) & ~3); }
+__host__ __device__ __forceinline__ size_t spec_gs_off(int m) { return 4 + 2 * (size_t)((m + 3) & ~3); }
+__host__ __device__ __forceinline__ size_t spec_rows_off(int m) { return spec_gs_off(m) + (size_t)m * UPD_BLK; }
+__host__ __device__ __forceinline__ size_t spec_floats(int m, int ns) { return spec_rows_off(m) + (size_t)m * ns; }
 
 #define UPD_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[k] = gtime(); } while (0)
 
@@ -99,7 +116,14 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     // progressive: it is released after this kernel's own wait (k_rank has reset the hand-over flags by then)
     if (!a.progressive) griddep_launch_dependents();
     int* flags = o.progress + (size_t)b * (m + 2);                 // [0] scalars + mean, [1 + i] pair i, [m + 1] early scalars (itr, live)
-    if (OVERLAP) {
+    const Scalars sc0 = *scp;
+    float* const spec = OVERLAP && a.spec ? a.spec + (size_t)b * a.spec_stride : nullptr;
+    int phase = OVERLAP ? a.phase : 0;
+    // resume only from rows that were computed for THIS generation (the host invalidates after a state setter; this is the
+    // belt to those braces): otherwise the whole update
+    if (phase == 2 && (!spec || reinterpret_cast<const int*>(spec)[0] != sc0.itr)) phase = 0;
+    if (phase == 1 && !spec) return;
+    if (OVERLAP && phase != 1) {
         // the previous generation's sampler has completed (graph order): reset its flags, then tell k_gate that this CTA
         // holds its SM (k_cost is released only then and fills the other SMs)
         for (int i = tid; i < m + 2; i += nthr) flags[i] = 0;
@@ -108,7 +132,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     }
     UPD_STAMP(0);
     // =============================== prologue: independent of k_rank ===============================
-    const Scalars sc0 = *scp;
     for (int i = tid; i < m; i += nthr) { order[i] = tg[i]; stamp[i] = vg[i]; ljslot[i] = (float)Ljd[i]; mbar_init(&rowbar[i], 1); mbar_init(&scalbar[i], 1); }
     if (tid == 0) { sh_key = ~0ull; if (SMEM) mbar_init(&sh_bar, 1); }
     fence_barrier_init();
@@ -152,7 +175,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     __syncthreads();
     const int live = min(itr + 1, m);
     const int slot_new = order[live - 1];
-    if (OVERLAP && tid == 0) {                                     // what the sampler needs to start on the finished pairs
+    if (OVERLAP && tid == 0 && phase != 1) {                       // what the sampler needs to start on the finished pairs
         scp->itr = itr + 1; scp->live = live;
         st_release_gpu(flags + m + 1, 1);
     }
@@ -167,7 +190,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         if (lane == 0 && live > 1) mbar_expect_tx(&sh_bar, row_bytes * (unsigned)(live - 1));
         __syncwarp();
         for (int i = lane; i + 1 < live; i += 32) {
-            const float* src = (i < first_stale ? Vb : Pb) + (size_t)order[i] * ns;
+            // phase 2: every row but the newest is final already (the speculative pass of the last tell_all left them in `spec`)
+            const float* src = phase == 2 ? spec + spec_rows_off(m) + (size_t)i * ns : (i < first_stale ? Vb : Pb) + (size_t)order[i] * ns;
             bulk_g2s(rows_s + (size_t)i * ns, src, row_bytes, &sh_bar);
         }
     }
@@ -175,9 +199,15 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     const float invK = (float)(1.0 / o.K);
     for (int i = tid; i < m; i += nthr) {
         const int slot = order[i];
-        tg[i] = slot;
-        vg[i] = (i == slot_new) ? itr : stamp[i];                   // stamp is per SLOT
+        if (phase != 1) {                                            // the speculative pass leaves the optimiser's state alone
+            tg[i] = slot;
+            vg[i] = (i == slot_new) ? itr : stamp[i];               // stamp is per SLOT
+        }
         lj_s[i] = (i < live) ? ljslot[slot] * invK : 0.f;           // rows >= first_stale are recomputed below
+        if (phase == 2 && i >= first_stale && i + 1 < live) {        // ... or were, by the speculative pass
+            lj_s[i] = spec[spec_lj_off() + i];
+            nv_s[i] = spec[spec_nv_off(m) + i];
+        }
     }
 
     // ---- best-so-far: first occurrence of the minimum in evaluation order; strict improvement, or the very first
@@ -349,7 +379,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         if (a.progressive) griddep_launch_dependents();
         post_rank(false);
     } else {
-        for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);   // untouched pairs: final already
+        if (phase != 1) for (int i = tid; i < first_stale; i += nthr) st_release_gpu(flags + 1 + i, 1);   // untouched pairs: final already
     }
 
     // ---- recompute v from the first stale position (lmcma.cpp:373-390) ----
@@ -388,7 +418,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         // The newest row (this generation's evolution path) is not part of the sweep: it takes its factors a BLOCK at a time
         // (newest_row below).  In the overlapped generation it does not even exist yet when the sweep starts.
         const int hi = live - 1;
-        const int base = warp < sw ? first_stale + (a.blocked ? warp * R : warp) : hi;     // warps >= sw own nothing
+        const int base = (warp < sw && phase != 2) ? first_stale + (a.blocked ? warp * R : warp) : hi;     // warps >= sw own nothing; phase 2: no sweep
         float4 y[R][NVB];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -398,7 +428,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             for (int it = 0; it < NVB; ++it) {
                 const int q = lane + 32 * it;
                 y[r][it] = (on && q < nq) ? reinterpret_cast<const float4*>(rows_s + (size_t)i * ns)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (on && q < nq) reinterpret_cast<float4*>(VPb + ((size_t)i * 2 + 1) * ns)[q] = y[r][it];   // pc_i at its (new) position
+                if (on && q < nq && phase != 1) reinterpret_cast<float4*>(VPb + ((size_t)i * 2 + 1) * ns)[q] = y[r][it];   // pc_i at its (new) position
             }
         }
         // y[0 .. n-1] are my pending rows in index order, y[0] the next one to become final (row `next`): when it does, the
@@ -484,9 +514,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
 #pragma unroll
             for (int it = 0; it < NVB; ++it) {
                 const int q = lane + 32 * it;
-                if (q < nq) { dst[q] = x[it]; dst2[q] = x[it]; }
+                if (q < nq && phase != 1) { dst[q] = x[it]; dst2[q] = x[it]; }
             }
-            if (a.progressive) {                                     // pair i of the mirror and Njs[i] are final
+            if (a.progressive && phase != 1) {                       // pair i of the mirror and Njs[i] are final
                 __syncwarp();
                 if (lane == 0) {
                     const double r = o.c1 / (1.0 - o.c1), t = sqrt(1.0 + r * (double)nv);
@@ -508,7 +538,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         //      reduction and scalar recurrence on the same numbers in the same order, so all of them hold the same e_k.  One
         //      warp walking 4 columns per lane took 1.2 us per block (2.4 K cycles of dependent loads and multiply-adds).
         //      Collective over warps 0 .. NVB-1. ----
-        auto newest_row = [&](const bool dry) {
+        auto newest_row = [&](const bool dry, const unsigned need) {
             const int q = lane + 32 * warp;
             const bool has = q < nq;
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -517,6 +547,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             double kn = 1.0;
             for (int j = 0; j + 1 < live; ++j) kn *= Kd;             // the same product the sweep forms step by step
             const int rr = lane >> 2, qq = lane & 3;                 // lanes 4 rr .. 4 rr + 3 look after row j0 + rr of the block
+            float* norm_part = chain_part + 2 * NVB * UPD_BLK * 32;  // behind the two dot-product stages: NVB norms, 2 verdicts of the dry pass
             int buf = 0;
 #pragma unroll 1
             for (int j0 = 0; j0 + 1 < live; j0 += UPD_BLK, buf ^= 1) {
@@ -540,7 +571,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     for (int i = 0; i < UPD_BLK; ++i) gi[i] = (rr > i && rr < nb) ? gg[i] : 0.f;
                 }
                 const float ljm = (rr < nb) ? lj_s[j0 + rr] : 0.f;
+                // dry pass: one thread looks for k_rank's tickets; its verdict crosses the barrier, so that every chain warp
+                // leaves the loop in the same block
+                if (dry && tid == 0) norm_part[4 + buf] = (*reinterpret_cast<const volatile int*>(o.rank_ticket + b) == (int)need) ? 1.f : 0.f;
                 named_bar_sync(3, 32 * NVB);
+                if (dry && norm_part[4 + buf] != 0.f) break;
                 float gs;                                            // g of my row: 8 lanes' partials per quarter and warp, then the 4 quarters
                 {
                     float sw[NVB];
@@ -586,7 +621,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             float2 nn = fmul2(lo2(x), lo2(x));
             nn = ffma2(hi2(x), hi2(x), nn);
             const float nw = warp_sum(nn.x + nn.y);
-            float* norm_part = chain_part + 2 * NVB * UPD_BLK * 32;  // behind the two dot-product stages
             if (lane == 0) norm_part[warp] = nw;
             if (has && !dry) {
                 reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns)[q] = x;
@@ -608,7 +642,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 }
             }
         };
-        if (first_stale == 0 && warp == 0 && hi > 0) { publish(y[0], 0, 1.0); retire_first(); }   // row 0 has no factors (v_0 = pc_0)
+        if (first_stale == 0 && warp == 0 && hi > 0 && phase != 2) { publish(y[0], 0, 1.0); retire_first(); }   // row 0 has no factors (v_0 = pc_0)
         double kp = 1.0;                                             // K^(j+1) inside step j
         for (int j = 0; j + 1 < hi; ++j) {
             kp *= Kd;
@@ -677,10 +711,39 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                 default: others(std::integral_constant<int, (R >= 5 ? 5 : 1)>()); break;
             }
         }
+        if (phase == 2) {
+            // ---- resume: the rows are in shared memory (bulk copies from `spec`, waited for above); commit the recomputed ones to
+            //      V and the mirror and publish them, a warp per row — what publish() did step by step in the sweep ----
+            for (int i = tid; i < m * UPD_BLK; i += nthr) Gs[i] = spec[spec_gs_off(m) + i];
+            for (int i = first_stale + warp; i < hi; i += UPD_WARPS) {
+                const float4* srow = reinterpret_cast<const float4*>(rows_s + (size_t)i * ns);
+                const float4* prow = reinterpret_cast<const float4*>(Pb + (size_t)order[i] * ns);
+                float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
+                float4* dst2 = reinterpret_cast<float4*>(VPb + (size_t)i * 2 * ns);
+                for (int q = lane; q < nq; q += 32) { const float4 x = srow[q]; dst[q] = x; dst2[q] = x; dst2[nq + q] = __ldcg(prow + q); }
+                __syncwarp();
+                if (lane == 0) {
+                    const double r = o.c1 / (1.0 - o.c1), t = sqrt(1.0 + r * (double)nv_s[i]);
+                    Njsb[i] = (float)(o.M * r / (t + 1.0));
+                    st_release_gpu(flags + 1 + i, 1);
+                }
+            }
+        }
         // every older row is final
         __syncthreads();
         UPD_STAMP(7);
-        for (int k = 1 + warp; k < hi; k += UPD_WARPS) gram_row(k);  // block Gram entries for the newest row's chain
+        if (phase != 2) for (int k = 1 + warp; k < hi; k += UPD_WARPS) gram_row(k);  // block Gram entries for the newest row's chain
+        if (phase == 1) {
+            // ---- speculative pass: leave the rows, their scalars and the Gram entries for the next tell_all and stop here ----
+            __syncthreads();
+            for (int i = tid; i < m * UPD_BLK; i += nthr) spec[spec_gs_off(m) + i] = Gs[i];
+            for (int i = tid; i < hi; i += nthr) { spec[spec_lj_off() + i] = lj_s[i]; spec[spec_nv_off(m) + i] = nv_s[i]; }
+            const float4* s4 = reinterpret_cast<const float4*>(rows_s);
+            float4* d4 = reinterpret_cast<float4*>(spec + spec_rows_off(m));
+            for (int i = tid; i < hi * nq; i += nthr) d4[i] = s4[i];
+            if (tid == 0) reinterpret_cast<int*>(spec)[0] = itr;
+            return;
+        }
         if (OVERLAP) {
             // ---------------- overlap: the part that needs this generation's ranks ----------------
             // Everything from here to the sampler's last chunk is the critical path of the single-query generation, and it is
@@ -692,14 +755,16 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             // both passes (a loop, not two inlined copies).  No dry pass when the ranks are already there (tell_all, where the
             // sweep is the longer branch).
             const unsigned need = (unsigned)o.RS;                    // k_rank: one ticket per CTA after its last store (k_rank.cuh)
+            // steps: 0 the chain, dry; 1 mean / step size / path, dry; 2 the same for real (after the ranks); 3 the chain for real.
+            // A dry step starts only while tickets are missing, and the dry chain gives up between two blocks once they are all there.
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const bool dry = pass == 0;
+            for (int step = 0; step < 4; ++step) {
+                const bool dry = step < 2;
                 if (dry) {
                     if (tid == 32) sh_dry = (*reinterpret_cast<const volatile int*>(o.rank_ticket + b) != (int)need && !a.no_dry) ? 1 : 0;
                     __syncthreads();
-                    if (!sh_dry) continue;
-                } else {
+                    if (!sh_dry) { step = 1; continue; }
+                } else if (step == 2) {
                     if (tid == 32) {
                         // plain polling by one thread (this wait is on the critical path); the fence is the acquire for the ranks /
                         // partial sums behind the tickets
@@ -714,15 +779,21 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
                     __syncthreads();
                     UPD_STAMP(8);
                 }
-                post_rank(dry);                                      // mean, step size, the new evolution path -> rows_s[live - 1]
-                // warps NVB.. track the best-so-far candidate (it reads X, which the sampler overwrites only after the newest pair
-                // has been published) while warps 0 .. NVB-1 run the newest row's chain
-                if (warp >= NVB) { if (!dry) best_so_far(NVB, nwarps - NVB); __syncthreads(); }
-                else { newest_row(dry); if (!dry) UPD_STAMP(9); }
+                if (step == 1 || step == 2) {
+                    post_rank(dry);                                  // mean, step size, the new evolution path -> rows_s[live - 1]
+                } else if (warp >= NVB) {
+                    // warps NVB.. track the best-so-far candidate (it reads X, which the sampler overwrites only after the newest
+                    // pair has been published) while warps 0 .. NVB-1 run the newest row's chain
+                    if (!dry) best_so_far(NVB, nwarps - NVB);
+                    __syncthreads();
+                } else {
+                    newest_row(dry, need);
+                    if (!dry) UPD_STAMP(9);
+                }
             }
         } else {
             __syncthreads();
-            if (warp < NVB) newest_row(false);
+            if (warp < NVB) newest_row(false, 0u);
         }
     } else {
         // ---------------- streaming sweep: pending rows stay in shared memory (or HBM/L2) ----------------

@@ -279,6 +279,7 @@ int launch_update_t(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream
 int launch_update(lmcma_b200_opt* o, const UpdateArgs& a_in, bool pdl, cudaStream_t st) {
     UpdateArgs a = a_in;
     if (a.sweep_warps <= 0) a.sweep_warps = o->upd_sweep_warps;     // callers that build UpdateArgs from scratch
+    if (a.phase == 0) o->spec_valid = false;                        // a whole update: whatever the speculative pass left is stale
     if (o->upd_gram) {
         int rc = o->upd_nvb == 4 ? launch_update_t<4, -1, false>(o, a, pdl, st) : launch_update_t<16, -1, false>(o, a, pdl, st);
         if (rc) return rc;
@@ -315,6 +316,7 @@ UpdateArgs update_args_local(lmcma_b200_opt* o) {
     a.blocked = o->tune.update_blocked;
     a.sweep_warps = o->upd_sweep_warps;
     a.no_dry = o->tune.update_dry ? 0 : 1;
+    a.spec = o->d_spec; a.spec_stride = (long long)o->spec_stride;
     return a;
 }
 
@@ -435,6 +437,8 @@ int lmcma_capi::check_lost(lmcma_b200_opt* o) {
     o->props->cosched = 0;
     if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
     if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
+    if (o->tell_graph_resume) { cudaGraphExecDestroy(o->tell_graph_resume); o->tell_graph_resume = nullptr; }
+    o->spec_valid = false;
     o->tell_graph_failed = true;
     o->mirror_dirty = true;
     return fail(LMCMA_B200_ERR_CUDA, "overlapped generation lost co-scheduling (%s): the branches of the CUDA graph did not run "
@@ -503,6 +507,8 @@ int ensure_graph(lmcma_b200_opt* o) {
 int ensure_tell_graph(lmcma_b200_opt* o) {
     if (o->tell_graph && o->tell_graph_for == o->stream) return ensure_mirror(o, o->stream);
     if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
+    if (o->tell_graph_resume) { cudaGraphExecDestroy(o->tell_graph_resume); o->tell_graph_resume = nullptr; }
+    o->spec_valid = false;
     cudaStream_t st = o->stream;
     const OptDev& d = o->d;
     int rc = ensure_mirror(o, st);
@@ -510,25 +516,45 @@ int ensure_tell_graph(lmcma_b200_opt* o) {
     if (!o->f_pinned && cudaHostAlloc(&o->f_pinned, (size_t)d.B * d.lambda * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError(); o->f_pinned = nullptr; o->tell_graph_failed = true; return 0;
     }
-    cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
-    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    UpdateArgs ua = update_args_local(o);
-    ua.progressive = 1;
-    ua.overlap = 1;
-    bool ok = cudaEventRecord(o->ev_fork, st) == cudaSuccess && cudaStreamWaitEvent(o->side_stream, o->ev_fork, 0) == cudaSuccess;
-    if (ok) ok = launch_update(o, ua, false, o->side_stream) == 0;
-    if (ok) ok = cudaEventRecord(o->ev_join, o->side_stream) == cudaSuccess;
-    if (ok) ok = cudaMemcpyAsync(d.fit, o->f_pinned, (size_t)d.B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess;
-    if (ok) { k_gate<<<(d.B + 31) / 32, 32, 0, st>>>(d); ok = cudaGetLastError() == cudaSuccess; }   // k_update has reset the flags and holds its SM
-    if (ok) ok = launch_rank(o, d.fit, RANK_PLAIN | RANK_KEEP_FLAGS, nullptr, st, false) == 0;
-    if (ok) ok = launch_sample(o, st, true, true, 2) == 0;
-    if (ok) ok = cudaStreamWaitEvent(st, o->ev_join, 0) == cudaSuccess;
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const bool spec = o->d_spec != nullptr;
+    if (o->tune.graph_dbg && !o->graph_dbg && cudaMalloc(&o->graph_dbg, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(o->graph_dbg, 0, 64 * sizeof(long long)); cudaDeviceSynchronize(); }
+    // resume = 0: the whole update; resume = 1: k_update picks up the rows the last graph's speculative pass left.  With the
+    // scratch both graphs END with that pass for the next generation, on the side branch behind k_update
+    auto capture = [&](int resume, cudaGraphExec_t* out) -> int {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        UpdateArgs ua = update_args_local(o);
+        ua.progressive = 1;
+        ua.overlap = 1;
+        ua.phase = resume ? 2 : 0;
+        ua.dbg = o->graph_dbg;                                   // LMCMA_B200_GRAPH_DBG: the timeline lmcma_b200_sync prints
+        const bool valid_before = o->spec_valid;
+        bool ok = cudaEventRecord(o->ev_fork, st) == cudaSuccess && cudaStreamWaitEvent(o->side_stream, o->ev_fork, 0) == cudaSuccess;
+        if (ok) ok = launch_update(o, ua, false, o->side_stream) == 0;
+        if (ok && spec) { UpdateArgs us = ua; us.phase = 1; us.dbg = nullptr; ok = launch_update(o, us, false, o->side_stream) == 0; }
+        o->spec_valid = valid_before;                            // capture enqueues nothing
+        if (ok) ok = cudaEventRecord(o->ev_join, o->side_stream) == cudaSuccess;
+        if (ok) ok = cudaMemcpyAsync(d.fit, o->f_pinned, (size_t)d.B * d.lambda * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess;
+        if (ok) { k_gate<<<(d.B + 31) / 32, 32, 0, st>>>(d); ok = cudaGetLastError() == cudaSuccess; }   // k_update has reset the flags and holds its SM
+        // the sampler is released when k_rank starts: the pairs it needs first are final (resume: at once; else as the sweep goes)
+        if (ok) ok = launch_rank(o, d.fit, RANK_PLAIN | RANK_KEEP_FLAGS | (o->tune.rank_late ? 0 : 4), nullptr, st, false) == 0;
+        if (ok) ok = launch_sample(o, st, true, true, 2) == 0;
+        if (ok) ok = cudaStreamWaitEvent(st, o->ev_join, 0) == cudaSuccess;
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (ok && e == cudaSuccess && cudaGraphInstantiate(out, graph, 0) != cudaSuccess) *out = nullptr;
+        if (graph) cudaGraphDestroy(graph);
+        return 0;
+    };
+    rc = capture(0, &o->tell_graph);
+    if (!rc && o->tell_graph && spec) rc = capture(1, &o->tell_graph_resume);
     g_launches.store(before);   // capture enqueues nothing
-    if (ok && e == cudaSuccess && cudaGraphInstantiate(&o->tell_graph, graph, 0) != cudaSuccess) o->tell_graph = nullptr;
-    if (graph) cudaGraphDestroy(graph);
-    if (!o->tell_graph) { cudaGetLastError(); o->tell_graph_failed = true; return 0; }
+    if (rc) return rc;
+    if (!o->tell_graph || (spec && !o->tell_graph_resume)) {
+        cudaGetLastError();
+        if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
+        o->tell_graph_failed = true; return 0;
+    }
     o->tell_graph_for = st;
     return 0;
 }
@@ -713,6 +739,11 @@ static int create_body(lmcma_b200_opt* o, DeviceProps* props, const lmcma_b200_c
         // the overlapped generation needs the two branches of a forked graph to run CONCURRENTLY: enabled only where a probe
         // has seen that happen (LMCMA_B200_OVERLAP=2 skips the probe)
         if (o->overlap && o->tune.overlap != 2 && probe_coschedule(o) != 1) o->overlap = false;
+        if (o->overlap && o->tune.tell_spec != 0) {              // scratch of the speculative update (best effort)
+            o->spec_stride = (spec_floats(m, d.ns) + 3) & ~(size_t)3;
+            if (cudaMalloc(&o->d_spec, B * o->spec_stride * sizeof(float)) != cudaSuccess) { cudaGetLastError(); o->d_spec = nullptr; }
+            else cudaMemset(o->d_spec, 0xff, B * o->spec_stride * sizeof(float));   // generation -1: matches nothing
+        }
     }
     if (!rc && o->upd_gram) {
         rc = dmalloc(&d.G, B * GRAM_KS * m * m);
@@ -741,6 +772,8 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
     if (o->tell_graph) cudaGraphExecDestroy(o->tell_graph);
+    if (o->tell_graph_resume) cudaGraphExecDestroy(o->tell_graph_resume);
+    cudaFree(o->d_spec);
     if (o->f_pinned) cudaFreeHost(o->f_pinned);
     if (o->err_host) cudaFreeHost(o->err_host);
     if (o->x_mirror) { unregister_mirror(o->x_mirror); cudaFreeHost(o->x_mirror); }
@@ -825,6 +858,8 @@ int lmcma_b200_ask_all_view(lmcma_b200_opt* o, const float** X_view, int64_t* ld
         register_mirror(o->x_mirror, floats * sizeof(float), d.X, d.ns, o->cfg.device);
         // the captured graphs carry the old kernel parameters (OptDev by value): rebuild them on next use
         if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
+        if (o->tell_graph_resume) { cudaGraphExecDestroy(o->tell_graph_resume); o->tell_graph_resume = nullptr; }
+        o->spec_valid = false;
     }
     if (!o->xh_fresh) {                                  // first use / after a fused run or a state setter: one ordinary copy
         CU(cudaMemcpyAsync(o->x_mirror, d.X, floats * sizeof(float), cudaMemcpyDeviceToHost, o->stream));
@@ -852,8 +887,10 @@ int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
         // the overlap saves.
         if ((rc = ensure_tell_graph(o)) == 0 && o->tell_graph) {
             memcpy(o->f_pinned, f, (size_t)d.B * d.lambda * sizeof(float));
-            CU(cudaGraphLaunch(o->tell_graph, o->stream));
-            g_launches += 4 + (o->d.tile_sorted ? 1 : 0);         // k_update, k_gate, (k_rank_tiles,) k_rank, k_sample
+            const bool resume = o->spec_valid && o->tell_graph_resume;   // the last tell_all graph left the next update's rows behind
+            CU(cudaGraphLaunch(resume ? o->tell_graph_resume : o->tell_graph, o->stream));
+            o->spec_valid = o->d_spec != nullptr;                 // ... and so does this one
+            g_launches += 4 + (o->d.tile_sorted ? 1 : 0) + (o->d_spec ? 1 : 0);   // k_update, k_gate, (k_rank_tiles,) k_rank, k_sample, (speculative k_update)
             o->xh_fresh = o->mirror_on;                          // the captured sampler writes the host mirror when it is on
             o->x_cache_valid = false;
             o->sample_idx = 0;
@@ -936,6 +973,7 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
     CU(cudaSetDevice(o->cfg.device));
     int rc = apply_l2_window(o->map, o->stream);
     if (rc) return rc;
+    o->spec_valid = false;                                       // the fused generations advance the state past what tell_all's speculative pass saw
     if (o->cfg.rng == LMCMA_B200_RNG_PHILOX) {
         if ((rc = ensure_graph(o))) return rc;
         if ((rc = ensure_mirror(o, o->stream))) return rc;       // a state setter since the last run: the graph's sampler reads the mirror

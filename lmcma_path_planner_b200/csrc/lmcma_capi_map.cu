@@ -11,6 +11,7 @@ namespace {
 template <int DIMS, int STORAGE, bool TRACE, int MINB = 7>
 int launch_cost_t(const MapDev& mp, const CostArgs& a0, int rows, int B, CostShape shape, cudaStream_t st) {
     CostArgs a = a0;
+    a.spt = (a.W + 1 + shape.tpt - 1) / shape.tpt;
     a.cb = shape.cb & ~1;                                       // even: k_cost zeroes two block records per store
     // segment records 36 B, sample offsets, per-block records 8 B (k_cost.cuh), 256-entry table (u8 storage)
     // + the candidate row (16-byte aligned)

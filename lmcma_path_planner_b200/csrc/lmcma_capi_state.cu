@@ -106,6 +106,7 @@ int lmcma_b200_get_i32(lmcma_b200_opt* o, int32_t which, int32_t* out, int64_t c
 
 int lmcma_b200_set_f64(lmcma_b200_opt* o, int32_t which, const double* in, int64_t count) {
     ARG(o && in, "null pointer");
+    o->spec_valid = false;                              // tell_all's speculative update saw the state before this call
     CU(cudaSetDevice(o->cfg.device));
     const OptDev& d = o->d;
     const size_t B = d.B;
@@ -141,6 +142,7 @@ int lmcma_b200_set_f64(lmcma_b200_opt* o, int32_t which, const double* in, int64
 
 int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_t count) {
     ARG(o && in, "null pointer");
+    o->spec_valid = false;                              // tell_all's speculative update saw the state before this call
     CU(cudaSetDevice(o->cfg.device));
     const OptDev& d = o->d;
     const size_t B = d.B, w = d.n * sizeof(float), p = d.ns * sizeof(float);
@@ -186,6 +188,7 @@ int lmcma_b200_set_f32(lmcma_b200_opt* o, int32_t which, const float* in, int64_
 
 int lmcma_b200_set_i32(lmcma_b200_opt* o, int32_t which, const int32_t* in, int64_t count) {
     ARG(o && in, "null pointer");
+    o->spec_valid = false;                              // tell_all's speculative update saw the state before this call
     CU(cudaSetDevice(o->cfg.device));
     const OptDev& d = o->d;
     const size_t B = d.B;

@@ -130,6 +130,7 @@ struct CostArgs {
     long long* cells;          // trace mode (nullable)
     long long max_cells;
     int cb;                    // capacity of the per-block record stage (32-sample blocks), set by the launcher
+    int spt;                   // segments per thread = ceil((W + 1) / threads per trajectory), set by the launcher
     long long* dbg;            // optional (LMCMA_B200_COST_DBG): 8 globaltimer stamps per CTA, [cta * 8 + k]
 };
 

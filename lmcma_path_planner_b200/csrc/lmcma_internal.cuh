@@ -81,6 +81,7 @@ struct Tuning {
     int rank_late = 0;      // fused generation: 1 = k_sample is released when k_rank's CTAs are done, 0 = when k_rank starts (it then works
                             // through the finished pairs beside the ranking: 66.5 -> 63.2 us per C2 generation once the newest row's
                             // chain stopped being the longer branch)
+    int tell_spec = 1;      // tell_all: speculative update of the next generation at the end of the graph (LMCMA_B200_TELL_SPEC=0: off)
     int update_dry = 1;     // overlapped generation: pre-execute the post-rank code while k_rank is busy (k_update.cuh)
     int graph_dbg = 0, dbg = 0, update_dbg = 0, cost_dbg = 0;
     static Tuning from_env() {
@@ -106,6 +107,7 @@ struct Tuning {
         t.tell_overlap = env_int("LMCMA_B200_TELL_OVERLAP", 1);
         t.rank_late = env_int("LMCMA_B200_RANK_LATE", 0);
         t.update_dry = env_int("LMCMA_B200_UPDATE_DRY", 1);
+        t.tell_spec = env_int("LMCMA_B200_TELL_SPEC", 1);
         t.rank_sorted = env_int("LMCMA_B200_RANK_SORTED", 1);
         t.graph_dbg = env_int("LMCMA_B200_GRAPH_DBG", 0);
         t.dbg = getenv("LMCMA_B200_DBG") ? 1 : 0;
@@ -192,6 +194,12 @@ struct lmcma_b200_opt {
     cudaGraphExec_t tell_graph = nullptr;     // tell_all of one query: H2D fitness -> k_rank -> k_sample, k_update on a side branch
     cudaStream_t tell_graph_for = nullptr;
     bool tell_graph_failed = false;
+    // speculative update (k_update.cuh, UpdateArgs::phase): every tell_all graph ends with the fitness-independent part of the
+    // NEXT generation's update (into d_spec, beside the sampler's tail and the candidates' trip across PCIe); the next tell_all
+    // resumes from it (tell_graph_resume) unless anything else touched the optimiser's state in between
+    cudaGraphExec_t tell_graph_resume = nullptr;
+    float* d_spec = nullptr; size_t spec_stride = 0;
+    bool spec_valid = false;
     float* f_pinned = nullptr;                // the graph's copy source (the caller's fitness array is copied here first)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool have_run_timing = false;

@@ -602,6 +602,41 @@ def test_progressive_and_overlapped_generations_are_bit_identical_to_the_serial_
         assert np.array_equal(dev.best()[1], state["serial"]["best_f"])
 
 
+def test_speculative_update_of_tell_all_never_shows_and_never_goes_stale(po, monkeypatch):
+    """Every tell_all graph ends with the fitness-independent part of the NEXT generation's update (k_update phase 1, into a
+    scratch buffer) and the next tell_all resumes from it (phase 2).  The optimiser's state between two calls must be the
+    state of the generation just told — getters never see the pass — and anything else that advances or overwrites the state
+    (fused generations, a setter) must make the next tell_all recompute: bit-identical to the same calls with the pass off."""
+    W, lam, m = 60, 256, 16
+    dist, start, goal = maps.config2_map(size=512, n_rects=48, seed=4, clamp=64.0)
+    lo, hi = maps.box_bounds((512, 512), W)
+    x0 = maps.straight_line(start, goal, W)
+    cm = L.CostMap(dist, "f32")
+    keys = ("X", "xmean", "V", "P", "sigma", "t", "vec", "Nj", "Lj", "pc")
+    trace = {}
+    for spec in ("0", "1"):
+        monkeypatch.setenv("LMCMA_B200_TELL_SPEC", spec)
+        dev = L.Optimizer(2 * W, x0=x0, lam=lam, m=m, lo=lo, hi=hi, sigma0=6.0, seed=5)
+        dev.attach_cost(cm, [start], [goal], W, L.LONGSAFE, 1e4)
+        snaps = []
+        for g in range(40):
+            r = cm.evaluate(dev.ask_all()[0], start, goal, W, L.LONGSAFE, 1e4)
+            dev.tell_all(r["f"])
+            snaps.append({k: dev.get(k).copy() for k in keys})    # between two calls: the generation just told
+            if g == 12:
+                dev.run(3)                                        # fused generations: the rows left behind are stale
+                snaps.append({k: dev.get(k).copy() for k in keys})
+            if g == 25:
+                dev.set("V", dev.get("V"))                        # a setter (same values): the next tell_all must not resume
+            if g == 30:
+                dev.set("sigma", dev.get("sigma") * 0.5)
+        trace[spec] = snaps
+    assert len(trace["0"]) == len(trace["1"])
+    for i, (a, b) in enumerate(zip(trace["0"], trace["1"])):
+        for k in keys:
+            assert np.array_equal(a[k], b[k]), (i, k)
+
+
 def test_cost_evaluate_page_locked_buffers_match_staged(po, golden_maps, monkeypatch):
     """lmcma_b200_cost_evaluate hands page-locked caller buffers to the kernel directly (candidates read across PCIe
     by the CTAs, results stored into the caller's arrays); pageable buffers are staged.  Same bits either way."""
