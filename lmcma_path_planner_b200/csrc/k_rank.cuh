@@ -88,12 +88,12 @@ __device__ __forceinline__ void tell_prologue(const OptDev& o, int b, int rs, un
         const int cnt4 = (lambda + 3) & ~3;
         for (int j = tid; j < cnt4; j += nthr) prev_s[j] = j < lambda ? prev[j] : __int_as_float(0x7f800000);
     }
-    const int rows_per = (o.pop_count + o.RS - 1) / o.RS;
-    const int r0 = rs * rows_per, r1 = min(o.pop_count, r0 + rows_per);
-    if (r1 > r0 && o.B == 1) {                                      // one query: latency; a batch is throughput-bound and only mu of the rows are read
-        const char* d0 = reinterpret_cast<const char*>(o.D + ((size_t)b * o.pop_count + r0) * o.ns);
-        const size_t bytes = (size_t)(r1 - r0) * o.ns * sizeof(float);
-        for (size_t ofs = (size_t)tid * 128; ofs < bytes; ofs += (size_t)nthr * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(d0 + ofs));
+    if (o.B == 1) {                                                   // one query: latency; a batch is throughput-bound and only mu of its rows are read
+        const int rows_per = (o.pop_count + o.RS - 1) / o.RS;
+        const int r0 = rs * rows_per, r1 = min(o.pop_count, r0 + rows_per);
+        const char* d0 = reinterpret_cast<const char*>(o.D + (size_t)r0 * o.ns);
+        const int bytes = (r1 - r0) * o.ns * (int)sizeof(float);     // a slice: at most TELL_MAX_ROWS rows
+        for (int ofs = tid * 128; ofs < bytes; ofs += nthr * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(d0 + ofs));
     }
 }
 
@@ -272,7 +272,7 @@ __device__ __forceinline__ void tell_pack_payload(const OptDev& o, float* __rest
 
 
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT) k_rank(OptDev o, const float* __restrict__ f_all, int mode, float* __restrict__ payload) {
+__global__ void __launch_bounds__(MAXT, 2) k_rank(OptDev o, const float* __restrict__ f_all, int mode, float* __restrict__ payload) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int sh_last;
     // Launched as a programmatic dependent of k_cost inside the fused generation.  The trigger for k_update comes AFTER
