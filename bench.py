@@ -43,8 +43,8 @@ FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cost launch of this workload, from the committed
 # `ncu --set full` capture (the map stays L2-resident between generations, so DRAM traffic is far BELOW the
 # algorithmic bytes: the kernel is bound by the L1 line rate of the gather, not by HBM)
-NCU_DRAM_BYTES_PER_LAUNCH = 2.381e6
-NCU_SOURCE = "profiles/r2l_full.md (k_cost<2,0,0,7>: dram_read 2.381 MB, dram_write 0)"
+NCU_DRAM_BYTES_PER_LAUNCH = 2.393e6
+NCU_SOURCE = "profiles/r2n_full.md (k_cost<2,0,0,7>: dram_read 2.393 MB, dram_write 0)"
 
 
 def peaks():
