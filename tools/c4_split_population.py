@@ -58,8 +58,10 @@ if rank == 0:
     print("split vs unsplit after %d generations: sigma %.6g vs %.6g, max |xmean diff| %.3g cells" % (3 + gens, ss, sw, dx))
     if strict:
         # same kernels, same Philox rows, same deterministic reductions: the split run differs from the unsplit one only by the
-        # association of the per-rank partial sums (FP32), which a short run cannot amplify
-        assert abs(ss - sw) <= 1e-9 * sw and dx < 1e-2, "split-population run differs from the unsplit optimiser"
+        # association of the per-rank partial sums (FP32): the means differ in their last bits, and among lambda^2 = 262 144 pairs
+        # of fitness values per generation a near-tie may then compare the other way — ONE such pair moves the step size by
+        # cs / lambda^2 ~ 1e-6 relative.  The bar allows a hundred of them over the run and a thousandth of a cell on the mean
+        assert abs(ss - sw) <= 1e-4 * sw and dx < 1e-3, "split-population run differs from the unsplit optimiser"
         print("strict check passed")
     else:
         # long free runs: FP32 rounding differences are amplified chaotically once a rank flips
