@@ -10,6 +10,7 @@ from lmcma_path_planner_b200 import maps, parallel
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 Q = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 gens = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+storage = sys.argv[3] if len(sys.argv) > 3 else "f32"     # "u8": distance clamped at 63 cells, quantised to 1/4 cell (a different map)
 W, lam, m = 200, 64, 40
 torch.cuda.set_device(local)
 if world > 1:
@@ -18,7 +19,7 @@ if world > 1:
 dmap, _, _ = maps.config2_map()
 starts, goals = maps.random_queries(dmap, Q, seed=7, min_sep=1024)
 off, cnt = parallel.shard_range(Q, world, rank)
-cmap = L.CostMap(dmap, "f32", device=local)
+cmap = L.CostMap(dmap if storage == "f32" else np.minimum(dmap, 63.0), storage, device=local)
 lo, hi = maps.box_bounds((4096, 4096), W)
 x0 = np.stack([maps.straight_line(starts[q], goals[q], W) for q in range(off, off + cnt)])
 opt = L.Optimizer(2 * W, x0=x0, lam=lam, m=m, batch=cnt, lo=lo, hi=hi, sigma0=32.0, seed=7 + rank, device=local)
@@ -35,8 +36,8 @@ if world > 1:
     t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
 pk = opt.profile_kernels(3)
 if rank == 0:
-    print("C3: %d queries x lambda %d on %d GPU(s): %.3f ms/generation (device), %.3g evals/s, %.1f query-generations/s" %
-          (Q, lam, world, ms / gens, Q * lam * gens / (ms * 1e-3), Q * gens / (ms * 1e-3)))
+    print("C3 (%s map): %d queries x lambda %d on %d GPU(s): %.3f ms/generation (device), %.3g evals/s, %.1f query-generations/s" %
+          (storage, Q, lam, world, ms / gens, Q * lam * gens / (ms * 1e-3), Q * gens / (ms * 1e-3)))
     print("per-kernel ms:", {k: round(v, 4) for k, v in pk.items()}, "mean nsamp", float(opt.get("nsamp").mean()))
     f0 = opt.best()[1]
     print("best f: min %.4g median %.4g" % (f0.min(), np.median(f0)))

@@ -32,6 +32,36 @@ __global__ void __launch_bounds__(256, 7) k(const float* __restrict__ brick, con
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(~0u, acc, o);
     if (lane == 0) atomicAdd(out + traj, acc);
 }
+// Two consecutive samples per lane (they are <= 1 cell apart in x and in y, so both lie in ONE 2 x 2 footprint):
+//   PAIR 0: two LDGs from the bricked layout (control: same arithmetic, twice the fetches of PAIR 1)
+//   PAIR 1: ONE tex2Dgather (the four texels of the bilinear footprint anchored at the smaller x / y) serves both
+template <int PAIR>
+__global__ void __launch_bounds__(256, 7) k2(const float* __restrict__ brick, cudaTextureObject_t texg, float slope, float* out) {
+    const int traj = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.f;
+    const int per = S / 8;
+#pragma unroll 2
+    for (int t0 = warp * per; t0 < (warp + 1) * per; t0 += 64) {
+        int ax, ay, bx, by;
+        cell(t0 + 2 * lane, traj, slope, ax, ay);
+        cell(t0 + 2 * lane + 1, traj, slope, bx, by);
+        float ga, gb;
+        if (PAIR == 0) {
+            ga = __ldg(brick + (((unsigned)ax << 2) + (unsigned)ay + ((unsigned)ay >> 2) * (unsigned)(N / 8 * 32 - 4)));
+            gb = __ldg(brick + (((unsigned)bx << 2) + (unsigned)by + ((unsigned)by >> 2) * (unsigned)(N / 8 * 32 - 4)));
+        } else {
+            const int x0 = min(ax, bx), y0 = min(ay, by);
+            const float4 q = tex2Dgather<float4>(texg, (float)x0 + 1.0f, (float)y0 + 1.0f, 0);   // w (x0,y0)  z (x0+1,y0)  x (x0,y0+1)  y (x0+1,y0+1)
+            const float lo_a = (ax == x0) ? q.w : q.z, hi_a = (ax == x0) ? q.x : q.y;
+            const float lo_b = (bx == x0) ? q.w : q.z, hi_b = (bx == x0) ? q.x : q.y;
+            ga = (ay == y0) ? lo_a : hi_a;
+            gb = (by == y0) ? lo_b : hi_b;
+        }
+        acc += fabsf(ga) + fabsf(gb);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(~0u, acc, o);
+    if (lane == 0) atomicAdd(out + traj, acc);
+}
 int main() {
     std::vector<float> h((size_t)N * N), hb((size_t)N * N);
     for (int y = 0; y < N; ++y) for (int x = 0; x < N; ++x) {
@@ -49,6 +79,11 @@ int main() {
     cudaTextureDesc td = {}; td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder; td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
     cudaTextureObject_t tex; CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
     cudaSurfaceObject_t surf; CK(cudaCreateSurfaceObject(&surf, &rd));
+    cudaArray_t arrg; CK(cudaMallocArray(&arrg, &fd, N, N, cudaArrayTextureGather));
+    CK(cudaMemcpy2DToArray(arrg, 0, 0, h.data(), N * 4, N * 4, N, cudaMemcpyHostToDevice));
+    cudaResourceDesc rdg = {}; rdg.resType = cudaResourceTypeArray; rdg.res.array.array = arrg;
+    cudaTextureDesc tdg = {}; tdg.addressMode[0] = tdg.addressMode[1] = cudaAddressModeClamp; tdg.filterMode = cudaFilterModePoint; tdg.readMode = cudaReadModeElementType; tdg.normalizedCoords = 0;
+    cudaTextureObject_t texg; CK(cudaCreateTextureObject(&texg, &rdg, &tdg, nullptr));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const char* names[4] = {"LDG bricked 8x4 x-major", "LDG row-major", "TEX point", "SULD"};
     for (float slope : {1.0f, 0.5f, 0.05f}) {
@@ -67,6 +102,20 @@ int main() {
             }
             std::vector<float> o(TRAJ); CK(cudaMemcpy(o.data(), dout + mode * TRAJ, TRAJ * 4, cudaMemcpyDeviceToHost));
             printf("  %-26s %8.2f us   %.1f Gsamples/s   check %.4f\n", names[mode], best * 1e3, (double)TRAJ * S / best * 1e-6, o[5] / 5.0);
+        }
+        const char* names2[2] = {"2 samples/lane: 2 x LDG", "2 samples/lane: 1 x TLD4"};
+        for (int pair = 0; pair < 2; ++pair) {
+            CK(cudaMemset(dout, 0, TRAJ * 4 * 4));
+            float best = 1e9f;
+            for (int rep = 0; rep < 6; ++rep) {
+                cudaEventRecord(e0);
+                if (pair == 0) k2<0><<<TRAJ, 256>>>(dbrick, texg, slope, dout);
+                else k2<1><<<TRAJ, 256>>>(dbrick, texg, slope, dout);
+                cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+                float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best) best = ms;
+            }
+            std::vector<float> o(TRAJ); CK(cudaMemcpy(o.data(), dout, TRAJ * 4, cudaMemcpyDeviceToHost));
+            printf("  %-26s %8.2f us   %.1f Gsamples/s   check %.4f\n", names2[pair], best * 1e3, (double)TRAJ * S / best * 1e-6, o[5] / 30.0);
         }
     }
     return 0;
