@@ -37,6 +37,9 @@ __device__ __forceinline__ int substeps_of(float linf) {
 }
 
 constexpr int COST_MAX_WARPS = 8;
+#ifndef COST_DEPTH
+#define COST_DEPTH 3
+#endif
 
 // what a map load returns before it is turned into the sign-tagged reciprocal clearance
 template <int STORAGE> struct RawCell { typedef float type; };
@@ -235,7 +238,11 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         clr_acc = fmaf(fabsf(g), wgt, clr_acc);
         coll += (int)(__float_as_uint(g) >> 31);
     };
-    raw_t p0 = idle, p1 = idle, p2 = idle; float w0 = 0.f, w1 = 0.f, w2 = 0.f; bool o0 = false, o1 = false, o2 = false;   // in flight
+    // blocks in flight per warp while the oldest is accumulated (COST_DEPTH, 3 unless the build says otherwise)
+    constexpr int DEPTH = COST_DEPTH;
+    raw_t pq[DEPTH]; float wq[DEPTH]; bool oq[DEPTH];
+#pragma unroll
+    for (int u = 0; u < DEPTH; ++u) { pq[u] = idle; wq[u] = 0.f; oq[u] = false; }
     // blocks [lb0, lb1) of the round that starts at block c0; the pipeline keeps running across calls
     auto run = [&](const int c0, const int lb0, const int lb1, const bool CHECK) {
         const bool has_tail = (c0 + lb1 == nblk);                 // the trajectory's last block may be partial
@@ -243,22 +250,27 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         const uint2* const bp_full = blkrec + (has_tail ? lb1 - 1 : lb1);
         int tl = ((c0 + lb0) << 5) + lane;
 #pragma unroll 1
-        for (; bp + 2 < bp_full; bp += 3, tl += 96) {             // three blocks in flight, the oldest is accumulated
-            raw_t r; float v; bool q;
-            fetch(bp, tl, false, false, CHECK, r, v, q);          accumulate(p0, w0, o0, CHECK); p0 = r; w0 = v; o0 = q;
-            fetch(bp + 1, tl + 32, false, false, CHECK, r, v, q); accumulate(p1, w1, o1, CHECK); p1 = r; w1 = v; o1 = q;
-            fetch(bp + 2, tl + 64, false, false, CHECK, r, v, q); accumulate(p2, w2, o2, CHECK); p2 = r; w2 = v; o2 = q;
+        for (; bp + (DEPTH - 1) < bp_full; bp += DEPTH, tl += 32 * DEPTH) {   // DEPTH blocks in flight, the oldest is accumulated
+#pragma unroll
+            for (int u = 0; u < DEPTH; ++u) {
+                raw_t r; float v; bool q;
+                fetch(bp + u, tl + 32 * u, false, false, CHECK, r, v, q); accumulate(pq[u], wq[u], oq[u], CHECK); pq[u] = r; wq[u] = v; oq[u] = q;
+            }
         }
 #pragma unroll 1
         for (; bp < bp_full; ++bp, tl += 32) {
             raw_t r; float v; bool q;
-            fetch(bp, tl, false, false, CHECK, r, v, q); accumulate(p0, w0, o0, CHECK);
-            p0 = p1; w0 = w1; o0 = o1; p1 = p2; w1 = w2; o1 = o2; p2 = r; w2 = v; o2 = q;
+            fetch(bp, tl, false, false, CHECK, r, v, q); accumulate(pq[0], wq[0], oq[0], CHECK);
+#pragma unroll
+            for (int u = 0; u + 1 < DEPTH; ++u) { pq[u] = pq[u + 1]; wq[u] = wq[u + 1]; oq[u] = oq[u + 1]; }
+            pq[DEPTH - 1] = r; wq[DEPTH - 1] = v; oq[DEPTH - 1] = q;
         }
         if (has_tail) {
             raw_t r; float v; bool q;
-            fetch(bp, min(tl, T - 1), true, tl >= T, CHECK, r, v, q); accumulate(p0, w0, o0, CHECK);
-            p0 = p1; w0 = w1; o0 = o1; p1 = p2; w1 = w2; o1 = o2; p2 = r; w2 = v; o2 = q;
+            fetch(bp, min(tl, T - 1), true, tl >= T, CHECK, r, v, q); accumulate(pq[0], wq[0], oq[0], CHECK);
+#pragma unroll
+            for (int u = 0; u + 1 < DEPTH; ++u) { pq[u] = pq[u + 1]; wq[u] = wq[u + 1]; oq[u] = oq[u + 1]; }
+            pq[DEPTH - 1] = r; wq[DEPTH - 1] = v; oq[DEPTH - 1] = q;
         }
     };
     for (int c0 = 0; c0 < nblk; c0 += a.cb) {
@@ -282,8 +294,8 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
         if (lb0 < lb1) { if (all_safe) run(c0, lb0, lb1, false); else run(c0, lb0, lb1, true); }
         if (c0 + a.cb < nblk) __syncthreads();                    // the stage is rebuilt
     }
-    if (all_safe) { accumulate(p0, w0, o0, false); accumulate(p1, w1, o1, false); accumulate(p2, w2, o2, false); }
-    else { accumulate(p0, w0, o0, true); accumulate(p1, w1, o1, true); accumulate(p2, w2, o2, true); }
+#pragma unroll
+    for (int u = 0; u < DEPTH; ++u) { if (all_safe) accumulate(pq[u], wq[u], oq[u], false); else accumulate(pq[u], wq[u], oq[u], true); }
 
     COST_STAMP(3);                                               // (max over warps) sample loop done
     // ---- 2c: the end samples (k = 0 and k = K) of my segments, by the same arithmetic as the sample loop ----

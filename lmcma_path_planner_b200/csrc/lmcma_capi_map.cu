@@ -34,10 +34,11 @@ int launch_cost(const MapDev& mp, const CostArgs& a, int rows, int B, CostShape 
         if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, true>(mp, a, rows, B, shape, st);
         return mp.storage == 0 ? launch_cost_t<3, 0, true>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, true>(mp, a, rows, B, shape, st);
     }
-    // seven CTAs per SM (32 registers, some spills) keep a 1024-trajectory population resident in ONE wave; from four waves
-    // on the tail no longer matters and the un-spilled 40-register build at six per SM is 7 % faster (C3-shaped batch: 0.280 ->
-    // 0.261 ms for 16384 trajectories, profiles/r2_cost_timeline.txt; the single C2 query: 31.0 vs 33.9 us the other way round)
-    const int minb = shape.minb ? shape.minb : ((long long)rows * B >= 4LL * 7 * 148 ? 6 : 7);
+    // seven CTAs per SM (32 registers, 28 / 36 B of spills outside the sample loop) keep a 1024-trajectory population resident in
+    // ONE wave.  The 40-register build at six per SM was 7 % faster from four waves on in round 1 (0.280 -> 0.261 ms for 16384
+    // trajectories); after round 2's instruction diet of the phases around the loop it is the other way round in 2-D (C3 batch
+    // of 262144 trajectories: 3.39 ms at seven per SM, 3.47 ms at six), so 2-D launches always take the seven-per-SM build
+    const int minb = shape.minb ? shape.minb : (mp.dims == 3 && (long long)rows * B >= 4LL * 7 * 148 ? 6 : 7);
     if (minb == 6) {
         if (mp.dims == 2) return mp.storage == 0 ? launch_cost_t<2, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<2, 1, false, 6>(mp, a, rows, B, shape, st);
         return mp.storage == 0 ? launch_cost_t<3, 0, false, 6>(mp, a, rows, B, shape, st) : launch_cost_t<3, 1, false, 6>(mp, a, rows, B, shape, st);

@@ -26,7 +26,9 @@ __global__ void __launch_bounds__(256, 7) k(const float* __restrict__ brick, con
         if (MODE == 0) g = __ldg(brick + (((unsigned)ix << 2) + (unsigned)iy + ((unsigned)iy >> 2) * (unsigned)(N / 8 * 32 - 4)));
         else if (MODE == 1) g = __ldg(rowmaj + (unsigned)iy * N + ix);
         else if (MODE == 2) g = tex2D<float>(tex, (float)ix + 0.5f, (float)iy + 0.5f);
-        else g = surf2Dread<float>(surf, ix * 4, iy, cudaBoundaryModeZero);
+        else if (MODE == 3) g = surf2Dread<float>(surf, ix * 4, iy, cudaBoundaryModeZero);
+        // control: the SAME arithmetic, but the 32 lanes read 32 consecutive words (one line): what the loop costs without a gather
+        else g = __ldg(rowmaj + ((((unsigned)iy * N + (unsigned)ix) & ~31u) + lane));
         acc += fabsf(g);
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(~0u, acc, o);
@@ -85,10 +87,10 @@ int main() {
     cudaTextureDesc tdg = {}; tdg.addressMode[0] = tdg.addressMode[1] = cudaAddressModeClamp; tdg.filterMode = cudaFilterModePoint; tdg.readMode = cudaReadModeElementType; tdg.normalizedCoords = 0;
     cudaTextureObject_t texg; CK(cudaCreateTextureObject(&texg, &rdg, &tdg, nullptr));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const char* names[4] = {"LDG bricked 8x4 x-major", "LDG row-major", "TEX point", "SULD"};
+    const char* names[5] = {"LDG bricked 8x4 x-major", "LDG row-major", "TEX point", "SULD", "control: coalesced LDG"};
     for (float slope : {1.0f, 0.5f, 0.05f}) {
         printf("slope %.2f\n", slope);
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 5; ++mode) {
             CK(cudaMemset(dout, 0, TRAJ * 4 * 4));
             float best = 1e9f;
             for (int rep = 0; rep < 6; ++rep) {
@@ -97,10 +99,11 @@ int main() {
                 if (mode == 1) k<1><<<TRAJ, 256>>>(dbrick, drow, tex, surf, slope, dout + TRAJ);
                 if (mode == 2) k<2><<<TRAJ, 256>>>(dbrick, drow, tex, surf, slope, dout + 2 * TRAJ);
                 if (mode == 3) k<3><<<TRAJ, 256>>>(dbrick, drow, tex, surf, slope, dout + 3 * TRAJ);
+                if (mode == 4) k<4><<<TRAJ, 256>>>(dbrick, drow, tex, surf, slope, dout);
                 cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
                 float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best) best = ms;
             }
-            std::vector<float> o(TRAJ); CK(cudaMemcpy(o.data(), dout + mode * TRAJ, TRAJ * 4, cudaMemcpyDeviceToHost));
+            std::vector<float> o(TRAJ); CK(cudaMemcpy(o.data(), dout + (mode & 3) * TRAJ, TRAJ * 4, cudaMemcpyDeviceToHost));
             printf("  %-26s %8.2f us   %.1f Gsamples/s   check %.4f\n", names[mode], best * 1e3, (double)TRAJ * S / best * 1e-6, o[5] / 5.0);
         }
         const char* names2[2] = {"2 samples/lane: 2 x LDG", "2 samples/lane: 1 x TLD4"};
