@@ -74,8 +74,15 @@ template <bool SMEM> __device__ __forceinline__ float4 ld_row4(const float4* p) 
 //        shared memory, or in HBM/L2 when SMEM is false); -1 = no sweep here: the recompute is done by the Gram-matrix
 //        kernels (k_gram.cuh) for shapes whose rows fit neither registers nor shared memory; this kernel then only
 //        hands them {first_stale, live}
-template <int NVB, int RMAX, bool SMEM, bool OVERLAP>
-__global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs a) {
+// WARPS = warps per CTA: 16 (one CTA per SM), or 8 with two CTAs per SM for BATCHED instances — one instance's sweep is a
+//        chain of dependent steps that leaves its SM two thirds idle (issue-active 32 %), two of them interleave.  Every
+//        floating-point result is the same for both sizes (same per-row operation order, same summation tree in the mean
+//        phase), so a batched instance stays bit-identical to the same instance run alone
+template <int NVB, int RMAX, bool SMEM, bool OVERLAP, int WARPS = UPD_WARPS>
+__global__ void __launch_bounds__(32 * WARPS, WARPS == UPD_WARPS ? 1 : 2) k_update(OptDev o, UpdateArgs a) {
+    static_assert(WARPS == 16 || WARPS == 8, "CTA sizes the mean phase's summation tree is written for");
+    static_assert(!OVERLAP || WARPS == UPD_WARPS, "the overlapped generation is a single-instance path");
+    static_assert(RMAX <= 0 || NVB <= WARPS, "the newest row's chain takes NVB warps");
     static_assert(!OVERLAP || (RMAX > 0 && SMEM), "the overlapped generation uses the register sweep");
     static_assert(RMAX <= 0 || SMEM, "the register sweep publishes finished rows through shared memory");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -88,7 +95,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     unsigned long long* rowbar = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)m * 20 + 7) & ~(size_t)7));   // m mbarriers: row i is final
     unsigned long long* scalbar = rowbar + m;                      // m mbarriers: |v_i|^2 and Lj_i / K are published
     float4* red4 = reinterpret_cast<float4*>(smem_raw + (((size_t)m * 36 + 8 + 127) & ~(size_t)127));                      // 128 float4 scratch
-    float* rows_s = reinterpret_cast<float*>(red4 + 128 * (UPD_GROUPS - 1));                                                                  // m x ns (SMEM)
+    float* rows_s = reinterpret_cast<float*>(red4 + 128 * (UPD_GROUPS - 1));   // (the same layout for every WARPS)                                                                  // m x ns (SMEM)
     float* Gs = rows_s + (size_t)m * ns;                           // register sweep: m x UPD_BLK, Gs[k][r] = v_k . v_(j0 + r), j0 = k rounded down to its block, r < k - j0
     // register sweep: lane-partial dot products of the newest row's chain, 2 stages x NVB warps x UPD_BLK rows x 32 lanes, + NVB norms
     float* chain_part = reinterpret_cast<float*>((reinterpret_cast<size_t>(Gs + (size_t)m * (UPD_BLK + 1)) + 15) & ~(size_t)15);
@@ -98,8 +105,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     __shared__ float am_v[UPD_WARPS];
     __shared__ int am_i[UPD_WARPS];
     const int b = blockIdx.x;
-    const int tid = threadIdx.x, nthr = UPD_THREADS;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = UPD_WARPS;
+    const int tid = threadIdx.x, nthr = 32 * WARPS;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = WARPS;
     Scalars* scp = o.sc + b;
     int* tg = o.t + (size_t)b * m;
     int* vg = o.vec + (size_t)b * m;
@@ -329,36 +336,46 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
     {
         const double* xm = o.xmean + (size_t)b * ns;
         const float* pc = o.pc + (size_t)b * ns;
-        const int tq = tid & 127, g = tid >> 7;                      // UPD_GROUPS x 128 threads
+        // UPD_GROUPS (4) VIRTUAL groups of 128 threads share the slices out (group g sums slices g, g + 4, ...); a CTA of 16
+        // warps has one hardware group per virtual group, a CTA of 8 warps runs two virtual groups per hardware group one after
+        // the other: the summation tree is the same
+        constexpr int HG = WARPS / 4, VPH = UPD_GROUPS / HG;         // hardware groups, virtual groups per hardware group
+        const int tq = tid & 127, h = tid >> 7;
         for (int q0 = 0; q0 < nq; q0 += 128) {
             const int q = q0 + tq;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 accv[VPH];
             double2 xm01 = make_double2(0.0, 0.0), xm23 = xm01;
-            float4 pc4 = acc;
-            if (q < nq) {
-                if (g == 0) {
-                    xm01 = reinterpret_cast<const double2*>(xm)[2 * q]; xm23 = reinterpret_cast<const double2*>(xm)[2 * q + 1];
-                    pc4 = reinterpret_cast<const float4*>(pc)[q];
-                }
-                const float4* sp = reinterpret_cast<const float4*>(a.slices + (size_t)b * a.inst_stride) + q;
-                const size_t sstride4 = (size_t)a.slice_stride >> 2;
-                int k = g;
-                for (; k + 7 * UPD_GROUPS < a.n_slices; k += 8 * UPD_GROUPS) {   // 8 loads in flight
-                    float4 v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = __ldcg(sp + (size_t)(k + UPD_GROUPS * u) * sstride4);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
-                }
-                for (; k < a.n_slices; k += UPD_GROUPS) { const float4 v = __ldcg(sp + (size_t)k * sstride4); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+            float4 pc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nq && h == 0) {
+                xm01 = reinterpret_cast<const double2*>(xm)[2 * q]; xm23 = reinterpret_cast<const double2*>(xm)[2 * q + 1];
+                pc4 = reinterpret_cast<const float4*>(pc)[q];
             }
-            if (g > 0) red4[(g - 1) * 128 + tq] = acc;
+#pragma unroll
+            for (int vi = 0; vi < VPH; ++vi) {
+                const int g = h + vi * HG;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < nq) {
+                    const float4* sp = reinterpret_cast<const float4*>(a.slices + (size_t)b * a.inst_stride) + q;
+                    const size_t sstride4 = (size_t)a.slice_stride >> 2;
+                    int k = g;
+                    for (; k + 7 * UPD_GROUPS < a.n_slices; k += 8 * UPD_GROUPS) {   // 8 loads in flight
+                        float4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = __ldcg(sp + (size_t)(k + UPD_GROUPS * u) * sstride4);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                    }
+                    for (; k < a.n_slices; k += UPD_GROUPS) { const float4 v = __ldcg(sp + (size_t)k * sstride4); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+                }
+                accv[vi] = acc;
+                if (g > 0) red4[(g - 1) * 128 + tq] = acc;
+            }
             __syncthreads();
-            if (g == 0 && q < nq) {
+            if (h == 0 && q < nq) {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int g2 = 0; g2 + 1 < UPD_GROUPS; ++g2) { const float4 u4 = red4[g2 * 128 + tq]; t.x += u4.x; t.y += u4.y; t.z += u4.z; t.w += u4.w; }
-                const float d[4] = {acc.x + t.x, acc.y + t.y, acc.z + t.z, acc.w + t.w};
+                const float d[4] = {accv[0].x + t.x, accv[0].y + t.y, accv[0].z + t.z, accv[0].w + t.w};
                 finish_column(q, d, xm01, xm23, pc4, dry);
             }
             __syncthreads();
@@ -715,7 +732,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
             // ---- resume: the rows are in shared memory (bulk copies from `spec`, waited for above); commit the recomputed ones to
             //      V and the mirror and publish them, a warp per row — what publish() did step by step in the sweep ----
             for (int i = tid; i < m * UPD_BLK; i += nthr) Gs[i] = spec[spec_gs_off(m) + i];
-            for (int i = first_stale + warp; i < hi; i += UPD_WARPS) {
+            for (int i = first_stale + warp; i < hi; i += WARPS) {
                 const float4* srow = reinterpret_cast<const float4*>(rows_s + (size_t)i * ns);
                 const float4* prow = reinterpret_cast<const float4*>(Pb + (size_t)order[i] * ns);
                 float4* dst = reinterpret_cast<float4*>(Vb + (size_t)order[i] * ns);
@@ -732,7 +749,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update(OptDev o, UpdateArgs 
         // every older row is final
         __syncthreads();
         UPD_STAMP(7);
-        if (phase != 2) for (int k = 1 + warp; k < hi; k += UPD_WARPS) gram_row(k);  // block Gram entries for the newest row's chain
+        if (phase != 2) for (int k = 1 + warp; k < hi; k += WARPS) gram_row(k);  // block Gram entries for the newest row's chain
         if (phase == 1) {
             // ---- speculative pass: leave the rows, their scalars and the Gram entries for the next tell_all and stop here ----
             __syncthreads();

@@ -258,13 +258,13 @@ int launch_rank(lmcma_b200_opt* o, const float* f_all, int mode, float* payload,
     return 0;
 }
 
-template <int NVB, int RMAX, bool SMEM, bool OVERLAP = false>
+template <int NVB, int RMAX, bool SMEM, bool OVERLAP = false, int WARPS = UPD_WARPS>
 int launch_update_t(lmcma_b200_opt* o, const UpdateArgs& a, bool pdl, cudaStream_t st) {
-    auto kern = k_update<NVB, RMAX, SMEM, OVERLAP>;
+    auto kern = k_update<NVB, RMAX, SMEM, OVERLAP, WARPS>;
     if (o->upd_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->upd_smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(o->d.B); cfg.blockDim = dim3(UPD_THREADS); cfg.dynamicSmemBytes = o->upd_smem; cfg.stream = st;
+    cfg.gridDim = dim3(o->d.B); cfg.blockDim = dim3(32 * WARPS); cfg.dynamicSmemBytes = o->upd_smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -300,6 +300,10 @@ int launch_update(lmcma_b200_opt* o, const UpdateArgs& a_in, bool pdl, cudaStrea
             if (o->upd_rmax == 3) return launch_update_t<4, 3, true, true>(o, a, pdl, st);
             if (o->upd_rmax == 5) return launch_update_t<4, 5, true, true>(o, a, pdl, st);
             return fail(LMCMA_B200_ERR_STATE, "overlapped generation without the register sweep");
+        }
+        if (o->upd_warps == 8) {                                 // batched instances: two CTAs of 8 warps per SM (configure_update)
+            if (o->upd_rmax == 3) return launch_update_t<4, 3, true, false, 8>(o, a, pdl, st);
+            if (o->upd_rmax == 5) return launch_update_t<4, 5, true, false, 8>(o, a, pdl, st);
         }
         if (o->upd_rmax == 3) return launch_update_t<4, 3, true>(o, a, pdl, st);
         if (o->upd_rmax == 5) return launch_update_t<4, 5, true>(o, a, pdl, st);
@@ -339,10 +343,15 @@ int configure_update(lmcma_b200_opt* o) {
     if (o->upd_gram) { o->upd_rows_in_smem = false; o->upd_smem = fixed; }
     // pending rows in registers when they fit: m <= 8 warps x RMAX rows of <= 128 float4 columns
     o->upd_rmax = 0;
+    o->upd_warps = UPD_WARPS;
     if (o->upd_nvb == 4 && o->upd_rows_in_smem && !o->upd_gram && !o->tune.update_streaming) {
-        o->upd_sweep_warps = UPD_WARPS;
+        // batched instances (two waves of one-CTA-per-SM launches or more) whose rows fit 8 warps x 5: CTAs of 8 warps, two per
+        // SM — the sweep of one instance is a chain of dependent steps that leaves its SM two thirds idle (k_update.cuh)
+        const bool two_per_sm = 2 * o->upd_smem + 4096 <= o->props->smem_optin && o->d.m <= 8 * 5;
+        if (o->tune.update_warps == 8 ? two_per_sm : (o->tune.update_warps == 0 && two_per_sm && o->d.B >= 2 * o->props->sm_count)) o->upd_warps = 8;
+        o->upd_sweep_warps = o->upd_warps;
         const int forced_sw = o->tune.update_sweep_warps;
-        if (forced_sw >= 1 && forced_sw <= UPD_WARPS) o->upd_sweep_warps = forced_sw;
+        if (forced_sw >= 1 && forced_sw <= o->upd_warps) o->upd_sweep_warps = forced_sw;
         if (o->d.m <= o->upd_sweep_warps * 3) o->upd_rmax = 3;
         else if (o->d.m <= o->upd_sweep_warps * 5) o->upd_rmax = 5;
     }

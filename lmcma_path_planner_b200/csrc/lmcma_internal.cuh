@@ -82,6 +82,7 @@ struct Tuning {
                             // through the finished pairs beside the ranking: 66.5 -> 63.2 us per C2 generation once the newest row's
                             // chain stopped being the longer branch)
     int tell_spec = 1;      // tell_all: speculative update of the next generation at the end of the graph (LMCMA_B200_TELL_SPEC=0: off)
+    int update_warps = 0;   // k_update CTA size: 0 = by batch size, 8 / 16 forced (LMCMA_B200_UPDATE_WARPS)
     int update_dry = 1;     // overlapped generation: pre-execute the post-rank code while k_rank is busy (k_update.cuh)
     int graph_dbg = 0, dbg = 0, update_dbg = 0, cost_dbg = 0;
     static Tuning from_env() {
@@ -108,6 +109,7 @@ struct Tuning {
         t.rank_late = env_int("LMCMA_B200_RANK_LATE", 0);
         t.update_dry = env_int("LMCMA_B200_UPDATE_DRY", 1);
         t.tell_spec = env_int("LMCMA_B200_TELL_SPEC", 1);
+        t.update_warps = env_int("LMCMA_B200_UPDATE_WARPS", 0);
         t.rank_sorted = env_int("LMCMA_B200_RANK_SORTED", 1);
         t.graph_dbg = env_int("LMCMA_B200_GRAPH_DBG", 0);
         t.dbg = getenv("LMCMA_B200_DBG") ? 1 : 0;
@@ -220,7 +222,7 @@ struct lmcma_b200_opt {
     bool mirror_on = false, mirror_suppressed = false, xh_fresh = false;
     int* err_host = nullptr;          // page-locked, mapped: OptDev::err (a kernel of the overlapped generation gave up on its partner)
     long long* graph_dbg = nullptr;   // LMCMA_B200_GRAPH_DBG: k_update's timeline inside the fused generation, printed by lmcma_b200_sync
-    int upd_nvb = 4, upd_rmax = 0, upd_sweep_warps = 16;
+    int upd_nvb = 4, upd_rmax = 0, upd_sweep_warps = 16, upd_warps = 16;
     bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
     bool upd_rows_in_smem = true;
     size_t upd_smem = 0, rank_smem = 0;

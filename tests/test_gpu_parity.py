@@ -212,6 +212,19 @@ def test_lmcma_teacher_forced_m_not_lambda(po):
     _teacher_forced(po, 400, 128, 40, 50, seed=3, sigma=0.5)
 
 
+def test_lmcma_teacher_forced_five_rows_per_warp(po):
+    """48 < m <= 80 with rows that fit shared memory: the register sweep with five pending rows per warp (k_update<4, 5>) and
+    the newest row's four-warp chain over eight blocks of factors, past the point where slots are recycled."""
+    _teacher_forced(po, 100, 64, 60, 70, seed=6, sigma=0.5)
+
+
+def test_lmcma_teacher_forced_eight_warp_update(po, monkeypatch):
+    """k_update as a CTA of 8 warps with five rows per warp (two CTAs per SM: what large batches of instances take) on the
+    C2 / C3 per-instance shape n = 400, m = 40, against the FP64 oracle past the point where slots are recycled."""
+    monkeypatch.setenv("LMCMA_B200_UPDATE_WARPS", "8")
+    _teacher_forced(po, 400, 128, 40, 50, seed=3, sigma=0.5)
+
+
 def test_lmcma_teacher_forced_large_n(po):
     """C4-like row length: n = 1500, m = 77 (multi-chunk bulk-copy pipeline, NV = 12)."""
     _teacher_forced(po, 1500, 32, 77, 6, seed=4, sigma=0.3)
@@ -321,9 +334,12 @@ def test_planning_c1_improves_and_best_cost_matches_oracle(po, golden_maps):
             assert ref["ncoll"][0] == 0
 
 
-def test_batched_instances_are_independent(po, golden_maps, monkeypatch):
-    """C3 mechanics: B instances in one launch == the same instances run one at a time."""
+@pytest.mark.parametrize("update_warps", ["0", "8"])
+def test_batched_instances_are_independent(po, golden_maps, monkeypatch, update_warps):
+    """C3 mechanics: B instances in one launch == the same instances run one at a time.  update_warps = 8: the batch's k_update
+    as CTAs of 8 warps, two per SM (what large batches take by themselves) against single instances on 16 warps."""
     monkeypatch.setenv("LMCMA_B200_COST_TPT", "64")   # same reduction tree whatever the query length
+    monkeypatch.setenv("LMCMA_B200_UPDATE_WARPS", update_warps)
     dist = po.edt_exact(golden_maps["problem2"])
     W = 12
     lo, hi = maps.box_bounds((100, 100), W)
@@ -335,8 +351,10 @@ def test_batched_instances_are_independent(po, golden_maps, monkeypatch):
     z0 = batched.get("Z")
     batched.run(12)
     for b in (0, 3, 4):
+        monkeypatch.setenv("LMCMA_B200_UPDATE_WARPS", "16")
         one = L.Optimizer(2 * W, x0=x0[b], lam=16, m=8, lo=lo, hi=hi, sigma0=4.0, rng="inject")
         one.attach_cost(cm, [starts[b]], [goals[b]], W)
+        monkeypatch.setenv("LMCMA_B200_UPDATE_WARPS", update_warps)
         # replay instance b's deviates: regenerate them with a batch whose instance index matches
         ref = L.Optimizer(2 * W, x0=x0, lam=16, m=8, batch=5, lo=lo, hi=hi, sigma0=4.0, seed=11, record_z=True)
         ref.attach_cost(cm, starts, goals, W)
