@@ -83,7 +83,7 @@ __device__ __forceinline__ int count_below(const float* a, int cnt, float v) {
 __device__ __forceinline__ void tell_prologue(const OptDev& o, int b, int rs, unsigned char* smem_raw) {
     const int tid = threadIdx.x, nthr = blockDim.x, lambda = o.lambda;
     if (lambda <= TELL_FTILE) {
-        float* prev_s = reinterpret_cast<float*>(smem_raw) + TELL_FTILE;
+        float* prev_s = reinterpret_cast<float*>(smem_raw) + o.rank_ftile;
         const float* prev = (o.tile_sorted ? o.prev_sorted : o.prev_fit) + (size_t)b * lambda;
         const int cnt4 = (lambda + 3) & ~3;
         for (int j = tid; j < cnt4; j += nthr) prev_s[j] = j < lambda ? prev[j] : __int_as_float(0x7f800000);
@@ -104,9 +104,12 @@ __device__ __forceinline__ void tell_phase_a(const OptDev& o, const float* __res
     const int rows_per = (o.pop_count + o.RS - 1) / o.RS;
     const int r0 = rs * rows_per, r1 = min(o.pop_count, r0 + rows_per), nrows = max(0, r1 - r0);
 
-    float* cur_s = reinterpret_cast<float*>(smem_raw);               // TELL_FTILE
-    float* prev_s = cur_s + TELL_FTILE;                              // TELL_FTILE
-    int* rk_s = reinterpret_cast<int*>(prev_s + TELL_FTILE);         // TELL_MAX_ROWS ranks of the slice's rows
+    // the staging tiles hold TELL_FTILE values, or just lambda (rounded up to 4) for small populations: a batch of small
+    // instances is then not limited to four CTAs per SM by 32 KB tiles it does not use (OptDev::rank_ftile, set at create)
+    const int ftile = o.rank_ftile;
+    float* cur_s = reinterpret_cast<float*>(smem_raw);               // ftile
+    float* prev_s = cur_s + ftile;                                   // ftile
+    int* rk_s = reinterpret_cast<int*>(prev_s + ftile);              // TELL_MAX_ROWS ranks of the slice's rows
     int* sel_row = rk_s + TELL_MAX_ROWS;                             // compacted selected rows (rank < mu)
     float* sel_w = reinterpret_cast<float*>(sel_row + TELL_MAX_ROWS);
     float4* red = reinterpret_cast<float4*>(sel_w + TELL_MAX_ROWS);  // 7 x 128 cross-group reduction

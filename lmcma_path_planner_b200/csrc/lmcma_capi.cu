@@ -248,7 +248,7 @@ int launch_rank(lmcma_b200_opt* o, const float* f_all, int mode, float* payload,
     if (o->rank_smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->rank_smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(o->d.RS, o->d.B); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = o->rank_smem; cfg.stream = st;
+    cfg.gridDim = dim3(o->d.RS, o->d.B); cfg.blockDim = dim3(o->rank_threads); cfg.dynamicSmemBytes = o->rank_smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -328,7 +328,11 @@ int configure_update(lmcma_b200_opt* o) {
     const int nq = o->d.ns / 4;
     if (nq > 512) return fail(LMCMA_B200_ERR_ARG, "n = %d too large (max 2048)", o->d.n);
     o->upd_nvb = nq <= 128 ? 4 : 16;
-    o->rank_smem = (size_t)2 * TELL_FTILE * 4 + (size_t)3 * TELL_MAX_ROWS * 4 + (size_t)7 * 128 * 16;
+    // k_rank: small populations (lambda <= 256) take CTAs of 256 threads and tiles of lambda values — the choice depends on
+    // lambda alone, so that a batched instance and the same instance run alone sum their partial sums in the same order
+    o->rank_threads = o->d.lambda <= 256 ? 256 : 1024;
+    o->d.rank_ftile = o->d.lambda <= 256 ? ((o->d.lambda + 3) & ~3) : TELL_FTILE;
+    o->rank_smem = (size_t)2 * o->d.rank_ftile * 4 + (size_t)3 * TELL_MAX_ROWS * 4 + (size_t)7 * 128 * 16;
     const size_t fixed = (((size_t)o->d.m * 36 + 8 + 127) & ~(size_t)127) + (size_t)2048 * (UPD_GROUPS - 1);
     // + the block Gram entries, and the stages of the newest row's multi-warp chain (k_update.cuh: chain_part)
     const size_t rows = (size_t)o->d.m * o->d.ns * sizeof(float) + (size_t)o->d.m * (UPD_BLK + 1) * sizeof(float) +

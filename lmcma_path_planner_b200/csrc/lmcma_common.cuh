@@ -87,6 +87,7 @@ struct OptDev {
     const float* w;    // mu recombination weights
     float* partial;    // B x RS x ns weighted partial sums of (x - xmean)
     int RS;
+    int rank_ftile;    // fitness values k_rank stages per shared-memory tile: TELL_FTILE, or lambda rounded up to 4 for small populations
     unsigned long long* S_count;   // B : #{(i,j): prev_j < cur_i}
     unsigned* done_count;          // B : tickets of k_rank (split-population payload packing)
     double c1, cc, cs, target, K, M, mueff;

@@ -226,6 +226,7 @@ struct lmcma_b200_opt {
     bool upd_gram = false; size_t coef_smem = 0;   // Gram-matrix recompute (k_gram.cuh) for rows that fit neither registers nor smem
     bool upd_rows_in_smem = true;
     size_t upd_smem = 0, rank_smem = 0;
+    int rank_threads = 1024;
     size_t cost_smem = 0;
 };
 
