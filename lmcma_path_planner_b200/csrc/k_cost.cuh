@@ -290,7 +290,11 @@ __global__ void __launch_bounds__(COST_MAX_WARPS * 32, MINB) k_cost(MapDev mp, C
             __syncthreads();
         }
         // 2b: a contiguous run of blocks per warp
-        const int lb0 = (int)(((unsigned)warp * (unsigned)nb) / (unsigned)nwarps), lb1 = (int)(((unsigned)(warp + 1) * (unsigned)nb) / (unsigned)nwarps);
+        // (the usual CTA has 1 / 2 / 4 / 8 warps: a shift instead of two integer divisions per warp and round)
+        const bool pow2 = (nwarps & (nwarps - 1)) == 0;
+        const int lg = 31 - __clz(nwarps);
+        const int lb0 = pow2 ? (int)(((unsigned)warp * (unsigned)nb) >> lg) : (int)(((unsigned)warp * (unsigned)nb) / (unsigned)nwarps);
+        const int lb1 = pow2 ? (int)(((unsigned)(warp + 1) * (unsigned)nb) >> lg) : (int)(((unsigned)(warp + 1) * (unsigned)nb) / (unsigned)nwarps);
         if (lb0 < lb1) { if (all_safe) run(c0, lb0, lb1, false); else run(c0, lb0, lb1, true); }
         if (c0 + a.cb < nblk) __syncthreads();                    // the stage is rebuilt
     }
