@@ -370,7 +370,46 @@ def run_e2e(args, L, K, torch, cmap, start, goal, lo, hi, x0, rank, local, flush
         calls = {k: v / args.steps * 1e3 for k, v in zip(("ask", "cost_evaluate", "tell_all"), parts)}
         return tt, calls
 
+    def measure_device_candidates():
+        # not the headline: the candidates never leave the device (no host view of X at all); only the fitness crosses PCIe, as
+        # the result of the evaluation (k_cost stores it into the caller's pinned array) and as the input of tell_all
+        o = L.Optimizer(2 * W, x0=x0, lam=LAM, m=M, lo=lo, hi=hi, sigma0=SIGMA0, seed=2000 + rank, rng="philox", device=local)
+        o.attach_cost(cmap, [start], [goal], W, L.LONGSAFE, 1e4)
+        parts = [0.0, 0.0]
+
+        def step():
+            t0 = time.perf_counter()
+            o.mg_evaluate(fh.ctypes.data)                        # page-locked host memory: the same address on the device (UVA)
+            o.sync()
+            t1 = time.perf_counter()
+            K.check(lib.lmcma_b200_tell_all(o._h, K.fptr(fh)))
+            t2 = time.perf_counter()
+            parts[0] += t1 - t0; parts[1] += t2 - t1
+
+        for _ in range(max(args.warmup, 3) + max(0, FILL - max(args.warmup, 3))):
+            step()
+        barrier()
+        parts[:] = [0.0, 0.0]
+        tt = 0.0
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step()
+            tt += time.perf_counter() - t0
+        o.close()
+        return tt, {k: v / args.steps * 1e3 for k, v in zip(("evaluate", "tell_all"), parts)}
+
     t_cb, calls_cb = measure(False)
+    try:
+        t_dc, calls_dc = measure_device_candidates()
+        variants["device_candidates"] = {"ms_per_step": t_dc / args.steps * 1e3, "calls_ms": calls_dc,
+                                         "h2d_bytes_per_step": LAM * 4, "d2h_bytes_per_step": LAM * 4,
+                                         "path": "NOT the headline (no host copy of the candidates exists): lmcma_b200_mg_evaluate on the "
+                                                 "optimiser's own device population into the caller's pinned fitness array -> "
+                                                 "lmcma_b200_sync -> lmcma_b200_tell_all (H2D f; update + sample)"}
+    except Exception as e:                                       # informational variant: never fails the bench
+        variants["device_candidates"] = {"error": str(e)[:200]}
     variants["caller_buffers"] = {"ms_per_step": t_cb / args.steps * 1e3, "calls_ms": calls_cb,
                                   "h2d_bytes_per_step": LAM * 2 * W * 4 + LAM * 4, "d2h_bytes_per_step": LAM * 2 * W * 4 + LAM * 12,
                                   "path": "lmcma_b200_ask_all (D2H X into the caller's pinned array) -> lmcma_b200_cost_evaluate (k_cost reads the "

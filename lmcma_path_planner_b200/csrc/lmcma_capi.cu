@@ -530,7 +530,11 @@ int ensure_tell_graph(lmcma_b200_opt* o) {
         cudaGetLastError(); o->f_pinned = nullptr; o->tell_graph_failed = true; return 0;
     }
     const long long before = g_launches.load();
-    const bool spec = o->d_spec != nullptr;
+    // the speculative pass pays only where something hides it: with the host mirror on, the candidates' trip across PCIe
+    // (35 us behind the sampler).  Without the mirror tell_all returns when the sampler is done, and a 25 us kernel behind
+    // k_update would be the longer branch of the graph (measured: tell_all 57 -> 69 us)
+    const bool spec = o->d_spec != nullptr && o->mirror_on && !o->mirror_suppressed;
+    o->tell_graph_spec = spec;
     if (o->tune.graph_dbg && !o->graph_dbg && cudaMalloc(&o->graph_dbg, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(o->graph_dbg, 0, 64 * sizeof(long long)); cudaDeviceSynchronize(); }
     // resume = 0: the whole update; resume = 1: k_update picks up the rows the last graph's speculative pass left.  With the
     // scratch both graphs END with that pass for the next generation, on the side branch behind k_update
@@ -902,8 +906,8 @@ int lmcma_b200_tell_all(lmcma_b200_opt* o, const float* f) {
             memcpy(o->f_pinned, f, (size_t)d.B * d.lambda * sizeof(float));
             const bool resume = o->spec_valid && o->tell_graph_resume;   // the last tell_all graph left the next update's rows behind
             CU(cudaGraphLaunch(resume ? o->tell_graph_resume : o->tell_graph, o->stream));
-            o->spec_valid = o->d_spec != nullptr;                 // ... and so does this one
-            g_launches += 4 + (o->d.tile_sorted ? 1 : 0) + (o->d_spec ? 1 : 0);   // k_update, k_gate, (k_rank_tiles,) k_rank, k_sample, (speculative k_update)
+            o->spec_valid = o->tell_graph_spec;                   // ... and so does this one
+            g_launches += 4 + (o->d.tile_sorted ? 1 : 0) + (o->tell_graph_spec ? 1 : 0);   // k_update, k_gate, (k_rank_tiles,) k_rank, k_sample, (speculative k_update)
             o->xh_fresh = o->mirror_on;                          // the captured sampler writes the host mirror when it is on
             o->x_cache_valid = false;
             o->sample_idx = 0;

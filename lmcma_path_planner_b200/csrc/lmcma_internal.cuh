@@ -202,6 +202,7 @@ struct lmcma_b200_opt {
     cudaGraphExec_t tell_graph_resume = nullptr;
     float* d_spec = nullptr; size_t spec_stride = 0;
     bool spec_valid = false;
+    bool tell_graph_spec = false;             // the tell graphs were captured with the speculative pass (host mirror on)
     float* f_pinned = nullptr;                // the graph's copy source (the caller's fitness array is copied here first)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool have_run_timing = false;

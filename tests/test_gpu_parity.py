@@ -638,7 +638,8 @@ def test_speculative_update_of_tell_all_never_shows_and_never_goes_stale(po, mon
         dev.attach_cost(cm, [start], [goal], W, L.LONGSAFE, 1e4)
         snaps = []
         for g in range(40):
-            r = cm.evaluate(dev.ask_all()[0], start, goal, W, L.LONGSAFE, 1e4)
+            # ask_all_view: the pass is part of tell_all only with the host mirror on (the candidates' trip across PCIe hides it)
+            r = cm.evaluate(np.array(dev.ask_all_view()[0]), start, goal, W, L.LONGSAFE, 1e4)
             dev.tell_all(r["f"])
             snaps.append({k: dev.get(k).copy() for k in keys})    # between two calls: the generation just told
             if g == 12:
