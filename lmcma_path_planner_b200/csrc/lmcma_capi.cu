@@ -349,10 +349,11 @@ int configure_update(lmcma_b200_opt* o) {
     o->upd_rmax = 0;
     o->upd_warps = UPD_WARPS;
     if (o->upd_nvb == 4 && o->upd_rows_in_smem && !o->upd_gram && !o->tune.update_streaming) {
-        // batched instances (two waves of one-CTA-per-SM launches or more) whose rows fit 8 warps x 5: CTAs of 8 warps, two per
+        // batched instances (more than one wave of one-CTA-per-SM launches: two 8-warp CTAs per SM take ~1.3x the time of one
+        // 16-warp CTA, so a second wave is what they beat) whose rows fit 8 warps x 5: CTAs of 8 warps, two per
         // SM — the sweep of one instance is a chain of dependent steps that leaves its SM two thirds idle (k_update.cuh)
         const bool two_per_sm = 2 * o->upd_smem + 4096 <= o->props->smem_optin && o->d.m <= 8 * 5;
-        if (o->tune.update_warps == 8 ? two_per_sm : (o->tune.update_warps == 0 && two_per_sm && o->d.B >= 2 * o->props->sm_count)) o->upd_warps = 8;
+        if (o->tune.update_warps == 8 ? two_per_sm : (o->tune.update_warps == 0 && two_per_sm && o->d.B > o->props->sm_count)) o->upd_warps = 8;
         o->upd_sweep_warps = o->upd_warps;
         const int forced_sw = o->tune.update_sweep_warps;
         if (forced_sw >= 1 && forced_sw <= o->upd_warps) o->upd_sweep_warps = forced_sw;
