@@ -450,6 +450,7 @@ int lmcma_capi::check_lost(lmcma_b200_opt* o) {
     o->overlap = false;
     o->props->cosched = 0;
     if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
+    if (o->graph_exec_multi) { cudaGraphExecDestroy(o->graph_exec_multi); o->graph_exec_multi = nullptr; }
     if (o->tell_graph) { cudaGraphExecDestroy(o->tell_graph); o->tell_graph = nullptr; }
     if (o->tell_graph_resume) { cudaGraphExecDestroy(o->tell_graph_resume); o->tell_graph_resume = nullptr; }
     o->spec_valid = false;
@@ -465,54 +466,69 @@ namespace {
 int ensure_graph(lmcma_b200_opt* o) {
     if (o->graph_exec && o->graph_built_for == o->stream) return 0;
     if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
+    if (o->graph_exec_multi) { cudaGraphExecDestroy(o->graph_exec_multi); o->graph_exec_multi = nullptr; }
     CostArgs ca;
     int rc = cost_args_for(o, &ca);
     if (rc) return rc;
     cudaStream_t st = o->stream;
     if ((rc = ensure_mirror(o, st))) return rc;
-    cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
     if (o->tune.graph_dbg && !o->graph_dbg && cudaMalloc(&o->graph_dbg, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(o->graph_dbg, 0, 64 * sizeof(long long)); cudaDeviceSynchronize(); }
-    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    o->mirror_suppressed = true;                             // fused generations keep the candidates on the device
-    UpdateArgs ua = update_args_local(o);
-    ua.progressive = o->progressive ? 1 : 0;                 // ensure_mirror above: the mirror is clean
-    ua.dbg = o->graph_dbg;
-    if (o->overlap) {
-        // side branch: k_update starts with the graph; main branch: k_gate (waits until k_update holds its SM) -> k_cost ->
-        // k_rank -> k_sample (released by k_rank, follows k_update's flags); join before the graph ends
-        ua.overlap = 1;
-        rc = 0;
-        if (cudaEventRecord(o->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(o->side_stream, o->ev_fork, 0) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph fork failed");
-        if (!rc) rc = launch_update(o, ua, false, o->side_stream);
-        if (!rc && cudaEventRecord(o->ev_join, o->side_stream) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph join record failed");
-        if (!rc) { k_gate<<<(o->d.B + 31) / 32, 32, 0, st>>>(o->d); g_launches++; }
-        if (!rc) rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
-        if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN | RANK_KEEP_FLAGS | (o->tune.rank_late ? 0 : 4), nullptr, st, true);
-        if (!rc) rc = launch_sample(o, st, true, true, 2);
-        if (!rc && cudaStreamWaitEvent(st, o->ev_join, 0) != cudaSuccess) rc = fail(LMCMA_B200_ERR_CUDA, "graph join failed");
-    } else {
-        rc = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
-        if (!rc) rc = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st, true);
-        if (!rc) rc = launch_update(o, ua, true, st);
-        if (!rc) rc = launch_sample(o, st, true, o->progressive);
+    // `reps` generations in ONE graph: between two graph launches the device idles for the launch latency of the next one
+    // (~5 us of a 52 us generation); inside a graph a generation follows the previous one as a plain dependency
+    auto capture = [&](int reps, cudaGraphExec_t* out) -> int {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        o->mirror_suppressed = true;                             // fused generations keep the candidates on the device
+        UpdateArgs ua = update_args_local(o);
+        ua.progressive = o->progressive ? 1 : 0;                 // ensure_mirror above: the mirror is clean
+        ua.dbg = o->graph_dbg;
+        int rc2 = 0;
+        for (int g = 0; g < reps && !rc2; ++g) {
+            if (o->overlap) {
+                // side branch: k_update starts with the generation; main branch: k_gate (waits until k_update holds its SM) ->
+                // k_cost -> k_rank -> k_sample (released by k_rank, follows k_update's flags); join before the generation ends
+                ua.overlap = 1;
+                if (cudaEventRecord(o->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(o->side_stream, o->ev_fork, 0) != cudaSuccess) rc2 = fail(LMCMA_B200_ERR_CUDA, "graph fork failed");
+                if (!rc2) rc2 = launch_update(o, ua, false, o->side_stream);
+                if (!rc2 && cudaEventRecord(o->ev_join, o->side_stream) != cudaSuccess) rc2 = fail(LMCMA_B200_ERR_CUDA, "graph join record failed");
+                if (!rc2) { k_gate<<<(o->d.B + 31) / 32, 32, 0, st>>>(o->d); g_launches++; }
+                if (!rc2) rc2 = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
+                if (!rc2) rc2 = launch_rank(o, o->d.fit, RANK_PLAIN | RANK_KEEP_FLAGS | (o->tune.rank_late ? 0 : 4), nullptr, st, true);
+                if (!rc2) rc2 = launch_sample(o, st, true, true, 2);
+                if (!rc2 && cudaStreamWaitEvent(st, o->ev_join, 0) != cudaSuccess) rc2 = fail(LMCMA_B200_ERR_CUDA, "graph join failed");
+            } else {
+                rc2 = launch_cost(o->map->dev, ca, o->d.pop_count, o->d.B, o->cost_shape, false, st);
+                if (!rc2) rc2 = launch_rank(o, o->d.fit, RANK_PLAIN, nullptr, st, true);
+                if (!rc2) rc2 = launch_update(o, ua, true, st);
+                if (!rc2) rc2 = launch_sample(o, st, true, o->progressive);
+            }
+        }
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        o->mirror_suppressed = false;
+        if (!rc2 && e == cudaSuccess) {
+            e = cudaGraphInstantiate(out, graph, 0);
+            if (e != cudaSuccess) *out = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (!rc2 && e != cudaSuccess) rc2 = fail(LMCMA_B200_ERR_CUDA, "graph capture / instantiate failed: %s", cudaGetErrorString(e));
+        return rc2;
+    };
+    rc = capture(1, &o->graph_exec);
+    if (!rc && o->tune.graph_unroll > 1 && capture(o->tune.graph_unroll, &o->graph_exec_multi) != 0) {   // optional: the single one still works
+        cudaGetLastError();
+        o->graph_exec_multi = nullptr;
     }
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
-    o->mirror_suppressed = false;
     g_launches.store(before);   // capture enqueues nothing
-    if (!rc && e == cudaSuccess) {
-        e = cudaGraphInstantiate(&o->graph_exec, graph, 0);
-        if (e != cudaSuccess) o->graph_exec = nullptr;
-    }
-    if (graph) cudaGraphDestroy(graph);
-    if ((rc || e != cudaSuccess) && o->overlap) {
+    if (rc && o->overlap) {
         // the forked graph could not be built here (capture / instantiation of the side branch): fall back to the linear one
         cudaGetLastError();
+        if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
+    if (o->graph_exec_multi) { cudaGraphExecDestroy(o->graph_exec_multi); o->graph_exec_multi = nullptr; }
         o->overlap = false;
         return ensure_graph(o);
     }
     if (rc) return rc;
-    if (e != cudaSuccess) return fail(LMCMA_B200_ERR_CUDA, "graph capture / instantiate failed: %s", cudaGetErrorString(e));
     o->graph_built_for = st;
     return 0;
 }
@@ -789,6 +805,7 @@ int lmcma_b200_destroy(lmcma_b200_opt* o) {
                     d.Nj, d.Lj, d.Njf, d.Njs, d.VPs, d.dbg, d.G, d.Cf, d.gram_hdr, d.t, d.vec, d.sc, d.best_x, d.S_count, d.done_count, d.progress, d.rank_ticket, d.resident, d.partial, o->d_lo, o->d_hi, o->d_w, o->d_ends};
     for (void* p : ptrs) cudaFree(p);
     if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
+    if (o->graph_exec_multi) cudaGraphExecDestroy(o->graph_exec_multi);
     if (o->tell_graph) cudaGraphExecDestroy(o->tell_graph);
     if (o->tell_graph_resume) cudaGraphExecDestroy(o->tell_graph_resume);
     cudaFree(o->d_spec);
@@ -980,6 +997,7 @@ int lmcma_b200_attach_cost(lmcma_b200_opt* o, lmcma_b200_map* map, const lmcma_b
     CU(cudaMemcpy(o->d_ends, e6.data(), e6.size() * sizeof(float), cudaMemcpyHostToDevice));
     o->cost_shape = pick_cost_shape(obj->waypoints, ends[0].start, ends[0].goal, map->dev.dims, o->tune);
     if (o->graph_exec) { cudaGraphExecDestroy(o->graph_exec); o->graph_exec = nullptr; }
+    if (o->graph_exec_multi) { cudaGraphExecDestroy(o->graph_exec_multi); o->graph_exec_multi = nullptr; }
     return 0;
 }
 
@@ -996,9 +1014,13 @@ int lmcma_b200_run(lmcma_b200_opt* o, int32_t generations) {
         if ((rc = ensure_graph(o))) return rc;
         if ((rc = ensure_mirror(o, o->stream))) return rc;       // a state setter since the last run: the graph's sampler reads the mirror
         CU(cudaEventRecord(o->ev0, o->stream));                  // after the (host-side) graph build: last_run_ms is device time
-        for (int g = 0; g < generations; ++g) {
-            CU(cudaGraphLaunch(o->graph_exec, o->stream));
-            g_launches += 4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0) + (o->overlap ? 1 : 0) + (o->d.tile_sorted ? 1 : 0);
+        const int unroll = o->graph_exec_multi ? o->tune.graph_unroll : 0;
+        for (int g = 0; g < generations;) {
+            const bool multi = unroll > 1 && generations - g >= unroll;
+            CU(cudaGraphLaunch(multi ? o->graph_exec_multi : o->graph_exec, o->stream));
+            const int done = multi ? unroll : 1;
+            g_launches += (long long)done * (4 + (o->d_Lf ? (o->cfg.rng == LMCMA_B200_RNG_PHILOX ? 2 : 1) : 0) + (o->upd_gram ? 3 : 0) + (o->overlap ? 1 : 0) + (o->d.tile_sorted ? 1 : 0));
+            g += done;
         }
     } else {
         if (o->cfg.rng == LMCMA_B200_RNG_INJECT && generations > 1)
