@@ -82,7 +82,7 @@ struct Tuning {
                             // through the finished pairs beside the ranking: 66.5 -> 63.2 us per C2 generation once the newest row's
                             // chain stopped being the longer branch)
     int tell_spec = 1;      // tell_all: speculative update of the next generation at the end of the graph (LMCMA_B200_TELL_SPEC=0: off)
-    int graph_unroll = 4;   // fused generations per CUDA graph for runs of at least that many (LMCMA_B200_GRAPH_UNROLL, 1 = off)
+    int graph_unroll = 8;   // fused generations per CUDA graph for runs of at least that many (LMCMA_B200_GRAPH_UNROLL, 1 = off)
     int update_warps = 0;   // k_update CTA size: 0 = by batch size, 8 / 16 forced (LMCMA_B200_UPDATE_WARPS)
     int update_dry = 1;     // overlapped generation: pre-execute the post-rank code while k_rank is busy (k_update.cuh)
     int graph_dbg = 0, dbg = 0, update_dbg = 0, cost_dbg = 0;
@@ -111,7 +111,7 @@ struct Tuning {
         t.update_dry = env_int("LMCMA_B200_UPDATE_DRY", 1);
         t.tell_spec = env_int("LMCMA_B200_TELL_SPEC", 1);
         t.update_warps = env_int("LMCMA_B200_UPDATE_WARPS", 0);
-        t.graph_unroll = env_int("LMCMA_B200_GRAPH_UNROLL", 4);
+        t.graph_unroll = env_int("LMCMA_B200_GRAPH_UNROLL", 8);
         if (t.graph_unroll < 1 || t.graph_unroll > 64) t.graph_unroll = 1;
         t.rank_sorted = env_int("LMCMA_B200_RANK_SORTED", 1);
         t.graph_dbg = env_int("LMCMA_B200_GRAPH_DBG", 0);
